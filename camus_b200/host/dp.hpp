@@ -1,0 +1,469 @@
+// Host-side consumer of the hot path: scorers, the level-1 network DP, traceback and the
+// extended-newick writer. These stay on the host in the drop-in (SURVEY.md §2 "OUT OF SCOPE",
+// §8(f) rank 1); they are restated here in C++ only so that results can be carried through to
+// the networks the reference's golden files hold.
+//
+// Mirrors: internal/score/scorers.go:47-144, internal/infer/main_dp.go:40-291,
+// internal/infer/helpers.go:9-110, internal/infer/traceback.go:6-57, internal/graphs/net.go:38-101.
+#pragma once
+#include <array>
+#include <cmath>
+#include <string>
+#include <type_traits>
+#include <vector>
+
+#include "treedata.hpp"
+
+namespace camus {
+
+struct Branch {
+  int u = 0, w = 0;
+  bool collide(const Branch& o) const { return u == o.u || u == o.w || w == o.u || w == o.w; }
+};
+
+// ------------------------------------------------------------------------------------------
+// Scorers (scorers.go). They own the two integer tables produced by the hot path and turn
+// them into the DP's score type. All float math is here, on the host, exactly as in Go.
+// ------------------------------------------------------------------------------------------
+struct ScoreTables {
+  int n = 0;
+  std::vector<uint64_t> totals;     // [u*n + w]  quartettotals.go:19-22
+  std::vector<uint64_t> penalties;  // [u*n + w]  penalty.go:11-29 (norm / sym only)
+  bool as_set = false;
+  uint64_t n_survivors = 0;  // len(qCounts)                 treedata.go:305-307
+  uint64_t sum_counts = 0;   // exact sum; truncated to u32  treedata.go:297-303
+};
+
+struct MaximizeScorer {
+  using S = uint64_t;
+  const ScoreTables* t;
+  S calc(int u, int w) const { return t->totals[(size_t)u * t->n + w]; }  // scorers.go:62-64
+};
+struct NormalizedScorer {
+  using S = double;
+  const ScoreTables* t;
+  int n_gtree;
+  S calc(int u, int w) const {  // scorers.go:101-103
+    size_t i = (size_t)u * t->n + w;
+    return double(t->totals[i]) / (double(n_gtree) * double(t->penalties[i]));
+  }
+};
+struct SymDiffScorer {
+  using S = double;
+  const ScoreTables* t;
+  int n_gtree;  // the reference never sets it (infer.go:84-85) -> 0
+  double alpha;
+  S calc(int u, int w) const {  // scorers.go:142-144
+    size_t i = (size_t)u * t->n + w;
+    return 2 * double(t->totals[i]) - alpha * double(t->penalties[i]) * double(n_gtree);
+  }
+};
+
+// QuartetTotals.PercentQuartetSat (quartettotals.go:25-40), with the uint32 truncation of
+// TotalNumQuartets / TotalNumUniqueQuartets (treedata.go:297-307).
+inline double percent_quartet_sat(const ScoreTables& t, const std::vector<Branch>& branches) {
+  uint64_t sum = 0;
+  for (const Branch& b : branches) sum += t.totals[(size_t)b.u * t.n + b.w];
+  uint32_t denom = t.as_set ? (uint32_t)t.n_survivors : (uint32_t)t.sum_counts;
+  return 100 * double(sum) / double(denom);
+}
+
+// ------------------------------------------------------------------------------------------
+// helpers.go
+// ------------------------------------------------------------------------------------------
+template <class S>
+inline bool best_split(const std::vector<S>& l, const std::vector<S>& r, int k, int& kl, int& kr) {
+  if ((int)l.size() + (int)r.size() - 2 < k) return false;
+  S best{};
+  bool found = false;
+  kl = kr = -1;
+  int lo = std::max(0, k - ((int)r.size() - 1)), hi = std::min(k, (int)l.size() - 1);
+  for (int i = lo; i <= hi; ++i) {
+    S cur = l[i] + r[k - i];
+    if (cur > best || !found) {
+      best = cur;
+      kl = i;
+      kr = k - i;
+      found = true;
+    }
+  }
+  return true;
+}
+
+template <class S>
+inline void solve_all_splits(const std::vector<S>& a, const std::vector<S>& b, int k,
+                             std::vector<std::array<int, 2>>& sol, std::vector<S>& sc) {
+  sol.clear();
+  sc.clear();
+  for (int i = 0; i <= k; ++i) {
+    int l, r;
+    if (!best_split(a, b, i, l, r)) break;
+    sol.push_back({l, r});
+    sc.push_back(a[l] + b[r]);
+  }
+}
+
+template <class S>
+inline bool four_way_best_split(const std::vector<S>* lists[4], int k, int idx[4]) {
+  int combined = 0;
+  for (int i = 0; i < 4; ++i) combined += (int)lists[i]->size();
+  if (combined - 4 < k) return false;
+  std::vector<std::array<int, 2>> s1, s2;
+  std::vector<S> c1, c2;
+  solve_all_splits(*lists[0], *lists[1], k, s1, c1);
+  solve_all_splits(*lists[2], *lists[3], k, s2, c2);
+  int i1, i2;
+  if (!best_split(c1, c2, k, i1, i2)) throw CamusError(Err::Internal, "did not find expected split");
+  idx[0] = s1[i1][0];
+  idx[1] = s1[i1][1];
+  idx[2] = s2[i2][0];
+  idx[3] = s2[i2][1];
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------
+// traceback.go, as an index arena instead of Go pointers. A "trace ref" names the entry
+// Traceback[v][k]; Go's `&dp.Traceback[v][k]` points at exactly that (immutable) slot.
+// ------------------------------------------------------------------------------------------
+struct TraceArena {
+  struct Trace {
+    bool cycle = false;
+    int prev0 = -1, prev1 = -1;    // noCycleTrace.prevs
+    int pathW = -1, pathU = -1;    // cycleTraceNode ids
+    int wDown = -1, uDown = -1;    // trace ids
+    Branch branch;
+  };
+  struct CTN {
+    int sib = -1;  // trace id
+    int p = -1;    // CTN id
+  };
+  std::vector<Trace> traces;
+  std::vector<CTN> ctns;
+
+  int add(const Trace& t) {
+    traces.push_back(t);
+    return (int)traces.size() - 1;
+  }
+  int add_ctn(int p, int sib) {
+    ctns.push_back({sib, p});
+    return (int)ctns.size() - 1;
+  }
+  void traceback(int id, std::vector<Branch>& out) const {
+    const Trace& t = traces[id];
+    if (!t.cycle) {  // noCycleTrace.traceback
+      if (t.prev0 < 0) return;
+      traceback(t.prev0, out);
+      traceback(t.prev1, out);
+      return;
+    }
+    traceback(t.wDown, out);  // cycleTrace.traceback
+    out.push_back(t.branch);
+    if (t.uDown >= 0) traceback(t.uDown, out);
+    if (t.pathU >= 0) trace_up(t.pathU, out);
+    if (t.pathW >= 0) trace_up(t.pathW, out);
+  }
+  void trace_up(int c, std::vector<Branch>& out) const {
+    traceback(ctns[c].sib, out);
+    if (ctns[c].p >= 0) trace_up(ctns[c].p, out);
+  }
+};
+
+struct DPResults {
+  std::vector<std::vector<Branch>> branches;  // per k = 1..m
+  std::vector<double> qsat;
+  std::vector<double> root_scores_f;  // DP[root][k] as double (for logging / tests)
+  std::vector<uint64_t> root_scores_u;
+};
+
+// ------------------------------------------------------------------------------------------
+// main_dp.go
+// ------------------------------------------------------------------------------------------
+template <class Scorer>
+class DP {
+  using S = typename Scorer::S;
+
+ public:
+  DP(const TreeData& td, const Scorer& sc) : td_(td), sc_(sc), n_(td.n()), dp_(n_), tb_(n_) {}
+
+  void run() {  // RunDP, main_dp.go:90-104 (gotree PostOrder = children in order, then node)
+    std::vector<int> order;
+    order.reserve(n_);
+    post_order(0, order);
+    for (int v : order) {
+      if (!td_.tip(v)) {
+        solve(v);
+      } else {
+        dp_[v].assign(1, S{});
+        TraceArena::Trace t;
+        tb_[v].assign(1, arena_.add(t));
+      }
+    }
+  }
+
+  const std::vector<S>& root_scores() const { return dp_[0]; }
+  std::vector<Branch> traceback(int k) const {
+    std::vector<Branch> out;
+    arena_.traceback(tb_[0][k], out);
+    return out;
+  }
+
+ private:
+  const TreeData& td_;
+  const Scorer& sc_;
+  int n_;
+  std::vector<std::vector<S>> dp_;
+  std::vector<std::vector<int>> tb_;
+  TraceArena arena_;
+  // cycleDP of the vertex being solved (main_dp.go:30-34)
+  std::vector<std::vector<S>> cs_;
+  std::vector<std::vector<int>> ct_;
+
+  void post_order(int v, std::vector<int>& out) const {
+    std::vector<std::pair<int, int>> st{{v, 0}};
+    while (!st.empty()) {
+      int x = st.back().first, i = st.back().second;
+      if (td_.tip(x) || i == 2) {
+        out.push_back(x);
+        st.pop_back();
+      } else {
+        st.back().second = i + 1;
+        st.push_back({td_.children[x][i], 0});
+      }
+    }
+  }
+  template <class F>
+  void subtree_pre(int v, F&& f) const {  // helpers.go:37-47
+    int end = td_.subtree_end[v];
+    for (int x = v; x < end; ++x) f(x);  // ids are preorder, so the subtree is an id interval
+  }
+  template <class F>
+  void subtree_post_helper(int cur, int other, F&& f) const {  // helpers.go:26-35
+    std::vector<int> order;
+    post_order(cur, order);
+    for (int x : order) f(x, other);
+  }
+
+  void cdp_update(int v, int prevK) {  // main_dp.go:40-72
+    subtree_pre(v, [&](int cur) {
+      if (prevK == 0) {
+        cs_[cur].clear();
+        ct_[cur].clear();
+      }
+      cs_[cur].push_back(S{});
+      ct_[cur].push_back(-1);
+      if (cur == v) return;
+      int p = td_.parent[cur];
+      if (p == v) return;
+      int sib = td_.sibling(cur);
+      int pK, sK;
+      if (!best_split(cs_[p], dp_[sib], prevK, pK, sK)) return;
+      cs_[cur][prevK] = cs_[p][pK] + dp_[sib][sK];
+      ct_[cur][prevK] = arena_.add_ctn(ct_[p][pK], tb_[sib][sK]);
+    });
+  }
+
+  struct Cand {
+    bool ok = false;
+    S score{};
+    int trace = -1;
+    Branch br;
+  };
+
+  Cand score_edges_down(int v, int prevK) {  // main_dp.go:219-244
+    Cand best;
+    subtree_pre(v, [&](int w) {
+      if (!should_calc_edge(v, w, td_)) return;
+      S edge = sc_.calc(v, w);
+      int wp, wd;
+      if (!best_split(cs_[w], dp_[w], prevK, wp, wd)) return;
+      S score = edge + cs_[w][wp] + dp_[w][wd];
+      if (score > best.score || !best.ok) {
+        TraceArena::Trace t;
+        t.cycle = true;
+        t.pathW = ct_[w][wp];
+        t.wDown = tb_[w][wd];
+        t.branch = {v, w};
+        best.trace = arena_.add(t);
+        best.br = t.branch;
+        best.score = score;
+        best.ok = true;
+      }
+    });
+    return best;
+  }
+
+  Cand score_edges_across(int u, int sub, int prevK) {  // main_dp.go:247-287
+    Cand best;
+    subtree_pre(sub, [&](int w) {
+      S edge = sc_.calc(u, w);
+      const std::vector<S>* lists[4] = {&cs_[w], &cs_[u], &dp_[w], &dp_[u]};
+      int idx[4];
+      if (!four_way_best_split(lists, prevK, idx)) return;
+      S score = edge + cs_[w][idx[0]] + cs_[u][idx[1]] + dp_[w][idx[2]] + dp_[u][idx[3]];
+      if (score > best.score || !best.ok) {
+        TraceArena::Trace t;
+        t.cycle = true;
+        t.pathW = ct_[w][idx[0]];
+        t.pathU = ct_[u][idx[1]];
+        t.wDown = tb_[w][idx[2]];
+        t.uDown = tb_[u][idx[3]];
+        t.branch = {u, w};
+        best.trace = arena_.add(t);
+        best.br = t.branch;
+        best.score = score;
+        best.ok = true;
+      }
+    });
+    return best;
+  }
+
+  Cand score_add_edge_k(int v, int k) {  // main_dp.go:178-216
+    int prevK = k - 1;
+    Cand best;
+    int bestLen = 0;
+    cdp_update(v, prevK);
+    auto consider = [&](const Cand& c) {
+      if (!c.ok) return;
+      int len = cycle_length(c.br.u, c.br.w, td_);
+      if (c.score > best.score || !best.ok || (c.score == best.score && len <= bestLen)) {
+        best = c;
+        bestLen = len;
+      }
+    };
+    for (int c : td_.children[v]) {
+      if (td_.tip(c)) continue;
+      consider(score_edges_down(v, prevK));
+    }
+    int c0 = td_.children[v][0], c1 = td_.children[v][1];
+    subtree_post_helper(c0, c1, [&](int u, int other) { consider(score_edges_across(u, other, prevK)); });
+    subtree_post_helper(c1, c0, [&](int u, int other) { consider(score_edges_across(u, other, prevK)); });
+    return best;
+  }
+
+  void solve(int v) {  // main_dp.go:130-166
+    int l = td_.children[v][0], r = td_.children[v][1];
+    std::vector<S> scores{dp_[l][0] + dp_[r][0]};
+    TraceArena::Trace t0;
+    t0.prev0 = tb_[l][0];
+    t0.prev1 = tb_[r][0];
+    std::vector<int> traces{arena_.add(t0)};
+    if (cs_.empty()) {
+      cs_.resize(n_);
+      ct_.resize(n_);
+    }
+    for (int k = 1;; ++k) {
+      S score{};
+      int bt = -1;
+      int lK, rK;
+      if (best_split(dp_[l], dp_[r], k, lK, rK)) {  // scoreNoAddEdgeK, main_dp.go:169-174
+        score = dp_[l][lK] + dp_[r][rK];
+        TraceArena::Trace t;
+        t.prev0 = tb_[l][lK];
+        t.prev1 = tb_[r][rK];
+        bt = arena_.add(t);
+      }
+      Cand e = score_add_edge_k(v, k);
+      if (e.ok && e.score > score) {
+        score = e.score;
+        bt = e.trace;
+      }
+      if (bt < 0 || scores[k - 1] >= score) break;
+      scores.push_back(score);
+      traces.push_back(bt);
+      if (k == n_ * n_) throw CamusError(Err::Internal, "runaway loop");
+    }
+    dp_[v] = std::move(scores);
+    tb_[v] = std::move(traces);
+  }
+};
+
+// ------------------------------------------------------------------------------------------
+// graphs.MakeNetwork + Network.Newick (net.go:38-101). The branch order (and so the #Hk
+// numbering) comes from Go's slices.SortFunc with a comparator that is not a total order; for
+// <= 12 branches Go runs a plain insertion sort, restated here. Above 12 Go switches to pdqsort
+// and the numbering is NOT reproduced (SURVEY.md §8c caution) -- the branch set still is.
+// ------------------------------------------------------------------------------------------
+inline std::string make_network_newick(const TreeData& td, std::vector<Branch> branches) {
+  auto cmp = [&](const Branch& a, const Branch& b) {
+    if (a.collide(b)) {
+      if (td.under(a.u, b.u) || td.under(a.u, b.w) || td.under(a.w, b.u) || td.under(a.w, b.w)) return -1;
+      return 1;
+    }
+    return 0;
+  };
+  for (size_t i = 1; i < branches.size(); ++i)
+    for (size_t j = i; j > 0 && cmp(branches[j], branches[j - 1]) < 0; --j) std::swap(branches[j], branches[j - 1]);
+  Tree t = td.tree;  // td.Clone()
+  auto graft = [&](int tip, int child) {  // gotree GraftTipOnEdge on the edge above `child`
+    int p = t.nodes[child].parent;
+    int m = t.add_node();
+    t.nodes[m].parent = p;
+    auto& pc = t.nodes[p].children;
+    *std::find(pc.begin(), pc.end(), child) = m;
+    t.nodes[m].children = {tip, child};
+    t.nodes[tip].parent = m;
+    t.nodes[child].parent = m;
+    return m;
+  };
+  for (size_t i = 0; i < branches.size(); ++i) {
+    std::string h = "#H" + std::to_string(i + 1);
+    int r = t.add_node();
+    t.nodes[r].name = h;
+    graft(r, td.id_to_node[branches[i].u]);
+    r = t.add_node();
+    t.nodes[r].name = "####";
+    int m = graft(r, td.id_to_node[branches[i].w]);
+    t.nodes[m].name = h;
+  }
+  std::string nwk = t.newick();
+  auto replace_all = [](std::string s, const std::string& a, const std::string& b) {
+    size_t p = 0;
+    while ((p = s.find(a, p)) != std::string::npos) {
+      s.replace(p, a.size(), b);
+      p += b.size();
+    }
+    return s;
+  };
+  nwk = replace_all(nwk, "####,", "");
+  nwk = replace_all(nwk, ",####", "");
+  return nwk;
+}
+
+enum class ScoreMode : int { Max = 0, Norm = 1, Sym = 2 };
+
+// infer.Infer after Preprocess + Scorer.Init (infer.go:79-95) and DP.collateResults
+// (main_dp.go:106-127): run the DP over precomputed tables.
+inline DPResults run_dp(const TreeData& td, const ScoreTables& tabs, ScoreMode mode, int n_gtrees, double alpha) {
+  DPResults res;
+  auto collate = [&](auto& dp) {
+    const auto& rs = dp.root_scores();
+    int m = (int)rs.size() - 1;
+    for (int k = 0; k <= m; ++k) {
+      res.root_scores_f.push_back(double(rs[k]));
+      if constexpr (std::is_same_v<std::decay_t<decltype(rs[k])>, uint64_t>) res.root_scores_u.push_back(rs[k]);
+    }
+    for (int k = 1; k <= m; ++k) {
+      res.branches.push_back(dp.traceback(k));
+      res.qsat.push_back(percent_quartet_sat(tabs, res.branches.back()));
+    }
+  };
+  if (mode == ScoreMode::Max) {
+    MaximizeScorer sc{&tabs};
+    DP<MaximizeScorer> dp(td, sc);
+    dp.run();
+    collate(dp);
+  } else if (mode == ScoreMode::Norm) {
+    NormalizedScorer sc{&tabs, n_gtrees};
+    DP<NormalizedScorer> dp(td, sc);
+    dp.run();
+    collate(dp);
+  } else {
+    SymDiffScorer sc{&tabs, 0, alpha};  // NGTree is never set for sym (infer.go:84-85)
+    DP<SymDiffScorer> dp(td, sc);
+    dp.run();
+    collate(dp);
+  }
+  return res;
+}
+
+}  // namespace camus

@@ -1,0 +1,136 @@
+// extern "C" surface of the host-side mirror (libcamus_host.so): parsing + flattening on one
+// side of the hot path, scorers + DP + network writer on the other. Used by the Python tests,
+// bench.py and the `camus` CLI. Contains NO quartet counting / scoring: that is the C-ABI in
+// include/camus_b200.h (CUDA) -- or, in tests only, the oracle.
+#include <cstring>
+#include <memory>
+
+#include "dp.hpp"
+
+using namespace camus;
+
+namespace {
+thread_local std::string g_err;
+int fail(const CamusError& e) {
+  g_err = e.what();
+  return (int)e.code;
+}
+}  // namespace
+
+struct camus_host_problem {
+  TreeData td;
+  ConstraintFlat cf;
+  GeneFlat gf;
+  int n_gene_trees = 0;
+  bool warned_missing = false;
+  double pct_no_support = 0;
+  std::string constraint_newick;
+};
+
+struct camus_host_results {
+  DPResults res;
+  std::vector<std::string> newicks;
+};
+
+extern "C" {
+
+const char* camus_host_last_error(void) { return g_err.c_str(); }
+
+// prep.ReadInputFiles + host half of prep.Preprocess (io.go:81-170, preprocess.go:26-44,87-100).
+// gene_format: 0 newick, 1 nexus. Returns 0 or a camus::Err code.
+int camus_host_load(const char* constraint_text, const char* gene_text, int gene_format, double min_support,
+                    camus_host_problem** out) {
+  try {
+    auto p = std::make_unique<camus_host_problem>();
+    Tree tre = read_constraint_text(constraint_text);
+    GeneTrees gts;
+    if (gene_text && *gene_text)
+      gts = gene_format == 1 ? read_gene_trees_nexus(gene_text) : read_gene_trees_newick(gene_text);
+    p->td = make_tree_data(std::move(tre));
+    p->cf = flatten_constraint(p->td);
+    p->pct_no_support = gts.trees.empty() ? 0 : percent_no_support(gts.trees);
+    p->gf = flatten_gene_trees(gts.trees, p->td, min_support, [&](const std::string&) { p->warned_missing = true; });
+    p->n_gene_trees = (int)gts.trees.size();
+    p->constraint_newick = p->td.tree.newick();
+    *out = p.release();
+    return 0;
+  } catch (const CamusError& e) {
+    return fail(e);
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return (int)Err::Internal;
+  }
+}
+
+void camus_host_free(camus_host_problem* p) { delete p; }
+
+void camus_host_dims(const camus_host_problem* p, int32_t* n_nodes, int32_t* n_taxa, int32_t* n_trees,
+                     int64_t* total_gene_nodes) {
+  *n_nodes = p->cf.n_nodes;
+  *n_taxa = p->cf.n_taxa;
+  *n_trees = p->gf.n_trees();
+  *total_gene_nodes = (int64_t)p->gf.parent.size();
+}
+const int32_t* camus_host_constraint_parent(const camus_host_problem* p) { return p->cf.parent.data(); }
+const int32_t* camus_host_constraint_child0(const camus_host_problem* p) { return p->cf.child0.data(); }
+const int32_t* camus_host_constraint_child1(const camus_host_problem* p) { return p->cf.child1.data(); }
+const int32_t* camus_host_constraint_tip_index(const camus_host_problem* p) { return p->cf.tip_index.data(); }
+const int64_t* camus_host_gene_node_off(const camus_host_problem* p) { return p->gf.node_off.data(); }
+const int32_t* camus_host_gene_parent(const camus_host_problem* p) { return p->gf.parent.data(); }
+const int32_t* camus_host_gene_taxon(const camus_host_problem* p) { return p->gf.taxon.data(); }
+int camus_host_warned_missing(const camus_host_problem* p) { return p->warned_missing; }
+double camus_host_percent_no_support(const camus_host_problem* p) { return p->pct_no_support; }
+const char* camus_host_constraint_newick(const camus_host_problem* p) { return p->constraint_newick.c_str(); }
+const char* camus_host_tip_name(const camus_host_problem* p, int tip_index) {
+  return (tip_index >= 0 && tip_index < p->td.n_leaves) ? p->td.tip_names[tip_index].c_str() : "";
+}
+const char* camus_host_node_name(const camus_host_problem* p, int id) {
+  return (id >= 0 && id < p->td.n()) ? p->td.tree.nodes[p->td.id_to_node[id]].name.c_str() : "";
+}
+int camus_host_should_calc_edge(const camus_host_problem* p, int u, int w) { return should_calc_edge(u, w, p->td); }
+int camus_host_cycle_length(const camus_host_problem* p, int u, int w) { return cycle_length(u, w, p->td); }
+
+// infer.Infer after Scorer.Init (infer.go:79-95): DP + traceback + MakeNetwork over the two
+// integer tables the hot path produced. mode: 0 max, 1 norm, 2 sym. penalties may be NULL for max.
+int camus_host_run_dp(const camus_host_problem* p, int mode, const uint64_t* totals, const uint64_t* penalties,
+                      int as_set, uint64_t n_survivors, uint64_t sum_counts, int n_gtrees, double alpha,
+                      camus_host_results** out) {
+  try {
+    ScoreTables tabs;
+    tabs.n = p->td.n();
+    size_t nn = (size_t)tabs.n * tabs.n;
+    tabs.totals.assign(totals, totals + nn);
+    if (penalties) tabs.penalties.assign(penalties, penalties + nn);
+    else tabs.penalties.assign(nn, 0);
+    tabs.as_set = as_set != 0;
+    tabs.n_survivors = n_survivors;
+    tabs.sum_counts = sum_counts;
+    auto r = std::make_unique<camus_host_results>();
+    r->res = run_dp(p->td, tabs, (ScoreMode)mode, n_gtrees, alpha);
+    for (auto& b : r->res.branches) r->newicks.push_back(make_network_newick(p->td, b));
+    *out = r.release();
+    return 0;
+  } catch (const CamusError& e) {
+    return fail(e);
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return (int)Err::Internal;
+  }
+}
+void camus_host_results_free(camus_host_results* r) { delete r; }
+int camus_host_results_count(const camus_host_results* r) { return (int)r->res.branches.size(); }
+// writes 2*k ints (u0,w0,u1,w1,...) for the k-branch solution (k = 1..count), traceback order
+int camus_host_results_branches(const camus_host_results* r, int k, int32_t* uw) {
+  if (k < 1 || k > (int)r->res.branches.size()) return -1;
+  const auto& b = r->res.branches[k - 1];
+  for (size_t i = 0; i < b.size(); ++i) {
+    uw[2 * i] = b[i].u;
+    uw[2 * i + 1] = b[i].w;
+  }
+  return (int)b.size();
+}
+double camus_host_results_qsat(const camus_host_results* r, int k) { return r->res.qsat[k - 1]; }
+double camus_host_results_root_score(const camus_host_results* r, int k) { return r->res.root_scores_f[k]; }
+const char* camus_host_results_newick(const camus_host_results* r, int k) { return r->newicks[k - 1].c_str(); }
+
+}  // extern "C"

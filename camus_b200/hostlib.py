@@ -1,0 +1,180 @@
+"""ctypes binding of libcamus_host.so: the host-side mirror of the reference's Go packages
+(parsing + flattening before the hot path, scorers + DP + network writer after it).
+
+Nothing here counts or scores quartets; that is `camus_b200.cabi` (CUDA, include/camus_b200.h).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import gzip
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import build
+
+# camus::Err (host/tree.hpp) <-> the reference's sentinel errors
+ERR_NAMES = {
+    1: "ErrUnrooted", 2: "ErrNonBinary", 3: "ErrMulTree", 4: "ErrTipNameMismatch",
+    5: "ErrInvalidFile", 6: "ErrInvalidFormat", 7: "ErrTypeOutRange", 8: "ErrInvalidScorerOption",
+    9: "ErrDevice", 10: "ErrInternal",
+}
+
+
+class CamusError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"{ERR_NAMES.get(code, code)}: {msg}")
+        self.code = code
+        self.name = ERR_NAMES.get(code, str(code))
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(build.HOST_SO):
+            build.build_host()
+        L = C.CDLL(build.HOST_SO)
+        L.camus_host_last_error.restype = C.c_char_p
+        L.camus_host_load.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_double, C.POINTER(C.c_void_p)]
+        L.camus_host_free.argtypes = [C.c_void_p]
+        L.camus_host_dims.argtypes = [C.c_void_p] + [C.POINTER(C.c_int32)] * 3 + [C.POINTER(C.c_int64)]
+        for nm in ("constraint_parent", "constraint_child0", "constraint_child1", "constraint_tip_index",
+                   "gene_parent", "gene_taxon"):
+            f = getattr(L, "camus_host_" + nm)
+            f.argtypes = [C.c_void_p]
+            f.restype = C.POINTER(C.c_int32)
+        L.camus_host_gene_node_off.argtypes = [C.c_void_p]
+        L.camus_host_gene_node_off.restype = C.POINTER(C.c_int64)
+        L.camus_host_warned_missing.argtypes = [C.c_void_p]
+        L.camus_host_percent_no_support.argtypes = [C.c_void_p]
+        L.camus_host_percent_no_support.restype = C.c_double
+        L.camus_host_constraint_newick.argtypes = [C.c_void_p]
+        L.camus_host_constraint_newick.restype = C.c_char_p
+        L.camus_host_tip_name.argtypes = [C.c_void_p, C.c_int]
+        L.camus_host_tip_name.restype = C.c_char_p
+        L.camus_host_node_name.argtypes = [C.c_void_p, C.c_int]
+        L.camus_host_node_name.restype = C.c_char_p
+        L.camus_host_should_calc_edge.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.camus_host_cycle_length.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.camus_host_run_dp.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_uint64,
+                                        C.c_uint64, C.c_int, C.c_double, C.POINTER(C.c_void_p)]
+        L.camus_host_results_free.argtypes = [C.c_void_p]
+        L.camus_host_results_count.argtypes = [C.c_void_p]
+        L.camus_host_results_branches.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int32)]
+        L.camus_host_results_qsat.argtypes = [C.c_void_p, C.c_int]
+        L.camus_host_results_qsat.restype = C.c_double
+        L.camus_host_results_root_score.argtypes = [C.c_void_p, C.c_int]
+        L.camus_host_results_root_score.restype = C.c_double
+        L.camus_host_results_newick.argtypes = [C.c_void_p, C.c_int]
+        L.camus_host_results_newick.restype = C.c_char_p
+        _lib = L
+    return _lib
+
+
+def read_text(path: str) -> str:
+    if path.endswith(".gz"):
+        with gzip.open(path, "rt") as f:
+            return f.read()
+    with open(path) as f:
+        return f.read()
+
+
+@dataclass
+class DPResult:
+    branches: list[list[tuple[int, int]]]  # per k
+    qsat: list[float]
+    root_scores: list[float]               # DP[root][k], k = 0..m
+    newicks: list[str]
+
+
+class Problem:
+    """Parsed + validated + flattened input: what the Go side hands to the C-ABI.
+
+    Mirrors prep.ReadInputFiles (io.go:81) and the host half of prep.Preprocess
+    (preprocess.go:26-44, 87-100)."""
+
+    def __init__(self, constraint_text: str, gene_text: str, fmt: str = "newick", min_support: float = 0.0):
+        L = lib()
+        h = C.c_void_p()
+        rc = L.camus_host_load(constraint_text.encode(), gene_text.encode(), 1 if fmt == "nexus" else 0,
+                               float(min_support), C.byref(h))
+        if rc != 0:
+            raise CamusError(rc, L.camus_host_last_error().decode())
+        self._h = h
+        nn, nt, ng = C.c_int32(), C.c_int32(), C.c_int32()
+        tot = C.c_int64()
+        L.camus_host_dims(h, C.byref(nn), C.byref(nt), C.byref(ng), C.byref(tot))
+        self.n_nodes, self.n_taxa, self.n_trees, self.total_gene_nodes = nn.value, nt.value, ng.value, tot.value
+
+        def arr(fn, n, dt):
+            if n == 0:
+                return np.zeros(0, dt)
+            return np.ctypeslib.as_array(fn(h), shape=(n,)).astype(dt, copy=True)
+
+        self.parent = arr(L.camus_host_constraint_parent, self.n_nodes, np.int32)
+        self.child0 = arr(L.camus_host_constraint_child0, self.n_nodes, np.int32)
+        self.child1 = arr(L.camus_host_constraint_child1, self.n_nodes, np.int32)
+        self.tip_index = arr(L.camus_host_constraint_tip_index, self.n_nodes, np.int32)
+        self.gene_node_off = arr(L.camus_host_gene_node_off, self.n_trees + 1, np.int64)
+        self.gene_parent = arr(L.camus_host_gene_parent, self.total_gene_nodes, np.int32)
+        self.gene_taxon = arr(L.camus_host_gene_taxon, self.total_gene_nodes, np.int32)
+        self.warned_missing = bool(L.camus_host_warned_missing(h))
+        self.constraint_newick = L.camus_host_constraint_newick(h).decode()
+        self.tip_names = [L.camus_host_tip_name(h, i).decode() for i in range(self.n_taxa)]
+        self.node_names = [L.camus_host_node_name(h, i).decode() for i in range(self.n_nodes)]
+
+    @classmethod
+    def from_files(cls, constraint_file: str, gene_file: str, fmt: str = "newick", min_support: float = 0.0):
+        return cls(read_text(constraint_file), read_text(gene_file), fmt, min_support)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().camus_host_free(self._h)
+            self._h = None
+
+    def node_id(self, label: str) -> int:
+        return self.node_names.index(label)
+
+    def tip_id(self, label: str) -> int:
+        return self.tip_names.index(label)
+
+    def should_calc_edge(self, u: int, w: int) -> bool:
+        return bool(lib().camus_host_should_calc_edge(self._h, u, w))
+
+    def cycle_length(self, u: int, w: int) -> int:
+        return lib().camus_host_cycle_length(self._h, u, w)
+
+    def run_dp(self, totals: np.ndarray, penalties: np.ndarray | None = None, mode: str = "max", as_set: bool = False,
+               n_survivors: int = 0, sum_counts: int = 0, n_gtrees: int | None = None, alpha: float = 0.1) -> DPResult:
+        """infer.Infer after Scorer.Init (infer.go:79-95): DP + traceback + MakeNetwork."""
+        L = lib()
+        totals = np.ascontiguousarray(totals, dtype=np.uint64)
+        assert totals.size == self.n_nodes * self.n_nodes
+        pen_p = None
+        if penalties is not None:
+            penalties = np.ascontiguousarray(penalties, dtype=np.uint64)
+            pen_p = penalties.ctypes.data_as(C.c_void_p)
+        r = C.c_void_p()
+        rc = L.camus_host_run_dp(self._h, {"max": 0, "norm": 1, "sym": 2}[mode], totals.ctypes.data_as(C.c_void_p),
+                                 pen_p, int(as_set), int(n_survivors), int(sum_counts),
+                                 int(self.n_trees if n_gtrees is None else n_gtrees), float(alpha), C.byref(r))
+        if rc != 0:
+            raise CamusError(rc, L.camus_host_last_error().decode())
+        try:
+            m = L.camus_host_results_count(r)
+            branches, qsat, newicks = [], [], []
+            roots = [L.camus_host_results_root_score(r, 0)]
+            for k in range(1, m + 1):
+                buf = (C.c_int32 * (2 * k))()
+                nb = L.camus_host_results_branches(r, k, buf)
+                branches.append([(buf[2 * i], buf[2 * i + 1]) for i in range(nb)])
+                qsat.append(L.camus_host_results_qsat(r, k))
+                roots.append(L.camus_host_results_root_score(r, k))
+                newicks.append(L.camus_host_results_newick(r, k).decode())
+            return DPResult(branches, qsat, roots, newicks)
+        finally:
+            L.camus_host_results_free(r)
