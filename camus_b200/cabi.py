@@ -1,0 +1,167 @@
+"""ctypes binding of the CUDA C-ABI (include/camus_b200.h, libcamus_b200.so).
+
+This is the same boundary a cgo shim binds. There is no fallback: if the library
+is missing or no sm_100 device is usable, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build
+
+STAGES = ["upload", "prep", "count", "filter", "score", "final", "penalty", "_"]
+
+_lib = None
+
+
+class CamusB200Error(RuntimeError):
+    pass
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(build.CUDA_SO):
+            raise CamusB200Error(
+                f"{build.CUDA_SO} is missing: build it with `python -m camus_b200.build cuda` "
+                "(there is no CPU fallback for the hot path)")
+        L = C.CDLL(build.CUDA_SO)
+        vp, u64p = C.c_void_p, C.POINTER(C.c_uint64)
+        L.camus_b200_create.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(C.c_int)]
+        L.camus_b200_destroy.argtypes = [vp]
+        L.camus_b200_last_error.argtypes = [vp]
+        L.camus_b200_last_error.restype = C.c_char_p
+        L.camus_b200_set_partition.argtypes = [vp, C.c_int, C.c_int]
+        L.camus_b200_set_constraint.argtypes = [vp, C.c_int32, C.c_int32, vp, vp, vp, vp]
+        L.camus_b200_add_gene_trees.argtypes = [vp, C.c_int32, vp, vp, vp]
+        L.camus_b200_clear_gene_trees.argtypes = [vp]
+        L.camus_b200_count_filter.argtypes = [vp, C.c_int, C.c_double, u64p, u64p]
+        L.camus_b200_quartet_totals.argtypes = [vp, C.c_int, vp]
+        L.camus_b200_edge_penalties.argtypes = [vp, vp]
+        L.camus_b200_export_quartets.argtypes = [vp, C.c_int, vp, vp, C.c_uint64, u64p]
+        L.camus_b200_quartet_totals_partial.argtypes = [vp, C.c_int]
+        L.camus_b200_partial_buffer.argtypes = [vp, C.POINTER(vp), u64p]
+        L.camus_b200_quartet_totals_finish.argtypes = [vp, vp]
+        L.camus_b200_stage_ms.argtypes = [vp, C.POINTER(C.c_float), u64p]
+        L.camus_b200_workload.argtypes = [vp, u64p, u64p, u64p]
+        _lib = L
+    return _lib
+
+
+EXPORTED = [
+    "camus_b200_create", "camus_b200_destroy", "camus_b200_last_error", "camus_b200_set_partition",
+    "camus_b200_set_constraint", "camus_b200_add_gene_trees", "camus_b200_clear_gene_trees",
+    "camus_b200_count_filter", "camus_b200_quartet_totals", "camus_b200_edge_penalties",
+    "camus_b200_export_quartets", "camus_b200_quartet_totals_partial", "camus_b200_partial_buffer",
+    "camus_b200_quartet_totals_finish", "camus_b200_stage_ms", "camus_b200_workload",
+]
+
+
+def _p(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class CamusB200:
+    """One context on one GPU. Method names and argument meaning follow include/camus_b200.h."""
+
+    def __init__(self, device: int = 0):
+        L = lib()
+        h = C.c_void_p()
+        dev = (C.c_int * 1)(device)
+        rc = L.camus_b200_create(C.byref(h), 1, dev)
+        if rc != 0:
+            raise CamusB200Error(L.camus_b200_last_error(None).decode())
+        self._h = h
+        self.n = 0
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().camus_b200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def _ck(self, rc: int):
+        if rc != 0:
+            raise CamusB200Error(f"[{rc}] " + lib().camus_b200_last_error(self._h).decode())
+
+    def set_partition(self, rank: int, world: int):
+        self._ck(lib().camus_b200_set_partition(self._h, rank, world))
+
+    def set_constraint(self, parent, child0, child1, tip_index, n_taxa: int):
+        a = [np.ascontiguousarray(x, np.int32) for x in (parent, child0, child1, tip_index)]
+        self.n = len(a[0])
+        self._ck(lib().camus_b200_set_constraint(self._h, self.n, n_taxa, *[_p(x) for x in a]))
+
+    def add_gene_trees(self, node_off, parent, taxon):
+        node_off = np.ascontiguousarray(node_off, np.int64)
+        parent = np.ascontiguousarray(parent, np.int32)
+        taxon = np.ascontiguousarray(taxon, np.int32)
+        self._ck(lib().camus_b200_add_gene_trees(self._h, len(node_off) - 1, _p(node_off), _p(parent), _p(taxon)))
+
+    def clear_gene_trees(self):
+        self._ck(lib().camus_b200_clear_gene_trees(self._h))
+
+    def load(self, prob):
+        """prob: camus_b200.hostlib.Problem (its flat arrays are what the Go side would pass)."""
+        self.set_constraint(prob.parent, prob.child0, prob.child1, prob.tip_index, prob.n_taxa)
+        if prob.n_trees:
+            self.add_gene_trees(prob.gene_node_off, prob.gene_parent, prob.gene_taxon)
+        return self
+
+    def count_filter(self, qmode: int = 0, threshold: float = 0.0):
+        ns, sc = C.c_uint64(), C.c_uint64()
+        self._ck(lib().camus_b200_count_filter(self._h, qmode, threshold, C.byref(ns), C.byref(sc)))
+        return ns.value, sc.value
+
+    def quartet_totals(self, as_set: bool = False, out: np.ndarray | None = None) -> np.ndarray:
+        if out is None:
+            out = np.empty((self.n, self.n), np.uint64)
+        self._ck(lib().camus_b200_quartet_totals(self._h, int(as_set), _p(out)))
+        return out
+
+    def edge_penalties(self, out: np.ndarray | None = None) -> np.ndarray:
+        if out is None:
+            out = np.empty((self.n, self.n), np.uint64)
+        self._ck(lib().camus_b200_edge_penalties(self._h, _p(out)))
+        return out
+
+    def export_quartets(self, raw: bool = False):
+        n = C.c_uint64()
+        self._ck(lib().camus_b200_export_quartets(self._h, int(raw), None, None, 0, C.byref(n)))
+        keys = np.zeros(n.value, np.uint64)
+        counts = np.zeros(n.value, np.uint32)
+        if n.value:
+            self._ck(lib().camus_b200_export_quartets(self._h, int(raw), _p(keys), _p(counts), n.value, C.byref(n)))
+        return keys, counts
+
+    # ---- split form for multi-process runs ----
+    def quartet_totals_partial(self, as_set: bool = False):
+        self._ck(lib().camus_b200_quartet_totals_partial(self._h, int(as_set)))
+
+    def partial_buffer(self):
+        ptr, n = C.c_void_p(), C.c_uint64()
+        self._ck(lib().camus_b200_partial_buffer(self._h, C.byref(ptr), C.byref(n)))
+        return ptr.value, n.value
+
+    def quartet_totals_finish(self, out: np.ndarray | None = None) -> np.ndarray:
+        if out is None:
+            out = np.empty((self.n, self.n), np.uint64)
+        self._ck(lib().camus_b200_quartet_totals_finish(self._h, _p(out)))
+        return out
+
+    # ---- instrumentation ----
+    def stage_ms(self):
+        ms = (C.c_float * 8)()
+        nl = C.c_uint64()
+        self._ck(lib().camus_b200_stage_ms(self._h, ms, C.byref(nl)))
+        return {STAGES[i]: ms[i] for i in range(7)}, nl.value
+
+    def workload(self):
+        r, c, b = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._ck(lib().camus_b200_workload(self._h, C.byref(r), C.byref(c), C.byref(b)))
+        return {"resolutions": r.value, "cells": c.value, "boxes": b.value}

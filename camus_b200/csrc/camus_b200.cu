@@ -1,0 +1,634 @@
+// libcamus_b200.so: context management + the C-ABI of include/camus_b200.h over the sm_100a
+// kernels in kernels_*.cuh. Host code here only validates and re-indexes the flat trees, plans
+// memory, launches kernels and copies results; every quartet is counted, filtered and scored on
+// the GPU. There is no CPU fallback.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "camus_b200.h"
+#include "kernels_count.cuh"
+#include "kernels_prep.cuh"
+#include "kernels_score.cuh"
+
+using namespace camus_dev;
+
+namespace {
+
+thread_local std::string g_create_err;
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  cudaError_t alloc(size_t count) {
+    if (count <= n && p) return cudaSuccess;
+    release();
+    if (count == 0) return cudaSuccess;
+    cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+    if (e == cudaSuccess) n = count;
+    return e;
+  }
+  size_t bytes() const { return n * sizeof(T); }
+};
+
+}  // namespace
+
+struct camus_b200 {
+  int device = 0;
+  std::string err;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  int rank = 0, world = 1;
+
+  // ---- constraint tree ----
+  int n = 0, N = 0, npad = 0, M = 0;
+  std::vector<int32_t> int_of_ref, rank_of_tip_h;
+  DevBuf<int32_t> d_parent, d_depth, d_sz, d_rc, d_nleaves, d_firstleaf, d_leafnode, d_tip_of_rank, d_ref_id, d_rank_of_tip;
+  DevBuf<uint32_t> d_lcaD;
+  ConstraintDev ct{};
+
+  // ---- gene trees (host staging until the next count) ----
+  std::vector<int64_t> h_node_off{0};
+  std::vector<int32_t> h_parent, h_taxon;
+  uint64_t resolutions = 0;
+  int G = 0, G32 = 0;
+  bool genes_dirty = true;  // triple planes need (re)building
+
+  // ---- device state ----
+  DevBuf<int64_t> d_node_off;
+  DevBuf<int32_t> d_gparent, d_gtaxon, d_nleaf;
+  DevBuf<uint16_t> d_depth_tmp, d_lrT, d_hT, d_Dt;
+  DevBuf<uint32_t> d_tri;
+  DevBuf<uint4> d_cells;
+  DevBuf<unsigned long long> d_Z, d_E, d_out, d_totals, d_keys, d_nout;
+  DevBuf<uint32_t> d_counts;
+  uint64_t box_lo = 0, box_hi = 0;  // this rank's partition
+  enum CellState { NONE, RAW, FILTERED } cell_state = NONE;
+  int last_qmode = 0;
+  double last_threshold = 0;
+  bool z_valid = false;
+  int z_as_set = -1;
+
+  float ms[CAMUS_B200_T_N] = {0};
+  uint64_t launches = 0;
+
+  int fail(int code, const std::string& m) {
+    err = m;
+    return code;
+  }
+};
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess)                                                                        \
+      return ctx->fail(CAMUS_B200_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
+  } while (0)
+
+#define CK_LAUNCH()              \
+  do {                           \
+    ++ctx->launches;             \
+    CK(cudaGetLastError());      \
+  } while (0)
+
+namespace {
+
+struct StageTimer {
+  camus_b200* ctx;
+  int stage;
+  StageTimer(camus_b200* c, int s) : ctx(c), stage(s) { cudaEventRecord(ctx->ev[0], ctx->stream); }
+  int stop() {
+    cudaEventRecord(ctx->ev[1], ctx->stream);
+    cudaError_t e = cudaEventSynchronize(ctx->ev[1]);
+    if (e != cudaSuccess) return ctx->fail(CAMUS_B200_ERR_CUDA, std::string("stage sync: ") + cudaGetErrorString(e));
+    float t = 0;
+    cudaEventElapsedTime(&t, ctx->ev[0], ctx->ev[1]);
+    ctx->ms[stage] += t;
+    return 0;
+  }
+};
+
+template <class T>
+int upload(camus_b200* ctx, DevBuf<T>& buf, const T* src, size_t count) {
+  CK(buf.alloc(std::max<size_t>(count, 1)));
+  if (count) CK(cudaMemcpyAsync(buf.p, src, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+  return 0;
+}
+
+int build_planes(camus_b200* ctx);
+int run_count(camus_b200* ctx);
+int run_filter(camus_b200* ctx, int qmode, double threshold, uint64_t* ns, uint64_t* sum);
+
+uint64_t cells_budget_boxes(size_t free_bytes) {
+  size_t reserve = (size_t)3 << 30;
+  size_t budget = free_bytes > reserve ? free_bytes - reserve : free_bytes / 2;
+  budget = std::min<size_t>(budget, (size_t)48 << 30);
+  return std::max<uint64_t>(1, budget / (kBoxCells * sizeof(uint4)));
+}
+
+}  // namespace
+
+extern "C" {
+
+int camus_b200_create(camus_b200** out, int n_gpus, const int* devices) {
+  if (!out) return CAMUS_B200_ERR_ARG;
+  *out = nullptr;
+  if (n_gpus != 1) {
+    g_create_err = "camus_b200_create: n_gpus must be 1 (one process per GPU; see camus_b200_set_partition)";
+    return CAMUS_B200_ERR_ARG;
+  }
+  int dev = devices ? devices[0] : 0;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    g_create_err = std::string("camus_b200_create: no usable CUDA device (") +
+                   (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0") + "); there is no CPU fallback";
+    return CAMUS_B200_ERR_CUDA;
+  }
+  if (dev < 0 || dev >= count) {
+    g_create_err = "camus_b200_create: device ordinal out of range";
+    return CAMUS_B200_ERR_ARG;
+  }
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, dev);
+  if (prop.major != 10) {
+    g_create_err = "camus_b200_create: device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                   ", this library is built for sm_100a only";
+    return CAMUS_B200_ERR_CUDA;
+  }
+  camus_b200* ctx = new camus_b200();
+  ctx->device = dev;
+  if (cudaSetDevice(dev) != cudaSuccess || cudaStreamCreate(&ctx->stream) != cudaSuccess ||
+      cudaEventCreate(&ctx->ev[0]) != cudaSuccess || cudaEventCreate(&ctx->ev[1]) != cudaSuccess) {
+    g_create_err = std::string("camus_b200_create: ") + cudaGetErrorString(cudaGetLastError());
+    delete ctx;
+    return CAMUS_B200_ERR_CUDA;
+  }
+  cudaFuncSetAttribute(k_count, cudaFuncAttributeMaxDynamicSharedMemorySize, kCountSmemBytes);
+  *out = ctx;
+  return CAMUS_B200_OK;
+}
+
+void camus_b200_destroy(camus_b200* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->ev[0]) cudaEventDestroy(ctx->ev[0]);
+  if (ctx->ev[1]) cudaEventDestroy(ctx->ev[1]);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* camus_b200_last_error(const camus_b200* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int camus_b200_set_partition(camus_b200* ctx, int rank, int world) {
+  if (!ctx || world < 1 || rank < 0 || rank >= world) return ctx ? ctx->fail(CAMUS_B200_ERR_ARG, "bad partition") : CAMUS_B200_ERR_ARG;
+  ctx->rank = rank;
+  ctx->world = world;
+  ctx->cell_state = camus_b200::NONE;
+  ctx->z_valid = false;
+  return 0;
+}
+
+int camus_b200_set_constraint(camus_b200* ctx, int32_t n_nodes, int32_t n_taxa, const int32_t* parent,
+                              const int32_t* child0, const int32_t* child1, const int32_t* tip_index) {
+  if (!ctx) return CAMUS_B200_ERR_ARG;
+  if (!parent || !child0 || !child1 || !tip_index || n_taxa < 2 || n_nodes != 2 * n_taxa - 1)
+    return ctx->fail(CAMUS_B200_ERR_ARG, "set_constraint: need a rooted binary tree (n_nodes = 2*n_taxa - 1)");
+  if (n_taxa > 32767) return ctx->fail(CAMUS_B200_ERR_ARG, "set_constraint: at most 32767 taxa (15-bit packing, quartet.go:17)");
+  CK(cudaSetDevice(ctx->device));
+  const int n = n_nodes, N = n_taxa;
+  int root = -1;
+  for (int i = 0; i < n; ++i) {
+    if (parent[i] < 0) {
+      if (root >= 0) return ctx->fail(CAMUS_B200_ERR_INPUT, "set_constraint: more than one root");
+      root = i;
+    }
+    bool tip = child0[i] < 0;
+    if (tip != (child1[i] < 0) || (tip && (tip_index[i] < 0 || tip_index[i] >= N)) || (!tip && (child0[i] >= n || child1[i] >= n)))
+      return ctx->fail(CAMUS_B200_ERR_INPUT, "set_constraint: node is neither a tip nor binary");
+  }
+  if (root < 0) return ctx->fail(CAMUS_B200_ERR_INPUT, "set_constraint: no root");
+  // internal preorder ids (left child = id + 1), DFS ranks of the leaves
+  std::vector<int32_t> ref_of_int, par(n), depth(n), sz(n, 1), rc(n, -1), nleaves(n, 0), firstleaf(n, 0);
+  std::vector<int32_t> leafnode(N), tip_of_rank(N);
+  ctx->int_of_ref.assign(n, -1);
+  ctx->rank_of_tip_h.assign(N, -1);
+  ref_of_int.reserve(n);
+  {
+    std::vector<int> st{root};
+    while (!st.empty()) {
+      int x = st.back();
+      st.pop_back();
+      if (ctx->int_of_ref[x] >= 0 || (int)ref_of_int.size() >= n)
+        return ctx->fail(CAMUS_B200_ERR_INPUT, "set_constraint: child pointers do not form a tree");
+      ctx->int_of_ref[x] = (int)ref_of_int.size();
+      ref_of_int.push_back(x);
+      if (child0[x] >= 0) {
+        st.push_back(child1[x]);
+        st.push_back(child0[x]);
+      }
+    }
+    if ((int)ref_of_int.size() != n) return ctx->fail(CAMUS_B200_ERR_INPUT, "set_constraint: unreachable nodes");
+  }
+  int nl = 0;
+  for (int i = 0; i < n; ++i) {
+    int r = ref_of_int[i];
+    par[i] = parent[r] < 0 ? -1 : ctx->int_of_ref[parent[r]];
+    if (par[i] >= i) return ctx->fail(CAMUS_B200_ERR_INPUT, "set_constraint: parent/child arrays disagree");
+    depth[i] = par[i] < 0 ? 0 : depth[par[i]] + 1;
+    if (child0[r] >= 0) {
+      rc[i] = ctx->int_of_ref[child1[r]];
+    } else {
+      if (nl >= N || ctx->rank_of_tip_h[tip_index[r]] >= 0) return ctx->fail(CAMUS_B200_ERR_INPUT, "set_constraint: tip indices are not a permutation");
+      leafnode[nl] = i;
+      tip_of_rank[nl] = tip_index[r];
+      ctx->rank_of_tip_h[tip_index[r]] = nl;
+      nleaves[i] = 1;
+      firstleaf[i] = nl;
+      ++nl;
+    }
+  }
+  if (nl != N) return ctx->fail(CAMUS_B200_ERR_INPUT, "set_constraint: leaf count mismatch");
+  for (int i = n - 1; i > 0; --i) {
+    sz[par[i]] += sz[i];
+    nleaves[par[i]] += nleaves[i];
+  }
+  for (int i = n - 1; i >= 0; --i)
+    if (rc[i] >= 0) firstleaf[i] = firstleaf[i + 1];
+  ctx->n = n;
+  ctx->N = N;
+  ctx->npad = (N + kSeg - 1) / kSeg * kSeg;
+  ctx->M = ctx->npad / kSeg;
+  if (upload(ctx, ctx->d_parent, par.data(), n) || upload(ctx, ctx->d_depth, depth.data(), n) ||
+      upload(ctx, ctx->d_sz, sz.data(), n) || upload(ctx, ctx->d_rc, rc.data(), n) ||
+      upload(ctx, ctx->d_nleaves, nleaves.data(), n) || upload(ctx, ctx->d_firstleaf, firstleaf.data(), n) ||
+      upload(ctx, ctx->d_leafnode, leafnode.data(), N) || upload(ctx, ctx->d_tip_of_rank, tip_of_rank.data(), N) ||
+      upload(ctx, ctx->d_ref_id, ref_of_int.data(), n) || upload(ctx, ctx->d_rank_of_tip, ctx->rank_of_tip_h.data(), N))
+    return CAMUS_B200_ERR_CUDA;
+  CK(ctx->d_lcaD.alloc((size_t)N * N));
+  ctx->ct = ConstraintDev{n, N, ctx->d_parent.p, ctx->d_depth.p, ctx->d_sz.p, ctx->d_rc.p, ctx->d_nleaves.p,
+                          ctx->d_firstleaf.p, ctx->d_leafnode.p, ctx->d_tip_of_rank.p, ctx->d_ref_id.p, ctx->d_lcaD.p};
+  dim3 grid((N + 127) / 128, N);
+  k_constraint_lca<<<grid, 128, 0, ctx->stream>>>(N, ctx->d_leafnode.p, ctx->d_parent.p, ctx->d_sz.p, ctx->d_depth.p, ctx->d_lcaD.p);
+  CK_LAUNCH();
+  CK(cudaStreamSynchronize(ctx->stream));
+  // taxon numbering changed: gene trees given for an earlier constraint are dropped
+  ctx->h_node_off.assign(1, 0);
+  ctx->h_parent.clear();
+  ctx->h_taxon.clear();
+  ctx->resolutions = 0;
+  ctx->G = 0;
+  ctx->genes_dirty = true;
+  ctx->cell_state = camus_b200::NONE;
+  ctx->z_valid = false;
+  return 0;
+}
+
+int camus_b200_clear_gene_trees(camus_b200* ctx) {
+  if (!ctx) return CAMUS_B200_ERR_ARG;
+  ctx->h_node_off.assign(1, 0);
+  ctx->h_parent.clear();
+  ctx->h_taxon.clear();
+  ctx->resolutions = 0;
+  ctx->G = 0;
+  ctx->genes_dirty = true;
+  ctx->cell_state = camus_b200::NONE;
+  ctx->z_valid = false;
+  return 0;
+}
+
+int camus_b200_add_gene_trees(camus_b200* ctx, int32_t n_trees, const int64_t* node_off, const int32_t* parent,
+                              const int32_t* taxon) {
+  if (!ctx) return CAMUS_B200_ERR_ARG;
+  if (ctx->n == 0) return ctx->fail(CAMUS_B200_ERR_ARG, "add_gene_trees: set the constraint tree first");
+  if (n_trees < 0 || !node_off || (n_trees > 0 && (!parent || !taxon))) return ctx->fail(CAMUS_B200_ERR_ARG, "add_gene_trees: null argument");
+  std::vector<int> stamp(ctx->N, -1);
+  std::vector<char> has_child;
+  uint64_t res = 0;
+  for (int g = 0; g < n_trees; ++g) {
+    int64_t b = node_off[g], e = node_off[g + 1];
+    int64_t nn = e - b;
+    if (nn <= 0 || nn > 65000) return ctx->fail(CAMUS_B200_ERR_INPUT, "add_gene_trees: tree " + std::to_string(g) + " has " + std::to_string(nn) + " nodes (1..65000 supported)");
+    has_child.assign(nn, 0);
+    uint64_t nl = 0;
+    for (int64_t i = 0; i < nn; ++i) {
+      int p = parent[b + i];
+      if ((i == 0) != (p < 0) || p >= i)
+        return ctx->fail(CAMUS_B200_ERR_INPUT, "add_gene_trees: tree " + std::to_string(g) + " is not in preorder (parent before child, single root)");
+      if (p >= 0) has_child[p] = 1;
+      int t = taxon[b + i];
+      if (t >= ctx->N) return ctx->fail(CAMUS_B200_ERR_INPUT, "add_gene_trees: taxon index out of range");
+      if (t >= 0) {
+        if (stamp[t] == g) return ctx->fail(CAMUS_B200_ERR_INPUT, "add_gene_trees: tree " + std::to_string(g) + " contains a taxon twice");
+        stamp[t] = g;
+        ++nl;
+      }
+    }
+    for (int64_t i = 0; i < nn; ++i)
+      if ((taxon[b + i] >= 0) == (has_child[i] != 0))
+        return ctx->fail(CAMUS_B200_ERR_INPUT, "add_gene_trees: tree " + std::to_string(g) + ": taxon set on an internal node or missing on a leaf");
+    res += choose4(nl);
+  }
+  int64_t base = ctx->h_node_off.back() - node_off[0];
+  for (int g = 0; g < n_trees; ++g) ctx->h_node_off.push_back(node_off[g + 1] + base);
+  size_t cnt = n_trees ? (size_t)(node_off[n_trees] - node_off[0]) : 0;
+  ctx->h_parent.insert(ctx->h_parent.end(), parent + (n_trees ? node_off[0] : 0), parent + (n_trees ? node_off[0] : 0) + cnt);
+  ctx->h_taxon.insert(ctx->h_taxon.end(), taxon + (n_trees ? node_off[0] : 0), taxon + (n_trees ? node_off[0] : 0) + cnt);
+  ctx->resolutions += res;
+  ctx->G = (int)ctx->h_node_off.size() - 1;
+  ctx->genes_dirty = true;
+  ctx->cell_state = camus_b200::NONE;
+  ctx->z_valid = false;
+  return 0;
+}
+
+}  // extern "C"
+
+namespace {
+
+// K0 + K1 + K1b: gene trees -> rooted-triple bit-planes in HBM.
+int build_planes(camus_b200* ctx) {
+  const int G = ctx->G, npad = ctx->npad;
+  ctx->G32 = (G + kLanes - 1) / kLanes;
+  const int G32 = std::max(ctx->G32, 1);
+  {
+    StageTimer t(ctx, CAMUS_B200_T_UPLOAD);
+    if (upload(ctx, ctx->d_node_off, ctx->h_node_off.data(), ctx->h_node_off.size()) ||
+        upload(ctx, ctx->d_gparent, ctx->h_parent.data(), ctx->h_parent.size()) ||
+        upload(ctx, ctx->d_gtaxon, ctx->h_taxon.data(), ctx->h_taxon.size()))
+      return CAMUS_B200_ERR_CUDA;
+    if (t.stop()) return CAMUS_B200_ERR_CUDA;
+  }
+  StageTimer t(ctx, CAMUS_B200_T_PREP);
+  size_t per_group = (size_t)npad * kLanes;
+  CK(ctx->d_depth_tmp.alloc(std::max<size_t>(ctx->h_parent.size(), 1)));
+  CK(ctx->d_nleaf.alloc(std::max(G, 1)));
+  CK(ctx->d_lrT.alloc(per_group * G32));
+  CK(ctx->d_hT.alloc(per_group * G32));
+  CK(cudaMemsetAsync(ctx->d_lrT.p, 0, ctx->d_lrT.bytes(), ctx->stream));
+  CK(cudaMemsetAsync(ctx->d_hT.p, 0, ctx->d_hT.bytes(), ctx->stream));
+  size_t tri_words = (size_t)num_tiles(ctx->M) * G32 * kTileWords;
+  size_t free_b = 0, total_b = 0;
+  CK(cudaMemGetInfo(&free_b, &total_b));
+  if (ctx->d_tri.n < tri_words && tri_words * 4 + ((size_t)4 << 30) > free_b + ctx->d_tri.bytes())
+    return ctx->fail(CAMUS_B200_ERR_NOMEM, "triple bit-planes need " + std::to_string(tri_words * 4 >> 20) + " MiB, device has " +
+                                               std::to_string(free_b >> 20) + " MiB free");
+  CK(ctx->d_tri.alloc(tri_words));
+  CK(cudaMemsetAsync(ctx->d_tri.p, 0, tri_words * 4, ctx->stream));
+  if (G > 0) {
+    k_tree_prepare<<<(G + 127) / 128, 128, 0, ctx->stream>>>(G, ctx->d_node_off.p, ctx->d_gparent.p, ctx->d_gtaxon.p,
+                                                            ctx->d_rank_of_tip.p, ctx->d_depth_tmp.p, ctx->d_lrT.p,
+                                                            ctx->d_hT.p, npad, ctx->d_nleaf.p);
+    CK_LAUNCH();
+    size_t dt_group = (size_t)npad * npad * kLanes;  // u16 elements
+    int gb_max = (int)std::max<size_t>(1, std::min<size_t>(ctx->G32, ((size_t)1 << 30) / (dt_group * 2)));
+    CK(ctx->d_Dt.alloc(dt_group * gb_max));
+    uint64_t n_pairs = choose2(npad);
+    for (int g0 = 0; g0 < ctx->G32; g0 += gb_max) {
+      int gb = std::min(gb_max, ctx->G32 - g0);
+      CK(cudaMemsetAsync(ctx->d_Dt.p, 0, dt_group * gb * 2, ctx->stream));
+      dim3 blk(kLanes, 8);
+      dim3 g1((npad + 7) / 8, gb);
+      k_depth_table<<<g1, blk, 0, ctx->stream>>>(g0, G, npad, ctx->d_nleaf.p, ctx->d_lrT.p, ctx->d_hT.p, ctx->d_Dt.p);
+      CK_LAUNCH();
+      dim3 g2((unsigned)((n_pairs + 7) / 8), gb);
+      k_triple_planes<<<g2, blk, 0, ctx->stream>>>(g0, G32, npad, ctx->d_Dt.p, ctx->d_tri.p, n_pairs);
+      CK_LAUNCH();
+    }
+  }
+  if (t.stop()) return CAMUS_B200_ERR_CUDA;
+  ctx->genes_dirty = false;
+  return 0;
+}
+
+// K2 over this rank's box range (whole range resident in d_cells).
+int run_count(camus_b200* ctx) {
+  uint64_t nb = num_boxes(ctx->M);
+  ctx->box_lo = nb * ctx->rank / ctx->world;
+  ctx->box_hi = nb * (ctx->rank + 1) / ctx->world;
+  uint64_t mine = ctx->box_hi - ctx->box_lo;
+  size_t free_b = 0, total_b = 0;
+  CK(cudaMemGetInfo(&free_b, &total_b));
+  if (ctx->d_cells.n < mine * kBoxCells && mine > cells_budget_boxes(free_b + ctx->d_cells.bytes()))
+    return ctx->fail(CAMUS_B200_ERR_NOMEM, "cell table of " + std::to_string(mine * kBoxCells * 16 >> 20) +
+                                               " MiB does not fit; streaming mode is not in this build");
+  CK(ctx->d_cells.alloc(std::max<uint64_t>(mine, 1) * kBoxCells));
+  StageTimer t(ctx, CAMUS_B200_T_COUNT);
+  const uint64_t max_grid = 1u << 30;
+  for (uint64_t b0 = 0; b0 < mine; b0 += max_grid) {
+    uint64_t nbx = std::min(max_grid, mine - b0);
+    CountParams prm{ctx->d_tri.p, std::max(ctx->G32, 1), ctx->box_lo + b0, ctx->d_cells.p + b0 * kBoxCells};
+    k_count<<<(unsigned)nbx, kCountThreads, kCountSmemBytes, ctx->stream>>>(prm);
+    CK_LAUNCH();
+  }
+  if (t.stop()) return CAMUS_B200_ERR_CUDA;
+  ctx->cell_state = camus_b200::RAW;
+  ctx->z_valid = false;
+  return 0;
+}
+
+int run_filter(camus_b200* ctx, int qmode, double threshold, uint64_t* ns, uint64_t* sum) {
+  uint64_t mine = ctx->box_hi - ctx->box_lo;
+  CK(ctx->d_totals.alloc(2));
+  StageTimer t(ctx, CAMUS_B200_T_FILTER);
+  CK(cudaMemsetAsync(ctx->d_totals.p, 0, 16, ctx->stream));
+  const uint64_t max_boxes = 1u << 26;
+  for (uint64_t b0 = 0; b0 < mine; b0 += max_boxes) {
+    uint64_t nbx = std::min(max_boxes, mine - b0);
+    FilterParams prm{ctx->d_cells.p + b0 * kBoxCells, ctx->box_lo + b0, qmode, threshold, ctx->d_totals.p};
+    k_filter<<<(unsigned)(nbx * 16), 256, 0, ctx->stream>>>(prm, ctx->ct);
+    CK_LAUNCH();
+  }
+  unsigned long long h[2] = {0, 0};
+  CK(cudaMemcpyAsync(h, ctx->d_totals.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
+  if (t.stop()) return CAMUS_B200_ERR_CUDA;
+  if (ns) *ns = h[0];
+  if (sum) *sum = h[1];
+  ctx->cell_state = camus_b200::FILTERED;
+  ctx->last_qmode = qmode;
+  ctx->last_threshold = threshold;
+  ctx->z_valid = false;
+  return 0;
+}
+
+int ensure_filtered(camus_b200* ctx) {
+  if (ctx->cell_state == camus_b200::FILTERED) return 0;
+  if (ctx->cell_state == camus_b200::NONE) return ctx->fail(CAMUS_B200_ERR_ARG, "call camus_b200_count_filter first");
+  int rc = run_count(ctx);
+  if (rc) return rc;
+  return run_filter(ctx, ctx->last_qmode, ctx->last_threshold, nullptr, nullptr);
+}
+
+int run_score(camus_b200* ctx, int as_set) {
+  int rc = ensure_filtered(ctx);
+  if (rc) return rc;
+  size_t zn = (size_t)ctx->n * ctx->n * 3;
+  CK(ctx->d_Z.alloc(zn));
+  StageTimer t(ctx, CAMUS_B200_T_SCORE);
+  CK(cudaMemsetAsync(ctx->d_Z.p, 0, zn * 8, ctx->stream));
+  uint64_t mine = ctx->box_hi - ctx->box_lo;
+  const uint64_t max_boxes = 1u << 26;
+  for (uint64_t b0 = 0; b0 < mine; b0 += max_boxes) {
+    uint64_t nbx = std::min(max_boxes, mine - b0);
+    ScoreParams prm{ctx->d_cells.p + b0 * kBoxCells, ctx->box_lo + b0, as_set, ctx->d_Z.p};
+    k_score<<<(unsigned)(nbx * 16), 256, 0, ctx->stream>>>(prm, ctx->ct);
+    CK_LAUNCH();
+  }
+  if (t.stop()) return CAMUS_B200_ERR_CUDA;
+  ctx->z_valid = true;
+  ctx->z_as_set = as_set;
+  return 0;
+}
+
+int run_finish(camus_b200* ctx, uint64_t* out) {
+  if (!ctx->z_valid) return ctx->fail(CAMUS_B200_ERR_ARG, "quartet_totals_finish: no partial table (call quartet_totals_partial)");
+  const int n = ctx->n;
+  size_t en = (size_t)(n + 1) * (n + 1);
+  CK(ctx->d_E.alloc(en));
+  CK(ctx->d_out.alloc((size_t)n * n));
+  StageTimer t(ctx, CAMUS_B200_T_FINAL);
+  CK(cudaMemsetAsync(ctx->d_E.p, 0, en * 8, ctx->stream));
+  k_expand<<<dim3((n + 127) / 128, n), 128, 0, ctx->stream>>>(ctx->d_Z.p, ctx->d_E.p, ctx->ct);
+  CK_LAUNCH();
+  k_row_scan<<<n, 256, 0, ctx->stream>>>(ctx->d_E.p, n);
+  CK_LAUNCH();
+  k_col_scan<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_E.p, n);
+  CK_LAUNCH();
+  k_mask_out<<<dim3((n + 127) / 128, n), 128, 0, ctx->stream>>>(ctx->d_E.p, ctx->d_out.p, ctx->ct);
+  CK_LAUNCH();
+  CK(cudaMemcpyAsync(out, ctx->d_out.p, (size_t)n * n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (t.stop()) return CAMUS_B200_ERR_CUDA;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int camus_b200_count_filter(camus_b200* ctx, int qmode, double threshold, uint64_t* n_survivors, uint64_t* sum_counts) {
+  if (!ctx) return CAMUS_B200_ERR_ARG;
+  if (ctx->n == 0) return ctx->fail(CAMUS_B200_ERR_ARG, "count_filter: set the constraint tree first");
+  if (qmode < 0 || qmode > 2 || !(threshold >= 0 && threshold <= 1))
+    return ctx->fail(CAMUS_B200_ERR_ARG, "count_filter: quartet mode in [0,2] and threshold in [0,1] (quartetfilter.go:41-61)");
+  CK(cudaSetDevice(ctx->device));
+  std::memset(ctx->ms, 0, sizeof(ctx->ms));
+  ctx->launches = 0;
+  int rc;
+  if (ctx->genes_dirty && (rc = build_planes(ctx))) return rc;
+  if ((rc = run_count(ctx))) return rc;
+  return run_filter(ctx, qmode, threshold, n_survivors, sum_counts);
+}
+
+int camus_b200_quartet_totals_partial(camus_b200* ctx, int as_set) {
+  if (!ctx) return CAMUS_B200_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  return run_score(ctx, as_set != 0);
+}
+
+int camus_b200_partial_buffer(camus_b200* ctx, void** dev_ptr, uint64_t* n_int64) {
+  if (!ctx || !dev_ptr || !n_int64) return CAMUS_B200_ERR_ARG;
+  if (!ctx->z_valid) return ctx->fail(CAMUS_B200_ERR_ARG, "partial_buffer: call quartet_totals_partial first");
+  *dev_ptr = ctx->d_Z.p;
+  *n_int64 = (uint64_t)ctx->n * ctx->n * 3;
+  return 0;
+}
+
+int camus_b200_quartet_totals_finish(camus_b200* ctx, uint64_t* out) {
+  if (!ctx || !out) return CAMUS_B200_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  return run_finish(ctx, out);
+}
+
+int camus_b200_quartet_totals(camus_b200* ctx, int as_set, uint64_t* out) {
+  if (!ctx || !out) return CAMUS_B200_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  int rc = run_score(ctx, as_set != 0);
+  if (rc) return rc;
+  return run_finish(ctx, out);
+}
+
+int camus_b200_edge_penalties(camus_b200* ctx, uint64_t* out) {
+  if (!ctx || !out) return CAMUS_B200_ERR_ARG;
+  if (ctx->n == 0) return ctx->fail(CAMUS_B200_ERR_ARG, "edge_penalties: set the constraint tree first");
+  CK(cudaSetDevice(ctx->device));
+  const int n = ctx->n;
+  CK(ctx->d_out.alloc((size_t)n * n));
+  StageTimer t(ctx, CAMUS_B200_T_PENALTY);
+  k_penalties<<<dim3((n + 127) / 128, n), 128, 0, ctx->stream>>>(ctx->d_out.p, ctx->ct);
+  CK_LAUNCH();
+  CK(cudaMemcpyAsync(out, ctx->d_out.p, (size_t)n * n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (t.stop()) return CAMUS_B200_ERR_CUDA;
+  return 0;
+}
+
+int camus_b200_export_quartets(camus_b200* ctx, int raw, uint64_t* keys, uint32_t* counts, uint64_t cap, uint64_t* n_out) {
+  if (!ctx || !n_out) return CAMUS_B200_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  if (ctx->cell_state == camus_b200::NONE) return ctx->fail(CAMUS_B200_ERR_ARG, "export_quartets: call camus_b200_count_filter first");
+  int rc;
+  if (raw) {
+    if (ctx->cell_state != camus_b200::RAW && (rc = run_count(ctx))) return rc;
+  } else if ((rc = ensure_filtered(ctx))) {
+    return rc;
+  }
+  uint64_t mine = ctx->box_hi - ctx->box_lo;
+  CK(ctx->d_nout.alloc(1));
+  CK(ctx->d_keys.alloc(std::max<uint64_t>(cap, 1)));
+  CK(ctx->d_counts.alloc(std::max<uint64_t>(cap, 1)));
+  CK(cudaMemsetAsync(ctx->d_nout.p, 0, 8, ctx->stream));
+  const uint64_t max_boxes = 1u << 26;
+  for (uint64_t b0 = 0; b0 < mine; b0 += max_boxes) {
+    uint64_t nbx = std::min(max_boxes, mine - b0);
+    ExportParams prm{ctx->d_cells.p + b0 * kBoxCells, ctx->box_lo + b0, ctx->d_keys.p, ctx->d_counts.p, cap, ctx->d_nout.p};
+    k_export<<<(unsigned)(nbx * 16), 256, 0, ctx->stream>>>(prm, ctx->ct);
+    CK_LAUNCH();
+  }
+  unsigned long long total = 0;
+  CK(cudaMemcpyAsync(&total, ctx->d_nout.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  *n_out = total;
+  uint64_t got = std::min<uint64_t>(total, cap);
+  if (got && keys && counts) {
+    std::vector<unsigned long long> k(got);
+    std::vector<uint32_t> c(got);
+    CK(cudaMemcpy(k.data(), ctx->d_keys.p, got * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(c.data(), ctx->d_counts.p, got * 4, cudaMemcpyDeviceToHost));
+    std::vector<uint32_t> order(got);
+    for (uint64_t i = 0; i < got; ++i) order[i] = (uint32_t)i;
+    std::sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return k[x] < k[y]; });
+    for (uint64_t i = 0; i < got; ++i) {
+      keys[i] = k[order[i]];
+      counts[i] = c[order[i]];
+    }
+  }
+  return 0;
+}
+
+int camus_b200_stage_ms(const camus_b200* ctx, float* ms, uint64_t* n_launches) {
+  if (!ctx) return CAMUS_B200_ERR_ARG;
+  if (ms) std::memcpy(ms, ctx->ms, sizeof(ctx->ms));
+  if (n_launches) *n_launches = ctx->launches;
+  return 0;
+}
+
+int camus_b200_workload(const camus_b200* ctx, uint64_t* resolutions, uint64_t* n_cells, uint64_t* n_boxes) {
+  if (!ctx) return CAMUS_B200_ERR_ARG;
+  if (resolutions) *resolutions = ctx->resolutions;
+  if (n_cells) *n_cells = choose4((uint64_t)ctx->N);
+  if (n_boxes) *n_boxes = ctx->n ? num_boxes(ctx->M) : 0;
+  return 0;
+}
+
+}  // extern "C"

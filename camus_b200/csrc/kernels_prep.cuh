@@ -1,0 +1,140 @@
+// Stage 1 kernels: flat gene trees -> per-tree LCA-depth tables -> rooted-triple bit-planes.
+//
+// Replaces what gotree's bipartition enumerator does behind graphs.QuartetsFromTree
+// (internal/graphs/quartet.go:112-123, gotree Quartets at :119): instead of enumerating
+// (pair | pair) emissions per edge, every gene tree is reduced to the rooted-triple relation
+// "D(a,b) > D(a,c)" on its LCA depths, stored as one bit per tree (32 trees per word), from which
+// the count kernel resolves 32 trees per logical instruction.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "layout.cuh"
+
+namespace camus_dev {
+
+// ---------------------------------------------------------------------------------------------
+// K0: one thread per gene tree walks its preorder arrays once.
+//   depth[i] = depth[parent[i]] + 1
+//   leaves in DFS order -> lr[pos] = DFS rank (in the CONSTRAINT tree) of the pos-th leaf
+//   h[pos] = 1 + depth of LCA(leaf pos, leaf pos+1) = depth of the node that follows leaf pos in
+//            preorder (it hangs off that LCA). 0 is reserved for "taxon absent".
+// Outputs are interleaved by tree group: [group][pos][lane], lane = tree % 32.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_tree_prepare(int n_trees, const int64_t* __restrict__ node_off, const int32_t* __restrict__ parent,
+                               const int32_t* __restrict__ taxon, const int32_t* __restrict__ rank_of_tip,
+                               uint16_t* __restrict__ depth_tmp, uint16_t* __restrict__ lrT, uint16_t* __restrict__ hT,
+                               int npad, int32_t* __restrict__ nleaf) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_trees) return;
+  int64_t base = node_off[g];
+  int nn = (int)(node_off[g + 1] - base);
+  size_t grp = (size_t)(g >> 5);
+  int lane = g & 31;
+  int pos = 0;
+  bool prev_leaf = false;
+  for (int i = 0; i < nn; ++i) {
+    int p = parent[base + i];
+    uint16_t d = p < 0 ? 0 : (uint16_t)(depth_tmp[base + p] + 1);
+    depth_tmp[base + i] = d;
+    if (prev_leaf) {
+      hT[(grp * npad + (pos - 1)) * kLanes + lane] = d;  // = depth(LCA) + 1
+      prev_leaf = false;
+    }
+    int t = taxon[base + i];
+    if (t >= 0) {
+      lrT[(grp * npad + pos) * kLanes + lane] = (uint16_t)rank_of_tip[t];
+      ++pos;
+      prev_leaf = true;
+    }
+  }
+  nleaf[g] = pos;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1: LCA-depth table of every tree of a group batch, in constraint DFS-rank coordinates:
+//   Dt[gb][lo][hi][lane] = 1 + depth of LCA(lo, hi) in tree (grp0+gb)*32+lane, 0 if absent.
+// D(p, q) for DFS positions p < q of one tree is the running minimum of h[p..q-1]. Warp = one
+// start position p, lane = tree; h/lr reads are coalesced 64 B rows.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_depth_table(int grp0, int n_trees, int npad, const int32_t* __restrict__ nleaf,
+                              const uint16_t* __restrict__ lrT, const uint16_t* __restrict__ hT,
+                              uint16_t* __restrict__ Dt) {
+  int gb = blockIdx.y;
+  size_t grp = (size_t)(grp0 + gb);
+  int lane = threadIdx.x;
+  int g = (int)grp * kLanes + lane;
+  int p = blockIdx.x * blockDim.y + threadIdx.y;
+  int nl = g < n_trees ? nleaf[g] : 0;
+  if (p + 1 >= nl) return;
+  const uint16_t* lr = lrT + grp * npad * kLanes + lane;
+  const uint16_t* h = hT + grp * npad * kLanes + lane;
+  uint16_t* D = Dt + (size_t)gb * npad * npad * kLanes + lane;
+  uint32_t a = lr[(size_t)p * kLanes];
+  uint32_t m = 0xFFFFu;
+  for (int q = p + 1; q < nl; ++q) {
+    m = min(m, (uint32_t)h[(size_t)(q - 1) * kLanes]);
+    uint32_t b = lr[(size_t)q * kLanes];
+    uint32_t lo = min(a, b), hi = max(a, b);
+    D[((size_t)lo * npad + hi) * kLanes] = (uint16_t)m;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1b: rooted-triple bit-planes. Warp = one taxon pair (a < b), loop over c > b, lane = tree.
+//   plane 0 (ab|c): D(a,b) > D(a,c)      plane 1 (ac|b): D(a,c) > D(a,b)      plane 2 (bc|a): D(b,c) > D(a,b)
+// each AND "all three taxa present" (the != 0 tests). A polytomy (all three equal) sets no bit.
+// __ballot_sync transposes 32 per-tree predicates into one word; lanes 0..2 store the 3 planes at
+// Tri[tile(a,b,c)][group][tile_word(plane, a%8, b%8, c%8)].
+// ---------------------------------------------------------------------------------------------
+__global__ void k_triple_planes(int grp0, int n_groups_total, int npad, const uint16_t* __restrict__ Dt,
+                                uint32_t* __restrict__ Tri, uint64_t n_pairs) {
+  int gb = blockIdx.y;
+  int grp = grp0 + gb;
+  int lane = threadIdx.x;
+  uint64_t pr = (uint64_t)blockIdx.x * blockDim.y + threadIdx.y;
+  if (pr >= n_pairs) return;
+  uint32_t a, b;
+  pair_unrank(pr, a, b);
+  const uint16_t* D = Dt + (size_t)gb * npad * npad * kLanes + lane;
+  uint32_t Dab = D[((size_t)a * npad + b) * kLanes];
+  const uint16_t* rowa = D + (size_t)a * npad * kLanes;
+  const uint16_t* rowb = D + (size_t)b * npad * kLanes;
+  uint32_t sa = a >> 3, sb = b >> 3;
+  for (uint32_t c = b + 1; c < (uint32_t)npad; ++c) {
+    uint32_t Dac = rowa[(size_t)c * kLanes];
+    uint32_t Dbc = rowb[(size_t)c * kLanes];
+    bool p0 = Dab > Dac && Dac != 0;
+    bool p1 = Dac > Dab && Dab != 0;
+    bool p2 = Dbc > Dab && Dab != 0;
+    uint32_t w0 = __ballot_sync(0xFFFFFFFFu, p0);
+    uint32_t w1 = __ballot_sync(0xFFFFFFFFu, p1);
+    uint32_t w2 = __ballot_sync(0xFFFFFFFFu, p2);
+    if (lane < 3) {
+      uint64_t tile = tile_index(sa, sb, c >> 3);
+      uint32_t w = lane == 0 ? w0 : (lane == 1 ? w1 : w2);
+      Tri[(tile * n_groups_total + grp) * kTileWords + tile_word(lane, a & 7, b & 7, c & 7)] = w;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Constraint tree: LCA of every leaf pair (DFS ranks), packed (depth << 16 | node id). Node ids
+// are preorder, so "y in subtree(x)" is an interval test.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_constraint_lca(int n_taxa, const int32_t* __restrict__ leafnode, const int32_t* __restrict__ parent,
+                                 const int32_t* __restrict__ sz, const int32_t* __restrict__ depth,
+                                 uint32_t* __restrict__ lcaD) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  int a = blockIdx.y;
+  if (b >= n_taxa) return;
+  int x = leafnode[a], y = leafnode[b];
+  if (a > b) {
+    int t = x;
+    x = y;
+    y = t;
+  }
+  while (!(x <= y && y < x + sz[x])) x = parent[x];
+  lcaD[(size_t)a * n_taxa + b] = ((uint32_t)depth[x] << 16) | (uint32_t)x;
+}
+
+}  // namespace camus_dev

@@ -1,0 +1,401 @@
+// Stage 3-5 kernels: filter + constraint removal (K3), edge-score scatter (K4), finalisation
+// scans + ShouldCalcEdge mask (K5), penalties, and export of the surviving quartets.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "layout.cuh"
+#include "ptx.cuh"
+
+namespace camus_dev {
+
+// Constraint tree on the device. Node ids are INTERNAL preorder ids (root 0, left child = id+1,
+// subtree(x) = [x, x+sz[x])); ref_id maps back to the caller's ids. Taxa are DFS ranks.
+struct ConstraintDev {
+  int n, n_taxa;
+  const int32_t* parent;
+  const int32_t* depth;
+  const int32_t* sz;
+  const int32_t* rc;          // right child, -1 at tips
+  const int32_t* nleaves;     // leaves below node
+  const int32_t* firstleaf;   // DFS rank of the first leaf below node
+  const int32_t* leafnode;    // [n_taxa] node id of the leaf with that DFS rank
+  const int32_t* tip_of_rank; // [n_taxa] gotree tip index of that leaf
+  const int32_t* ref_id;      // [n]
+  const uint32_t* lcaD;       // [n_taxa][n_taxa] (depth << 16 | node) of the LCA of two leaves
+};
+
+struct CellCoords {
+  uint32_t a, b, c, d;
+  bool valid;
+};
+
+// 256 consecutive cells of one box per CTA; thread 0 unranks the box.
+__device__ __forceinline__ CellCoords decode_cell(uint64_t box0, int n_taxa, uint32_t* s_seg) {
+  if (threadIdx.x == 0) {
+    uint32_t sa, sb, sc, sd;
+    box_unrank(box0 + (blockIdx.x >> 4), sa, sb, sc, sd);
+    s_seg[0] = sa;
+    s_seg[1] = sb;
+    s_seg[2] = sc;
+    s_seg[3] = sd;
+  }
+  __syncthreads();
+  uint32_t local = ((blockIdx.x & 15u) << 8) | threadIdx.x;
+  CellCoords cc;
+  cc.a = s_seg[0] * 8 + (local & 7);
+  cc.b = s_seg[1] * 8 + ((local >> 3) & 7);
+  cc.c = s_seg[2] * 8 + ((local >> 6) & 7);
+  cc.d = s_seg[3] * 8 + (local >> 9);
+  cc.valid = cc.a < cc.b && cc.b < cc.c && cc.c < cc.d && cc.d < (uint32_t)n_taxa;
+  return cc;
+}
+
+// Topology the constraint tree displays on DFS-ordered a<b<c<d: 0 = ab|cd, 2 = ad|bc (never ac|bd).
+// g1,g2,g3 = packed LCAs of (a,b), (b,c), (c,d); the shallowest gap is the root split.
+__device__ __forceinline__ int constraint_topology(uint32_t g1, uint32_t g2, uint32_t g3) {
+  if (g2 < g1 && g2 < g3) return 0;
+  if (g1 < g3) return g2 < g3 ? 0 : 2;
+  return g1 < g2 ? 2 : 0;
+}
+
+// partner of taxon position i (0..3 = a,b,c,d) in topology t (0 ab|cd, 1 ac|bd, 2 ad|bc)
+__device__ __forceinline__ int partner_of(int t, int i) { return t == 0 ? (i ^ 1) : (t == 1 ? (i ^ 2) : (3 - i)); }
+
+// ---------------------------------------------------------------------------------------------
+// K3: prep.filterQuartets (internal/prep/quartetfilter.go:67-96) applied once per 4-set, then the
+// constraint-quartet removal (internal/prep/preprocess.go:51-57), then the two scalars
+// len(qCounts) and sum of counts (internal/graphs/treedata.go:297-307). In place on the cells.
+// Ties in the sort keep the reference's topology order 0b1100, 0b1010, 0b0110, which is defined
+// on taxa sorted by TIP INDEX (quartet.go:169-177), hence the rank computation below.
+// ---------------------------------------------------------------------------------------------
+struct FilterParams {
+  uint4* cells;
+  uint64_t box0;
+  int qmode;
+  double threshold;
+  unsigned long long* totals;  // [0] n_survivors, [1] sum_counts
+};
+
+__global__ void __launch_bounds__(256) k_filter(FilterParams prm, ConstraintDev ct) {
+  __shared__ uint32_t s_seg[4];
+  __shared__ unsigned long long s_red[2][8];
+  CellCoords cc = decode_cell(prm.box0, ct.n_taxa, s_seg);
+  size_t idx = (size_t)blockIdx.x * 256 + threadIdx.x;
+  uint4 v = prm.cells[idx];
+  uint32_t c[3] = {v.x, v.y, v.z};
+  unsigned long long ns = 0, sum = 0;
+  if (!cc.valid) {
+    if (c[0] | c[1] | c[2]) prm.cells[idx] = make_uint4(0, 0, 0, 0);
+  } else {
+    bool changed = false;
+    if (prm.qmode != 0 && (c[0] | c[1] | c[2])) {
+      int ti[4] = {ct.tip_of_rank[cc.a], ct.tip_of_rank[cc.b], ct.tip_of_rank[cc.c], ct.tip_of_rank[cc.d]};
+      int s0 = 0;
+#pragma unroll
+      for (int i = 1; i < 4; ++i)
+        if (ti[i] < ti[s0]) s0 = i;
+      // rho[t] = position (0,1,2) of topology t in the reference's AllQuartets() order
+      int rho[3];
+#pragma unroll
+      for (int t = 0; t < 3; ++t) {
+        int p = partner_of(t, s0), r = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) r += (j != s0 && ti[j] < ti[p]);
+        rho[t] = r;
+      }
+      // stable sort of the three topologies by count (insertion sort on 3 elements in Go)
+      int o[3] = {0, 1, 2};
+      auto less = [&](int x, int y) { return c[x] < c[y] || (c[x] == c[y] && rho[x] < rho[y]); };
+      if (less(o[1], o[0])) { int t = o[0]; o[0] = o[1]; o[1] = t; }
+      if (less(o[2], o[1])) { int t = o[1]; o[1] = o[2]; o[2] = t; }
+      if (less(o[1], o[0])) { int t = o[0]; o[0] = o[1]; o[1] = t; }
+      uint32_t lo = c[o[0]], mid = c[o[1]];
+      uint32_t s = lo + mid;
+      bool keep = __double2uint_rz(prm.threshold * (double)s) < mid - lo;  // Threshold.Keep
+      if (!keep) {
+        c[o[0]] = 0;
+        c[o[1]] = 0;
+      } else if (prm.qmode == 2) {
+        c[o[0]] = 0;
+      }
+      changed = true;
+    }
+    if (c[0] | c[1] | c[2]) {
+      uint32_t g1 = ct.lcaD[(size_t)cc.a * ct.n_taxa + cc.b];
+      uint32_t g2 = ct.lcaD[(size_t)cc.b * ct.n_taxa + cc.c];
+      uint32_t g3 = ct.lcaD[(size_t)cc.c * ct.n_taxa + cc.d];
+      int T = constraint_topology(g1, g2, g3);
+      if (c[T]) {
+        c[T] = 0;
+        changed = true;
+      }
+    }
+    if (changed) prm.cells[idx] = make_uint4(c[0], c[1], c[2], 0);
+    ns = (c[0] != 0) + (c[1] != 0) + (c[2] != 0);
+    sum = (unsigned long long)c[0] + c[1] + c[2];
+  }
+  // block reduction -> two 64-bit atomics per CTA
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    ns += __shfl_xor_sync(0xFFFFFFFFu, ns, off);
+    sum += __shfl_xor_sync(0xFFFFFFFFu, sum, off);
+  }
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+    s_red[0][warp] = ns;
+    s_red[1][warp] = sum;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long a = 0, b = 0;
+    for (int i = 0; i < 8; ++i) {
+      a += s_red[0][i];
+      b += s_red[1][i];
+    }
+    if (a) red_add_u64(&prm.totals[0], a);
+    if (b) red_add_u64(&prm.totals[1], b);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4: edge-score scatter. Replaces graphs.mapQuartetsToVertices + the per-(u,w) QuartetScore loop
+// (internal/graphs/treedata.go:197-222, internal/score/quartettotals.go:78-157) by the
+// per-quartet form of SURVEY.md Appendix A: a surviving quartet q with weight c and bottom taxon
+// beta adds c to every (u, w) with
+//     w on the path from leaf beta up to, excluding, m(beta) = lowest ancestor shared with
+//       another taxon of q,
+//     u in the component, holding beta's partner x in q, of T minus the junction J of the other
+//       three taxa: LEFT(J) = subtree(J+1), RIGHT(J) = subtree(rc[J]), OUT(J) = all but the two.
+// Accumulated as  Z[w-point][J][component] += c at w-point = leaf(beta), -= c at w-point = m,
+// i.e. two 64-bit reductions per (quartet, bottom); K5 expands Z into the n x n table.
+// ---------------------------------------------------------------------------------------------
+struct ScoreParams {
+  const uint4* cells;
+  uint64_t box0;
+  int as_set;
+  unsigned long long* Z;  // [n][n][3] two's-complement int64
+};
+
+__global__ void __launch_bounds__(256) k_score(ScoreParams prm, ConstraintDev ct) {
+  __shared__ uint32_t s_seg[4];
+  CellCoords cc = decode_cell(prm.box0, ct.n_taxa, s_seg);
+  if (!cc.valid) return;
+  uint4 v = prm.cells[(size_t)blockIdx.x * 256 + threadIdx.x];
+  if (!(v.x | v.y | v.z)) return;
+  const uint32_t cnt[3] = {v.x, v.y, v.z};
+  const uint32_t x[4] = {cc.a, cc.b, cc.c, cc.d};
+  const uint32_t g1 = ct.lcaD[(size_t)cc.a * ct.n_taxa + cc.b];
+  const uint32_t g2 = ct.lcaD[(size_t)cc.b * ct.n_taxa + cc.c];
+  const uint32_t g3 = ct.lcaD[(size_t)cc.c * ct.n_taxa + cc.d];
+  const size_t n = (size_t)ct.n;
+#pragma unroll
+  for (int be = 0; be < 4; ++be) {
+    uint32_t h1, h2, m;
+    if (be == 0) {
+      h1 = g2; h2 = g3; m = g1;
+    } else if (be == 1) {
+      h1 = min(g1, g2); h2 = g3; m = max(g1, g2);
+    } else if (be == 2) {
+      h1 = g1; h2 = min(g2, g3); m = max(g2, g3);
+    } else {
+      h1 = g1; h2 = g2; m = g3;
+    }
+    const bool first = h1 > h2;  // junction is the LCA of the first two of the other three
+    const uint32_t J = (first ? h1 : h2) & 0xFFFFu;
+    const size_t row_leaf = ((size_t)ct.leafnode[x[be]] * n + J) * 3;
+    const size_t row_m = ((size_t)(m & 0xFFFFu) * n + J) * 3;
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+      if (cnt[t] == 0) continue;
+      int p = partner_of(t, be);
+      int pos = p - (p > be ? 1 : 0);                 // position of the partner among the other three
+      int comp = first ? pos : (pos + 2) % 3;         // 0 LEFT, 1 RIGHT, 2 OUT
+      unsigned long long w = prm.as_set ? 1ull : (unsigned long long)cnt[t];
+      red_add_u64(&prm.Z[row_leaf + comp], w);
+      red_add_u64(&prm.Z[row_m + comp], (unsigned long long)(-(long long)w));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K5a: expand Z[w][J][comp] into a difference table over u: E[w][u], u in [0, n].
+//   LEFT  : +v at J+1,   -v at rc[J]
+//   RIGHT : +v at rc[J], -v at J+sz[J]
+//   OUT   : +v at 0,     -v at J+1,   +v at J+sz[J]
+// ---------------------------------------------------------------------------------------------
+__global__ void k_expand(const unsigned long long* __restrict__ Z, unsigned long long* __restrict__ E, ConstraintDev ct) {
+  int J = blockIdx.x * blockDim.x + threadIdx.x;
+  int w = blockIdx.y;
+  if (J >= ct.n || ct.rc[J] < 0) return;
+  const size_t n = (size_t)ct.n, ld = n + 1;
+  const unsigned long long* z = Z + ((size_t)w * n + J) * 3;
+  long long vL = (long long)z[0], vR = (long long)z[1], vO = (long long)z[2];
+  if (!(vL | vR | vO)) return;
+  unsigned long long* row = E + (size_t)w * ld;
+  long long at1 = vL - vO, at2 = vR - vL, at3 = vO - vR;
+  if (at1) atomicAdd(&row[J + 1], (unsigned long long)at1);
+  if (at2) atomicAdd(&row[ct.rc[J]], (unsigned long long)at2);
+  if (at3) atomicAdd(&row[J + ct.sz[J]], (unsigned long long)at3);
+  if (vO) atomicAdd(&row[0], (unsigned long long)vO);
+}
+
+// K5b: inclusive prefix sum along u of every row (one CTA per row).
+__global__ void __launch_bounds__(256) k_row_scan(unsigned long long* __restrict__ E, int n) {
+  __shared__ unsigned long long s_part[256];
+  const size_t ld = (size_t)n + 1;
+  unsigned long long* row = E + (size_t)blockIdx.x * ld;
+  int chunk = (n + 255) / 256;
+  int lo = threadIdx.x * chunk, hi = min(n, lo + chunk);
+  unsigned long long acc = 0;
+  for (int u = lo; u < hi; ++u) acc += row[u];
+  s_part[threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long run = 0;
+    for (int i = 0; i < 256; ++i) {
+      unsigned long long t = s_part[i];
+      s_part[i] = run;
+      run += t;
+    }
+  }
+  __syncthreads();
+  acc = s_part[threadIdx.x];
+  for (int u = lo; u < hi; ++u) {
+    acc += row[u];
+    row[u] = acc;
+  }
+}
+
+// K5c: exclusive prefix sum down every column (over w); row n receives the column total, so that
+// the subtree sum over w' in [w, w+sz[w]) is E[w+sz[w]][u] - E[w][u].
+__global__ void k_col_scan(unsigned long long* __restrict__ E, int n) {
+  int u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= n) return;
+  const size_t ld = (size_t)n + 1;
+  unsigned long long acc = 0;
+  for (int w = 0; w < n; ++w) {
+    unsigned long long t = E[(size_t)w * ld + u];
+    E[(size_t)w * ld + u] = acc;
+    acc += t;
+  }
+  E[(size_t)n * ld + u] = acc;
+}
+
+__device__ __forceinline__ int node_lca(const ConstraintDev& ct, int u, int w) {
+  if (u <= w && w < u + ct.sz[u]) return u;
+  if (w <= u && u < w + ct.sz[w]) return w;
+  return (int)(ct.lcaD[(size_t)ct.firstleaf[u] * ct.n_taxa + ct.firstleaf[w]] & 0xFFFFu);
+}
+// score.ShouldCalcEdge / CycleLength (internal/score/quartettotals.go:63-74)
+__device__ __forceinline__ bool should_calc_edge(const ConstraintDev& ct, int u, int w, int& v) {
+  v = node_lca(ct, u, w);
+  int len = (ct.depth[u] - ct.depth[v]) + (ct.depth[w] - ct.depth[v]) + 1 + (v == u ? 1 : 0);
+  bool u_under_w = u > w && u < w + ct.sz[w];
+  return !u_under_w && len > 3 && u != 0 && w != 0;
+}
+
+// K5d: quartetTotals[u][w] in the caller's node ids, 0 where !ShouldCalcEdge.
+__global__ void k_mask_out(const unsigned long long* __restrict__ E, unsigned long long* __restrict__ out, ConstraintDev ct) {
+  int w = blockIdx.x * blockDim.x + threadIdx.x;
+  int u = blockIdx.y;
+  if (w >= ct.n) return;
+  const size_t ld = (size_t)ct.n + 1;
+  int v;
+  unsigned long long val = 0;
+  if (should_calc_edge(ct, u, w, v)) val = E[(size_t)(w + ct.sz[w]) * ld + u] - E[(size_t)w * ld + u];
+  out[(size_t)ct.ref_id[u] * ct.n + ct.ref_id[w]] = val;
+}
+
+// ---------------------------------------------------------------------------------------------
+// score.CalculateEdgePenalties (internal/score/penalty.go:11-86): sizes of the subtrees hanging
+// off the cycle of (u, w), third elementary symmetric polynomial, uint64 wrap-around.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_penalties(unsigned long long* __restrict__ out, ConstraintDev ct) {
+  int w = blockIdx.x * blockDim.x + threadIdx.x;
+  int u = blockIdx.y;
+  if (w >= ct.n) return;
+  int v;
+  unsigned long long pen = 0;
+  if (should_calc_edge(ct, u, w, v)) {
+    unsigned long long c1 = 0, c2 = 0, c3 = 0;
+    auto add = [&](unsigned long long s) {
+      c3 += s * c2;
+      c2 += s * c1;
+      c1 += s;
+    };
+    auto walk_up = [&](int start, int end) {  // collectNodesUpPath without its first element
+      int cur = start, p;
+      do {
+        p = ct.parent[cur];
+        int sib = ct.rc[p] == cur ? p + 1 : ct.rc[p];
+        add((unsigned long long)ct.nleaves[sib]);
+        cur = p;
+      } while (p != end);
+    };
+    if (u == v) {
+      walk_up(w, ct.parent[v]);
+    } else {
+      walk_up(w, v);
+      add((unsigned long long)ct.nleaves[u]);
+      walk_up(u, v);
+    }
+    add((unsigned long long)(ct.n_taxa - ct.nleaves[v]));
+    pen = (unsigned long long)ct.nleaves[w] * c3;
+  }
+  out[(size_t)ct.ref_id[u] * ct.n + ct.ref_id[w]] = pen;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Export: every non-zero (cell, topology) as a reference-packed key (graphs/quartet.go:67-109):
+// taxa sorted by tip index in 15-bit fields, topology nibble with bit i set iff sorted taxon i is
+// on the side NOT holding sorted taxon 0.
+// ---------------------------------------------------------------------------------------------
+struct ExportParams {
+  const uint4* cells;
+  uint64_t box0;
+  unsigned long long* keys;
+  uint32_t* counts;
+  unsigned long long cap;
+  unsigned long long* n_out;
+};
+
+__global__ void __launch_bounds__(256) k_export(ExportParams prm, ConstraintDev ct) {
+  __shared__ uint32_t s_seg[4];
+  CellCoords cc = decode_cell(prm.box0, ct.n_taxa, s_seg);
+  if (!cc.valid) return;
+  uint4 v = prm.cells[(size_t)blockIdx.x * 256 + threadIdx.x];
+  if (!(v.x | v.y | v.z)) return;
+  const uint32_t cnt[3] = {v.x, v.y, v.z};
+  int ti[4] = {ct.tip_of_rank[cc.a], ct.tip_of_rank[cc.b], ct.tip_of_rank[cc.c], ct.tip_of_rank[cc.d]};
+  int pos[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int r = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) r += (ti[j] < ti[i]);
+    pos[i] = r;
+  }
+  unsigned long long base = 0;
+  int s0 = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    base |= (unsigned long long)ti[i] << (15 * pos[i]);
+    if (pos[i] == 0) s0 = i;
+  }
+#pragma unroll
+  for (int t = 0; t < 3; ++t) {
+    if (!cnt[t]) continue;
+    int p = partner_of(t, s0);
+    unsigned nib = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (j != s0 && j != p) nib |= 1u << pos[j];
+    unsigned long long slot = atomicAdd(prm.n_out, 1ull);
+    if (slot < prm.cap) {
+      prm.keys[slot] = base | ((unsigned long long)nib << 60);
+      prm.counts[slot] = cnt[t];
+    }
+  }
+}
+
+}  // namespace camus_dev

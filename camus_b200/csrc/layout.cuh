@@ -1,0 +1,97 @@
+// Index math shared by host and device code: how 4-taxon sets ("cells"), their 8x8x8x8 boxes
+// and the 8x8x8 triple tiles are laid out in HBM. See DESIGN.md "Data layout in HBM".
+//
+// Taxa are renumbered by their rank in a depth-first walk of the CONSTRAINT tree (DFS rank), not
+// by gotree tip index: with that order the constraint tree never displays ac|bd on a<b<c<d, the
+// LCA of two leaves is a range minimum, and subtrees are id intervals. The reference's packing
+// (graphs/quartet.go:67-109, taxa sorted by tip index) is produced only at export time.
+#pragma once
+#include <cstdint>
+
+#if defined(__CUDACC__)
+#define CAMUS_HD __host__ __device__ __forceinline__
+#else
+#define CAMUS_HD inline
+#endif
+
+namespace camus_dev {
+
+constexpr int kSeg = 8;                    // taxa per segment
+constexpr int kTileWords = 3 * 8 * 8 * 8;  // one triple tile: 3 planes x 512 triples (u32 bit-planes)
+constexpr int kTileBytes = kTileWords * 4;  // 6144
+constexpr int kBoxCells = 8 * 8 * 8 * 8;   // 4096 cells per box
+constexpr int kLanes = 32;                 // gene trees per bit-plane word ("tree group")
+
+CAMUS_HD uint64_t choose2(uint64_t x) { return x < 2 ? 0 : x * (x - 1) / 2; }
+CAMUS_HD uint64_t choose3(uint64_t x) { return x < 3 ? 0 : x * (x - 1) / 2 * (x - 2) / 3; }
+CAMUS_HD uint64_t choose4(uint64_t x) { return x < 4 ? 0 : x * (x - 1) / 2 * (x - 2) / 3 * (x - 3) / 4; }
+
+// tile (s0 <= s1 <= s2) and box (sa <= sb <= sc <= sd) ranks: colex order over multisets
+CAMUS_HD uint64_t tile_index(uint32_t s0, uint32_t s1, uint32_t s2) {
+  return choose3((uint64_t)s2 + 2) + choose2((uint64_t)s1 + 1) + s0;
+}
+CAMUS_HD uint64_t box_index(uint32_t sa, uint32_t sb, uint32_t sc, uint32_t sd) {
+  return choose4((uint64_t)sd + 3) + choose3((uint64_t)sc + 2) + choose2((uint64_t)sb + 1) + sa;
+}
+CAMUS_HD uint64_t num_tiles(uint32_t m) { return choose3((uint64_t)m + 2); }
+CAMUS_HD uint64_t num_boxes(uint32_t m) { return choose4((uint64_t)m + 3); }
+
+// largest s with choose_k(s + k - 1) <= r
+CAMUS_HD uint32_t unrank4(uint64_t r) {
+  double x = sqrt(sqrt(24.0 * (double)r));
+  int64_t s = (int64_t)x - 2;
+  if (s < 0) s = 0;
+  while (choose4((uint64_t)s + 4) <= r) ++s;
+  while (s > 0 && choose4((uint64_t)s + 3) > r) --s;
+  return (uint32_t)s;
+}
+CAMUS_HD uint32_t unrank3(uint64_t r) {
+  double x = cbrt(6.0 * (double)r);
+  int64_t s = (int64_t)x - 2;
+  if (s < 0) s = 0;
+  while (choose3((uint64_t)s + 3) <= r) ++s;
+  while (s > 0 && choose3((uint64_t)s + 2) > r) --s;
+  return (uint32_t)s;
+}
+CAMUS_HD uint32_t unrank2(uint64_t r) {
+  double x = sqrt(2.0 * (double)r);
+  int64_t s = (int64_t)x - 2;
+  if (s < 0) s = 0;
+  while (choose2((uint64_t)s + 2) <= r) ++s;
+  while (s > 0 && choose2((uint64_t)s + 1) > r) --s;
+  return (uint32_t)s;
+}
+CAMUS_HD void box_unrank(uint64_t r, uint32_t& sa, uint32_t& sb, uint32_t& sc, uint32_t& sd) {
+  sd = unrank4(r);
+  r -= choose4((uint64_t)sd + 3);
+  sc = unrank3(r);
+  r -= choose3((uint64_t)sc + 2);
+  sb = unrank2(r);
+  r -= choose2((uint64_t)sb + 1);
+  sa = (uint32_t)r;
+}
+// pair (a < b) <-> rank choose2(b) + a
+CAMUS_HD void pair_unrank(uint64_t r, uint32_t& a, uint32_t& b) {
+  double x = sqrt(2.0 * (double)r);
+  int64_t s = (int64_t)x - 1;
+  if (s < 1) s = 1;
+  while (choose2((uint64_t)s + 1) <= r) ++s;
+  while (s > 1 && choose2((uint64_t)s) > r) --s;
+  b = (uint32_t)s;
+  a = (uint32_t)(r - choose2((uint64_t)s));
+}
+
+// Word offset inside a triple tile for plane p and local triple (x, y, z), x/y/z in 0..7 being
+// the positions of the tile's three segments. The (x pair, y pair) 2x2 micro-block is contiguous
+// so that one 128-bit shared load fetches what a count thread needs (kernels_count.cuh).
+CAMUS_HD uint32_t tile_word(uint32_t p, uint32_t x, uint32_t y, uint32_t z) {
+  return (((p * 8 + z) * 4 + (y >> 1)) * 4 + (x >> 1)) * 4 + (y & 1) * 2 + (x & 1);
+}
+// planes of triple (p < q < r): 0 = pq|r, 1 = pr|q, 2 = qr|p
+
+// cell inside a box, a fastest
+CAMUS_HD uint32_t cell_local(uint32_t al, uint32_t bl, uint32_t cl, uint32_t dl) {
+  return ((dl * 8 + cl) * 8 + bl) * 8 + al;
+}
+
+}  // namespace camus_dev

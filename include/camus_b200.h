@@ -1,0 +1,117 @@
+/* camus_b200.h -- C-ABI of the B200-native CAMUS hot path (libcamus_b200.so).
+ *
+ * The reference (jsdoublel/camus, pure Go) has no FFI; the seam is cut at the Go function bodies
+ * listed below. Every exported Go signature stays as it is; these entry points
+ * replace the BODIES of:
+ *
+ *   camus_b200_set_constraint   <- graphs.MakeTreeData tables          internal/graphs/treedata.go:27-51
+ *   camus_b200_add_gene_trees   <- input of prep.processQuartets       internal/prep/preprocess.go:71-101
+ *   camus_b200_count_filter     <- prep.processQuartets                internal/prep/preprocess.go:71-124
+ *                                  + prep.filterQuartets               internal/prep/quartetfilter.go:76-96
+ *                                  + constraint-quartet removal        internal/prep/preprocess.go:51-57
+ *                                  + TotalNumQuartets / ..Unique..     internal/graphs/treedata.go:297-307
+ *   camus_b200_quartet_totals   <- score.CalculateQuartetTotals        internal/score/quartettotals.go:43-61
+ *                                  (+ graphs.mapQuartetsToVertices     internal/graphs/treedata.go:197-222)
+ *   camus_b200_edge_penalties   <- score.CalculateEdgePenalties        internal/score/penalty.go:11-29
+ *   camus_b200_export_quartets  <- the map[Quartet]uint32 itself       internal/graphs/quartet.go:11-31
+ *
+ * Conventions: plain pointers + sizes, host memory, valid for the duration of the call only (cgo
+ * rule: no pointer is kept after return). All functions return 0 on success, non-zero on failure
+ * (message via camus_b200_last_error); the library never aborts the process. One context per
+ * device; a context is not re-entrant. Calls are synchronous. There is NO CPU fallback: without a
+ * usable CUDA device camus_b200_create fails.
+ */
+#ifndef CAMUS_B200_H
+#define CAMUS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct camus_b200 camus_b200;
+
+enum {
+  CAMUS_B200_OK = 0,
+  CAMUS_B200_ERR_ARG = 1,     /* bad argument / call order */
+  CAMUS_B200_ERR_CUDA = 2,    /* CUDA runtime failure */
+  CAMUS_B200_ERR_NOMEM = 3,   /* problem does not fit the device */
+  CAMUS_B200_ERR_INPUT = 4    /* malformed flat tree */
+};
+
+/* n_gpus must be 1 in this release (one context per process and device; multi-GPU runs use one
+ * process per GPU and camus_b200_set_partition). devices[0] = CUDA ordinal, NULL = device 0. */
+int camus_b200_create(camus_b200** out, int n_gpus, const int* devices);
+void camus_b200_destroy(camus_b200* ctx);
+/* ctx may be NULL: returns the last error of a failed camus_b200_create on this thread. */
+const char* camus_b200_last_error(const camus_b200* ctx);
+
+/* Multi-process sharding of the 4-taxon-set index space: this context counts / filters / scores
+ * only partition `rank` of `world`. Every rank must be given ALL gene trees. After
+ * camus_b200_count_filter and camus_b200_quartet_totals_partial the caller sums the partial
+ * buffers over ranks (NCCL all-reduce on the device pointers returned below) and then calls
+ * camus_b200_quartet_totals_finish. Default is (0, 1). */
+int camus_b200_set_partition(camus_b200* ctx, int rank, int world);
+
+/* Constraint tree in reference node-id order (preprocess.go:28-30), rooted, binary.
+ * parent[i] = -1 at the root; child0/child1 = -1 at tips, child order = TreeData.Children order;
+ * tip_index[i] = constraint tip index (gotree UpdateTipIndex) at tips, -1 at internal nodes. */
+int camus_b200_set_constraint(camus_b200* ctx, int32_t n_nodes, int32_t n_taxa, const int32_t* parent,
+                              const int32_t* child0, const int32_t* child1, const int32_t* tip_index);
+
+/* Gene trees as CSR over nodes, flattened by the host AFTER UpdateTipIndex, the missing-taxa check
+ * and CollapseLowSupport (preprocess.go:87-100). Per tree: nodes in preorder (parent before
+ * child), parent[] = index local to the tree or -1 at its root, taxon[] = constraint tip index at
+ * leaves, -1 at internal nodes. Multifurcations, unifurcations and missing taxa are allowed;
+ * rooting does not matter. May be called several times; trees accumulate. */
+int camus_b200_add_gene_trees(camus_b200* ctx, int32_t n_trees, const int64_t* node_off /*[n_trees+1]*/,
+                              const int32_t* parent, const int32_t* taxon);
+/* Drop all gene trees (the constraint stays). */
+int camus_b200_clear_gene_trees(camus_b200* ctx);
+
+/* Count every gene-tree quartet topology, apply the -q mode (0/1/2) and -t threshold filter,
+ * remove the topologies the constraint tree displays. n_survivors = len(qCounts)
+ * (preprocess.go:58), sum_counts = exact sum of surviving counts (Go truncates it to uint32,
+ * treedata.go:297-303). With a partition set these are this rank's partial values. */
+int camus_b200_count_filter(camus_b200* ctx, int qmode, double threshold, uint64_t* n_survivors,
+                            uint64_t* sum_counts);
+
+/* quartetTotals[u][w] (row-major n*n, reference node ids), 0 where !ShouldCalcEdge.
+ * as_set != 0 counts every surviving quartet once (-asSet, and always in sym mode). */
+int camus_b200_quartet_totals(camus_b200* ctx, int as_set, uint64_t* out /*[n*n]*/);
+/* penalties[u][w] (row-major n*n), 0 where !ShouldCalcEdge. Needs only the constraint tree. */
+int camus_b200_edge_penalties(camus_b200* ctx, uint64_t* out /*[n*n]*/);
+
+/* Surviving quartets in the reference's packing (quartet.go:11-31), sorted by key. Only available
+ * when the whole cell table fits on the device (parity / debug; TreeData.Quartets on small
+ * inputs). Call with cap = 0 to query n_out. raw != 0 exports the counts before filter/removal. */
+int camus_b200_export_quartets(camus_b200* ctx, int raw, uint64_t* keys, uint32_t* counts, uint64_t cap,
+                               uint64_t* n_out);
+
+/* ---- split form of quartet_totals for multi-process runs ---- */
+int camus_b200_quartet_totals_partial(camus_b200* ctx, int as_set);
+/* device pointer + element count of the partial junction table (int64 elements) to be summed */
+int camus_b200_partial_buffer(camus_b200* ctx, void** dev_ptr, uint64_t* n_int64);
+int camus_b200_quartet_totals_finish(camus_b200* ctx, uint64_t* out /*[n*n]*/);
+
+/* ---- instrumentation (bench.py) ---- */
+enum {
+  CAMUS_B200_T_UPLOAD = 0,   /* host->device copies of the flat trees            */
+  CAMUS_B200_T_PREP = 1,     /* tree walk + LCA-depth tables + triple bit-planes */
+  CAMUS_B200_T_COUNT = 2,    /* quartet count kernel                             */
+  CAMUS_B200_T_FILTER = 3,   /* filter + constraint removal + totals             */
+  CAMUS_B200_T_SCORE = 4,    /* edge-score scatter                               */
+  CAMUS_B200_T_FINAL = 5,    /* scans + mask + copy-out                          */
+  CAMUS_B200_T_PENALTY = 6,
+  CAMUS_B200_T_N = 8
+};
+/* CUDA-event milliseconds of the last run of each stage and the number of kernel launches. */
+int camus_b200_stage_ms(const camus_b200* ctx, float* ms /*[CAMUS_B200_T_N]*/, uint64_t* n_launches);
+/* resolutions = sum over gene trees of C(leaves,4): the unit of the throughput metric. */
+int camus_b200_workload(const camus_b200* ctx, uint64_t* resolutions, uint64_t* n_cells, uint64_t* n_boxes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CAMUS_B200_H */

@@ -1,0 +1,58 @@
+"""CPU-side checks of the C-ABI library: it loads, exports every symbol include/camus_b200.h
+declares, and fails loudly (no fallback) when there is no GPU. No compute calls here."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from camus_b200 import build, cabi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    build.build_cuda()
+    return cabi.lib()
+
+
+def test_header_symbols_exported(lib):
+    hdr = open(os.path.join(ROOT, "include", "camus_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = sorted(set(re.findall(r"\b(camus_b200_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 14
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in camus_b200.h but not exported"
+    assert sorted(cabi.EXPORTED) == names
+
+
+def test_create_without_gpu_fails_loudly(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    h = C.c_void_p()
+    rc = lib.camus_b200_create(C.byref(h), 1, None)
+    assert rc != 0 and not h.value
+    msg = lib.camus_b200_last_error(None).decode()
+    assert "no CPU fallback" in msg
+    with pytest.raises(cabi.CamusB200Error):
+        cabi.CamusB200(0)
+
+
+def test_create_rejects_multi_gpu_in_one_context(lib):
+    h = C.c_void_p()
+    assert lib.camus_b200_create(C.byref(h), 2, None) != 0
+
+
+def test_product_does_not_import_oracle():
+    """The oracle is test infrastructure: nothing under camus_b200/ or include/ may reference it."""
+    bad = []
+    for base in ("camus_b200", "include"):
+        for dp, _, fs in os.walk(os.path.join(ROOT, base)):
+            for f in fs:
+                if f.endswith((".py", ".cpp", ".hpp", ".cu", ".cuh", ".h")):
+                    txt = open(os.path.join(dp, f), errors="ignore").read()
+                    if re.search(r"^\s*(from|import)\s+oracle\b|#include\s+\".*oracle|liboracle", txt, flags=re.M):
+                        bad.append(os.path.join(dp, f))
+    assert not bad, bad

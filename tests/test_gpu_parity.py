@@ -1,0 +1,281 @@
+"""GPU parity: the CUDA path, called through the C-ABI (include/camus_b200.h), against the oracle
+and the reference's golden vectors. Bit-exact: everything on this path is integer."""
+import os
+from collections import Counter
+
+import numpy as np
+import pytest
+
+from camus_b200 import synth
+from camus_b200.hostlib import Problem, read_text
+from oracle import oracle as orc
+from tests.golden import ref_kats as K
+
+pytestmark = pytest.mark.gpu
+
+REF = os.path.join(os.path.dirname(__file__), "golden", "ref")
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    from camus_b200.cabi import CamusB200
+    g = CamusB200(0)
+    yield g
+    g.close()
+
+
+def qkey(prob, quad):
+    return orc.pack_quartet(*(prob.tip_id(x) for x in quad))
+
+
+def as_dict(kc):
+    return {int(k): int(c) for k, c in zip(*kc)}
+
+
+def compare_all(gpu, prob, qmode, thr, literal=False, as_sets=(False, True), penalties=True):
+    """count/filter scalars, raw counts, survivors, totals (both weights), penalties vs the oracle."""
+    o = orc.Oracle().load(prob)
+    want = o.count_filter(qmode, thr, literal)
+    gpu.load(prob)
+    got = gpu.count_filter(qmode, thr)
+    assert got == want
+    gk, gc = gpu.export_quartets(raw=False)
+    ok, oc = o.export_quartets()
+    assert np.array_equal(gk, ok) and np.array_equal(gc, oc)
+    for as_set in as_sets:
+        assert np.array_equal(gpu.quartet_totals(as_set), o.quartet_totals(as_set, literal)), f"totals as_set={as_set}"
+    gk, gc = gpu.export_quartets(raw=True)
+    ok, oc = o.export_raw_counts()
+    assert np.array_equal(gk, ok) and np.array_equal(gc, oc)
+    # totals must survive the raw export (recount + refilter)
+    assert np.array_equal(gpu.quartet_totals(False), o.quartet_totals(False, literal))
+    if penalties:
+        assert np.array_equal(gpu.edge_penalties(), o.edge_penalties())
+    return o
+
+
+# ------------------------------------------------------------------ reference KATs on the GPU
+@pytest.mark.parametrize("name,tre,qmode,thr,genes,expected", K.PROCESS_QUARTETS)
+def test_process_quartets(gpu, name, tre, qmode, thr, genes, expected):
+    prob = Problem(tre, "\n".join(genes))
+    gpu.load(prob)
+    gpu.count_filter(qmode, thr)
+    assert as_dict(gpu.export_quartets()) == dict(Counter(qkey(prob, q) for q in expected))
+
+
+def test_quartets_total_kats(gpu):
+    # quartettotals_test.go:121-153; the quartet tables are produced by gene trees with missing taxa
+    for which, (tre, qs) in (("A", K.TOTALS_TREE_A), ("B", K.TOTALS_TREE_B)):
+        genes = []
+        for (a, b, c, d), cnt in qs:
+            genes += ["((%s,%s),(%s,%s));" % (a, b, c, d)] * cnt
+        prob = Problem(tre, "\n".join(genes))
+        gpu.load(prob)
+        gpu.count_filter(0, 0.0)
+        tot = gpu.quartet_totals(False)
+        for w_, _, u, w, want in K.QUARTETS_TOTAL:
+            if w_ == which:
+                assert tot[prob.node_id(u), prob.node_id(w)] == want
+        for u in range(prob.n_nodes):
+            for w in range(prob.n_nodes):
+                if not prob.should_calc_edge(u, w):
+                    assert tot[u, w] == 0
+        assert (tot > 0).any()
+
+
+def test_penalty_kats(gpu):
+    prob = Problem(K.PENALTY_TREE, "")
+    gpu.load(prob)
+    o = orc.Oracle(1).load(prob)
+    assert np.array_equal(gpu.edge_penalties(), o.edge_penalties())
+    prob = Problem(K.TOTALS_TREE_B[0], "")
+    gpu.load(prob)
+    o = orc.Oracle(1).load(prob)
+    pen = gpu.edge_penalties()
+    assert np.array_equal(pen, o.edge_penalties())
+    assert (pen > 0).any()
+
+
+def _infer_gpu(gpu, prob, qmode, thr, mode, alpha):
+    gpu.load(prob)
+    n_surv, sum_counts = gpu.count_filter(qmode, thr)
+    as_set = mode == "sym"
+    tot = gpu.quartet_totals(as_set)
+    pen = gpu.edge_penalties() if mode != "max" else None
+    return prob.run_dp(tot, pen, mode, as_set, n_surv, sum_counts, prob.n_trees, alpha), n_surv
+
+
+@pytest.mark.parametrize("name,tre,genes,nedges,network", K.INFER)
+def test_infer_small(gpu, name, tre, genes, nedges, network):
+    prob = Problem(tre, "\n".join(genes))
+    res, _ = _infer_gpu(gpu, prob, 0, 0.0, "max", 0.0)
+    assert len(res.branches) == nedges
+    assert res.newicks[-1] == network
+
+
+@pytest.mark.parametrize("qmode,thr,mode,alpha,nnets,golden", K.INFER_LARGE)
+def test_infer_large_golden(gpu, qmode, thr, mode, alpha, nnets, golden):
+    prob = Problem.from_files(os.path.join(REF, "infer_constraint.nwk"), os.path.join(REF, "infer_gene-trees.nwk.gz"))
+    res, n_surv = _infer_gpu(gpu, prob, qmode, thr, mode, alpha)
+    want = [l.strip() for l in read_text(os.path.join(REF, golden)).split("\n") if l.strip()]
+    assert res.newicks == want
+    assert n_surv == (14423 if qmode == 0 else 1150)
+
+
+@pytest.mark.parametrize("qmode,thr", [(0, 0.0), (1, 0.3), (2, 0.5), (2, 0.0), (1, 1.0)])
+def test_dataset_vs_literal_oracle(gpu, qmode, thr):
+    prob = Problem.from_files(os.path.join(REF, "infer_constraint.nwk"), os.path.join(REF, "infer_gene-trees.nwk.gz"))
+    compare_all(gpu, prob, qmode, thr, literal=True)
+
+
+# ----------------------------------------------------------------- synthetic configurations
+@pytest.mark.parametrize("qmode,thr", [(0, 0.0), (1, 0.25), (2, 0.5)])
+def test_config1_vs_oracle(gpu, qmode, thr):
+    s, c = synth.make_config(1)
+    prob = Problem(s.constraint, s.genes, s.fmt, c["min_support"])
+    compare_all(gpu, prob, qmode, thr)
+
+
+def test_config1_literal_and_networks(gpu):
+    s, c = synth.make_config(1)
+    prob = Problem(s.constraint, s.genes, s.fmt, c["min_support"])
+    o = compare_all(gpu, prob, c["qmode"], c["threshold"], literal=True, as_sets=(False,))
+    res, _ = _infer_gpu(gpu, prob, c["qmode"], c["threshold"], "max", 0.0)
+    ns, sc = o.count_filter(c["qmode"], c["threshold"], True)
+    ref = prob.run_dp(o.quartet_totals(False, True), None, "max", False, ns, sc)
+    assert res.newicks == ref.newicks and res.qsat == ref.qsat and len(res.newicks) >= 1
+
+
+def test_config4_like_polytomies_missing_taxa_nexus(gpu):
+    s = synth.make(60, 100, 4, support=True, drop_frac=0.1, nexus=True)
+    prob = Problem(s.constraint, s.genes, s.fmt, 0.7)
+    assert prob.warned_missing
+    compare_all(gpu, prob, 2, 0.5, literal=True)
+    compare_all(gpu, prob, 0, 0.0)
+
+
+def test_config5_like_sym_norm(gpu):
+    s = synth.make(48, 150, 5)
+    prob = Problem(s.constraint, s.genes)
+    o = orc.Oracle().load(prob)
+    ns, sc = o.count_filter(2, 0.5, False)
+    for mode in ("sym", "norm"):
+        res, _ = _infer_gpu(gpu, prob, 2, 0.5, mode, 0.5)
+        as_set = mode == "sym"
+        ref = prob.run_dp(o.quartet_totals(as_set, False), o.edge_penalties(), mode, as_set, ns, sc, prob.n_trees, 0.5)
+        assert res.newicks == ref.newicks
+        # float scores come from identical integer tables through identical host code: exact
+        assert res.root_scores == ref.root_scores or all(
+            abs(a - b) <= 1e-9 * max(1.0, abs(b)) for a, b in zip(res.root_scores, ref.root_scores))
+
+
+@pytest.mark.parametrize("n_taxa,n_trees", [(4, 3), (5, 40), (8, 33), (9, 31), (17, 64), (23, 70)])
+def test_small_shapes(gpu, n_taxa, n_trees):
+    s = synth.make(n_taxa, n_trees, 100 + n_taxa, drop_frac=0.15 if n_taxa > 6 else 0.0)
+    prob = Problem(s.constraint, s.genes)
+    compare_all(gpu, prob, 0, 0.0, literal=True)
+    compare_all(gpu, prob, 2, 0.3)
+
+
+def test_deep_caterpillars_and_star(gpu):
+    labs = ["t%04d" % i for i in range(30)]
+    cat = labs[0]
+    for l in labs[1:]:
+        cat = "(%s,%s)" % (cat, l)
+    rev = labs[-1]
+    for l in reversed(labs[:-1]):
+        rev = "(%s,%s)" % (rev, l)
+    star = "(" + ",".join(labs) + ")"
+    half = "((" + ",".join(labs[:15]) + "),(" + ",".join(labs[15:]) + "))"
+    genes = [cat + ";", rev + ";", star + ";", half + ";", rev + ";"] * 8
+    s = synth.make(30, 1, 7)
+    prob = Problem(s.constraint, "\n".join(genes))
+    compare_all(gpu, prob, 0, 0.0, literal=True)
+    prob = Problem(cat + ";", "\n".join(genes))
+    compare_all(gpu, prob, 1, 0.0, literal=True)
+
+
+def test_no_gene_trees_and_reuse(gpu):
+    s = synth.make(12, 5, 9)
+    prob = Problem(s.constraint, "")
+    gpu.load(prob)
+    assert gpu.count_filter(2, 0.5) == (0, 0)
+    assert not gpu.quartet_totals(False).any()
+    # the same context is reused for a different problem afterwards
+    prob = Problem(s.constraint, s.genes)
+    compare_all(gpu, prob, 0, 0.0, literal=True)
+
+
+def test_bad_inputs_are_errors_not_crashes(gpu):
+    from camus_b200.cabi import CamusB200Error
+    s = synth.make(10, 2, 3)
+    prob = Problem(s.constraint, s.genes)
+    gpu.load(prob)
+    with pytest.raises(CamusB200Error):
+        gpu.count_filter(3, 0.5)
+    with pytest.raises(CamusB200Error):
+        gpu.count_filter(1, 1.5)
+    bad_parent = prob.gene_parent.copy()
+    bad_parent[1] = 5  # parent after child
+    with pytest.raises(CamusB200Error):
+        gpu.add_gene_trees(prob.gene_node_off, bad_parent, prob.gene_taxon)
+    bad_taxon = prob.gene_taxon.copy()
+    bad_taxon[bad_taxon >= 0] = 0  # duplicate taxon
+    with pytest.raises(CamusB200Error):
+        gpu.add_gene_trees(prob.gene_node_off, prob.gene_parent, bad_taxon)
+    with pytest.raises(CamusB200Error):
+        gpu.set_constraint(prob.parent[:-1], prob.child0[:-1], prob.child1[:-1], prob.tip_index[:-1], prob.n_taxa)
+
+
+# ------------------------------------------------- mid / full size: oracle + size-free properties
+def test_mid_size_vs_oracle(gpu):
+    s = synth.make(96, 100, 11)
+    prob = Problem(s.constraint, s.genes)
+    o = orc.Oracle().load(prob)
+    want = o.count_filter(2, 0.5, False)
+    gpu.load(prob)
+    assert gpu.count_filter(2, 0.5) == want
+    for as_set in (False, True):
+        assert np.array_equal(gpu.quartet_totals(as_set), o.quartet_totals(as_set, False))
+    assert np.array_equal(gpu.edge_penalties(), o.edge_penalties())
+
+
+def test_config2_full_size_properties(gpu):
+    """200 taxa x 1000 trees (BASELINE.json configs[1]): linearity in the gene trees, order
+    independence, and the counting identity sum(raw) = R for complete binary trees."""
+    s, c = synth.make_config(2)
+    prob = Problem(s.constraint, s.genes)
+    off, par, tax = prob.gene_node_off, prob.gene_parent, prob.gene_taxon
+    gpu.load(prob)
+    ns_all, sum_all = gpu.count_filter(0, 0.0)
+    tot_all = gpu.quartet_totals(False)
+    R = gpu.workload()["resolutions"]
+    assert R == 1000 * (200 * 199 * 198 * 197 // 24)
+
+    def sub(lo, hi):
+        o = off[lo:hi + 1] - off[lo]
+        return o, par[off[lo]:off[hi]], tax[off[lo]:off[hi]]
+
+    parts = []
+    for lo, hi in ((0, 333), (333, 1000)):
+        gpu.clear_gene_trees()
+        gpu.add_gene_trees(*sub(lo, hi))
+        ns, sm = gpu.count_filter(0, 0.0)
+        parts.append((sm, gpu.quartet_totals(False)))
+    assert parts[0][0] + parts[1][0] == sum_all
+    assert np.array_equal(parts[0][1] + parts[1][1], tot_all)
+    # reversed tree order, added in two calls
+    gpu.clear_gene_trees()
+    gpu.add_gene_trees(*sub(500, 1000))
+    gpu.add_gene_trees(*sub(0, 500))
+    assert gpu.count_filter(0, 0.0) == (ns_all, sum_all)
+    assert np.array_equal(gpu.quartet_totals(False), tot_all)
+    # every complete binary tree resolves every 4-set exactly once: the counts the constraint
+    # removal drops are the only difference between sum(survivors) and R
+    gpu.load(prob)
+    ns2, sum2 = gpu.count_filter(2, 0.5)
+    assert 0 < ns2 <= ns_all and sum2 <= sum_all < R
+    tot2 = gpu.quartet_totals(False)
+    assert (tot2 <= tot_all).all() and tot2.any()
+    mask = np.array([[prob.should_calc_edge(u, w) for w in range(0, prob.n_nodes, 7)] for u in range(0, prob.n_nodes, 7)])
+    assert not tot_all[::7, ::7][~mask].any()
