@@ -38,6 +38,7 @@ def lib() -> C.CDLL:
         L.camus_b200_set_constraint.argtypes = [vp, C.c_int32, C.c_int32, vp, vp, vp, vp]
         L.camus_b200_add_gene_trees.argtypes = [vp, C.c_int32, vp, vp, vp]
         L.camus_b200_clear_gene_trees.argtypes = [vp]
+        L.camus_b200_set_score_hint.argtypes = [vp, C.c_int]
         L.camus_b200_count_filter.argtypes = [vp, C.c_int, C.c_double, u64p, u64p]
         L.camus_b200_quartet_totals.argtypes = [vp, C.c_int, vp]
         L.camus_b200_edge_penalties.argtypes = [vp, vp]
@@ -45,6 +46,7 @@ def lib() -> C.CDLL:
         L.camus_b200_quartet_totals_partial.argtypes = [vp, C.c_int]
         L.camus_b200_partial_buffer.argtypes = [vp, C.POINTER(vp), u64p]
         L.camus_b200_quartet_totals_finish.argtypes = [vp, vp]
+        L.camus_b200_run_resident.argtypes = [vp, C.c_int, C.c_double, C.c_int, vp, u64p, u64p]
         L.camus_b200_stage_ms.argtypes = [vp, C.POINTER(C.c_float), u64p]
         L.camus_b200_workload.argtypes = [vp, u64p, u64p, u64p]
         _lib = L
@@ -54,9 +56,9 @@ def lib() -> C.CDLL:
 EXPORTED = [
     "camus_b200_create", "camus_b200_destroy", "camus_b200_last_error", "camus_b200_set_partition",
     "camus_b200_set_constraint", "camus_b200_add_gene_trees", "camus_b200_clear_gene_trees",
-    "camus_b200_count_filter", "camus_b200_quartet_totals", "camus_b200_edge_penalties",
+    "camus_b200_set_score_hint", "camus_b200_count_filter", "camus_b200_quartet_totals", "camus_b200_edge_penalties",
     "camus_b200_export_quartets", "camus_b200_quartet_totals_partial", "camus_b200_partial_buffer",
-    "camus_b200_quartet_totals_finish", "camus_b200_stage_ms", "camus_b200_workload",
+    "camus_b200_quartet_totals_finish", "camus_b200_run_resident", "camus_b200_stage_ms", "camus_b200_workload",
 ]
 
 
@@ -113,6 +115,9 @@ class CamusB200:
             self.add_gene_trees(prob.gene_node_off, prob.gene_parent, prob.gene_taxon)
         return self
 
+    def set_score_hint(self, as_set: bool):
+        self._ck(lib().camus_b200_set_score_hint(self._h, int(as_set)))
+
     def count_filter(self, qmode: int = 0, threshold: float = 0.0):
         ns, sc = C.c_uint64(), C.c_uint64()
         self._ck(lib().camus_b200_count_filter(self._h, qmode, threshold, C.byref(ns), C.byref(sc)))
@@ -155,6 +160,27 @@ class CamusB200:
         return out
 
     # ---- instrumentation ----
+    def run_resident(self, qmode: int, threshold: float, as_set: bool, out: np.ndarray | None = None,
+                     partial_only: bool = False):
+        ns, sc = C.c_uint64(), C.c_uint64()
+        if partial_only:
+            self._ck(lib().camus_b200_run_resident(self._h, qmode, threshold, int(as_set), None, C.byref(ns), C.byref(sc)))
+            return None, ns.value, sc.value
+        if out is None:
+            out = np.empty((self.n, self.n), np.uint64)
+        self._ck(lib().camus_b200_run_resident(self._h, qmode, threshold, int(as_set), _p(out), C.byref(ns), C.byref(sc)))
+        return out, ns.value, sc.value
+
+    def partial_tensor(self):
+        """The partial junction table as a zero-copy torch int64 tensor (for torch.distributed)."""
+        import torch
+        ptr, n = self.partial_buffer()
+
+        class _Holder:
+            __cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 2}
+
+        return torch.as_tensor(_Holder(), device="cuda")
+
     def stage_ms(self):
         ms = (C.c_float * 8)()
         nl = C.c_uint64()

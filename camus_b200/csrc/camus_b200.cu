@@ -80,6 +80,9 @@ struct camus_b200 {
   double last_threshold = 0;
   bool z_valid = false;
   int z_as_set = -1;
+  bool counted = false;      // count_filter has run for the current trees / partition
+  bool use_fused = true;     // count + filter + score in one kernel (no cell table); CAMUS_B200_UNFUSED=1 disables
+  int as_set_hint = 0;       // weight the fused pass of count_filter scores with
 
   float ms[CAMUS_B200_T_N] = {0};
   uint64_t launches = 0;
@@ -127,7 +130,7 @@ int upload(camus_b200* ctx, DevBuf<T>& buf, const T* src, size_t count) {
   return 0;
 }
 
-int build_planes(camus_b200* ctx);
+int build_planes(camus_b200* ctx, bool do_upload);
 int run_count(camus_b200* ctx);
 int run_filter(camus_b200* ctx, int qmode, double threshold, uint64_t* ns, uint64_t* sum);
 
@@ -176,7 +179,9 @@ int camus_b200_create(camus_b200** out, int n_gpus, const int* devices) {
     delete ctx;
     return CAMUS_B200_ERR_CUDA;
   }
-  cudaFuncSetAttribute(k_count, cudaFuncAttributeMaxDynamicSharedMemorySize, kCountSmemBytes);
+  cudaFuncSetAttribute(k_count<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCountSmemBytes);
+  cudaFuncSetAttribute(k_count<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCountSmemBytes);
+  if (const char* e = getenv("CAMUS_B200_UNFUSED")) ctx->use_fused = !(e[0] == '1');
   *out = ctx;
   return CAMUS_B200_OK;
 }
@@ -198,6 +203,7 @@ int camus_b200_set_partition(camus_b200* ctx, int rank, int world) {
   ctx->world = world;
   ctx->cell_state = camus_b200::NONE;
   ctx->z_valid = false;
+  ctx->counted = false;
   return 0;
 }
 
@@ -293,6 +299,7 @@ int camus_b200_set_constraint(camus_b200* ctx, int32_t n_nodes, int32_t n_taxa, 
   ctx->genes_dirty = true;
   ctx->cell_state = camus_b200::NONE;
   ctx->z_valid = false;
+  ctx->counted = false;
   return 0;
 }
 
@@ -306,6 +313,7 @@ int camus_b200_clear_gene_trees(camus_b200* ctx) {
   ctx->genes_dirty = true;
   ctx->cell_state = camus_b200::NONE;
   ctx->z_valid = false;
+  ctx->counted = false;
   return 0;
 }
 
@@ -351,6 +359,7 @@ int camus_b200_add_gene_trees(camus_b200* ctx, int32_t n_trees, const int64_t* n
   ctx->genes_dirty = true;
   ctx->cell_state = camus_b200::NONE;
   ctx->z_valid = false;
+  ctx->counted = false;
   return 0;
 }
 
@@ -359,11 +368,11 @@ int camus_b200_add_gene_trees(camus_b200* ctx, int32_t n_trees, const int64_t* n
 namespace {
 
 // K0 + K1 + K1b: gene trees -> rooted-triple bit-planes in HBM.
-int build_planes(camus_b200* ctx) {
+int build_planes(camus_b200* ctx, bool do_upload = true) {
   const int G = ctx->G, npad = ctx->npad;
   ctx->G32 = (G + kLanes - 1) / kLanes;
   const int G32 = std::max(ctx->G32, 1);
-  {
+  if (do_upload) {
     StageTimer t(ctx, CAMUS_B200_T_UPLOAD);
     if (upload(ctx, ctx->d_node_off, ctx->h_node_off.data(), ctx->h_node_off.size()) ||
         upload(ctx, ctx->d_gparent, ctx->h_parent.data(), ctx->h_parent.size()) ||
@@ -386,7 +395,7 @@ int build_planes(camus_b200* ctx) {
     return ctx->fail(CAMUS_B200_ERR_NOMEM, "triple bit-planes need " + std::to_string(tri_words * 4 >> 20) + " MiB, device has " +
                                                std::to_string(free_b >> 20) + " MiB free");
   CK(ctx->d_tri.alloc(tri_words));
-  CK(cudaMemsetAsync(ctx->d_tri.p, 0, tri_words * 4, ctx->stream));
+  if (G == 0) CK(cudaMemsetAsync(ctx->d_tri.p, 0, tri_words * 4, ctx->stream));
   if (G > 0) {
     k_tree_prepare<<<(G + 127) / 128, 128, 0, ctx->stream>>>(G, ctx->d_node_off.p, ctx->d_gparent.p, ctx->d_gtaxon.p,
                                                             ctx->d_rank_of_tip.p, ctx->d_depth_tmp.p, ctx->d_lrT.p,
@@ -395,7 +404,7 @@ int build_planes(camus_b200* ctx) {
     size_t dt_group = (size_t)npad * npad * kLanes;  // u16 elements
     int gb_max = (int)std::max<size_t>(1, std::min<size_t>(ctx->G32, ((size_t)1 << 30) / (dt_group * 2)));
     CK(ctx->d_Dt.alloc(dt_group * gb_max));
-    uint64_t n_pairs = choose2(npad);
+    const unsigned n_tiles = (unsigned)num_tiles(ctx->M);
     for (int g0 = 0; g0 < ctx->G32; g0 += gb_max) {
       int gb = std::min(gb_max, ctx->G32 - g0);
       CK(cudaMemsetAsync(ctx->d_Dt.p, 0, dt_group * gb * 2, ctx->stream));
@@ -403,8 +412,7 @@ int build_planes(camus_b200* ctx) {
       dim3 g1((npad + 7) / 8, gb);
       k_depth_table<<<g1, blk, 0, ctx->stream>>>(g0, G, npad, ctx->d_nleaf.p, ctx->d_lrT.p, ctx->d_hT.p, ctx->d_Dt.p);
       CK_LAUNCH();
-      dim3 g2((unsigned)((n_pairs + 7) / 8), gb);
-      k_triple_planes<<<g2, blk, 0, ctx->stream>>>(g0, G32, npad, ctx->d_Dt.p, ctx->d_tri.p, n_pairs);
+      k_triple_planes<<<dim3(n_tiles, gb), 256, 0, ctx->stream>>>(g0, G32, npad, ctx->d_Dt.p, ctx->d_tri.p);
       CK_LAUNCH();
     }
   }
@@ -413,29 +421,64 @@ int build_planes(camus_b200* ctx) {
   return 0;
 }
 
-// K2 over this rank's box range (whole range resident in d_cells).
-int run_count(camus_b200* ctx) {
+void set_box_range(camus_b200* ctx) {
   uint64_t nb = num_boxes(ctx->M);
   ctx->box_lo = nb * ctx->rank / ctx->world;
   ctx->box_hi = nb * (ctx->rank + 1) / ctx->world;
+}
+
+// Fused K2+K3+K4 over this rank's box range: counts stay in registers, survivors are scored
+// straight into the junction table Z. No cell table.
+int run_fused(camus_b200* ctx, int qmode, double threshold, int as_set, uint64_t* ns, uint64_t* sum) {
+  set_box_range(ctx);
+  uint64_t mine = ctx->box_hi - ctx->box_lo;
+  size_t zn = (size_t)ctx->n * ctx->n * 3;
+  CK(ctx->d_Z.alloc(zn));
+  CK(ctx->d_totals.alloc(2));
+  StageTimer t(ctx, CAMUS_B200_T_COUNT);
+  CK(cudaMemsetAsync(ctx->d_Z.p, 0, zn * 8, ctx->stream));
+  CK(cudaMemsetAsync(ctx->d_totals.p, 0, 16, ctx->stream));
+  const uint64_t max_grid = 1u << 30;
+  for (uint64_t b0 = 0; b0 < mine; b0 += max_grid) {
+    uint64_t nbx = std::min(max_grid, mine - b0);
+    CountParams prm{ctx->d_tri.p, std::max(ctx->G32, 1), ctx->box_lo + b0, nullptr};
+    FusedParams fz{qmode, threshold, as_set, ctx->d_Z.p, ctx->d_totals.p};
+    k_count<true><<<(unsigned)nbx, kCountThreads, kCountSmemBytes, ctx->stream>>>(prm, fz, ctx->ct);
+    CK_LAUNCH();
+  }
+  unsigned long long h[2] = {0, 0};
+  CK(cudaMemcpyAsync(h, ctx->d_totals.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
+  if (t.stop()) return CAMUS_B200_ERR_CUDA;
+  if (ns) *ns = h[0];
+  if (sum) *sum = h[1];
+  ctx->last_qmode = qmode;
+  ctx->last_threshold = threshold;
+  ctx->z_valid = true;
+  ctx->z_as_set = as_set;
+  ctx->counted = true;
+  return 0;
+}
+
+// K2 (table mode) over this rank's box range (whole range resident in d_cells).
+int run_count(camus_b200* ctx) {
+  set_box_range(ctx);
   uint64_t mine = ctx->box_hi - ctx->box_lo;
   size_t free_b = 0, total_b = 0;
   CK(cudaMemGetInfo(&free_b, &total_b));
   if (ctx->d_cells.n < mine * kBoxCells && mine > cells_budget_boxes(free_b + ctx->d_cells.bytes()))
     return ctx->fail(CAMUS_B200_ERR_NOMEM, "cell table of " + std::to_string(mine * kBoxCells * 16 >> 20) +
-                                               " MiB does not fit; streaming mode is not in this build");
+                                               " MiB does not fit on the device (only the fused path scales to this size)");
   CK(ctx->d_cells.alloc(std::max<uint64_t>(mine, 1) * kBoxCells));
   StageTimer t(ctx, CAMUS_B200_T_COUNT);
   const uint64_t max_grid = 1u << 30;
   for (uint64_t b0 = 0; b0 < mine; b0 += max_grid) {
     uint64_t nbx = std::min(max_grid, mine - b0);
     CountParams prm{ctx->d_tri.p, std::max(ctx->G32, 1), ctx->box_lo + b0, ctx->d_cells.p + b0 * kBoxCells};
-    k_count<<<(unsigned)nbx, kCountThreads, kCountSmemBytes, ctx->stream>>>(prm);
+    k_count<false><<<(unsigned)nbx, kCountThreads, kCountSmemBytes, ctx->stream>>>(prm, FusedParams{}, ctx->ct);
     CK_LAUNCH();
   }
   if (t.stop()) return CAMUS_B200_ERR_CUDA;
   ctx->cell_state = camus_b200::RAW;
-  ctx->z_valid = false;
   return 0;
 }
 
@@ -459,19 +502,22 @@ int run_filter(camus_b200* ctx, int qmode, double threshold, uint64_t* ns, uint6
   ctx->cell_state = camus_b200::FILTERED;
   ctx->last_qmode = qmode;
   ctx->last_threshold = threshold;
-  ctx->z_valid = false;
+  ctx->counted = true;
   return 0;
 }
 
 int ensure_filtered(camus_b200* ctx) {
   if (ctx->cell_state == camus_b200::FILTERED) return 0;
-  if (ctx->cell_state == camus_b200::NONE) return ctx->fail(CAMUS_B200_ERR_ARG, "call camus_b200_count_filter first");
+  if (!ctx->counted) return ctx->fail(CAMUS_B200_ERR_ARG, "call camus_b200_count_filter first");
   int rc = run_count(ctx);
   if (rc) return rc;
   return run_filter(ctx, ctx->last_qmode, ctx->last_threshold, nullptr, nullptr);
 }
 
 int run_score(camus_b200* ctx, int as_set) {
+  if (!ctx->counted) return ctx->fail(CAMUS_B200_ERR_ARG, "call camus_b200_count_filter first");
+  if (ctx->z_valid && ctx->z_as_set == as_set) return 0;
+  if (ctx->use_fused) return run_fused(ctx, ctx->last_qmode, ctx->last_threshold, as_set, nullptr, nullptr);
   int rc = ensure_filtered(ctx);
   if (rc) return rc;
   size_t zn = (size_t)ctx->n * ctx->n * 3;
@@ -526,9 +572,42 @@ int camus_b200_count_filter(camus_b200* ctx, int qmode, double threshold, uint64
   std::memset(ctx->ms, 0, sizeof(ctx->ms));
   ctx->launches = 0;
   int rc;
-  if (ctx->genes_dirty && (rc = build_planes(ctx))) return rc;
+  if (ctx->genes_dirty && (rc = build_planes(ctx, true))) return rc;
+  ctx->cell_state = camus_b200::NONE;
+  ctx->z_valid = false;
+  if (ctx->use_fused) return run_fused(ctx, qmode, threshold, ctx->as_set_hint, n_survivors, sum_counts);
   if ((rc = run_count(ctx))) return rc;
   return run_filter(ctx, qmode, threshold, n_survivors, sum_counts);
+}
+
+int camus_b200_set_score_hint(camus_b200* ctx, int as_set) {
+  if (!ctx) return CAMUS_B200_ERR_ARG;
+  ctx->as_set_hint = as_set != 0;
+  return 0;
+}
+
+int camus_b200_run_resident(camus_b200* ctx, int qmode, double threshold, int as_set, uint64_t* out,
+                            uint64_t* n_survivors, uint64_t* sum_counts) {
+  if (!ctx) return CAMUS_B200_ERR_ARG;
+  if (ctx->genes_dirty || ctx->n == 0)
+    return ctx->fail(CAMUS_B200_ERR_ARG, "run_resident: the gene trees are not on the device yet (call camus_b200_count_filter once)");
+  if (qmode < 0 || qmode > 2 || !(threshold >= 0 && threshold <= 1)) return ctx->fail(CAMUS_B200_ERR_ARG, "run_resident: bad filter options");
+  CK(cudaSetDevice(ctx->device));
+  std::memset(ctx->ms, 0, sizeof(ctx->ms));
+  ctx->launches = 0;
+  int rc;
+  if ((rc = build_planes(ctx, false))) return rc;
+  ctx->cell_state = camus_b200::NONE;
+  ctx->z_valid = false;
+  if (ctx->use_fused) {
+    if ((rc = run_fused(ctx, qmode, threshold, as_set != 0, n_survivors, sum_counts))) return rc;
+  } else {
+    if ((rc = run_count(ctx))) return rc;
+    if ((rc = run_filter(ctx, qmode, threshold, n_survivors, sum_counts))) return rc;
+    if ((rc = run_score(ctx, as_set != 0))) return rc;
+  }
+  if (!out) return 0;  // multi-process: the caller all-reduces the partial table, then calls ..._finish
+  return run_finish(ctx, out);
 }
 
 int camus_b200_quartet_totals_partial(camus_b200* ctx, int as_set) {
@@ -576,11 +655,11 @@ int camus_b200_edge_penalties(camus_b200* ctx, uint64_t* out) {
 int camus_b200_export_quartets(camus_b200* ctx, int raw, uint64_t* keys, uint32_t* counts, uint64_t cap, uint64_t* n_out) {
   if (!ctx || !n_out) return CAMUS_B200_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
-  if (ctx->cell_state == camus_b200::NONE) return ctx->fail(CAMUS_B200_ERR_ARG, "export_quartets: call camus_b200_count_filter first");
+  if (!ctx->counted) return ctx->fail(CAMUS_B200_ERR_ARG, "export_quartets: call camus_b200_count_filter first");
   int rc;
   if (raw) {
     if (ctx->cell_state != camus_b200::RAW && (rc = run_count(ctx))) return rc;
-  } else if ((rc = ensure_filtered(ctx))) {
+  } else if ((rc = ensure_filtered(ctx))) {  // the table pipeline (K2 -> K3); Z, if any, stays valid
     return rc;
   }
   uint64_t mine = ctx->box_hi - ctx->box_lo;

@@ -18,6 +18,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include "kernels_score.cuh"
 #include "layout.cuh"
 #include "ptx.cuh"
 
@@ -33,7 +34,17 @@ struct CountParams {
   const uint32_t* tri;  // [tile][group][kTileWords]
   int n_groups;
   uint64_t box0;   // first box rank of this launch
-  uint4* cells;    // [box - box0][kBoxCells] = (c(ab|cd), c(ac|bd), c(ad|bc), 0)
+  uint4* cells;    // table mode: [box - box0][kBoxCells] = (c(ab|cd), c(ac|bd), c(ad|bc), 0)
+};
+
+// Fused mode: the counts never leave the registers. The epilogue applies K3 (filter + constraint
+// removal + scalars) and K4 (edge-score scatter into Z) per cell; no cell table exists in HBM.
+struct FusedParams {
+  int qmode;
+  double threshold;
+  int as_set;
+  unsigned long long* Z;       // [n][n][3]
+  unsigned long long* totals;  // [0] n_survivors, [1] sum_counts
 };
 
 __device__ __forceinline__ uint32_t pick(const uint4& v, int hi, int lo) {
@@ -41,7 +52,8 @@ __device__ __forceinline__ uint32_t pick(const uint4& v, int hi, int lo) {
   return k == 0 ? v.x : (k == 1 ? v.y : (k == 2 ? v.z : v.w));
 }
 
-__global__ void __launch_bounds__(kCountThreads, 2) k_count(CountParams prm) {
+template <bool kFused>
+__global__ void __launch_bounds__(kCountThreads, 2) k_count(CountParams prm, FusedParams fz, ConstraintDev ct) {
   extern __shared__ __align__(128) uint32_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kCountStages * kStageWords);
   __shared__ uint32_t s_seg[4];
@@ -135,18 +147,74 @@ __global__ void __launch_bounds__(kCountThreads, 2) k_count(CountParams prm) {
     }
   }
 
-  uint4* out = prm.cells + (size_t)blockIdx.x * kBoxCells;
+  if constexpr (!kFused) {
+    uint4* out = prm.cells + (size_t)blockIdx.x * kBoxCells;
 #pragma unroll
-  for (int ll = 0; ll < 2; ++ll)
+    for (int ll = 0; ll < 2; ++ll)
 #pragma unroll
-    for (int kk = 0; kk < 2; ++kk)
+      for (int kk = 0; kk < 2; ++kk)
 #pragma unroll
-      for (int j = 0; j < 2; ++j)
+        for (int j = 0; j < 2; ++j)
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const int c = ((ll * 2 + kk) * 2 + j) * 2 + i;
-          out[cell_local(2 * ta + i, 2 * tb + j, 2 * tc + kk, 2 * td + ll)] = make_uint4(cnt[c][0], cnt[c][1], cnt[c][2], 0u);
-        }
+          for (int i = 0; i < 2; ++i) {
+            const int c = ((ll * 2 + kk) * 2 + j) * 2 + i;
+            out[cell_local(2 * ta + i, 2 * tb + j, 2 * tc + kk, 2 * td + ll)] = make_uint4(cnt[c][0], cnt[c][1], cnt[c][2], 0u);
+          }
+  } else {
+    // ---- fused K3 + K4 on the register-resident counts ----
+    __shared__ unsigned long long s_red[2][kCountThreads / 32];
+    const uint32_t N = (uint32_t)ct.n_taxa;
+    const uint32_t a0 = sa * 8 + 2 * ta, b0 = sb * 8 + 2 * tb, c0 = sc * 8 + 2 * tc, d0 = sd * 8 + 2 * td;
+    unsigned long long ns = 0, sum = 0;
+#pragma unroll
+    for (int ll = 0; ll < 2; ++ll)
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const int ci = ((ll * 2 + kk) * 2 + j) * 2 + i;
+            const uint32_t x[4] = {a0 + i, b0 + j, c0 + kk, d0 + ll};
+            uint32_t c[3] = {cnt[ci][0], cnt[ci][1], cnt[ci][2]};
+            const bool valid = x[0] < x[1] && x[1] < x[2] && x[2] < x[3] && x[3] < N;
+            if (!valid || !(c[0] | c[1] | c[2])) continue;
+            if (fz.qmode != 0) {
+              const int ti[4] = {ct.tip_of_rank[x[0]], ct.tip_of_rank[x[1]], ct.tip_of_rank[x[2]], ct.tip_of_rank[x[3]]};
+              apply_filter(c, ti, fz.qmode, fz.threshold);
+              if (!(c[0] | c[1] | c[2])) continue;
+            }
+            const uint32_t g1 = ct.lcaD[(size_t)x[0] * N + x[1]];
+            const uint32_t g2 = ct.lcaD[(size_t)x[1] * N + x[2]];
+            const uint32_t g3 = ct.lcaD[(size_t)x[2] * N + x[3]];
+            if (constraint_topology(g1, g2, g3) == 0) c[0] = 0;
+            else c[2] = 0;
+            if (!(c[0] | c[1] | c[2])) continue;
+            ns += (c[0] != 0) + (c[1] != 0) + (c[2] != 0);
+            sum += (unsigned long long)c[0] + c[1] + c[2];
+            score_cell(c, x, g1, g2, g3, ct, fz.Z, fz.as_set);
+          }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      ns += __shfl_xor_sync(0xFFFFFFFFu, ns, off);
+      sum += __shfl_xor_sync(0xFFFFFFFFu, sum, off);
+    }
+    if ((tid & 31) == 0) {
+      s_red[0][tid >> 5] = ns;
+      s_red[1][tid >> 5] = sum;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      unsigned long long t0 = 0, t1 = 0;
+#pragma unroll
+      for (int w = 0; w < kCountThreads / 32; ++w) {
+        t0 += s_red[0][w];
+        t1 += s_red[1][w];
+      }
+      if (t0) red_add_u64(&fz.totals[0], t0);
+      if (t1) red_add_u64(&fz.totals[1], t1);
+    }
+  }
 }
 
 }  // namespace camus_dev

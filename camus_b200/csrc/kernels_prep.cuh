@@ -80,41 +80,61 @@ __global__ void k_depth_table(int grp0, int n_trees, int npad, const int32_t* __
 }
 
 // ---------------------------------------------------------------------------------------------
-// K1b: rooted-triple bit-planes. Warp = one taxon pair (a < b), loop over c > b, lane = tree.
+// K1b: rooted-triple bit-planes for taxa a < b < c (DFS ranks), lane = tree.
 //   plane 0 (ab|c): D(a,b) > D(a,c)      plane 1 (ac|b): D(a,c) > D(a,b)      plane 2 (bc|a): D(b,c) > D(a,b)
 // each AND "all three taxa present" (the != 0 tests). A polytomy (all three equal) sets no bit.
 // __ballot_sync transposes 32 per-tree predicates into one word; lanes 0..2 store the 3 planes at
 // Tri[tile(a,b,c)][group][tile_word(plane, a%8, b%8, c%8)].
 // ---------------------------------------------------------------------------------------------
-__global__ void k_triple_planes(int grp0, int n_groups_total, int npad, const uint16_t* __restrict__ Dt,
-                                uint32_t* __restrict__ Tri, uint64_t n_pairs) {
-  int gb = blockIdx.y;
-  int grp = grp0 + gb;
-  int lane = threadIdx.x;
-  uint64_t pr = (uint64_t)blockIdx.x * blockDim.y + threadIdx.y;
-  if (pr >= n_pairs) return;
-  uint32_t a, b;
-  pair_unrank(pr, a, b);
-  const uint16_t* D = Dt + (size_t)gb * npad * npad * kLanes + lane;
-  uint32_t Dab = D[((size_t)a * npad + b) * kLanes];
-  const uint16_t* rowa = D + (size_t)a * npad * kLanes;
-  const uint16_t* rowb = D + (size_t)b * npad * kLanes;
-  uint32_t sa = a >> 3, sb = b >> 3;
-  for (uint32_t c = b + 1; c < (uint32_t)npad; ++c) {
-    uint32_t Dac = rowa[(size_t)c * kLanes];
-    uint32_t Dbc = rowb[(size_t)c * kLanes];
-    bool p0 = Dab > Dac && Dac != 0;
-    bool p1 = Dac > Dab && Dab != 0;
-    bool p2 = Dbc > Dab && Dab != 0;
-    uint32_t w0 = __ballot_sync(0xFFFFFFFFu, p0);
-    uint32_t w1 = __ballot_sync(0xFFFFFFFFu, p1);
-    uint32_t w2 = __ballot_sync(0xFFFFFFFFu, p2);
-    if (lane < 3) {
-      uint64_t tile = tile_index(sa, sb, c >> 3);
-      uint32_t w = lane == 0 ? w0 : (lane == 1 ? w1 : w2);
-      Tri[(tile * n_groups_total + grp) * kTileWords + tile_word(lane, a & 7, b & 7, c & 7)] = w;
-    }
+// One CTA builds one whole tile (s0 <= s1 <= s2) of one tree group: the 3 x 64 pair-depth rows it
+// needs are staged in shared memory (coalesced 64 B rows of Dt), 8 warps x 64 triples ballot into
+// a shared 6 KB image of the tile, which is then written to HBM with 128-bit coalesced stores.
+// Every word of every tile is written, so Tri needs no memset.
+__global__ void __launch_bounds__(256) k_triple_planes(int grp0, int n_groups_total, int npad,
+                                                       const uint16_t* __restrict__ Dt, uint32_t* __restrict__ Tri) {
+  __shared__ uint16_t s_d[3][64][kLanes];  // [ab | ac | bc][i*8+j][lane]
+  __shared__ __align__(16) uint32_t s_out[kTileWords];
+  __shared__ uint32_t s_seg[3];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gb = blockIdx.y;
+  const uint64_t tile = blockIdx.x;
+  if (tid == 0) {
+    uint64_t r = tile;
+    uint32_t s2 = unrank3(r);
+    r -= choose3((uint64_t)s2 + 2);
+    uint32_t s1 = unrank2(r);
+    r -= choose2((uint64_t)s1 + 1);
+    s_seg[0] = (uint32_t)r;
+    s_seg[1] = s1;
+    s_seg[2] = s2;
   }
+  __syncthreads();
+  const uint32_t a0 = s_seg[0] * 8, b0 = s_seg[1] * 8, c0 = s_seg[2] * 8;
+  const uint16_t* D = Dt + (size_t)gb * npad * npad * kLanes;
+#pragma unroll
+  for (int it = 0; it < 3 * 64 / 8; ++it) {
+    int pr = it * 8 + warp;  // 0..191
+    int which = pr >> 6, i = (pr >> 3) & 7, j = pr & 7;
+    uint32_t x = (which == 2 ? b0 : a0) + i;
+    uint32_t y = (which == 0 ? b0 : c0) + j;
+    s_d[which][pr & 63][lane] = x < y ? D[((size_t)x * npad + y) * kLanes + lane] : (uint16_t)0;
+  }
+  __syncthreads();
+#pragma unroll 4
+  for (int it = 0; it < 64; ++it) {
+    int t = warp * 64 + it;
+    int x = t & 7, y = (t >> 3) & 7, z = t >> 6;
+    uint32_t Dab = s_d[0][x * 8 + y][lane], Dac = s_d[1][x * 8 + z][lane], Dbc = s_d[2][y * 8 + z][lane];
+    bool ok = Dab != 0 && Dac != 0 && Dbc != 0;  // all present, and a < b < c in rank order
+    uint32_t w0 = __ballot_sync(0xFFFFFFFFu, ok && Dab > Dac);
+    uint32_t w1 = __ballot_sync(0xFFFFFFFFu, ok && Dac > Dab);
+    uint32_t w2 = __ballot_sync(0xFFFFFFFFu, ok && Dbc > Dab);
+    if (lane < 3) s_out[tile_word(lane, x, y, z)] = lane == 0 ? w0 : (lane == 1 ? w1 : w2);
+  }
+  __syncthreads();
+  uint4* dst = reinterpret_cast<uint4*>(Tri + (tile * n_groups_total + (grp0 + gb)) * kTileWords);
+  const uint4* src = reinterpret_cast<const uint4*>(s_out);
+  for (int i = tid; i < kTileWords / 4; i += 256) dst[i] = src[i];
 }
 
 // ---------------------------------------------------------------------------------------------

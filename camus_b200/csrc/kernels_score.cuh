@@ -61,6 +61,46 @@ __device__ __forceinline__ int constraint_topology(uint32_t g1, uint32_t g2, uin
 // partner of taxon position i (0..3 = a,b,c,d) in topology t (0 ab|cd, 1 ac|bd, 2 ad|bc)
 __device__ __forceinline__ int partner_of(int t, int i) { return t == 0 ? (i ^ 1) : (t == 1 ? (i ^ 2) : (3 - i)); }
 
+// prep.filterQuartets + Threshold.Keep for one 4-set (internal/prep/quartetfilter.go:67-96).
+// c[] = counts of ab|cd, ac|bd, ad|bc (DFS order); ti[] = gotree tip indices of a,b,c,d.
+__device__ __forceinline__ void apply_filter(uint32_t c[3], const int ti[4], int qmode, double threshold) {
+  // pos[i] = rank of taxon i among the four by tip index; the taxon with pos 0 is "taxon 0" of the
+  // reference's packing. rho[t] = position (0,1,2) of topology t in the reference's AllQuartets()
+  // order = pos of taxon 0's partner, minus one. All loops unroll to selects (no local arrays).
+  int pos[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int r = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) r += (ti[j] < ti[i]);
+    pos[i] = r;
+  }
+  int rho[3];
+#pragma unroll
+  for (int t = 0; t < 3; ++t) {
+    int r = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r += (pos[i] == 0) ? (pos[partner_of(t, i)] - 1) : 0;
+    rho[t] = r;
+  }
+  // stable sort of the three topologies by count (insertion sort on 3 elements in Go): the keys
+  // (count, rho) are distinct, so min / middle / max are well defined; no indexed local arrays.
+  const unsigned long long k0 = ((unsigned long long)c[0] << 2) | (unsigned)rho[0];
+  const unsigned long long k1 = ((unsigned long long)c[1] << 2) | (unsigned)rho[1];
+  const unsigned long long k2 = ((unsigned long long)c[2] << 2) | (unsigned)rho[2];
+  const unsigned long long kmin = min(k0, min(k1, k2)), kmax = max(k0, max(k1, k2));
+  const unsigned long long kmid = k0 ^ k1 ^ k2 ^ kmin ^ kmax;
+  const uint32_t lo = (uint32_t)(kmin >> 2), mid = (uint32_t)(kmid >> 2);
+  const uint32_t s = lo + mid;
+  const bool keep = __double2uint_rz(threshold * (double)s) < mid - lo;  // Threshold.Keep
+  const unsigned long long cut = !keep ? kmid : (qmode == 2 ? kmin : 0ull);  // delete keys <= cut
+  if (!keep || qmode == 2) {
+    if (k0 <= cut) c[0] = 0;
+    if (k1 <= cut) c[1] = 0;
+    if (k2 <= cut) c[2] = 0;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // K3: prep.filterQuartets (internal/prep/quartetfilter.go:67-96) applied once per 4-set, then the
 // constraint-quartet removal (internal/prep/preprocess.go:51-57), then the two scalars
@@ -90,44 +130,19 @@ __global__ void __launch_bounds__(256) k_filter(FilterParams prm, ConstraintDev 
     bool changed = false;
     if (prm.qmode != 0 && (c[0] | c[1] | c[2])) {
       int ti[4] = {ct.tip_of_rank[cc.a], ct.tip_of_rank[cc.b], ct.tip_of_rank[cc.c], ct.tip_of_rank[cc.d]};
-      int s0 = 0;
-#pragma unroll
-      for (int i = 1; i < 4; ++i)
-        if (ti[i] < ti[s0]) s0 = i;
-      // rho[t] = position (0,1,2) of topology t in the reference's AllQuartets() order
-      int rho[3];
-#pragma unroll
-      for (int t = 0; t < 3; ++t) {
-        int p = partner_of(t, s0), r = 0;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) r += (j != s0 && ti[j] < ti[p]);
-        rho[t] = r;
-      }
-      // stable sort of the three topologies by count (insertion sort on 3 elements in Go)
-      int o[3] = {0, 1, 2};
-      auto less = [&](int x, int y) { return c[x] < c[y] || (c[x] == c[y] && rho[x] < rho[y]); };
-      if (less(o[1], o[0])) { int t = o[0]; o[0] = o[1]; o[1] = t; }
-      if (less(o[2], o[1])) { int t = o[1]; o[1] = o[2]; o[2] = t; }
-      if (less(o[1], o[0])) { int t = o[0]; o[0] = o[1]; o[1] = t; }
-      uint32_t lo = c[o[0]], mid = c[o[1]];
-      uint32_t s = lo + mid;
-      bool keep = __double2uint_rz(prm.threshold * (double)s) < mid - lo;  // Threshold.Keep
-      if (!keep) {
-        c[o[0]] = 0;
-        c[o[1]] = 0;
-      } else if (prm.qmode == 2) {
-        c[o[0]] = 0;
-      }
+      apply_filter(c, ti, prm.qmode, prm.threshold);
       changed = true;
     }
     if (c[0] | c[1] | c[2]) {
       uint32_t g1 = ct.lcaD[(size_t)cc.a * ct.n_taxa + cc.b];
       uint32_t g2 = ct.lcaD[(size_t)cc.b * ct.n_taxa + cc.c];
       uint32_t g3 = ct.lcaD[(size_t)cc.c * ct.n_taxa + cc.d];
-      int T = constraint_topology(g1, g2, g3);
-      if (c[T]) {
-        c[T] = 0;
-        changed = true;
+      if (constraint_topology(g1, g2, g3) == 0) {
+        changed |= c[0] != 0;
+        c[0] = 0;
+      } else {
+        changed |= c[2] != 0;
+        c[2] = 0;
       }
     }
     if (changed) prm.cells[idx] = make_uint4(c[0], c[1], c[2], 0);
@@ -176,17 +191,10 @@ struct ScoreParams {
   unsigned long long* Z;  // [n][n][3] two's-complement int64
 };
 
-__global__ void __launch_bounds__(256) k_score(ScoreParams prm, ConstraintDev ct) {
-  __shared__ uint32_t s_seg[4];
-  CellCoords cc = decode_cell(prm.box0, ct.n_taxa, s_seg);
-  if (!cc.valid) return;
-  uint4 v = prm.cells[(size_t)blockIdx.x * 256 + threadIdx.x];
-  if (!(v.x | v.y | v.z)) return;
-  const uint32_t cnt[3] = {v.x, v.y, v.z};
-  const uint32_t x[4] = {cc.a, cc.b, cc.c, cc.d};
-  const uint32_t g1 = ct.lcaD[(size_t)cc.a * ct.n_taxa + cc.b];
-  const uint32_t g2 = ct.lcaD[(size_t)cc.b * ct.n_taxa + cc.c];
-  const uint32_t g3 = ct.lcaD[(size_t)cc.c * ct.n_taxa + cc.d];
+// One cell's contribution to Z (see the K4 comment above). x[] = DFS ranks a<b<c<d, g1..g3 = packed
+// LCAs of (a,b), (b,c), (c,d), cnt[] = surviving counts per topology.
+__device__ __forceinline__ void score_cell(const uint32_t cnt[3], const uint32_t x[4], uint32_t g1, uint32_t g2,
+                                           uint32_t g3, const ConstraintDev& ct, unsigned long long* Z, int as_set) {
   const size_t n = (size_t)ct.n;
 #pragma unroll
   for (int be = 0; be < 4; ++be) {
@@ -210,11 +218,25 @@ __global__ void __launch_bounds__(256) k_score(ScoreParams prm, ConstraintDev ct
       int p = partner_of(t, be);
       int pos = p - (p > be ? 1 : 0);                 // position of the partner among the other three
       int comp = first ? pos : (pos + 2) % 3;         // 0 LEFT, 1 RIGHT, 2 OUT
-      unsigned long long w = prm.as_set ? 1ull : (unsigned long long)cnt[t];
-      red_add_u64(&prm.Z[row_leaf + comp], w);
-      red_add_u64(&prm.Z[row_m + comp], (unsigned long long)(-(long long)w));
+      unsigned long long w = as_set ? 1ull : (unsigned long long)cnt[t];
+      red_add_u64(&Z[row_leaf + comp], w);
+      red_add_u64(&Z[row_m + comp], (unsigned long long)(-(long long)w));
     }
   }
+}
+
+__global__ void __launch_bounds__(256) k_score(ScoreParams prm, ConstraintDev ct) {
+  __shared__ uint32_t s_seg[4];
+  CellCoords cc = decode_cell(prm.box0, ct.n_taxa, s_seg);
+  if (!cc.valid) return;
+  uint4 v = prm.cells[(size_t)blockIdx.x * 256 + threadIdx.x];
+  if (!(v.x | v.y | v.z)) return;
+  const uint32_t cnt[3] = {v.x, v.y, v.z};
+  const uint32_t x[4] = {cc.a, cc.b, cc.c, cc.d};
+  const uint32_t g1 = ct.lcaD[(size_t)cc.a * ct.n_taxa + cc.b];
+  const uint32_t g2 = ct.lcaD[(size_t)cc.b * ct.n_taxa + cc.c];
+  const uint32_t g3 = ct.lcaD[(size_t)cc.c * ct.n_taxa + cc.d];
+  score_cell(cnt, x, g1, g2, g3, ct, prm.Z, prm.as_set);
 }
 
 // ---------------------------------------------------------------------------------------------

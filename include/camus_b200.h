@@ -77,6 +77,11 @@ int camus_b200_clear_gene_trees(camus_b200* ctx);
 int camus_b200_count_filter(camus_b200* ctx, int qmode, double threshold, uint64_t* n_survivors,
                             uint64_t* sum_counts);
 
+/* Optional: tell the next count_filter which weight (-asSet or counts) quartet_totals will ask
+ * for, so its fused count+filter+score pass already produces the right table (scorers.go:23-38:
+ * the Go side knows AsSet before Preprocess). A mismatch only costs a second pass. */
+int camus_b200_set_score_hint(camus_b200* ctx, int as_set);
+
 /* quartetTotals[u][w] (row-major n*n, reference node ids), 0 where !ShouldCalcEdge.
  * as_set != 0 counts every surviving quartet once (-asSet, and always in sym mode). */
 int camus_b200_quartet_totals(camus_b200* ctx, int as_set, uint64_t* out /*[n*n]*/);
@@ -106,6 +111,12 @@ enum {
   CAMUS_B200_T_PENALTY = 6,
   CAMUS_B200_T_N = 8
 };
+/* Re-run the whole hot path (LCA tables -> bit-planes -> count -> filter -> score -> finalise)
+ * from the flat gene trees ALREADY resident in HBM (uploaded by an earlier count_filter): the
+ * device-resident leg of the benchmark. Results as count_filter + quartet_totals. out == NULL
+ * stops after the partial junction table (multi-process: all-reduce it, then call ..._finish). */
+int camus_b200_run_resident(camus_b200* ctx, int qmode, double threshold, int as_set, uint64_t* out /*[n*n]*/,
+                            uint64_t* n_survivors, uint64_t* sum_counts);
 /* CUDA-event milliseconds of the last run of each stage and the number of kernel launches. */
 int camus_b200_stage_ms(const camus_b200* ctx, float* ms /*[CAMUS_B200_T_N]*/, uint64_t* n_launches);
 /* resolutions = sum over gene trees of C(leaves,4): the unit of the throughput metric. */

@@ -73,7 +73,106 @@ std::array<Quartet, 3> all_quartets(Quartet q) {
           base | (uint64_t(kTopo3) << kTopoShift)};
 }
 
-using QMap = std::unordered_map<Quartet, uint32_t>;
+// map[Quartet]uint32 of the reference. Open addressing with linear probing (Go's maps are
+// bucketed open-addressing tables too; a node-based std::unordered_map would make the CPU
+// baseline several times slower than the Go code it stands for). Key 0 (NilQuartet) = empty.
+class QMap {
+ public:
+  struct KV {
+    Quartet first;
+    uint32_t second;
+  };
+  struct iterator {
+    const QMap* m;
+    size_t i;
+    KV operator*() const { return KV{m->keys_[i], m->vals_[i]}; }
+    iterator& operator++() {
+      ++i;
+      while (i < m->keys_.size() && m->keys_[i] == 0) ++i;
+      return *this;
+    }
+    bool operator!=(const iterator& o) const { return i != o.i; }
+  };
+  iterator begin() const {
+    iterator it{this, 0};
+    while (it.i < keys_.size() && keys_[it.i] == 0) ++it.i;
+    return it;
+  }
+  iterator end() const { return iterator{this, keys_.size()}; }
+  size_t size() const { return count_; }
+  void clear() {
+    keys_.clear();
+    vals_.clear();
+    count_ = 0;
+  }
+  uint32_t& operator[](Quartet k) {
+    if ((count_ + 1) * 10 > keys_.size() * 7) grow();
+    size_t i = slot(k);
+    while (keys_[i] != 0 && keys_[i] != k) i = (i + 1) & mask();
+    if (keys_[i] == 0) {
+      keys_[i] = k;
+      vals_[i] = 0;
+      ++count_;
+    }
+    return vals_[i];
+  }
+  const uint32_t* find(Quartet k) const {
+    if (keys_.empty()) return nullptr;
+    size_t i = slot(k);
+    while (keys_[i] != 0) {
+      if (keys_[i] == k) return &vals_[i];
+      i = (i + 1) & mask();
+    }
+    return nullptr;
+  }
+  size_t count(Quartet k) const { return find(k) ? 1 : 0; }
+  uint32_t at(Quartet k) const { return *find(k); }
+  void erase(Quartet k) {  // backward-shift deletion
+    if (keys_.empty()) return;
+    size_t i = slot(k);
+    while (keys_[i] != 0 && keys_[i] != k) i = (i + 1) & mask();
+    if (keys_[i] == 0) return;
+    --count_;
+    size_t j = i;
+    for (;;) {
+      j = (j + 1) & mask();
+      if (keys_[j] == 0) break;
+      size_t h = slot(keys_[j]);
+      if (((j - h) & mask()) >= ((j - i) & mask())) {
+        keys_[i] = keys_[j];
+        vals_[i] = vals_[j];
+        i = j;
+      }
+    }
+    keys_[i] = 0;
+  }
+
+ private:
+  std::vector<Quartet> keys_;
+  std::vector<uint32_t> vals_;
+  size_t count_ = 0;
+  size_t mask() const { return keys_.size() - 1; }
+  size_t slot(Quartet k) const {
+    uint64_t z = k;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return size_t(z ^ (z >> 31)) & mask();
+  }
+  void grow() {
+    size_t cap = keys_.empty() ? 64 : keys_.size() * 2;
+    std::vector<Quartet> ok(cap, 0);
+    std::vector<uint32_t> ov(cap, 0);
+    ok.swap(keys_);
+    ov.swap(vals_);
+    for (size_t i = 0; i < ok.size(); ++i)
+      if (ok[i] != 0) {
+        size_t j = slot(ok[i]);
+        while (keys_[j] != 0) j = (j + 1) & mask();
+        keys_[j] = ok[i];
+        vals_[j] = ov[i];
+      }
+  }
+};
 
 struct FlatTree {  // rooted tree given by parent pointers; children in index order
   int n = 0;
@@ -206,10 +305,10 @@ bool threshold_keep(double thresh, uint32_t c0, uint32_t c1, uint32_t c2) {
 void filter_quartets(QMap& qc, int mode, double thresh) {
   std::vector<Quartet> keys;
   keys.reserve(qc.size());
-  for (auto& kv : qc) keys.push_back(kv.first);
+  for (auto kv :qc) keys.push_back(kv.first);
   auto get = [&](Quartet q) -> uint32_t {
-    auto it = qc.find(q);
-    return it == qc.end() ? 0 : it->second;
+    const uint32_t* v = qc.find(q);
+    return v ? *v : 0;
   };
   for (Quartet q : keys) {
     if (!qc.count(q)) continue;
@@ -238,6 +337,7 @@ struct Ctx {
   QMap raw, q;  // raw = processQuartets output; q = after filter + constraint removal
   bool counted = false;
   std::vector<std::vector<Quartet>> qset;  // treedata.go:197-222
+  bool qset_valid = false;
   uint64_t literal_emissions = 0;
 
   bool in_leafset(int node, int tip) const { return (leafset[node][tip >> 6] >> (tip & 63)) & 1; }
@@ -294,10 +394,14 @@ void build_tree_tables(Ctx& c) {
 }
 
 // graphs.mapQuartetsToVertices (treedata.go:197-222)
+// Built lazily (first literal totals / lookup): the reference runs it inside MakeTreeData at the
+// end of Preprocess; keeping it out of count_filter lets bench.py time the count stage alone.
 void map_quartets_to_vertices(Ctx& c) {
+  if (c.qset_valid) return;
+  c.qset_valid = true;
   c.qset.assign(c.n, {});
   for (int v = 0; v < c.n; v++)
-    for (auto& kv : c.q) {
+    for (auto kv :c.q) {
       int found = 0;
       for (int i = 0; i < 4; i++) found += c.in_leafset(v, q_taxon(kv.first, i));
       if (found >= 3) c.qset[v].push_back(kv.first);
@@ -449,7 +553,7 @@ void totals_scatter(const Ctx& c, bool asSet, uint64_t* out) {
   // diff[w][u], u in [0, n]
   std::vector<int64_t> diff((size_t)n * (n + 1), 0);
   auto deeper = [&](int x, int y) { return c.depth[x] >= c.depth[y] ? x : y; };
-  for (auto& kv : c.q) {
+  for (auto kv :c.q) {
     Quartet q = kv.first;
     int64_t wgt = asSet ? 1 : (int64_t)kv.second;
     int leaf[4];
@@ -574,7 +678,7 @@ int oracle_set_quartets(oracle_ctx* c, uint64_t n, const uint64_t* keys, const u
   c->q.clear();
   for (uint64_t i = 0; i < n; i++) c->q[keys[i]] = counts[i];
   c->counted = true;
-  map_quartets_to_vertices(*c);
+  c->qset_valid = false;
   return 0;
 }
 
@@ -590,7 +694,7 @@ int oracle_tree_quartets(int32_t n_nodes, const int32_t* parent, const int32_t* 
   if (literal) enumerate_quartets_literal(t, [&](Quartet q) { m[q] = 1; });
   else enumerate_quartets_fast(t, [&](Quartet q) { m[q] = 1; });
   std::vector<Quartet> ks;
-  for (auto& kv : m) ks.push_back(kv.first);
+  for (auto kv :m) ks.push_back(kv.first);
   std::sort(ks.begin(), ks.end());
   *n_out = ks.size();
   for (uint64_t i = 0; i < ks.size() && i < cap; i++) keys[i] = ks[i];
@@ -609,11 +713,11 @@ int oracle_count_filter(oracle_ctx* c, int qmode, double threshold, int literal,
     QMap tq;  // treeQuartets[...] = 1 (quartet.go:119-121): a set per tree
     if (literal) enumerate_quartets_literal(c->genes[g], [&](Quartet q) { tq[q] = 1; }, &em[t]);
     else enumerate_quartets_fast(c->genes[g], [&](Quartet q) { tq[q] = 1; });
-    for (auto& kv : tq) local[t][kv.first] += kv.second;  // shards[..].counts[q] += c (:105-110)
+    for (auto kv :tq) local[t][kv.first] += kv.second;  // shards[..].counts[q] += c (:105-110)
   });
   c->raw.clear();
   for (auto& m : local)
-    for (auto& kv : m) c->raw[kv.first] += kv.second;  // merge (:117-122)
+    for (auto kv :m) c->raw[kv.first] += kv.second;  // merge (:117-122)
   for (auto e : em) c->literal_emissions += e;
   c->q = c->raw;
   if (qmode != 0) filter_quartets(c->q, qmode, threshold);
@@ -630,9 +734,9 @@ int oracle_count_filter(oracle_ctx* c, int qmode, double threshold, int literal,
   if (literal) enumerate_quartets_literal(ct, del);
   else enumerate_quartets_fast(ct, del);
   c->counted = true;
-  map_quartets_to_vertices(*c);
+  c->qset_valid = false;
   uint64_t sum = 0;
-  for (auto& kv : c->q) sum += kv.second;
+  for (auto kv :c->q) sum += kv.second;
   if (n_survivors) *n_survivors = c->q.size();
   if (sum_counts) *sum_counts = sum;
   return 0;
@@ -641,7 +745,9 @@ int oracle_count_filter(oracle_ctx* c, int qmode, double threshold, int literal,
 uint64_t oracle_literal_emissions(const oracle_ctx* c) { return c->literal_emissions; }
 
 static int export_map(const QMap& m, uint64_t* keys, uint32_t* counts, uint64_t cap, uint64_t* n_out) {
-  std::vector<std::pair<Quartet, uint32_t>> v(m.begin(), m.end());
+  std::vector<std::pair<Quartet, uint32_t>> v;
+  v.reserve(m.size());
+  for (auto kv : m) v.emplace_back(kv.first, kv.second);
   std::sort(v.begin(), v.end());
   *n_out = v.size();
   for (uint64_t i = 0; i < v.size() && i < cap; i++) {
@@ -676,6 +782,7 @@ int oracle_quartet_totals(oracle_ctx* c, int as_set, int literal, int nthreads, 
     return 0;
   }
   std::memset(out, 0, sizeof(uint64_t) * n * n);
+  map_quartets_to_vertices(*c);
   parallel_for(n, std::max(1, nthreads), [&](int u, int) {
     for (int w = 0; w < n; w++)
       if (should_calc_edge(*c, u, w)) out[(size_t)u * n + w] = quartets_total(*c, u, w, as_set != 0);
@@ -696,14 +803,17 @@ int oracle_edge_penalties(oracle_ctx* c, uint64_t* out) {
 // score.calculatePenalty for one pair, without the ShouldCalcEdge mask (penalty_test.go calls it so)
 uint64_t oracle_calculate_penalty(const oracle_ctx* c, int u, int w) { return calculate_penalty(*c, u, w); }
 
-int oracle_quartet_score(const oracle_ctx* c, uint64_t q, int u, int w) {
+int oracle_quartet_score(oracle_ctx* c, uint64_t q, int u, int w) {
   int v = c->lca[u][w];
   return quartet_score(*c, q, u, w, v, get_w_subtree(*c, u, w, v));
 }
 int oracle_should_calc_edge(const oracle_ctx* c, int u, int w) { return should_calc_edge(*c, u, w); }
 int oracle_cycle_length(const oracle_ctx* c, int u, int w) { return cycle_length(*c, u, w); }
 int oracle_lca(const oracle_ctx* c, int a, int b) { return c->lca[a][b]; }
-uint64_t oracle_num_quartets_at(const oracle_ctx* c, int v) { return c->qset[v].size(); }
+uint64_t oracle_num_quartets_at(oracle_ctx* c, int v) {
+  map_quartets_to_vertices(*c);
+  return c->qset[v].size();
+}
 // pack four constraint tip indices with the pairing (t0,t1 | t2,t3) (quartet.go:67-89)
 uint64_t oracle_pack_quartet(int t0, int t1, int t2, int t3) {
   int16_t ids[4] = {(int16_t)t0, (int16_t)t1, (int16_t)t2, (int16_t)t3};

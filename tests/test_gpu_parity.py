@@ -54,6 +54,32 @@ def compare_all(gpu, prob, qmode, thr, literal=False, as_sets=(False, True), pen
     return o
 
 
+@pytest.mark.parametrize("qmode,thr", [(0, 0.0), (2, 0.5)])
+def test_fused_and_table_pipelines_agree(gpu, qmode, thr, monkeypatch):
+    """count_filter runs the fused kernel (counts never leave registers); CAMUS_B200_UNFUSED=1
+    selects the K2 -> K3 -> K4 pipeline over a cell table in HBM. Same results, both vs the oracle."""
+    from camus_b200.cabi import CamusB200
+    monkeypatch.setenv("CAMUS_B200_UNFUSED", "1")
+    table = CamusB200(0)
+    monkeypatch.delenv("CAMUS_B200_UNFUSED")
+    for s, ms in ((synth.make(60, 100, 4, support=True, drop_frac=0.1, nexus=True), 0.7), (synth.make_config(1)[0], 0.0)):
+        prob = Problem(s.constraint, s.genes, s.fmt, ms)
+        o = orc.Oracle().load(prob)
+        want = o.count_filter(qmode, thr, False)
+        for ctx in (gpu, table):
+            ctx.load(prob)
+            for hint in (False, True):
+                ctx.set_score_hint(hint)
+                assert ctx.count_filter(qmode, thr) == want
+                for as_set in (True, False):
+                    assert np.array_equal(ctx.quartet_totals(as_set), o.quartet_totals(as_set, False))
+        gpu.set_score_hint(False)
+        ms_f, _ = gpu.stage_ms()
+        ms_t, _ = table.stage_ms()
+        assert ms_f["filter"] == 0 and ms_f["score"] == 0  # fused: one kernel
+    table.close()
+
+
 # ------------------------------------------------------------------ reference KATs on the GPU
 @pytest.mark.parametrize("name,tre,qmode,thr,genes,expected", K.PROCESS_QUARTETS)
 def test_process_quartets(gpu, name, tre, qmode, thr, genes, expected):
