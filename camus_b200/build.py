@@ -76,6 +76,7 @@ def build_cuda(force: bool = False, verbose: bool = False) -> str:
                "-cudart", "static"]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
+        cmd += os.environ.get("CAMUS_NVCC_EXTRA", "").split()
         _run(cmd)
     return CUDA_SO
 

@@ -24,11 +24,12 @@ class CamusB200Error(RuntimeError):
 def lib() -> C.CDLL:
     global _lib
     if _lib is None:
-        if not os.path.exists(build.CUDA_SO):
+        so = os.environ.get("CAMUS_B200_LIB", build.CUDA_SO)  # override: A/B builds of the same library
+        if not os.path.exists(so):
             raise CamusB200Error(
-                f"{build.CUDA_SO} is missing: build it with `python -m camus_b200.build cuda` "
+                f"{so} is missing: build it with `python -m camus_b200.build cuda` "
                 "(there is no CPU fallback for the hot path)")
-        L = C.CDLL(build.CUDA_SO)
+        L = C.CDLL(so)
         vp, u64p = C.c_void_p, C.POINTER(C.c_uint64)
         L.camus_b200_create.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(C.c_int)]
         L.camus_b200_destroy.argtypes = [vp]

@@ -73,7 +73,7 @@ struct camus_b200 {
   DevBuf<uint32_t> d_tri;
   DevBuf<uint4> d_cells;
   DevBuf<unsigned long long> d_Z, d_E, d_out, d_totals, d_keys, d_nout;
-  DevBuf<uint32_t> d_counts;
+  DevBuf<uint32_t> d_counts, d_thr_tab;
   uint64_t box_lo = 0, box_hi = 0;  // this rank's partition
   enum CellState { NONE, RAW, FILTERED } cell_state = NONE;
   int last_qmode = 0;
@@ -389,11 +389,13 @@ int build_planes(camus_b200* ctx, bool do_upload = true) {
   CK(cudaMemsetAsync(ctx->d_lrT.p, 0, ctx->d_lrT.bytes(), ctx->stream));
   CK(cudaMemsetAsync(ctx->d_hT.p, 0, ctx->d_hT.bytes(), ctx->stream));
   size_t tri_words = (size_t)num_tiles(ctx->M) * G32 * kTileWords;
-  size_t free_b = 0, total_b = 0;
-  CK(cudaMemGetInfo(&free_b, &total_b));
-  if (ctx->d_tri.n < tri_words && tri_words * 4 + ((size_t)4 << 30) > free_b + ctx->d_tri.bytes())
-    return ctx->fail(CAMUS_B200_ERR_NOMEM, "triple bit-planes need " + std::to_string(tri_words * 4 >> 20) + " MiB, device has " +
-                                               std::to_string(free_b >> 20) + " MiB free");
+  if (ctx->d_tri.n < tri_words) {  // only query the driver when the table has to grow
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    if (tri_words * 4 + ((size_t)4 << 30) > free_b + ctx->d_tri.bytes())
+      return ctx->fail(CAMUS_B200_ERR_NOMEM, "triple bit-planes need " + std::to_string(tri_words * 4 >> 20) +
+                                                 " MiB, device has " + std::to_string(free_b >> 20) + " MiB free");
+  }
   CK(ctx->d_tri.alloc(tri_words));
   if (G == 0) CK(cudaMemsetAsync(ctx->d_tri.p, 0, tri_words * 4, ctx->stream));
   if (G > 0) {
@@ -421,6 +423,14 @@ int build_planes(camus_b200* ctx, bool do_upload = true) {
   return 0;
 }
 
+int make_thr_table(camus_b200* ctx, double threshold) {
+  int nt = ctx->G + 2;  // the sum of the two smallest counts never exceeds the number of trees
+  CK(ctx->d_thr_tab.alloc(nt));
+  k_threshold_table<<<(nt + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_thr_tab.p, nt, threshold);
+  CK_LAUNCH();
+  return 0;
+}
+
 void set_box_range(camus_b200* ctx) {
   uint64_t nb = num_boxes(ctx->M);
   ctx->box_lo = nb * ctx->rank / ctx->world;
@@ -433,17 +443,27 @@ int run_fused(camus_b200* ctx, int qmode, double threshold, int as_set, uint64_t
   set_box_range(ctx);
   uint64_t mine = ctx->box_hi - ctx->box_lo;
   size_t zn = (size_t)ctx->n * ctx->n * 3;
-  CK(ctx->d_Z.alloc(zn));
+  static const int rep_env = getenv("CAMUS_B200_ZREP") ? atoi(getenv("CAMUS_B200_ZREP")) : 0;
+  // privatised copies of Z spread the hot (w-point, junction) entries over several L2 lines
+  int rep = rep_env > 0 ? rep_env : 32;
+  while (rep > 1 && zn * rep * 8 > ((size_t)4 << 30)) rep >>= 1;
+  CK(ctx->d_Z.alloc(zn * rep));
   CK(ctx->d_totals.alloc(2));
   StageTimer t(ctx, CAMUS_B200_T_COUNT);
-  CK(cudaMemsetAsync(ctx->d_Z.p, 0, zn * 8, ctx->stream));
+  if (make_thr_table(ctx, threshold)) return CAMUS_B200_ERR_CUDA;
+  CK(cudaMemsetAsync(ctx->d_Z.p, 0, zn * rep * 8, ctx->stream));
   CK(cudaMemsetAsync(ctx->d_totals.p, 0, 16, ctx->stream));
   const uint64_t max_grid = 1u << 30;
   for (uint64_t b0 = 0; b0 < mine; b0 += max_grid) {
     uint64_t nbx = std::min(max_grid, mine - b0);
-    CountParams prm{ctx->d_tri.p, std::max(ctx->G32, 1), ctx->box_lo + b0, nullptr};
-    FusedParams fz{qmode, threshold, as_set, ctx->d_Z.p, ctx->d_totals.p};
+    CountParams prm{ctx->d_tri.p, std::max(ctx->G32, 1), ctx->box_lo + b0, nullptr, ctx->G};
+    static const int dbg = getenv("CAMUS_B200_DEBUG") ? atoi(getenv("CAMUS_B200_DEBUG")) : 0;
+    FusedParams fz{qmode, threshold, ctx->d_thr_tab.p, as_set, ctx->d_Z.p, ctx->d_totals.p, rep, (unsigned long long)zn, dbg};
     k_count<true><<<(unsigned)nbx, kCountThreads, kCountSmemBytes, ctx->stream>>>(prm, fz, ctx->ct);
+    CK_LAUNCH();
+  }
+  if (rep > 1) {
+    k_sum_replicas<<<(unsigned)((zn + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_Z.p, zn, rep);
     CK_LAUNCH();
   }
   unsigned long long h[2] = {0, 0};
@@ -463,17 +483,19 @@ int run_fused(camus_b200* ctx, int qmode, double threshold, int as_set, uint64_t
 int run_count(camus_b200* ctx) {
   set_box_range(ctx);
   uint64_t mine = ctx->box_hi - ctx->box_lo;
-  size_t free_b = 0, total_b = 0;
-  CK(cudaMemGetInfo(&free_b, &total_b));
-  if (ctx->d_cells.n < mine * kBoxCells && mine > cells_budget_boxes(free_b + ctx->d_cells.bytes()))
-    return ctx->fail(CAMUS_B200_ERR_NOMEM, "cell table of " + std::to_string(mine * kBoxCells * 16 >> 20) +
-                                               " MiB does not fit on the device (only the fused path scales to this size)");
+  if (ctx->d_cells.n < mine * kBoxCells) {
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    if (mine > cells_budget_boxes(free_b + ctx->d_cells.bytes()))
+      return ctx->fail(CAMUS_B200_ERR_NOMEM, "cell table of " + std::to_string(mine * kBoxCells * 16 >> 20) +
+                                                 " MiB does not fit on the device (only the fused path scales to this size)");
+  }
   CK(ctx->d_cells.alloc(std::max<uint64_t>(mine, 1) * kBoxCells));
   StageTimer t(ctx, CAMUS_B200_T_COUNT);
   const uint64_t max_grid = 1u << 30;
   for (uint64_t b0 = 0; b0 < mine; b0 += max_grid) {
     uint64_t nbx = std::min(max_grid, mine - b0);
-    CountParams prm{ctx->d_tri.p, std::max(ctx->G32, 1), ctx->box_lo + b0, ctx->d_cells.p + b0 * kBoxCells};
+    CountParams prm{ctx->d_tri.p, std::max(ctx->G32, 1), ctx->box_lo + b0, ctx->d_cells.p + b0 * kBoxCells, ctx->G};
     k_count<false><<<(unsigned)nbx, kCountThreads, kCountSmemBytes, ctx->stream>>>(prm, FusedParams{}, ctx->ct);
     CK_LAUNCH();
   }
@@ -486,11 +508,12 @@ int run_filter(camus_b200* ctx, int qmode, double threshold, uint64_t* ns, uint6
   uint64_t mine = ctx->box_hi - ctx->box_lo;
   CK(ctx->d_totals.alloc(2));
   StageTimer t(ctx, CAMUS_B200_T_FILTER);
+  if (make_thr_table(ctx, threshold)) return CAMUS_B200_ERR_CUDA;
   CK(cudaMemsetAsync(ctx->d_totals.p, 0, 16, ctx->stream));
   const uint64_t max_boxes = 1u << 26;
   for (uint64_t b0 = 0; b0 < mine; b0 += max_boxes) {
     uint64_t nbx = std::min(max_boxes, mine - b0);
-    FilterParams prm{ctx->d_cells.p + b0 * kBoxCells, ctx->box_lo + b0, qmode, threshold, ctx->d_totals.p};
+    FilterParams prm{ctx->d_cells.p + b0 * kBoxCells, ctx->box_lo + b0, qmode, threshold, ctx->d_thr_tab.p, ctx->d_totals.p};
     k_filter<<<(unsigned)(nbx * 16), 256, 0, ctx->stream>>>(prm, ctx->ct);
     CK_LAUNCH();
   }

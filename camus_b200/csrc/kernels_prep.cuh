@@ -94,6 +94,7 @@ __global__ void __launch_bounds__(256) k_triple_planes(int grp0, int n_groups_to
                                                        const uint16_t* __restrict__ Dt, uint32_t* __restrict__ Tri) {
   __shared__ uint16_t s_d[3][64][kLanes];  // [ab | ac | bc][i*8+j][lane]
   __shared__ __align__(16) uint32_t s_out[kTileWords];
+  __shared__ uint32_t s_scratch[8][64];
   __shared__ uint32_t s_seg[3];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int gb = blockIdx.y;
@@ -120,16 +121,30 @@ __global__ void __launch_bounds__(256) k_triple_planes(int grp0, int n_groups_to
     s_d[which][pr & 63][lane] = x < y ? D[((size_t)x * npad + y) * kLanes + lane] : (uint16_t)0;
   }
   __syncthreads();
-#pragma unroll 4
-  for (int it = 0; it < 64; ++it) {
-    int t = warp * 64 + it;
-    int x = t & 7, y = (t >> 3) & 7, z = t >> 6;
-    uint32_t Dab = s_d[0][x * 8 + y][lane], Dac = s_d[1][x * 8 + z][lane], Dbc = s_d[2][y * 8 + z][lane];
-    bool ok = Dab != 0 && Dac != 0 && Dbc != 0;  // all present, and a < b < c in rank order
-    uint32_t w0 = __ballot_sync(0xFFFFFFFFu, ok && Dab > Dac);
-    uint32_t w1 = __ballot_sync(0xFFFFFFFFu, ok && Dac > Dab);
-    uint32_t w2 = __ballot_sync(0xFFFFFFFFu, ok && Dbc > Dab);
-    if (lane < 3) s_out[tile_word(lane, x, y, z)] = lane == 0 ? w0 : (lane == 1 ? w1 : w2);
+  // warp = z (third taxon of the tile); the 8 D(a,c) values are hoisted, D(b,c) once per y, so a
+  // triple costs one shared load, a 3-way min, four compares, three ballots and one store.
+  const int z = warp;
+  uint32_t Dac[8];
+#pragma unroll
+  for (int x = 0; x < 8; ++x) Dac[x] = s_d[1][x * 8 + z][lane];
+  // lanes 0..2 store planes 0..2 at tile_word(lane, x, y, z); the other lanes store to a per-warp
+  // scratch row so that the store needs no predicate / divergence. The plane is picked with two
+  // bitwise muxes on lane-constant masks instead of compare + select.
+  uint32_t* out_lane = lane < 3 ? s_out + lane * 512 + z * 64 : s_scratch[warp];
+  const uint32_t m0 = lane == 0 ? 0xFFFFFFFFu : 0u, m01 = lane <= 1 ? 0xFFFFFFFFu : 0u;
+#pragma unroll
+  for (int y = 0; y < 8; ++y) {
+    const uint32_t Dbc = s_d[2][y * 8 + z][lane];
+#pragma unroll
+    for (int x = 0; x < 8; ++x) {
+      const uint32_t Dab = s_d[0][x * 8 + y][lane];
+      const bool ok = min(Dab, min(Dac[x], Dbc)) != 0;  // all present, and a < b < c in rank order
+      const uint32_t w0 = __ballot_sync(0xFFFFFFFFu, ok && Dab > Dac[x]);
+      const uint32_t w1 = __ballot_sync(0xFFFFFFFFu, ok && Dac[x] > Dab);
+      const uint32_t w2 = __ballot_sync(0xFFFFFFFFu, ok && Dbc > Dab);
+      const uint32_t w01 = (w0 & m0) | (w1 & ~m0);
+      out_lane[((y >> 1) * 4 + (x >> 1)) * 4 + (y & 1) * 2 + (x & 1)] = (w01 & m01) | (w2 & ~m01);
+    }
   }
   __syncthreads();
   uint4* dst = reinterpret_cast<uint4*>(Tri + (tile * n_groups_total + (grp0 + gb)) * kTileWords);

@@ -101,6 +101,37 @@ __device__ __forceinline__ void apply_filter(uint32_t c[3], const int ti[4], int
   }
 }
 
+// Threshold.Keep's uint32(float64(t) * float64(sum)) for every possible sum of two counts (at most
+// the number of gene trees): one table lookup per cell instead of fp64 arithmetic.
+__global__ void k_threshold_table(uint32_t* __restrict__ tab, int n, double threshold) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) tab[i] = __double2uint_rz(threshold * (double)i);
+}
+
+// Same result as apply_filter, without the tip-index ranks on the common path: the reference's
+// tie order only matters when the two LARGEST counts are equal and the cell fails Keep (then one
+// of the two survives); a tie between the two smallest always fails Keep and deletes both.
+__device__ __forceinline__ void filter_cell(uint32_t c[3], const uint32_t x[4], int qmode, double threshold,
+                                            const uint32_t* __restrict__ thr_tab, const int32_t* __restrict__ tip_of_rank) {
+  const uint32_t lo = min(c[0], min(c[1], c[2])), hi = max(c[0], max(c[1], c[2]));
+  const uint32_t mid = c[0] + c[1] + c[2] - lo - hi;
+  const bool keep = __ldg(&thr_tab[lo + mid]) < mid - lo;
+  if (keep) {
+    if (qmode == 2) {  // mid > lo here, so the minimum is unique
+      if (c[0] == lo) c[0] = 0;
+      else if (c[1] == lo) c[1] = 0;
+      else c[2] = 0;
+    }
+  } else if (mid != hi) {
+    if (c[0] != hi) c[0] = 0;
+    if (c[1] != hi) c[1] = 0;
+    if (c[2] != hi) c[2] = 0;
+  } else {
+    const int ti[4] = {tip_of_rank[x[0]], tip_of_rank[x[1]], tip_of_rank[x[2]], tip_of_rank[x[3]]};
+    apply_filter(c, ti, qmode, threshold);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // K3: prep.filterQuartets (internal/prep/quartetfilter.go:67-96) applied once per 4-set, then the
 // constraint-quartet removal (internal/prep/preprocess.go:51-57), then the two scalars
@@ -113,6 +144,7 @@ struct FilterParams {
   uint64_t box0;
   int qmode;
   double threshold;
+  const uint32_t* thr_tab;     // k_threshold_table
   unsigned long long* totals;  // [0] n_survivors, [1] sum_counts
 };
 
@@ -129,8 +161,8 @@ __global__ void __launch_bounds__(256) k_filter(FilterParams prm, ConstraintDev 
   } else {
     bool changed = false;
     if (prm.qmode != 0 && (c[0] | c[1] | c[2])) {
-      int ti[4] = {ct.tip_of_rank[cc.a], ct.tip_of_rank[cc.b], ct.tip_of_rank[cc.c], ct.tip_of_rank[cc.d]};
-      apply_filter(c, ti, prm.qmode, prm.threshold);
+      const uint32_t x[4] = {cc.a, cc.b, cc.c, cc.d};
+      filter_cell(c, x, prm.qmode, prm.threshold, prm.thr_tab, ct.tip_of_rank);
       changed = true;
     }
     if (c[0] | c[1] | c[2]) {
@@ -193,8 +225,16 @@ struct ScoreParams {
 
 // One cell's contribution to Z (see the K4 comment above). x[] = DFS ranks a<b<c<d, g1..g3 = packed
 // LCAs of (a,b), (b,c), (c,d), cnt[] = surviving counts per topology.
+// acc(index, value) adds a signed value to Z[index]: straight to HBM (GlobalAcc) or through the
+// per-CTA shared-memory aggregator of the fused kernel (SmemAcc, kernels_count.cuh).
+struct GlobalAcc {
+  unsigned long long* Z;
+  __device__ __forceinline__ void operator()(size_t idx, long long v) const { red_add_u64(&Z[idx], (unsigned long long)v); }
+};
+
+template <class Acc>
 __device__ __forceinline__ void score_cell(const uint32_t cnt[3], const uint32_t x[4], uint32_t g1, uint32_t g2,
-                                           uint32_t g3, const ConstraintDev& ct, unsigned long long* Z, int as_set) {
+                                           uint32_t g3, const ConstraintDev& ct, Acc& acc, int as_set) {
   const size_t n = (size_t)ct.n;
 #pragma unroll
   for (int be = 0; be < 4; ++be) {
@@ -218,9 +258,9 @@ __device__ __forceinline__ void score_cell(const uint32_t cnt[3], const uint32_t
       int p = partner_of(t, be);
       int pos = p - (p > be ? 1 : 0);                 // position of the partner among the other three
       int comp = first ? pos : (pos + 2) % 3;         // 0 LEFT, 1 RIGHT, 2 OUT
-      unsigned long long w = as_set ? 1ull : (unsigned long long)cnt[t];
-      red_add_u64(&Z[row_leaf + comp], w);
-      red_add_u64(&Z[row_m + comp], (unsigned long long)(-(long long)w));
+      const long long w = as_set ? 1ll : (long long)cnt[t];
+      acc(row_leaf + comp, w);
+      acc(row_m + comp, -w);
     }
   }
 }
@@ -236,7 +276,8 @@ __global__ void __launch_bounds__(256) k_score(ScoreParams prm, ConstraintDev ct
   const uint32_t g1 = ct.lcaD[(size_t)cc.a * ct.n_taxa + cc.b];
   const uint32_t g2 = ct.lcaD[(size_t)cc.b * ct.n_taxa + cc.c];
   const uint32_t g3 = ct.lcaD[(size_t)cc.c * ct.n_taxa + cc.d];
-  score_cell(cnt, x, g1, g2, g3, ct, prm.Z, prm.as_set);
+  GlobalAcc acc{prm.Z};
+  score_cell(cnt, x, g1, g2, g3, ct, acc, prm.as_set);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -259,6 +300,15 @@ __global__ void k_expand(const unsigned long long* __restrict__ Z, unsigned long
   if (at2) atomicAdd(&row[ct.rc[J]], (unsigned long long)at2);
   if (at3) atomicAdd(&row[J + ct.sz[J]], (unsigned long long)at3);
   if (vO) atomicAdd(&row[0], (unsigned long long)vO);
+}
+
+// Sum the privatised copies of Z into copy 0.
+__global__ void k_sum_replicas(unsigned long long* __restrict__ Z, size_t zn, int rep) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= zn) return;
+  unsigned long long acc = Z[i];
+  for (int r = 1; r < rep; ++r) acc += Z[(size_t)r * zn + i];
+  Z[i] = acc;
 }
 
 // K5b: inclusive prefix sum along u of every row (one CTA per row).

@@ -40,6 +40,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 __device__ __forceinline__ void red_add_u64(unsigned long long* addr, unsigned long long v) {
   asm volatile("red.global.add.u64 [%0], %1;" ::"l"(addr), "l"(v) : "memory");
 }
