@@ -285,37 +285,52 @@ def run_ours(args):
 
     if rank == 0:
         peak, peak_src = load_peaks()
-        cells = gpu.workload()["cells"]
-        # algorithmic bytes, SURVEY.md 8(d) convention: 8 B per resolution + 16 B per cell + 24 B per table entry
-        b_alg = 8 * R + 16 * cells + 24 * n * n
-        # dominant kernel = the stage with the largest device time (one launch per stage at this size)
-        kern_stage = max(("prep", "count", "filter", "score", "final"), key=lambda k: stage_ms[k])
-        kern_ms = stage_ms[kern_stage]
-        alg_bytes_kernel = {
-            "count": 8 * R / world, "filter": 32 * cells / world, "score": 16 * cells / world,
-            "prep": 2.0 * prob.n_taxa ** 2 * prob.n_trees, "final": 24 * n * n,
-        }[kern_stage]
+        wl = gpu.workload()
+        cells, num_boxes = wl["cells"], wl["boxes"]
+        m_seg = -(-prob.n_taxa // 8)
+        num_tiles = (m_seg + 2) * (m_seg + 1) * m_seg // 6
+        # ---- roofline of the dominant kernel: the fused k_count<true> (count + filter + score) ----
+        # Algorithmic bytes per launch, SURVEY.md 8(d) convention: 8 B per resolution (one count
+        # cell read + written per (gene tree, 4-set)) + 16 B per cell (one 128-bit cell read by
+        # filter / score), for the share of the 4-set space this rank owns.
+        alg_bytes_kernel = (8 * R + 16 * cells) / world
+        kern_ms = stage_ms["count"]
+        n_launch = max(1, -(-num_boxes // world // (1 << 30)))
         achieved = alg_bytes_kernel / (kern_ms * 1e-3) / 1e9
+        b_alg = 8 * R + 16 * cells + 24 * n * n
+        # Bytes the kernel's own design has to move per launch: four 6 KB triple tiles per
+        # (box, tree group), read once each (HBM or L2), and one pass over the junction tables.
+        groups = -(-prob.n_trees // 32)
+        design_bytes = (num_boxes / world) * groups * 4 * 6144
+        traffic = None
+        tf = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tf):
+            traffic = json.load(open(tf)).get(f"config{args.config}_k_count_dram_bytes_per_launch")
         h2d = int(prob.gene_node_off.nbytes + prob.gene_parent.nbytes + prob.gene_taxon.nbytes)
         line = {
             "metric": METRIC, "value": R / dt_res, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dt_res * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u32", "data": "synthetic",
-            "config": {"workload": workload_name(args.config, c), "resolutions_per_step": R, "cells": cells,
-                       "sharding": f"4-taxon-set index space / {world}, all trees on every rank",
-                       "l2": "no explicit flush: the per-step working set (bit-planes + cell table) is rebuilt every step and is far larger than the 126 MB L2"},
+            "config": {"workload": workload_name(args.config, c), "resolutions_per_step": R, "cells": cells, "boxes": num_boxes,
+                       "sharding": f"4-taxon-set index space / {world}, all trees on every rank, one NCCL all-reduce of the junction table",
+                       "l2": "no explicit flush: the rooted-triple bit-planes streamed by every step "
+                             f"({design_bytes * world / 1e9:.1f} GB of tile reads over a {groups * 6144 * num_tiles / 1e9:.2f} GB table) exceed the 126 MB L2 many times over"},
             "clocks": clocks,
             "e2e": {"value": R / dt_e2e, "unit": UNIT, "ms_per_step": dt_e2e * 1e3, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": int(out.nbytes + 16)},
             "gpu_launches": int(launches) * args.steps,
             "stage_ms": {k: round(v, 4) for k, v in stage_ms.items()},
-            "roofline": {"bound": "hbm", "kernel": {"count": "k_count", "score": "k_score", "filter": "k_filter",
-                                                    "prep": "k_tree_prepare+k_depth_table+k_triple_planes", "final": "k_expand..k_mask_out"}[kern_stage],
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes_kernel,
-                         "launch_ms": kern_ms},
-            "roofline_whole_path": {"algorithmic_bytes": b_alg, "achieved": b_alg / dt_res / 1e9, "frac": b_alg / dt_res / 1e9 / peak,
-                                    "note": "SURVEY.md 8(d) convention (8 B per resolution); the bit-sliced kernels resolve 32 trees per word, so this exceeds 1"},
+            "roofline": {"bound": "hbm", "kernel": "k_count<true> (count + filter + score, fused)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes_kernel / n_launch,
+                         "launch_ms": kern_ms / n_launch,
+                         "design_bytes_per_launch": design_bytes / n_launch,
+                         "design_achieved": design_bytes / (kern_ms * 1e-3) / 1e9,
+                         "note": "achieved uses the survey's accounting (8 B per resolution); the kernel resolves 32 gene trees per "
+                                 "32-bit word in registers, so it moves ~250x fewer bytes than that model and frac exceeds 1; "
+                                 "design_* = bytes of triple tiles the kernel actually streams (L2 + HBM); it is bound by the "
+                                 "POPC (XU) pipe, see DESIGN.md"},
+            "roofline_whole_path": {"algorithmic_bytes": b_alg, "achieved": b_alg / dt_res / 1e9, "frac": b_alg / dt_res / 1e9 / peak},
             "result": {"n_survivors": first[0], "sum_counts": first[1]},
         }
         if not args.no_cpu:
@@ -337,7 +352,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", type=int, default=2)
+    ap.add_argument("--config", type=int, default=3, help="BASELINE.json configs[] index + 1 (3 = 1000 taxa x 1000 trees)")
     ap.add_argument("--taxa", type=int, default=None)
     ap.add_argument("--trees", type=int, default=None)
     ap.add_argument("--ref-trees", type=int, default=8, help="gene trees per CPU-reference sample")

@@ -74,7 +74,7 @@ struct camus_b200 {
   DevBuf<uint4> d_cells;
   DevBuf<unsigned long long> d_Z, d_E, d_out, d_totals, d_keys, d_nout;
   DevBuf<uint32_t> d_counts, d_thr_tab;
-  uint64_t box_lo = 0, box_hi = 0;  // this rank's partition
+  uint64_t n_local = 0, chunk = 1;  // this rank's share of the boxes (BoxMap)
   enum CellState { NONE, RAW, FILTERED } cell_state = NONE;
   int last_qmode = 0;
   double last_threshold = 0;
@@ -414,7 +414,7 @@ int build_planes(camus_b200* ctx, bool do_upload = true) {
       dim3 g1((npad + 7) / 8, gb);
       k_depth_table<<<g1, blk, 0, ctx->stream>>>(g0, G, npad, ctx->d_nleaf.p, ctx->d_lrT.p, ctx->d_hT.p, ctx->d_Dt.p);
       CK_LAUNCH();
-      k_triple_planes<<<dim3(n_tiles, gb), 256, 0, ctx->stream>>>(g0, G32, npad, ctx->d_Dt.p, ctx->d_tri.p);
+      k_triple_planes<<<n_tiles, 256, 0, ctx->stream>>>(g0, gb, G32, npad, ctx->d_Dt.p, ctx->d_tri.p);
       CK_LAUNCH();
     }
   }
@@ -433,15 +433,15 @@ int make_thr_table(camus_b200* ctx, double threshold) {
 
 void set_box_range(camus_b200* ctx) {
   uint64_t nb = num_boxes(ctx->M);
-  ctx->box_lo = nb * ctx->rank / ctx->world;
-  ctx->box_hi = nb * (ctx->rank + 1) / ctx->world;
+  ctx->chunk = partition_chunk(nb, (uint32_t)ctx->world);
+  ctx->n_local = local_box_count(nb, ctx->chunk, (uint32_t)ctx->rank, (uint32_t)ctx->world);
 }
 
 // Fused K2+K3+K4 over this rank's box range: counts stay in registers, survivors are scored
 // straight into the junction table Z. No cell table.
 int run_fused(camus_b200* ctx, int qmode, double threshold, int as_set, uint64_t* ns, uint64_t* sum) {
   set_box_range(ctx);
-  uint64_t mine = ctx->box_hi - ctx->box_lo;
+  uint64_t mine = ctx->n_local;
   size_t zn = (size_t)ctx->n * ctx->n * 3;
   static const int rep_env = getenv("CAMUS_B200_ZREP") ? atoi(getenv("CAMUS_B200_ZREP")) : 0;
   // privatised copies of Z spread the hot (w-point, junction) entries over several L2 lines
@@ -456,7 +456,7 @@ int run_fused(camus_b200* ctx, int qmode, double threshold, int as_set, uint64_t
   const uint64_t max_grid = 1u << 30;
   for (uint64_t b0 = 0; b0 < mine; b0 += max_grid) {
     uint64_t nbx = std::min(max_grid, mine - b0);
-    CountParams prm{ctx->d_tri.p, std::max(ctx->G32, 1), ctx->box_lo + b0, nullptr, ctx->G};
+    CountParams prm{ctx->d_tri.p, std::max(ctx->G32, 1), BoxMap{b0, ctx->chunk, (uint32_t)ctx->rank, (uint32_t)ctx->world}, nullptr, ctx->G};
     static const int dbg = getenv("CAMUS_B200_DEBUG") ? atoi(getenv("CAMUS_B200_DEBUG")) : 0;
     FusedParams fz{qmode, threshold, ctx->d_thr_tab.p, as_set, ctx->d_Z.p, ctx->d_totals.p, rep, (unsigned long long)zn, dbg};
     k_count<true><<<(unsigned)nbx, kCountThreads, kCountSmemBytes, ctx->stream>>>(prm, fz, ctx->ct);
@@ -482,7 +482,7 @@ int run_fused(camus_b200* ctx, int qmode, double threshold, int as_set, uint64_t
 // K2 (table mode) over this rank's box range (whole range resident in d_cells).
 int run_count(camus_b200* ctx) {
   set_box_range(ctx);
-  uint64_t mine = ctx->box_hi - ctx->box_lo;
+  uint64_t mine = ctx->n_local;
   if (ctx->d_cells.n < mine * kBoxCells) {
     size_t free_b = 0, total_b = 0;
     CK(cudaMemGetInfo(&free_b, &total_b));
@@ -495,7 +495,7 @@ int run_count(camus_b200* ctx) {
   const uint64_t max_grid = 1u << 30;
   for (uint64_t b0 = 0; b0 < mine; b0 += max_grid) {
     uint64_t nbx = std::min(max_grid, mine - b0);
-    CountParams prm{ctx->d_tri.p, std::max(ctx->G32, 1), ctx->box_lo + b0, ctx->d_cells.p + b0 * kBoxCells, ctx->G};
+    CountParams prm{ctx->d_tri.p, std::max(ctx->G32, 1), BoxMap{b0, ctx->chunk, (uint32_t)ctx->rank, (uint32_t)ctx->world}, ctx->d_cells.p + b0 * kBoxCells, ctx->G};
     k_count<false><<<(unsigned)nbx, kCountThreads, kCountSmemBytes, ctx->stream>>>(prm, FusedParams{}, ctx->ct);
     CK_LAUNCH();
   }
@@ -505,7 +505,7 @@ int run_count(camus_b200* ctx) {
 }
 
 int run_filter(camus_b200* ctx, int qmode, double threshold, uint64_t* ns, uint64_t* sum) {
-  uint64_t mine = ctx->box_hi - ctx->box_lo;
+  uint64_t mine = ctx->n_local;
   CK(ctx->d_totals.alloc(2));
   StageTimer t(ctx, CAMUS_B200_T_FILTER);
   if (make_thr_table(ctx, threshold)) return CAMUS_B200_ERR_CUDA;
@@ -513,7 +513,7 @@ int run_filter(camus_b200* ctx, int qmode, double threshold, uint64_t* ns, uint6
   const uint64_t max_boxes = 1u << 26;
   for (uint64_t b0 = 0; b0 < mine; b0 += max_boxes) {
     uint64_t nbx = std::min(max_boxes, mine - b0);
-    FilterParams prm{ctx->d_cells.p + b0 * kBoxCells, ctx->box_lo + b0, qmode, threshold, ctx->d_thr_tab.p, ctx->d_totals.p};
+    FilterParams prm{ctx->d_cells.p + b0 * kBoxCells, BoxMap{b0, ctx->chunk, (uint32_t)ctx->rank, (uint32_t)ctx->world}, qmode, threshold, ctx->d_thr_tab.p, ctx->d_totals.p};
     k_filter<<<(unsigned)(nbx * 16), 256, 0, ctx->stream>>>(prm, ctx->ct);
     CK_LAUNCH();
   }
@@ -547,11 +547,11 @@ int run_score(camus_b200* ctx, int as_set) {
   CK(ctx->d_Z.alloc(zn));
   StageTimer t(ctx, CAMUS_B200_T_SCORE);
   CK(cudaMemsetAsync(ctx->d_Z.p, 0, zn * 8, ctx->stream));
-  uint64_t mine = ctx->box_hi - ctx->box_lo;
+  uint64_t mine = ctx->n_local;
   const uint64_t max_boxes = 1u << 26;
   for (uint64_t b0 = 0; b0 < mine; b0 += max_boxes) {
     uint64_t nbx = std::min(max_boxes, mine - b0);
-    ScoreParams prm{ctx->d_cells.p + b0 * kBoxCells, ctx->box_lo + b0, as_set, ctx->d_Z.p};
+    ScoreParams prm{ctx->d_cells.p + b0 * kBoxCells, BoxMap{b0, ctx->chunk, (uint32_t)ctx->rank, (uint32_t)ctx->world}, as_set, ctx->d_Z.p};
     k_score<<<(unsigned)(nbx * 16), 256, 0, ctx->stream>>>(prm, ctx->ct);
     CK_LAUNCH();
   }
@@ -685,7 +685,7 @@ int camus_b200_export_quartets(camus_b200* ctx, int raw, uint64_t* keys, uint32_
   } else if ((rc = ensure_filtered(ctx))) {  // the table pipeline (K2 -> K3); Z, if any, stays valid
     return rc;
   }
-  uint64_t mine = ctx->box_hi - ctx->box_lo;
+  uint64_t mine = ctx->n_local;
   CK(ctx->d_nout.alloc(1));
   CK(ctx->d_keys.alloc(std::max<uint64_t>(cap, 1)));
   CK(ctx->d_counts.alloc(std::max<uint64_t>(cap, 1)));
@@ -693,7 +693,7 @@ int camus_b200_export_quartets(camus_b200* ctx, int raw, uint64_t* keys, uint32_
   const uint64_t max_boxes = 1u << 26;
   for (uint64_t b0 = 0; b0 < mine; b0 += max_boxes) {
     uint64_t nbx = std::min(max_boxes, mine - b0);
-    ExportParams prm{ctx->d_cells.p + b0 * kBoxCells, ctx->box_lo + b0, ctx->d_keys.p, ctx->d_counts.p, cap, ctx->d_nout.p};
+    ExportParams prm{ctx->d_cells.p + b0 * kBoxCells, BoxMap{b0, ctx->chunk, (uint32_t)ctx->rank, (uint32_t)ctx->world}, ctx->d_keys.p, ctx->d_counts.p, cap, ctx->d_nout.p};
     k_export<<<(unsigned)(nbx * 16), 256, 0, ctx->stream>>>(prm, ctx->ct);
     CK_LAUNCH();
   }

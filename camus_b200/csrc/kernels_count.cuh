@@ -45,8 +45,8 @@ constexpr int kCountSmemBytes = kCountStages * kStageBytes + 128;  // + full/emp
 struct CountParams {
   const uint32_t* tri;  // [tile][group][kTileWords]
   int n_groups;
-  uint64_t box0;   // first box rank of this launch
-  uint4* cells;    // table mode: [box - box0][kBoxCells] = (c(ab|cd), c(ac|bd), c(ad|bc), 0)
+  BoxMap bm;       // blockIdx.x -> global box rank
+  uint4* cells;    // table mode: [local box][kBoxCells] = (c(ab|cd), c(ac|bd), c(ad|bc), 0)
   int n_trees;     // for the mask of the last (partial) tree group
 };
 
@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(kCountThreads, 2) k_count(CountParams prm, Fus
 
   if (tid == 0) {
     uint32_t sa, sb, sc, sd;
-    box_unrank(prm.box0 + blockIdx.x, sa, sb, sc, sd);
+    box_unrank(prm.bm.global(blockIdx.x), sa, sb, sc, sd);
     s_seg[0] = sa;
     s_seg[1] = sb;
     s_seg[2] = sc;

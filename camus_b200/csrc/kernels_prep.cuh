@@ -90,14 +90,13 @@ __global__ void k_depth_table(int grp0, int n_trees, int npad, const int32_t* __
 // needs are staged in shared memory (coalesced 64 B rows of Dt), 8 warps x 64 triples ballot into
 // a shared 6 KB image of the tile, which is then written to HBM with 128-bit coalesced stores.
 // Every word of every tile is written, so Tri needs no memset.
-__global__ void __launch_bounds__(256) k_triple_planes(int grp0, int n_groups_total, int npad,
+__global__ void __launch_bounds__(256) k_triple_planes(int grp0, int n_batch, int n_groups_total, int npad,
                                                        const uint16_t* __restrict__ Dt, uint32_t* __restrict__ Tri) {
   __shared__ uint16_t s_d[3][64][kLanes];  // [ab | ac | bc][i*8+j][lane]
   __shared__ __align__(16) uint32_t s_out[kTileWords];
   __shared__ uint32_t s_scratch[8][64];
   __shared__ uint32_t s_seg[3];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int gb = blockIdx.y;
   const uint64_t tile = blockIdx.x;
   if (tid == 0) {
     uint64_t r = tile;
@@ -111,6 +110,9 @@ __global__ void __launch_bounds__(256) k_triple_planes(int grp0, int n_groups_to
   }
   __syncthreads();
   const uint32_t a0 = s_seg[0] * 8, b0 = s_seg[1] * 8, c0 = s_seg[2] * 8;
+  // the CTA walks all tree groups of the batch: the tile unranking and address set-up are paid once
+  for (int gb = 0; gb < n_batch; ++gb) {
+  if (gb) __syncthreads();  // s_d / s_out of the previous group are free again
   const uint16_t* D = Dt + (size_t)gb * npad * npad * kLanes;
 #pragma unroll
   for (int it = 0; it < 3 * 64 / 8; ++it) {
@@ -150,6 +152,7 @@ __global__ void __launch_bounds__(256) k_triple_planes(int grp0, int n_groups_to
   uint4* dst = reinterpret_cast<uint4*>(Tri + (tile * n_groups_total + (grp0 + gb)) * kTileWords);
   const uint4* src = reinterpret_cast<const uint4*>(s_out);
   for (int i = tid; i < kTileWords / 4; i += 256) dst[i] = src[i];
+  }
 }
 
 // ---------------------------------------------------------------------------------------------

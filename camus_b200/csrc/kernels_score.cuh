@@ -30,10 +30,10 @@ struct CellCoords {
 };
 
 // 256 consecutive cells of one box per CTA; thread 0 unranks the box.
-__device__ __forceinline__ CellCoords decode_cell(uint64_t box0, int n_taxa, uint32_t* s_seg) {
+__device__ __forceinline__ CellCoords decode_cell(const BoxMap& bm, int n_taxa, uint32_t* s_seg) {
   if (threadIdx.x == 0) {
     uint32_t sa, sb, sc, sd;
-    box_unrank(box0 + (blockIdx.x >> 4), sa, sb, sc, sd);
+    box_unrank(bm.global(blockIdx.x >> 4), sa, sb, sc, sd);
     s_seg[0] = sa;
     s_seg[1] = sb;
     s_seg[2] = sc;
@@ -141,7 +141,7 @@ __device__ __forceinline__ void filter_cell(uint32_t c[3], const uint32_t x[4], 
 // ---------------------------------------------------------------------------------------------
 struct FilterParams {
   uint4* cells;
-  uint64_t box0;
+  BoxMap bm;
   int qmode;
   double threshold;
   const uint32_t* thr_tab;     // k_threshold_table
@@ -151,7 +151,7 @@ struct FilterParams {
 __global__ void __launch_bounds__(256) k_filter(FilterParams prm, ConstraintDev ct) {
   __shared__ uint32_t s_seg[4];
   __shared__ unsigned long long s_red[2][8];
-  CellCoords cc = decode_cell(prm.box0, ct.n_taxa, s_seg);
+  CellCoords cc = decode_cell(prm.bm, ct.n_taxa, s_seg);
   size_t idx = (size_t)blockIdx.x * 256 + threadIdx.x;
   uint4 v = prm.cells[idx];
   uint32_t c[3] = {v.x, v.y, v.z};
@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(256) k_filter(FilterParams prm, ConstraintDev 
 // ---------------------------------------------------------------------------------------------
 struct ScoreParams {
   const uint4* cells;
-  uint64_t box0;
+  BoxMap bm;
   int as_set;
   unsigned long long* Z;  // [n][n][3] two's-complement int64
 };
@@ -267,7 +267,7 @@ __device__ __forceinline__ void score_cell(const uint32_t cnt[3], const uint32_t
 
 __global__ void __launch_bounds__(256) k_score(ScoreParams prm, ConstraintDev ct) {
   __shared__ uint32_t s_seg[4];
-  CellCoords cc = decode_cell(prm.box0, ct.n_taxa, s_seg);
+  CellCoords cc = decode_cell(prm.bm, ct.n_taxa, s_seg);
   if (!cc.valid) return;
   uint4 v = prm.cells[(size_t)blockIdx.x * 256 + threadIdx.x];
   if (!(v.x | v.y | v.z)) return;
@@ -424,7 +424,7 @@ __global__ void k_penalties(unsigned long long* __restrict__ out, ConstraintDev 
 // ---------------------------------------------------------------------------------------------
 struct ExportParams {
   const uint4* cells;
-  uint64_t box0;
+  BoxMap bm;
   unsigned long long* keys;
   uint32_t* counts;
   unsigned long long cap;
@@ -433,7 +433,7 @@ struct ExportParams {
 
 __global__ void __launch_bounds__(256) k_export(ExportParams prm, ConstraintDev ct) {
   __shared__ uint32_t s_seg[4];
-  CellCoords cc = decode_cell(prm.box0, ct.n_taxa, s_seg);
+  CellCoords cc = decode_cell(prm.bm, ct.n_taxa, s_seg);
   if (!cc.valid) return;
   uint4 v = prm.cells[(size_t)blockIdx.x * 256 + threadIdx.x];
   if (!(v.x | v.y | v.z)) return;

@@ -6,6 +6,7 @@
 // LCA of two leaves is a range minimum, and subtrees are id intervals. The reference's packing
 // (graphs/quartet.go:67-109, taxa sorted by tip index) is produced only at export time.
 #pragma once
+#include <cmath>
 #include <cstdint>
 
 #if defined(__CUDACC__)
@@ -38,7 +39,8 @@ CAMUS_HD uint64_t num_boxes(uint32_t m) { return choose4((uint64_t)m + 3); }
 
 // largest s with choose_k(s + k - 1) <= r
 CAMUS_HD uint32_t unrank4(uint64_t r) {
-  double x = sqrt(sqrt(24.0 * (double)r));
+  // fp32 estimate + exact integer fix-up (fp64 is slow on B200 and the fix-up loops are exact)
+  float x = sqrtf(sqrtf(24.0f * (float)r));
   int64_t s = (int64_t)x - 2;
   if (s < 0) s = 0;
   while (choose4((uint64_t)s + 4) <= r) ++s;
@@ -46,7 +48,7 @@ CAMUS_HD uint32_t unrank4(uint64_t r) {
   return (uint32_t)s;
 }
 CAMUS_HD uint32_t unrank3(uint64_t r) {
-  double x = cbrt(6.0 * (double)r);
+  float x = cbrtf(6.0f * (float)r);
   int64_t s = (int64_t)x - 2;
   if (s < 0) s = 0;
   while (choose3((uint64_t)s + 3) <= r) ++s;
@@ -54,7 +56,7 @@ CAMUS_HD uint32_t unrank3(uint64_t r) {
   return (uint32_t)s;
 }
 CAMUS_HD uint32_t unrank2(uint64_t r) {
-  double x = sqrt(2.0 * (double)r);
+  float x = sqrtf(2.0f * (float)r);
   int64_t s = (int64_t)x - 2;
   if (s < 0) s = 0;
   while (choose2((uint64_t)s + 2) <= r) ++s;
@@ -72,13 +74,37 @@ CAMUS_HD void box_unrank(uint64_t r, uint32_t& sa, uint32_t& sb, uint32_t& sc, u
 }
 // pair (a < b) <-> rank choose2(b) + a
 CAMUS_HD void pair_unrank(uint64_t r, uint32_t& a, uint32_t& b) {
-  double x = sqrt(2.0 * (double)r);
+  float x = sqrtf(2.0f * (float)r);
   int64_t s = (int64_t)x - 1;
   if (s < 1) s = 1;
   while (choose2((uint64_t)s + 1) <= r) ++s;
   while (s > 1 && choose2((uint64_t)s) > r) --s;
   b = (uint32_t)s;
   a = (uint32_t)(r - choose2((uint64_t)s));
+}
+
+// Multi-rank split of the box index space: boxes are dealt to ranks in chunks, round-robin
+// (rank r owns chunks r, r+world, ...), which balances the ranks (score-scatter cost varies
+// along the index space) while neighbouring CTAs still share triple tiles in L2.
+// Local box index l of a rank <-> global box rank. Mirrored by camus_b200/partition.py.
+struct BoxMap {
+  uint64_t first;  // local index of blockIdx 0 of this launch
+  uint64_t chunk;  // boxes per chunk
+  uint32_t rank, world;
+  CAMUS_HD uint64_t global(uint64_t i) const {
+    uint64_t l = first + i;
+    return ((l / chunk) * world + rank) * chunk + l % chunk;
+  }
+};
+CAMUS_HD uint64_t partition_chunk(uint64_t nb, uint32_t world) {
+  uint64_t c = nb / ((uint64_t)world * 64);
+  return c < 1 ? 1 : (c > 2048 ? 2048 : c);
+}
+CAMUS_HD uint64_t local_box_count(uint64_t nb, uint64_t chunk, uint32_t rank, uint32_t world) {
+  uint64_t round = chunk * world, full = nb / round, rem = nb % round;
+  uint64_t lo = (uint64_t)rank * chunk;
+  uint64_t extra = rem > lo ? (rem - lo < chunk ? rem - lo : chunk) : 0;
+  return full * chunk + extra;
 }
 
 // Word offset inside a triple tile for plane p and local triple (x, y, z), x/y/z in 0..7 being

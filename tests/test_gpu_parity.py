@@ -253,6 +253,40 @@ def test_bad_inputs_are_errors_not_crashes(gpu):
         gpu.set_constraint(prob.parent[:-1], prob.child0[:-1], prob.child1[:-1], prob.tip_index[:-1], prob.n_taxa)
 
 
+@pytest.mark.parametrize("world", [2, 5])
+def test_partitions_on_one_gpu(gpu, world):
+    """camus_b200_set_partition: every rank's box range, run one after the other on this GPU, gives
+    the survivors the host-side mirror (camus_b200.partition) assigns to it; partial junction
+    tables add up to the single-rank table."""
+    import torch
+    from camus_b200 import partition as part
+    s = synth.make(44, 90, 21, drop_frac=0.05)
+    prob = Problem(s.constraint, s.genes)
+    o = orc.Oracle().load(prob)
+    o.count_filter(2, 0.3, False)
+    keys, counts = o.export_quartets()
+    want_tot = o.quartet_totals(False, False)
+    owner = part.owner_of_quartets(keys, part.dfs_rank_of_tip(prob.parent, prob.child0, prob.child1, prob.tip_index), world)
+    acc = None
+    try:
+        for r in range(world):
+            gpu.set_partition(r, world)
+            gpu.load(prob)
+            ns, sc = gpu.count_filter(2, 0.3)
+            assert (ns, sc) == (int((owner == r).sum()), int(counts[owner == r].sum()))
+            gk, gc = gpu.export_quartets()
+            assert np.array_equal(gk, keys[owner == r]) and np.array_equal(gc, counts[owner == r])
+            gpu.quartet_totals_partial(False)
+            z = gpu.partial_tensor().clone()
+            acc = z if acc is None else acc + z
+        # last rank's context receives the summed table, as after an all-reduce
+        gpu.partial_tensor().copy_(acc)
+        torch.cuda.synchronize()
+        assert np.array_equal(gpu.quartet_totals_finish(), want_tot)
+    finally:
+        gpu.set_partition(0, 1)
+
+
 # ------------------------------------------------- mid / full size: oracle + size-free properties
 def test_mid_size_vs_oracle(gpu):
     s = synth.make(96, 100, 11)

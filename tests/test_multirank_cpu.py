@@ -1,0 +1,81 @@
+"""N>1 path on CPU (gloo, world_size 2 and 3): the box-range partition of the 4-taxon-set space is
+a disjoint cover, and summing per-rank partial edge tables with one all-reduce reproduces the
+single-rank result. The per-rank work is done by the oracle restricted to the quartets that fall
+into the rank's box range (the GPU does the same with camus_b200_set_partition)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from camus_b200 import partition as part
+from camus_b200 import synth
+from camus_b200.hostlib import Problem
+from oracle import oracle as orc
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        s = synth.make(26, 40, 77, drop_frac=0.1)
+        prob = Problem(s.constraint, s.genes)
+        o = orc.Oracle(1).load(prob)
+        o.count_filter(2, 0.3, False)
+        keys, counts = o.export_quartets()
+        r_of_tip = part.dfs_rank_of_tip(prob.parent, prob.child0, prob.child1, prob.tip_index)
+        owner = part.owner_of_quartets(keys, r_of_tip, world)
+        mine = owner == rank
+        o.set_quartets(keys[mine], counts[mine])
+        partial = torch.from_numpy(o.quartet_totals(False, False).astype(np.int64))
+        scal = torch.tensor([int(mine.sum()), int(counts[mine].sum())], dtype=torch.int64)
+        part.allreduce_partials(partial, scal)
+        if rank == 0:
+            o.set_quartets(keys, counts)
+            full = o.quartet_totals(False, False).astype(np.int64)
+            q.put((bool(np.array_equal(partial.numpy(), full)), int(scal[0]) == len(keys), int(scal[1]) == int(counts.sum()),
+                   int(mine.sum())))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_partial_tables_sum_to_the_full_table(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    same, ns_ok, sum_ok, n0 = q.get(timeout=10)
+    assert same and ns_ok and sum_ok and n0 > 0
+
+
+def test_box_ranges_cover_the_index_space():
+    for n_taxa in (4, 9, 26, 200, 1000):
+        nb = part.num_boxes(n_taxa)
+        for world in (1, 2, 3, 4, 8):
+            counts = [part.local_box_count(nb, r, world) for r in range(world)]
+            assert sum(counts) == nb
+            if nb <= 30000:
+                own = [part.owner_of_box(b, nb, world) for b in range(nb)]
+                assert [own.count(r) for r in range(world)] == counts
+            if nb >= 64 * world:
+                assert max(counts) - min(counts) <= part.partition_chunk(nb, world)
+    m = 5
+    seen = sorted(part.box_index(a, b, c, d) for d in range(m) for c in range(d + 1) for b in range(c + 1) for a in range(b + 1))
+    assert seen == list(range(part.choose(m + 3, 4)))
