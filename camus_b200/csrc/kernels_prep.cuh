@@ -92,7 +92,7 @@ __global__ void k_depth_table(int grp0, int n_trees, int npad, const int32_t* __
 // Every word of every tile is written, so Tri needs no memset.
 __global__ void __launch_bounds__(256) k_triple_planes(int grp0, int n_batch, int n_groups_total, int npad,
                                                        const uint16_t* __restrict__ Dt, uint32_t* __restrict__ Tri) {
-  __shared__ uint16_t s_d[3][64][kLanes];  // [ab | ac | bc][i*8+j][lane]
+  __shared__ __align__(16) uint16_t s_d[3][64][kLanes];  // [ab | ac | bc][i*8+j][lane]
   __shared__ __align__(16) uint32_t s_out[kTileWords];
   __shared__ uint32_t s_scratch[8][64];
   __shared__ uint32_t s_seg[3];
@@ -114,13 +114,17 @@ __global__ void __launch_bounds__(256) k_triple_planes(int grp0, int n_batch, in
   for (int gb = 0; gb < n_batch; ++gb) {
   if (gb) __syncthreads();  // s_d / s_out of the previous group are free again
   const uint16_t* D = Dt + (size_t)gb * npad * npad * kLanes;
+  // stage the 3 x 64 pair rows: for a fixed first taxon the 8 rows (y0..y0+7) are 512 contiguous
+  // bytes of Dt, so one warp-wide 128-bit load moves a whole (which, i) segment
 #pragma unroll
-  for (int it = 0; it < 3 * 64 / 8; ++it) {
-    int pr = it * 8 + warp;  // 0..191
-    int which = pr >> 6, i = (pr >> 3) & 7, j = pr & 7;
-    uint32_t x = (which == 2 ? b0 : a0) + i;
-    uint32_t y = (which == 0 ? b0 : c0) + j;
-    s_d[which][pr & 63][lane] = x < y ? D[((size_t)x * npad + y) * kLanes + lane] : (uint16_t)0;
+  for (int it = 0; it < 3; ++it) {
+    const int seg = it * 8 + warp;  // 0..23
+    const int which = seg >> 3, i = seg & 7, j = lane >> 2;
+    const uint32_t x = (which == 2 ? b0 : a0) + i;
+    const uint32_t y0 = which == 0 ? b0 : c0;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (x < y0 + j) v = *reinterpret_cast<const uint4*>(D + ((size_t)x * npad + y0 + j) * kLanes + (lane & 3) * 8);
+    *reinterpret_cast<uint4*>(&s_d[which][i * 8 + j][(lane & 3) * 8]) = v;
   }
   __syncthreads();
   // warp = z (third taxon of the tile); the 8 D(a,c) values are hoisted, D(b,c) once per y, so a
