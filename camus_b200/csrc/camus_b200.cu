@@ -83,6 +83,8 @@ struct camus_b200 {
   bool counted = false;      // count_filter has run for the current trees / partition
   bool use_fused = true;     // count + filter + score in one kernel (no cell table); CAMUS_B200_UNFUSED=1 disables
   int as_set_hint = 0;       // weight the fused pass of count_filter scores with
+  bool all_complete = true;  // every gene tree so far holds all taxa and is fully resolved
+  bool allow_complete = true;  // CAMUS_B200_NO_COMPLETE=1 forces the general kernel (A/B, tests)
 
   float ms[CAMUS_B200_T_N] = {0};
   uint64_t launches = 0;
@@ -179,8 +181,11 @@ int camus_b200_create(camus_b200** out, int n_gpus, const int* devices) {
     delete ctx;
     return CAMUS_B200_ERR_CUDA;
   }
-  cudaFuncSetAttribute(k_count<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCountSmemBytes);
-  cudaFuncSetAttribute(k_count<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCountSmemBytes);
+  cudaFuncSetAttribute(k_count<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCountSmemBytes);
+  cudaFuncSetAttribute(k_count<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCountSmemBytes);
+  cudaFuncSetAttribute(k_count<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCountSmemBytes);
+  cudaFuncSetAttribute(k_count<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCountSmemBytes);
+  if (const char* e = getenv("CAMUS_B200_NO_COMPLETE")) ctx->allow_complete = !(e[0] == '1');
   if (const char* e = getenv("CAMUS_B200_UNFUSED")) ctx->use_fused = !(e[0] == '1');
   *out = ctx;
   return CAMUS_B200_OK;
@@ -295,6 +300,7 @@ int camus_b200_set_constraint(camus_b200* ctx, int32_t n_nodes, int32_t n_taxa, 
   ctx->h_parent.clear();
   ctx->h_taxon.clear();
   ctx->resolutions = 0;
+  ctx->all_complete = true;
   ctx->G = 0;
   ctx->genes_dirty = true;
   ctx->cell_state = camus_b200::NONE;
@@ -309,6 +315,7 @@ int camus_b200_clear_gene_trees(camus_b200* ctx) {
   ctx->h_parent.clear();
   ctx->h_taxon.clear();
   ctx->resolutions = 0;
+  ctx->all_complete = true;
   ctx->G = 0;
   ctx->genes_dirty = true;
   ctx->cell_state = camus_b200::NONE;
@@ -324,18 +331,23 @@ int camus_b200_add_gene_trees(camus_b200* ctx, int32_t n_trees, const int64_t* n
   if (n_trees < 0 || !node_off || (n_trees > 0 && (!parent || !taxon))) return ctx->fail(CAMUS_B200_ERR_ARG, "add_gene_trees: null argument");
   std::vector<int> stamp(ctx->N, -1);
   std::vector<char> has_child;
+  std::vector<int> n_child;
   uint64_t res = 0;
   for (int g = 0; g < n_trees; ++g) {
     int64_t b = node_off[g], e = node_off[g + 1];
     int64_t nn = e - b;
     if (nn <= 0 || nn > 65000) return ctx->fail(CAMUS_B200_ERR_INPUT, "add_gene_trees: tree " + std::to_string(g) + " has " + std::to_string(nn) + " nodes (1..65000 supported)");
     has_child.assign(nn, 0);
+    n_child.assign(nn, 0);
     uint64_t nl = 0;
     for (int64_t i = 0; i < nn; ++i) {
       int p = parent[b + i];
       if ((i == 0) != (p < 0) || p >= i)
         return ctx->fail(CAMUS_B200_ERR_INPUT, "add_gene_trees: tree " + std::to_string(g) + " is not in preorder (parent before child, single root)");
-      if (p >= 0) has_child[p] = 1;
+      if (p >= 0) {
+        has_child[p] = 1;
+        ++n_child[p];
+      }
       int t = taxon[b + i];
       if (t >= ctx->N) return ctx->fail(CAMUS_B200_ERR_INPUT, "add_gene_trees: taxon index out of range");
       if (t >= 0) {
@@ -348,6 +360,12 @@ int camus_b200_add_gene_trees(camus_b200* ctx, int32_t n_trees, const int64_t* n
       if ((taxon[b + i] >= 0) == (has_child[i] != 0))
         return ctx->fail(CAMUS_B200_ERR_INPUT, "add_gene_trees: tree " + std::to_string(g) + ": taxon set on an internal node or missing on a leaf");
     res += choose4(nl);
+    // complete + fully resolved: all taxa present, every internal node binary (the root may be a
+    // trifurcation, i.e. the unrooted form of a binary tree)
+    bool complete = nl == (uint64_t)ctx->N;
+    for (int64_t i = 0; i < nn && complete; ++i)
+      if (n_child[i] != 0 && n_child[i] != 2 && !(i == 0 && n_child[i] == 3)) complete = false;
+    if (!complete) ctx->all_complete = false;
   }
   int64_t base = ctx->h_node_off.back() - node_off[0];
   for (int g = 0; g < n_trees; ++g) ctx->h_node_off.push_back(node_off[g + 1] + base);
@@ -459,7 +477,10 @@ int run_fused(camus_b200* ctx, int qmode, double threshold, int as_set, uint64_t
     CountParams prm{ctx->d_tri.p, std::max(ctx->G32, 1), BoxMap{b0, ctx->chunk, (uint32_t)ctx->rank, (uint32_t)ctx->world}, nullptr, ctx->G};
     static const int dbg = getenv("CAMUS_B200_DEBUG") ? atoi(getenv("CAMUS_B200_DEBUG")) : 0;
     FusedParams fz{qmode, threshold, ctx->d_thr_tab.p, as_set, ctx->d_Z.p, ctx->d_totals.p, rep, (unsigned long long)zn, dbg};
-    k_count<true><<<(unsigned)nbx, kCountThreads, kCountSmemBytes, ctx->stream>>>(prm, fz, ctx->ct);
+    if (ctx->all_complete && ctx->allow_complete && ctx->G > 0)
+      k_count<true, true><<<(unsigned)nbx, kCountThreads, kCountSmemBytes, ctx->stream>>>(prm, fz, ctx->ct);
+    else
+      k_count<true, false><<<(unsigned)nbx, kCountThreads, kCountSmemBytes, ctx->stream>>>(prm, fz, ctx->ct);
     CK_LAUNCH();
   }
   if (rep > 1) {
@@ -496,7 +517,10 @@ int run_count(camus_b200* ctx) {
   for (uint64_t b0 = 0; b0 < mine; b0 += max_grid) {
     uint64_t nbx = std::min(max_grid, mine - b0);
     CountParams prm{ctx->d_tri.p, std::max(ctx->G32, 1), BoxMap{b0, ctx->chunk, (uint32_t)ctx->rank, (uint32_t)ctx->world}, ctx->d_cells.p + b0 * kBoxCells, ctx->G};
-    k_count<false><<<(unsigned)nbx, kCountThreads, kCountSmemBytes, ctx->stream>>>(prm, FusedParams{}, ctx->ct);
+    if (ctx->all_complete && ctx->allow_complete && ctx->G > 0)
+      k_count<false, true><<<(unsigned)nbx, kCountThreads, kCountSmemBytes, ctx->stream>>>(prm, FusedParams{}, ctx->ct);
+    else
+      k_count<false, false><<<(unsigned)nbx, kCountThreads, kCountSmemBytes, ctx->stream>>>(prm, FusedParams{}, ctx->ct);
     CK_LAUNCH();
   }
   if (t.stop()) return CAMUS_B200_ERR_CUDA;

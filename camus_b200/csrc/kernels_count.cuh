@@ -69,7 +69,11 @@ __device__ __forceinline__ uint32_t pick(const uint4& v, int hi, int lo) {
   return k == 0 ? v.x : (k == 1 ? v.y : (k == 2 ? v.z : v.w));
 }
 
-template <bool kFused>
+// kComplete: every gene tree holds every taxon and is fully resolved (host-checked in
+// camus_b200_add_gene_trees). Then each tree resolves each cell, so count(ad|bc) = G - count(ab|cd)
+// - count(ac|bd): the third topology word, its POPC (the XU pipe is the kernel's narrowest) and
+// the four planes only it reads are skipped; the ring then carries 16 KB instead of 24 KB per stage.
+template <bool kFused, bool kComplete>
 __global__ void __launch_bounds__(kCountThreads, 2) k_count(CountParams prm, FusedParams fz, ConstraintDev ct) {
   extern __shared__ __align__(128) uint32_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kCountStages * kStageWords);
@@ -104,11 +108,22 @@ __global__ void __launch_bounds__(kCountThreads, 2) k_count(CountParams prm, Fus
   auto issue = [&](int g) {
     int s = g % kCountStages;
     uint32_t* dst = smem + s * kStageWords;
-    mbar_arrive_expect_tx(&bars[s], kStageBytes);
-    bulk_g2s(dst, src0 + (size_t)g * gstride, kTileBytes, &bars[s]);
-    bulk_g2s(dst + kTileWords, src1 + (size_t)g * gstride, kTileBytes, &bars[s]);
-    bulk_g2s(dst + 2 * kTileWords, src2 + (size_t)g * gstride, kTileBytes, &bars[s]);
-    bulk_g2s(dst + 3 * kTileWords, src3 + (size_t)g * gstride, kTileBytes, &bars[s]);
+    constexpr int P = kTileWords / 3;  // words per plane (2 KB)
+    if constexpr (!kComplete) {
+      mbar_arrive_expect_tx(&bars[s], kStageBytes);
+      bulk_g2s(dst, src0 + (size_t)g * gstride, kTileBytes, &bars[s]);
+      bulk_g2s(dst + kTileWords, src1 + (size_t)g * gstride, kTileBytes, &bars[s]);
+      bulk_g2s(dst + 2 * kTileWords, src2 + (size_t)g * gstride, kTileBytes, &bars[s]);
+      bulk_g2s(dst + 3 * kTileWords, src3 + (size_t)g * gstride, kTileBytes, &bars[s]);
+    } else {  // planes read by ab|cd and ac|bd only: abc{0,1} abd{0,2} acd{0,2} bcd{1,2}
+      mbar_arrive_expect_tx(&bars[s], 8 * P * 4);
+      bulk_g2s(dst, src0 + (size_t)g * gstride, 2 * P * 4, &bars[s]);
+      bulk_g2s(dst + kTileWords, src1 + (size_t)g * gstride, P * 4, &bars[s]);
+      bulk_g2s(dst + kTileWords + 2 * P, src1 + (size_t)g * gstride + 2 * P, P * 4, &bars[s]);
+      bulk_g2s(dst + 2 * kTileWords, src2 + (size_t)g * gstride, P * 4, &bars[s]);
+      bulk_g2s(dst + 2 * kTileWords + 2 * P, src2 + (size_t)g * gstride + 2 * P, P * 4, &bars[s]);
+      bulk_g2s(dst + 3 * kTileWords + P, src3 + (size_t)g * gstride + P, 2 * P * 4, &bars[s]);
+    }
   };
 
   if (tid == 0)
@@ -176,10 +191,11 @@ __global__ void __launch_bounds__(kCountThreads, 2) k_count(CountParams prm, Fus
             const uint32_t BCD0 = pick(bcd[0], kk, j), BCD1 = pick(bcd[1], kk, j), BCD2 = pick(bcd[2], kk, j);
             const uint32_t t0 = (ABC0 & ABD0) | (ACD2 & BCD2);  // ab|cd
             const uint32_t t1 = (ABC1 & ACD0) | (ABD2 & BCD1);  // ac|bd
-            const uint32_t t2 = (ABD1 & ACD1) | (ABC2 & BCD0);  // ad|bc
             const int c = ((ll * 2 + kk) * 2 + j) * 2 + i;
             cnt[c][0] += __popc(t0);
             cnt[c][1] += __popc(t1);
+            if constexpr (kComplete) continue;
+            const uint32_t t2 = (ABD1 & ACD1) | (ABC2 & BCD0);  // ad|bc
 #if CAMUS_POPC_SKIP
             const uint32_t un = vm & ~(t0 | t1 | t2);
             if (__any_sync(0xFFFFFFFFu, un != 0)) cnt[c][2] += __popc(un);
@@ -201,6 +217,11 @@ __global__ void __launch_bounds__(kCountThreads, 2) k_count(CountParams prm, Fus
   }
 #else
   (void)vm_unused_guard;
+  if constexpr (kComplete) {
+    const uint32_t gt = (uint32_t)prm.n_trees;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) cnt[c][2] = gt - cnt[c][0] - cnt[c][1];
+  }
 #endif
 
   if constexpr (!kFused) {

@@ -80,6 +80,39 @@ def test_fused_and_table_pipelines_agree(gpu, qmode, thr, monkeypatch):
     table.close()
 
 
+def test_complete_tree_specialisation(gpu, monkeypatch):
+    """When every gene tree holds all taxa and is binary the count kernel derives the third
+    topology count as G - c0 - c1 (k_count<.., true>). Same results as the general kernel
+    (CAMUS_B200_NO_COMPLETE=1), and one incomplete / unresolved tree switches it off."""
+    from camus_b200.cabi import CamusB200
+    monkeypatch.setenv("CAMUS_B200_NO_COMPLETE", "1")
+    general = CamusB200(0)
+    monkeypatch.delenv("CAMUS_B200_NO_COMPLETE")
+    s = synth.make(41, 77, 31)  # complete binary trees, 77 = 2 full groups + 13
+    prob = Problem(s.constraint, s.genes)
+    o = orc.Oracle().load(prob)
+    for qmode, thr in ((0, 0.0), (2, 0.4)):
+        want = o.count_filter(qmode, thr, False)
+        for ctx in (gpu, general):
+            ctx.load(prob)
+            assert ctx.count_filter(qmode, thr) == want
+            assert np.array_equal(ctx.quartet_totals(False), o.quartet_totals(False, False))
+            for a, b in zip(ctx.export_quartets(raw=True), o.export_raw_counts()):
+                assert np.array_equal(a, b)
+    # add one star tree and one tree with a missing taxon: the specialisation must switch itself off
+    labs = prob.tip_names
+    extra = "(" + ",".join(labs) + ");\n(" + ",".join(labs[:-1]) + ");\n"
+    prob2 = Problem(s.constraint, s.genes + extra)
+    o2 = orc.Oracle().load(prob2)
+    want = o2.count_filter(1, 0.2, False)
+    gpu.load(prob2)
+    assert gpu.count_filter(1, 0.2) == want
+    assert np.array_equal(gpu.quartet_totals(False), o2.quartet_totals(False, False))
+    for a, b in zip(gpu.export_quartets(raw=True), o2.export_raw_counts()):
+        assert np.array_equal(a, b)
+    general.close()
+
+
 # ------------------------------------------------------------------ reference KATs on the GPU
 @pytest.mark.parametrize("name,tre,qmode,thr,genes,expected", K.PROCESS_QUARTETS)
 def test_process_quartets(gpu, name, tre, qmode, thr, genes, expected):
