@@ -181,10 +181,10 @@ int camus_b200_create(camus_b200** out, int n_gpus, const int* devices) {
     delete ctx;
     return CAMUS_B200_ERR_CUDA;
   }
-  cudaFuncSetAttribute(k_count<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCountSmemBytes);
-  cudaFuncSetAttribute(k_count<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCountSmemBytes);
-  cudaFuncSetAttribute(k_count<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCountSmemBytes);
-  cudaFuncSetAttribute(k_count<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCountSmemBytes);
+  cudaFuncSetAttribute(k_count<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CountCfg<false>::kSmemBytes);
+  cudaFuncSetAttribute(k_count<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CountCfg<false>::kSmemBytes);
+  cudaFuncSetAttribute(k_count<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CountCfg<true>::kSmemBytes);
+  cudaFuncSetAttribute(k_count<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CountCfg<true>::kSmemBytes);
   if (const char* e = getenv("CAMUS_B200_NO_COMPLETE")) ctx->allow_complete = !(e[0] == '1');
   if (const char* e = getenv("CAMUS_B200_UNFUSED")) ctx->use_fused = !(e[0] == '1');
   *out = ctx;
@@ -441,6 +441,9 @@ int build_planes(camus_b200* ctx, bool do_upload = true) {
   return 0;
 }
 
+// the complete-tree kernel packs two 16-bit counters per register
+bool use_complete(const camus_b200* ctx) { return ctx->all_complete && ctx->allow_complete && ctx->G > 0 && ctx->G <= 65535; }
+
 int make_thr_table(camus_b200* ctx, double threshold) {
   int nt = ctx->G + 2;  // the sum of the two smallest counts never exceeds the number of trees
   CK(ctx->d_thr_tab.alloc(nt));
@@ -477,10 +480,10 @@ int run_fused(camus_b200* ctx, int qmode, double threshold, int as_set, uint64_t
     CountParams prm{ctx->d_tri.p, std::max(ctx->G32, 1), BoxMap{b0, ctx->chunk, (uint32_t)ctx->rank, (uint32_t)ctx->world}, nullptr, ctx->G};
     static const int dbg = getenv("CAMUS_B200_DEBUG") ? atoi(getenv("CAMUS_B200_DEBUG")) : 0;
     FusedParams fz{qmode, threshold, ctx->d_thr_tab.p, as_set, ctx->d_Z.p, ctx->d_totals.p, rep, (unsigned long long)zn, dbg};
-    if (ctx->all_complete && ctx->allow_complete && ctx->G > 0)
-      k_count<true, true><<<(unsigned)nbx, kCountThreads, kCountSmemBytes, ctx->stream>>>(prm, fz, ctx->ct);
+    if (use_complete(ctx))
+      k_count<true, true><<<(unsigned)nbx, kCountThreads, CountCfg<true>::kSmemBytes, ctx->stream>>>(prm, fz, ctx->ct);
     else
-      k_count<true, false><<<(unsigned)nbx, kCountThreads, kCountSmemBytes, ctx->stream>>>(prm, fz, ctx->ct);
+      k_count<true, false><<<(unsigned)nbx, kCountThreads, CountCfg<false>::kSmemBytes, ctx->stream>>>(prm, fz, ctx->ct);
     CK_LAUNCH();
   }
   if (rep > 1) {
@@ -517,10 +520,10 @@ int run_count(camus_b200* ctx) {
   for (uint64_t b0 = 0; b0 < mine; b0 += max_grid) {
     uint64_t nbx = std::min(max_grid, mine - b0);
     CountParams prm{ctx->d_tri.p, std::max(ctx->G32, 1), BoxMap{b0, ctx->chunk, (uint32_t)ctx->rank, (uint32_t)ctx->world}, ctx->d_cells.p + b0 * kBoxCells, ctx->G};
-    if (ctx->all_complete && ctx->allow_complete && ctx->G > 0)
-      k_count<false, true><<<(unsigned)nbx, kCountThreads, kCountSmemBytes, ctx->stream>>>(prm, FusedParams{}, ctx->ct);
+    if (use_complete(ctx))
+      k_count<false, true><<<(unsigned)nbx, kCountThreads, CountCfg<true>::kSmemBytes, ctx->stream>>>(prm, FusedParams{}, ctx->ct);
     else
-      k_count<false, false><<<(unsigned)nbx, kCountThreads, kCountSmemBytes, ctx->stream>>>(prm, FusedParams{}, ctx->ct);
+      k_count<false, false><<<(unsigned)nbx, kCountThreads, CountCfg<false>::kSmemBytes, ctx->stream>>>(prm, FusedParams{}, ctx->ct);
     CK_LAUNCH();
   }
   if (t.stop()) return CAMUS_B200_ERR_CUDA;
