@@ -83,7 +83,9 @@ struct camus_b200 {
   bool counted = false;      // count_filter has run for the current trees / partition
   bool use_fused = true;     // count + filter + score in one kernel (no cell table); CAMUS_B200_UNFUSED=1 disables
   int as_set_hint = 0;       // weight the fused pass of count_filter scores with
+  int max_depth = 0;         // deepest node over all gene trees
   bool all_complete = true;  // every gene tree so far holds all taxa and is fully resolved
+  bool allow_half = true;      // CAMUS_B200_NO_HALF=1 forces the integer plane builder (A/B, tests)
   bool allow_complete = true;  // CAMUS_B200_NO_COMPLETE=1 forces the general kernel (A/B, tests)
 
   float ms[CAMUS_B200_T_N] = {0};
@@ -186,6 +188,7 @@ int camus_b200_create(camus_b200** out, int n_gpus, const int* devices) {
   cudaFuncSetAttribute(k_count<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CountCfg<true>::kSmemBytes);
   cudaFuncSetAttribute(k_count<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CountCfg<true>::kSmemBytes);
   if (const char* e = getenv("CAMUS_B200_NO_COMPLETE")) ctx->allow_complete = !(e[0] == '1');
+  if (const char* e = getenv("CAMUS_B200_NO_HALF")) ctx->allow_half = !(e[0] == '1');
   if (const char* e = getenv("CAMUS_B200_UNFUSED")) ctx->use_fused = !(e[0] == '1');
   *out = ctx;
   return CAMUS_B200_OK;
@@ -301,6 +304,7 @@ int camus_b200_set_constraint(camus_b200* ctx, int32_t n_nodes, int32_t n_taxa, 
   ctx->h_taxon.clear();
   ctx->resolutions = 0;
   ctx->all_complete = true;
+  ctx->max_depth = 0;
   ctx->G = 0;
   ctx->genes_dirty = true;
   ctx->cell_state = camus_b200::NONE;
@@ -316,6 +320,7 @@ int camus_b200_clear_gene_trees(camus_b200* ctx) {
   ctx->h_taxon.clear();
   ctx->resolutions = 0;
   ctx->all_complete = true;
+  ctx->max_depth = 0;
   ctx->G = 0;
   ctx->genes_dirty = true;
   ctx->cell_state = camus_b200::NONE;
@@ -331,7 +336,7 @@ int camus_b200_add_gene_trees(camus_b200* ctx, int32_t n_trees, const int64_t* n
   if (n_trees < 0 || !node_off || (n_trees > 0 && (!parent || !taxon))) return ctx->fail(CAMUS_B200_ERR_ARG, "add_gene_trees: null argument");
   std::vector<int> stamp(ctx->N, -1);
   std::vector<char> has_child;
-  std::vector<int> n_child;
+  std::vector<int> n_child, depth_h;
   uint64_t res = 0;
   for (int g = 0; g < n_trees; ++g) {
     int64_t b = node_off[g], e = node_off[g + 1];
@@ -339,6 +344,7 @@ int camus_b200_add_gene_trees(camus_b200* ctx, int32_t n_trees, const int64_t* n
     if (nn <= 0 || nn > 65000) return ctx->fail(CAMUS_B200_ERR_INPUT, "add_gene_trees: tree " + std::to_string(g) + " has " + std::to_string(nn) + " nodes (1..65000 supported)");
     has_child.assign(nn, 0);
     n_child.assign(nn, 0);
+    depth_h.assign(nn, 0);
     uint64_t nl = 0;
     for (int64_t i = 0; i < nn; ++i) {
       int p = parent[b + i];
@@ -347,6 +353,8 @@ int camus_b200_add_gene_trees(camus_b200* ctx, int32_t n_trees, const int64_t* n
       if (p >= 0) {
         has_child[p] = 1;
         ++n_child[p];
+        depth_h[i] = depth_h[p] + 1;
+        if (depth_h[i] > ctx->max_depth) ctx->max_depth = depth_h[i];
       }
       int t = taxon[b + i];
       if (t >= ctx->N) return ctx->fail(CAMUS_B200_ERR_INPUT, "add_gene_trees: taxon index out of range");
@@ -425,14 +433,23 @@ int build_planes(camus_b200* ctx, bool do_upload = true) {
     int gb_max = (int)std::max<size_t>(1, std::min<size_t>(ctx->G32, ((size_t)1 << 30) / (dt_group * 2)));
     CK(ctx->d_Dt.alloc(dt_group * gb_max));
     const unsigned n_tiles = (unsigned)num_tiles(ctx->M);
+    // packed fp16 compares need exact depths: depth + 1 <= 2048 (checked in add_gene_trees)
+    const bool half_path = ctx->max_depth + 1 <= 2048 && ctx->allow_half;
     for (int g0 = 0; g0 < ctx->G32; g0 += gb_max) {
       int gb = std::min(gb_max, ctx->G32 - g0);
-      CK(cudaMemsetAsync(ctx->d_Dt.p, 0, dt_group * gb * 2, ctx->stream));
+      // integer depths: 0 = absent; fp16 depths: 0xFFFF = NaN = absent
+      CK(cudaMemsetAsync(ctx->d_Dt.p, half_path ? 0xFF : 0, dt_group * gb * 2, ctx->stream));
       dim3 blk(kLanes, 8);
       dim3 g1((npad + 7) / 8, gb);
-      k_depth_table<<<g1, blk, 0, ctx->stream>>>(g0, G, npad, ctx->d_nleaf.p, ctx->d_lrT.p, ctx->d_hT.p, ctx->d_Dt.p);
+      if (half_path)
+        k_depth_table<true><<<g1, blk, 0, ctx->stream>>>(g0, G, npad, ctx->d_nleaf.p, ctx->d_lrT.p, ctx->d_hT.p, ctx->d_Dt.p);
+      else
+        k_depth_table<false><<<g1, blk, 0, ctx->stream>>>(g0, G, npad, ctx->d_nleaf.p, ctx->d_lrT.p, ctx->d_hT.p, ctx->d_Dt.p);
       CK_LAUNCH();
-      k_triple_planes<<<n_tiles, 256, 0, ctx->stream>>>(g0, gb, G32, npad, ctx->d_Dt.p, ctx->d_tri.p);
+      if (half_path)
+        k_triple_planes_h2<<<n_tiles, 256, 0, ctx->stream>>>(g0, gb, G32, npad, ctx->d_Dt.p, ctx->d_tri.p);
+      else
+        k_triple_planes<<<n_tiles, 256, 0, ctx->stream>>>(g0, gb, G32, npad, ctx->d_Dt.p, ctx->d_tri.p);
       CK_LAUNCH();
     }
   }

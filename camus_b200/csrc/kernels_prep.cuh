@@ -6,11 +6,14 @@
 // "D(a,b) > D(a,c)" on its LCA depths, stored as one bit per tree (32 trees per word), from which
 // the count kernel resolves 32 trees per logical instruction.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include "layout.cuh"
 
 namespace camus_dev {
+
+constexpr int kPlanePad = 516;  // padded plane stride (words) of the shared tile image in K1b
 
 // ---------------------------------------------------------------------------------------------
 // K0: one thread per gene tree walks its preorder arrays once.
@@ -56,6 +59,9 @@ __global__ void k_tree_prepare(int n_trees, const int64_t* __restrict__ node_off
 // D(p, q) for DFS positions p < q of one tree is the running minimum of h[p..q-1]. Warp = one
 // start position p, lane = tree; h/lr reads are coalesced 64 B rows.
 // ---------------------------------------------------------------------------------------------
+// kHalf: store the value as an fp16 bit pattern (exact up to 2048) for the packed-compare K1b; the
+// buffer is then pre-filled with 0xFFFF = NaN, so "absent" fails every ordered comparison.
+template <bool kHalf>
 __global__ void k_depth_table(int grp0, int n_trees, int npad, const int32_t* __restrict__ nleaf,
                               const uint16_t* __restrict__ lrT, const uint16_t* __restrict__ hT,
                               uint16_t* __restrict__ Dt) {
@@ -75,7 +81,7 @@ __global__ void k_depth_table(int grp0, int n_trees, int npad, const int32_t* __
     m = min(m, (uint32_t)h[(size_t)(q - 1) * kLanes]);
     uint32_t b = lr[(size_t)q * kLanes];
     uint32_t lo = min(a, b), hi = max(a, b);
-    D[((size_t)lo * npad + hi) * kLanes] = (uint16_t)m;
+    D[((size_t)lo * npad + hi) * kLanes] = kHalf ? __half_as_ushort(__ushort2half_rn((unsigned short)m)) : (uint16_t)m;
   }
 }
 
@@ -93,8 +99,11 @@ __global__ void k_depth_table(int grp0, int n_trees, int npad, const int32_t* __
 __global__ void __launch_bounds__(256) k_triple_planes(int grp0, int n_batch, int n_groups_total, int npad,
                                                        const uint16_t* __restrict__ Dt, uint32_t* __restrict__ Tri) {
   __shared__ __align__(16) uint16_t s_d[3][64][kLanes];  // [ab | ac | bc][i*8+j][lane]
-  __shared__ __align__(16) uint32_t s_out[kTileWords];
-  __shared__ uint32_t s_scratch[8][64];
+  // Tile image: the 3 planes are padded to 516 words so that lanes 0..2 (one plane each) hit
+  // different banks, and the dummy row the other 29 lanes write to sits 16 banks away.
+  __shared__ __align__(128) uint32_t s_img[3 * kPlanePad + 4 + 8 * 64];
+  uint32_t* const s_out = s_img;
+  uint32_t* const s_scr = s_img + 3 * kPlanePad + 4;
   __shared__ uint32_t s_seg[3];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint64_t tile = blockIdx.x;
@@ -136,7 +145,7 @@ __global__ void __launch_bounds__(256) k_triple_planes(int grp0, int n_batch, in
   // lanes 0..2 store planes 0..2 at tile_word(lane, x, y, z); the other lanes store to a per-warp
   // scratch row so that the store needs no predicate / divergence. The plane is picked with two
   // bitwise muxes on lane-constant masks instead of compare + select.
-  uint32_t* out_lane = lane < 3 ? s_out + lane * 512 + z * 64 : s_scratch[warp];
+  uint32_t* out_lane = lane < 3 ? s_out + lane * kPlanePad + z * 64 : s_scr + warp * 64;
   const uint32_t m0 = lane == 0 ? 0xFFFFFFFFu : 0u, m01 = lane <= 1 ? 0xFFFFFFFFu : 0u;
 #pragma unroll
   for (int y = 0; y < 8; ++y) {
@@ -154,8 +163,116 @@ __global__ void __launch_bounds__(256) k_triple_planes(int grp0, int n_batch, in
   }
   __syncthreads();
   uint4* dst = reinterpret_cast<uint4*>(Tri + (tile * n_groups_total + (grp0 + gb)) * kTileWords);
-  const uint4* src = reinterpret_cast<const uint4*>(s_out);
-  for (int i = tid; i < kTileWords / 4; i += 256) dst[i] = src[i];
+  for (int i = tid; i < kTileWords / 4; i += 256)
+    dst[i] = *reinterpret_cast<const uint4*>(s_out + (i >> 7) * kPlanePad + (i & 127) * 4);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1b, packed form (default): depths are fp16 (exact: the host checks depth + 1 <= 2048), absent
+// pairs are NaN. One setp.gt.f16x2 compares TWO triples (y, y+1) per lane and yields two
+// predicates; NaN makes every comparison false, so no presence test is needed. The integer
+// kernel above spends 6 ALU-pipe instructions per triple (min3, 4 ISETP, SEL) and is bound by that
+// pipe; here the compares run on the FMA pipe and a triple costs ~8 issue slots.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cmp2_ballot(uint32_t a2, uint32_t b2, uint32_t& lo, uint32_t& hi) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q;\n"
+      "setp.gt.f16x2 p|q, %2, %3;\n"
+      "vote.sync.ballot.b32 %0, p, 0xffffffff;\n"
+      "vote.sync.ballot.b32 %1, q, 0xffffffff;\n"
+      "}\n"
+      : "=r"(lo), "=r"(hi)
+      : "r"(a2), "r"(b2));
+}
+
+__global__ void __launch_bounds__(256) k_triple_planes_h2(int grp0, int n_batch, int n_groups_total, int npad,
+                                                          const uint16_t* __restrict__ Dt, uint32_t* __restrict__ Tri) {
+  // [ab | bc][first index][second-index pair][lane] as half2 (second index 2j, 2j+1); [ac][x][z][lane] as half
+  __shared__ __align__(16) uint32_t s_ab[8][4][kLanes];
+  __shared__ __align__(16) uint32_t s_bc[4][8][kLanes];  // [y pair][z][lane] = (D(y,z), D(y+1,z))
+  __shared__ __align__(16) uint16_t s_ac[8][8][kLanes];
+  // Tile image: the 3 planes are padded to 516 words so that lanes 0..2 (one plane each) hit
+  // different banks, and the dummy row the other 29 lanes write to sits 16 banks away.
+  __shared__ __align__(128) uint32_t s_img[3 * kPlanePad + 4 + 8 * 64];
+  uint32_t* const s_out = s_img;
+  uint32_t* const s_scr = s_img + 3 * kPlanePad + 4;
+  __shared__ uint32_t s_seg[3];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint64_t tile = blockIdx.x;
+  if (tid == 0) {
+    uint64_t r = tile;
+    uint32_t s2 = unrank3(r);
+    r -= choose3((uint64_t)s2 + 2);
+    uint32_t s1 = unrank2(r);
+    r -= choose2((uint64_t)s1 + 1);
+    s_seg[0] = (uint32_t)r;
+    s_seg[1] = s1;
+    s_seg[2] = s2;
+  }
+  __syncthreads();
+  const uint32_t a0 = s_seg[0] * 8, b0 = s_seg[1] * 8, c0 = s_seg[2] * 8;
+  const int z = warp;
+  uint32_t* out_lane = lane < 3 ? s_out + lane * kPlanePad + z * 64 : s_scr + warp * 64;
+  const uint32_t m0 = lane == 0 ? 0xFFFFFFFFu : 0u, m01 = lane <= 1 ? 0xFFFFFFFFu : 0u;
+  for (int gb = 0; gb < n_batch; ++gb) {
+    if (gb) __syncthreads();
+    const uint16_t* D = Dt + (size_t)gb * npad * npad * kLanes;
+    // fill: warp w stages row i = w of each table; lane loads its own u16 of 8 consecutive rows
+    {
+      const int i = warp;
+      uint32_t v[8];
+      // ab: x = a0+i, y = b0..b0+7 -> packed pairs
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t x = a0 + i, y = b0 + j;
+        v[j] = x < y ? (uint32_t)D[((size_t)x * npad + y) * kLanes + lane] : 0xFFFFu;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s_ab[i][j][lane] = v[2 * j] | (v[2 * j + 1] << 16);
+      // ac: x = a0+i, z = c0..c0+7
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t x = a0 + i, y = c0 + j;
+        s_ac[i][j][lane] = x < y ? D[((size_t)x * npad + y) * kLanes + lane] : (uint16_t)0xFFFFu;
+      }
+      // bc: y = b0+i, z = c0..c0+7, stored as [y pair][z] halves of a u32
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t x = b0 + i, y = c0 + j;
+        const uint16_t d = x < y ? D[((size_t)x * npad + y) * kLanes + lane] : (uint16_t)0xFFFFu;
+        reinterpret_cast<uint16_t*>(&s_bc[i >> 1][j][lane])[i & 1] = d;
+      }
+    }
+    __syncthreads();
+    uint32_t ac2[8];
+#pragma unroll
+    for (int x = 0; x < 8; ++x) {
+      const uint32_t h = s_ac[x][z][lane];
+      ac2[x] = h | (h << 16);
+    }
+#pragma unroll
+    for (int yp = 0; yp < 4; ++yp) {
+      const uint32_t bc2 = s_bc[yp][z][lane];
+#pragma unroll
+      for (int x = 0; x < 8; ++x) {
+        const uint32_t ab2 = s_ab[x][yp][lane];
+        uint32_t w0a, w0b, w1a, w1b, w2a, w2b;
+        cmp2_ballot(ab2, ac2[x], w0a, w0b);  // ab|c : D(a,b) > D(a,c)
+        cmp2_ballot(ac2[x], ab2, w1a, w1b);  // ac|b : D(a,c) > D(a,b)
+        cmp2_ballot(bc2, ab2, w2a, w2b);     // bc|a : D(b,c) > D(a,b)
+        const uint32_t sa_ = (((w0a & m0) | (w1a & ~m0)) & m01) | (w2a & ~m01);
+        const uint32_t sb_ = (((w0b & m0) | (w1b & ~m0)) & m01) | (w2b & ~m01);
+        // y = 2*yp and 2*yp+1: tile_word offsets ((y>>1)*4 + (x>>1))*4 + (y&1)*2 + (x&1)
+        out_lane[(yp * 4 + (x >> 1)) * 4 + (x & 1)] = sa_;
+        out_lane[(yp * 4 + (x >> 1)) * 4 + 2 + (x & 1)] = sb_;
+      }
+    }
+    __syncthreads();
+    uint4* dst = reinterpret_cast<uint4*>(Tri + (tile * n_groups_total + (grp0 + gb)) * kTileWords);
+    for (int i = tid; i < kTileWords / 4; i += 256)
+      dst[i] = *reinterpret_cast<const uint4*>(s_out + (i >> 7) * kPlanePad + (i & 127) * 4);
   }
 }
 

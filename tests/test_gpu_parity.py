@@ -80,6 +80,26 @@ def test_fused_and_table_pipelines_agree(gpu, qmode, thr, monkeypatch):
     table.close()
 
 
+def test_integer_and_fp16_plane_builders_agree(gpu, monkeypatch):
+    """k_triple_planes_h2 (packed fp16 compares, NaN = absent) is the default; trees deeper than
+    2047 fall back to the integer kernel, forced here with CAMUS_B200_NO_HALF=1."""
+    from camus_b200.cabi import CamusB200
+    monkeypatch.setenv("CAMUS_B200_NO_HALF", "1")
+    integer = CamusB200(0)
+    monkeypatch.delenv("CAMUS_B200_NO_HALF")
+    for s, ms in ((synth.make(52, 70, 8, support=True, drop_frac=0.12, nexus=True), 0.6), (synth.make(37, 40, 9), 0.0)):
+        prob = Problem(s.constraint, s.genes, s.fmt, ms)
+        o = orc.Oracle().load(prob)
+        want = o.count_filter(0, 0.0, False)
+        for ctx in (gpu, integer):
+            ctx.load(prob)
+            assert ctx.count_filter(0, 0.0) == want
+            for a, b in zip(ctx.export_quartets(raw=True), o.export_raw_counts()):
+                assert np.array_equal(a, b)
+            assert np.array_equal(ctx.quartet_totals(False), o.quartet_totals(False, False))
+    integer.close()
+
+
 def test_complete_tree_specialisation(gpu, monkeypatch):
     """When every gene tree holds all taxa and is binary the count kernel derives the third
     topology count as G - c0 - c1 (k_count<.., true>). Same results as the general kernel
