@@ -189,10 +189,7 @@ __device__ __forceinline__ void cmp2_ballot(uint32_t a2, uint32_t b2, uint32_t& 
 
 __global__ void __launch_bounds__(256) k_triple_planes_h2(int grp0, int n_batch, int n_groups_total, int npad,
                                                           const uint16_t* __restrict__ Dt, uint32_t* __restrict__ Tri) {
-  // [ab | bc][first index][second-index pair][lane] as half2 (second index 2j, 2j+1); [ac][x][z][lane] as half
-  __shared__ __align__(16) uint32_t s_ab[8][4][kLanes];
-  __shared__ __align__(16) uint32_t s_bc[4][8][kLanes];  // [y pair][z][lane] = (D(y,z), D(y+1,z))
-  __shared__ __align__(16) uint16_t s_ac[8][8][kLanes];
+  __shared__ __align__(16) uint16_t s_d[3][64][kLanes];  // [ab | ac | bc][i*8+j][lane], fp16 bits, NaN = absent
   // Tile image: the 3 planes are padded to 516 words so that lanes 0..2 (one plane each) hit
   // different banks, and the dummy row the other 29 lanes write to sits 16 banks away.
   __shared__ __align__(128) uint32_t s_img[3 * kPlanePad + 4 + 8 * 64];
@@ -219,45 +216,30 @@ __global__ void __launch_bounds__(256) k_triple_planes_h2(int grp0, int n_batch,
   for (int gb = 0; gb < n_batch; ++gb) {
     if (gb) __syncthreads();
     const uint16_t* D = Dt + (size_t)gb * npad * npad * kLanes;
-    // fill: warp w stages row i = w of each table; lane loads its own u16 of 8 consecutive rows
-    {
-      const int i = warp;
-      uint32_t v[8];
-      // ab: x = a0+i, y = b0..b0+7 -> packed pairs
+    // stage the 3 x 64 pair rows with warp-wide 128-bit copies (8 rows = 512 contiguous bytes)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const uint32_t x = a0 + i, y = b0 + j;
-        v[j] = x < y ? (uint32_t)D[((size_t)x * npad + y) * kLanes + lane] : 0xFFFFu;
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) s_ab[i][j][lane] = v[2 * j] | (v[2 * j + 1] << 16);
-      // ac: x = a0+i, z = c0..c0+7
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const uint32_t x = a0 + i, y = c0 + j;
-        s_ac[i][j][lane] = x < y ? D[((size_t)x * npad + y) * kLanes + lane] : (uint16_t)0xFFFFu;
-      }
-      // bc: y = b0+i, z = c0..c0+7, stored as [y pair][z] halves of a u32
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const uint32_t x = b0 + i, y = c0 + j;
-        const uint16_t d = x < y ? D[((size_t)x * npad + y) * kLanes + lane] : (uint16_t)0xFFFFu;
-        reinterpret_cast<uint16_t*>(&s_bc[i >> 1][j][lane])[i & 1] = d;
-      }
+    for (int it = 0; it < 3; ++it) {
+      const int seg = it * 8 + warp;  // 0..23
+      const int which = seg >> 3, i = seg & 7, j = lane >> 2;
+      const uint32_t x = (which == 2 ? b0 : a0) + i;
+      const uint32_t y0 = which == 0 ? b0 : c0;
+      uint4 v = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);  // NaN: wrong rank order
+      if (x < y0 + j) v = *reinterpret_cast<const uint4*>(D + ((size_t)x * npad + y0 + j) * kLanes + (lane & 3) * 8);
+      *reinterpret_cast<uint4*>(&s_d[which][i * 8 + j][(lane & 3) * 8]) = v;
     }
     __syncthreads();
     uint32_t ac2[8];
 #pragma unroll
     for (int x = 0; x < 8; ++x) {
-      const uint32_t h = s_ac[x][z][lane];
+      const uint32_t h = s_d[1][x * 8 + z][lane];
       ac2[x] = h | (h << 16);
     }
 #pragma unroll
     for (int yp = 0; yp < 4; ++yp) {
-      const uint32_t bc2 = s_bc[yp][z][lane];
+      const uint32_t bc2 = (uint32_t)s_d[2][(2 * yp) * 8 + z][lane] | ((uint32_t)s_d[2][(2 * yp + 1) * 8 + z][lane] << 16);
 #pragma unroll
       for (int x = 0; x < 8; ++x) {
-        const uint32_t ab2 = s_ab[x][yp][lane];
+        const uint32_t ab2 = (uint32_t)s_d[0][x * 8 + 2 * yp][lane] | ((uint32_t)s_d[0][x * 8 + 2 * yp + 1][lane] << 16);
         uint32_t w0a, w0b, w1a, w1b, w2a, w2b;
         cmp2_ballot(ab2, ac2[x], w0a, w0b);  // ab|c : D(a,b) > D(a,c)
         cmp2_ballot(ac2[x], ab2, w1a, w1b);  // ac|b : D(a,c) > D(a,b)
