@@ -145,6 +145,13 @@ k_count(CountParams prm, FusedParams fz, ConstraintDev ct) {
 #pragma unroll
     for (int t = 0; t < kCnt; ++t) cnt[c][t] = 0;
 
+  // per-thread uint4 offsets inside a plane, (z * 4 + ty) * 4 + tx, hoisted out of the group loop
+  const uint32_t o_abc = ((2 * tc) * 4 + tb) * 4 + ta;  // + 16 per kk
+  const uint32_t o_abd = ((2 * td) * 4 + tb) * 4 + ta;  // + 16 per ll
+  const uint32_t o_acd = ((2 * td) * 4 + tc) * 4 + ta;
+  const uint32_t o_bcd = ((2 * td) * 4 + tc) * 4 + tb;
+  constexpr int kPlaneU4 = kPlaneWords / 4;
+
   for (int g = 0; g < G; ++g) {
     const int s = g % kCountStages;
     // everyone has finished group g-1, whose stage is the one refilled now
@@ -153,26 +160,22 @@ k_count(CountParams prm, FusedParams fz, ConstraintDev ct) {
     mbar_wait(&bars[s], (uint32_t)((g / kCountStages) & 1));
 
     const uint4* st = reinterpret_cast<const uint4*>(smem + s * Cfg::kStageWords);
-    // uint4 index inside a plane: (z * 4 + ty) * 4 + tx
-    auto ld = [&](int role, int plane, int z, int ty, int tx) -> uint4 {
-      return st[plane_slot<kComplete>(role, plane) * (kPlaneWords / 4) + (z * 4 + ty) * 4 + tx];
-    };
+    auto ld = [&](int role, int plane, uint32_t off) -> uint4 { return st[plane_slot<kComplete>(role, plane) * kPlaneU4 + off]; };
 
     uint4 abc[3][2];
 #pragma unroll
     for (int p = 0; p < (kComplete ? 2 : 3); ++p)
 #pragma unroll
-      for (int kk = 0; kk < 2; ++kk) abc[p][kk] = ld(0, p, 2 * tc + kk, tb, ta);
+      for (int kk = 0; kk < 2; ++kk) abc[p][kk] = ld(0, p, o_abc + 16 * kk);
 
 #pragma unroll
     for (int ll = 0; ll < 2; ++ll) {
-      const int z = 2 * td + ll;
       uint4 abd[3], acd[3], bcd[3];
 #pragma unroll
       for (int p = 0; p < 3; ++p) {
-        if (!kComplete || p != 1) abd[p] = ld(1, p, z, tb, ta);
-        if (!kComplete || p != 1) acd[p] = ld(2, p, z, tc, ta);
-        if (!kComplete || p != 0) bcd[p] = ld(3, p, z, tc, tb);
+        if (!kComplete || p != 1) abd[p] = ld(1, p, o_abd + 16 * ll);
+        if (!kComplete || p != 1) acd[p] = ld(2, p, o_acd + 16 * ll);
+        if (!kComplete || p != 0) bcd[p] = ld(3, p, o_bcd + 16 * ll);
       }
 #pragma unroll
       for (int kk = 0; kk < 2; ++kk)
