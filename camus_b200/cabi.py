@@ -44,6 +44,7 @@ def lib() -> C.CDLL:
         L.camus_b200_quartet_totals.argtypes = [vp, C.c_int, vp]
         L.camus_b200_edge_penalties.argtypes = [vp, vp]
         L.camus_b200_export_quartets.argtypes = [vp, C.c_int, vp, vp, C.c_uint64, u64p]
+        L.camus_b200_query_cells.argtypes = [vp, C.c_int32, vp, vp]
         L.camus_b200_quartet_totals_partial.argtypes = [vp, C.c_int]
         L.camus_b200_partial_buffer.argtypes = [vp, C.POINTER(vp), u64p]
         L.camus_b200_quartet_totals_finish.argtypes = [vp, vp]
@@ -58,7 +59,7 @@ EXPORTED = [
     "camus_b200_create", "camus_b200_destroy", "camus_b200_last_error", "camus_b200_set_partition",
     "camus_b200_set_constraint", "camus_b200_add_gene_trees", "camus_b200_clear_gene_trees",
     "camus_b200_set_score_hint", "camus_b200_count_filter", "camus_b200_quartet_totals", "camus_b200_edge_penalties",
-    "camus_b200_export_quartets", "camus_b200_quartet_totals_partial", "camus_b200_partial_buffer",
+    "camus_b200_export_quartets", "camus_b200_query_cells", "camus_b200_quartet_totals_partial", "camus_b200_partial_buffer",
     "camus_b200_quartet_totals_finish", "camus_b200_run_resident", "camus_b200_stage_ms", "camus_b200_workload",
 ]
 
@@ -144,6 +145,13 @@ class CamusB200:
         if n.value:
             self._ck(lib().camus_b200_export_quartets(self._h, int(raw), _p(keys), _p(counts), n.value, C.byref(n)))
         return keys, counts
+
+    def query_cells(self, quads) -> np.ndarray:
+        """Raw counts of arbitrary 4-taxon sets (tip indices), reference topology order."""
+        quads = np.ascontiguousarray(quads, np.int32).reshape(-1, 4)
+        out = np.zeros((len(quads), 3), np.uint32)
+        self._ck(lib().camus_b200_query_cells(self._h, len(quads), _p(quads), _p(out)))
+        return out
 
     # ---- split form for multi-process runs ----
     def quartet_totals_partial(self, as_set: bool = False):

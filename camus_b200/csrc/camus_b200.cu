@@ -762,6 +762,30 @@ int camus_b200_export_quartets(camus_b200* ctx, int raw, uint64_t* keys, uint32_
   return 0;
 }
 
+int camus_b200_query_cells(camus_b200* ctx, int32_t n_query, const int32_t* quads, uint32_t* counts) {
+  if (!ctx || n_query < 0 || (n_query && (!quads || !counts))) return CAMUS_B200_ERR_ARG;
+  if (ctx->genes_dirty || ctx->n == 0) return ctx->fail(CAMUS_B200_ERR_ARG, "query_cells: call camus_b200_count_filter first");
+  for (int i = 0; i < 4 * n_query; ++i)
+    if (quads[i] < 0 || quads[i] >= ctx->N) return ctx->fail(CAMUS_B200_ERR_ARG, "query_cells: tip index out of range");
+  for (int q = 0; q < n_query; ++q)
+    for (int i = 0; i < 4; ++i)
+      for (int j = i + 1; j < 4; ++j)
+        if (quads[4 * q + i] == quads[4 * q + j]) return ctx->fail(CAMUS_B200_ERR_ARG, "query_cells: repeated taxon in a 4-set");
+  if (n_query == 0) return 0;
+  CK(cudaSetDevice(ctx->device));
+  DevBuf<int32_t> dq;
+  DevBuf<uint32_t> dc;
+  CK(dq.alloc((size_t)4 * n_query));
+  CK(dc.alloc((size_t)3 * n_query));
+  CK(cudaMemcpyAsync(dq.p, quads, (size_t)16 * n_query, cudaMemcpyHostToDevice, ctx->stream));
+  k_query_cells<<<(n_query + 127) / 128, 128, 0, ctx->stream>>>(n_query, dq.p, dc.p, ctx->d_tri.p, std::max(ctx->G32, 1),
+                                                                ctx->d_rank_of_tip.p, ctx->d_tip_of_rank.p);
+  CK_LAUNCH();
+  CK(cudaMemcpyAsync(counts, dc.p, (size_t)12 * n_query, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
 int camus_b200_stage_ms(const camus_b200* ctx, float* ms, uint64_t* n_launches) {
   if (!ctx) return CAMUS_B200_ERR_ARG;
   if (ms) std::memcpy(ms, ctx->ms, sizeof(ctx->ms));

@@ -418,6 +418,48 @@ __global__ void k_penalties(unsigned long long* __restrict__ out, ConstraintDev 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Parity probe: raw topology counts of arbitrary 4-taxon sets, read straight from the triple
+// bit-planes with scalar loads (an independent, slow reading of the same table k_count streams).
+// quads = 4 constraint tip indices per query; out = 3 counts per query in the REFERENCE's
+// topology order for taxa sorted by tip index: s0s1|s2s3, s0s2|s1s3, s0s3|s1s2 (quartet.go:23-25).
+// ---------------------------------------------------------------------------------------------
+__global__ void k_query_cells(int n_query, const int32_t* __restrict__ quads, uint32_t* __restrict__ out,
+                              const uint32_t* __restrict__ tri, int n_groups, const int32_t* __restrict__ rank_of_tip,
+                              const int32_t* __restrict__ tip_of_rank) {
+  int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n_query) return;
+  uint32_t x[4];
+  for (int i = 0; i < 4; ++i) x[i] = (uint32_t)rank_of_tip[quads[4 * q + i]];
+  for (int i = 0; i < 3; ++i)
+    for (int j = i + 1; j < 4; ++j)
+      if (x[j] < x[i]) {
+        uint32_t t = x[i];
+        x[i] = x[j];
+        x[j] = t;
+      }
+  const uint32_t a = x[0], b = x[1], c = x[2], d = x[3];
+  auto word = [&](uint32_t p, uint32_t u, uint32_t v, uint32_t w, int g) {  // plane p of triple u < v < w
+    return tri[(tile_index(u >> 3, v >> 3, w >> 3) * n_groups + g) * kTileWords + tile_word(p, u & 7, v & 7, w & 7)];
+  };
+  uint32_t cnt[3] = {0, 0, 0};
+  for (int g = 0; g < n_groups; ++g) {
+    cnt[0] += __popc((word(0, a, b, c, g) & word(0, a, b, d, g)) | (word(2, a, c, d, g) & word(2, b, c, d, g)));
+    cnt[1] += __popc((word(1, a, b, c, g) & word(0, a, c, d, g)) | (word(2, a, b, d, g) & word(1, b, c, d, g)));
+    cnt[2] += __popc((word(1, a, b, d, g) & word(1, a, c, d, g)) | (word(2, a, b, c, g) & word(0, b, c, d, g)));
+  }
+  int ti[4] = {tip_of_rank[a], tip_of_rank[b], tip_of_rank[c], tip_of_rank[d]};
+  int pos[4];
+  for (int i = 0; i < 4; ++i) {
+    int r = 0;
+    for (int j = 0; j < 4; ++j) r += (ti[j] < ti[i]);
+    pos[i] = r;
+  }
+  for (int t = 0; t < 3; ++t)
+    for (int i = 0; i < 4; ++i)
+      if (pos[i] == 0) out[3 * q + pos[partner_of(t, i)] - 1] = cnt[t];
+}
+
+// ---------------------------------------------------------------------------------------------
 // Export: every non-zero (cell, topology) as a reference-packed key (graphs/quartet.go:67-109):
 // taxa sorted by tip index in 15-bit fields, topology nibble with bit i set iff sorted taxon i is
 // on the side NOT holding sorted taxon 0.

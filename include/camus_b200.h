@@ -94,6 +94,12 @@ int camus_b200_edge_penalties(camus_b200* ctx, uint64_t* out /*[n*n]*/);
 int camus_b200_export_quartets(camus_b200* ctx, int raw, uint64_t* keys, uint32_t* counts, uint64_t cap,
                                uint64_t* n_out);
 
+/* Parity probe for sizes whose cell table cannot be exported: raw (pre-filter) counts of n_query
+ * arbitrary 4-taxon sets, read from the bit-plane table with an independent scalar kernel.
+ * quads = 4 distinct constraint tip indices per query; counts = 3 per query, in the reference's
+ * topology order for the taxa sorted by tip index (0b1100, 0b1010, 0b0110; quartet.go:23-25). */
+int camus_b200_query_cells(camus_b200* ctx, int32_t n_query, const int32_t* quads, uint32_t* counts);
+
 /* ---- split form of quartet_totals for multi-process runs ---- */
 int camus_b200_quartet_totals_partial(camus_b200* ctx, int as_set);
 /* device pointer + element count of the partial junction table (int64 elements) to be summed */

@@ -765,6 +765,43 @@ int oracle_export_raw_counts(const oracle_ctx* c, uint64_t* keys, uint32_t* coun
   return export_map(c->raw, keys, counts, cap, n_out);
 }
 
+// Raw counts of given 4-taxon sets (tip indices): per gene tree the four-point test on LCA depths
+// (SURVEY.md Appendix B), LCAs by climbing. out[3*q + t], t in the order 0b1100, 0b1010, 0b0110 for
+// the taxa sorted by tip index. Lets the tests check sampled cells at sizes where no table fits.
+int oracle_count_cells(oracle_ctx* c, int32_t n_query, const int32_t* quads, uint32_t* out) {
+  std::memset(out, 0, sizeof(uint32_t) * 3 * n_query);
+  for (const FlatTree& t : c->genes) {
+    std::vector<int> depth(t.n, 0), leaf_of(c->n_taxa, -1);
+    for (int i = 0; i < t.n; i++) {
+      if (t.parent[i] >= 0) depth[i] = depth[t.parent[i]] + 1;  // preorder: parents first
+      if (t.taxon[i] >= 0) leaf_of[t.taxon[i]] = i;
+    }
+    auto D = [&](int x, int y) {
+      while (x != y) {
+        if (depth[x] >= depth[y]) x = t.parent[x];
+        else y = t.parent[y];
+      }
+      return depth[x];
+    };
+    for (int q = 0; q < n_query; q++) {
+      int s[4] = {quads[4 * q], quads[4 * q + 1], quads[4 * q + 2], quads[4 * q + 3]};
+      std::sort(s, s + 4);
+      int l[4];
+      bool ok = true;
+      for (int i = 0; i < 4; i++) {
+        l[i] = leaf_of[s[i]];
+        ok = ok && l[i] >= 0;
+      }
+      if (!ok) continue;
+      int s1 = D(l[0], l[1]) + D(l[2], l[3]), s2 = D(l[0], l[2]) + D(l[1], l[3]), s3 = D(l[0], l[3]) + D(l[1], l[2]);
+      int mx = std::max(s1, std::max(s2, s3));
+      if ((s1 == mx) + (s2 == mx) + (s3 == mx) != 1) continue;
+      out[3 * q + (s1 == mx ? 0 : (s2 == mx ? 1 : 2))]++;
+    }
+  }
+  return 0;
+}
+
 // score.CalculateQuartetTotals (quartettotals.go:43-61). literal=1: per-(u,w) QuartetScore loop
 // over td.Quartets(v); 0: scatter form. out[u*n+w], 0 where !ShouldCalcEdge.
 int oracle_quartet_totals(oracle_ctx* c, int as_set, int literal, int nthreads, uint64_t* out) {

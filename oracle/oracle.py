@@ -45,6 +45,7 @@ def lib() -> C.CDLL:
         L.oracle_literal_emissions.restype = C.c_uint64
         L.oracle_export_quartets.argtypes = [vp, vp, vp, C.c_uint64, u64p]
         L.oracle_export_raw_counts.argtypes = [vp, vp, vp, C.c_uint64, u64p]
+        L.oracle_count_cells.argtypes = [vp, C.c_int32, vp, vp]
         L.oracle_quartet_totals.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp]
         L.oracle_edge_penalties.argtypes = [vp, vp]
         L.oracle_quartet_score.argtypes = [vp, C.c_uint64, C.c_int, C.c_int]
@@ -149,6 +150,13 @@ class Oracle:
 
     def export_raw_counts(self):
         return self._export(lib().oracle_export_raw_counts)
+
+    def count_cells(self, quads) -> np.ndarray:
+        """Raw topology counts of the given 4-taxon sets (tip indices), reference topology order."""
+        quads = np.ascontiguousarray(quads, np.int32).reshape(-1, 4)
+        out = np.zeros((len(quads), 3), np.uint32)
+        lib().oracle_count_cells(self._h, len(quads), _p(quads), _p(out))
+        return out
 
     def quartet_totals(self, as_set: bool = False, literal: bool = True) -> np.ndarray:
         out = np.zeros((self.n, self.n), np.uint64)

@@ -285,6 +285,25 @@ def test_no_gene_trees_and_reuse(gpu):
     compare_all(gpu, prob, 0, 0.0, literal=True)
 
 
+def test_query_cells_probe(gpu):
+    """camus_b200_query_cells against the exported raw table (GPU) and the oracle, polytomies and
+    missing taxa included."""
+    s = synth.make(45, 70, 12, support=True, drop_frac=0.1, nexus=True)
+    prob = Problem(s.constraint, s.genes, s.fmt, 0.7)
+    gpu.load(prob)
+    gpu.count_filter(0, 0.0)
+    rng = np.random.default_rng(3)
+    quads = np.array([rng.choice(45, 4, replace=False) for _ in range(2000)], np.int32)
+    got = gpu.query_cells(quads)
+    o = orc.Oracle().load(prob)
+    assert np.array_equal(got, o.count_cells(quads))
+    raw = as_dict(gpu.export_quartets(raw=True))
+    for q, g in zip(quads[:300], got[:300]):
+        t = sorted(int(x) for x in q)
+        base = sum(t[i] << (15 * i) for i in range(4))
+        assert [raw.get(base | (tp << 60), 0) for tp in (0b1100, 0b1010, 0b0110)] == [int(x) for x in g]
+
+
 def test_bad_inputs_are_errors_not_crashes(gpu):
     from camus_b200.cabi import CamusB200Error
     s = synth.make(10, 2, 3)
@@ -351,6 +370,52 @@ def test_mid_size_vs_oracle(gpu):
     for as_set in (False, True):
         assert np.array_equal(gpu.quartet_totals(as_set), o.quartet_totals(as_set, False))
     assert np.array_equal(gpu.edge_penalties(), o.edge_penalties())
+
+
+def test_config3_taxa_scale_properties(gpu):
+    """1000 taxa (BASELINE.json configs[2] taxon count; 96 gene trees to keep it to seconds):
+    10.7 M boxes. Exact agreement with the oracle on 4000 sampled 4-taxon sets (four-point test on
+    the host vs camus_b200_query_cells), linearity over tree subsets, order independence,
+    agreement of the complete-tree and general kernels."""
+    s, c = synth.make_config(3, n_trees=96)
+    prob = Problem(s.constraint, s.genes)
+    off, par, tax = prob.gene_node_off, prob.gene_parent, prob.gene_taxon
+    gpu.load(prob)
+    ns_all, sum_all = gpu.count_filter(0, 0.0)
+    tot_all = gpu.quartet_totals(False)
+    assert gpu.workload()["resolutions"] == 96 * (1000 * 999 * 998 * 997 // 24)
+    # sampled cells of the 1000-taxon bit-plane table against the oracle's four-point counts
+    rng = np.random.default_rng(7)
+    quads = np.array([rng.choice(1000, 4, replace=False) for _ in range(4000)], np.int32)
+    quads[:64, :] = np.arange(64)[:, None] + np.array([0, 1, 2, 3])  # neighbouring tips: diagonal boxes
+    o = orc.Oracle().load(prob)
+    assert np.array_equal(gpu.query_cells(quads), o.count_cells(quads))
+
+    def sub(lo, hi):
+        return off[lo:hi + 1] - off[lo], par[off[lo]:off[hi]], tax[off[lo]:off[hi]]
+
+    acc_sum, acc_tot = 0, np.zeros_like(tot_all)
+    for lo, hi in ((0, 40), (40, 96)):
+        gpu.clear_gene_trees()
+        gpu.add_gene_trees(*sub(lo, hi))
+        _, sm = gpu.count_filter(0, 0.0)
+        acc_sum += sm
+        acc_tot += gpu.quartet_totals(False)
+    assert acc_sum == sum_all and np.array_equal(acc_tot, tot_all)
+    # a star tree switches to the general kernel and adds nothing
+    gpu.clear_gene_trees()
+    gpu.add_gene_trees(*sub(50, 96))
+    gpu.add_gene_trees(*sub(0, 50))
+    star = Problem(s.constraint, "(" + ",".join(prob.tip_names) + ");")
+    gpu.add_gene_trees(star.gene_node_off, star.gene_parent, star.gene_taxon)
+    assert gpu.count_filter(0, 0.0) == (ns_all, sum_all)
+    assert np.array_equal(gpu.quartet_totals(False), tot_all)
+    # filtered run: every row/column masked by ShouldCalcEdge is zero, totals shrink
+    gpu.load(prob)
+    ns2, sum2 = gpu.count_filter(2, 0.5)
+    tot2 = gpu.quartet_totals(False)
+    assert 0 < ns2 < ns_all and sum2 < sum_all and (tot2 <= tot_all).all() and tot2.any()
+    assert not tot2[0].any() and not tot2[:, 0].any()
 
 
 def test_config2_full_size_properties(gpu):
