@@ -22,7 +22,7 @@ HOST_SO = os.path.join(LIB, "libcamus_host.so")
 CUDA_SO = os.path.join(LIB, "libcamus_b200.so")
 CLI_BIN = os.path.join(LIB, "camus")
 
-CXXFLAGS = ["-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-Wall", "-Wextra"]
+CXXFLAGS = ["-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-Wall", "-Wextra", "-pthread"]
 NVCCFLAGS = [
     "-std=c++17", "-O3", "-lineinfo",
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -7,8 +7,12 @@
 // internal/infer/helpers.go:9-110, internal/infer/traceback.go:6-57, internal/graphs/net.go:38-101.
 #pragma once
 #include <array>
+#include <atomic>
 #include <cmath>
+#include <condition_variable>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <type_traits>
 #include <vector>
 
@@ -108,8 +112,8 @@ inline bool four_way_best_split(const std::vector<S>* lists[4], int k, int idx[4
   int combined = 0;
   for (int i = 0; i < 4; ++i) combined += (int)lists[i]->size();
   if (combined - 4 < k) return false;
-  std::vector<std::array<int, 2>> s1, s2;
-  std::vector<S> c1, c2;
+  thread_local std::vector<std::array<int, 2>> s1, s2;  // scratch, reused across the ~1e9 calls
+  thread_local std::vector<S> c1, c2;
   solve_all_splits(*lists[0], *lists[1], k, s1, c1);
   solve_all_splits(*lists[2], *lists[3], k, s2, c2);
   int i1, i2;
@@ -168,6 +172,79 @@ struct TraceArena {
   }
 };
 
+// Minimal persistent pool for the DP's widest loop (scoreEdgesAcross over all u). The reference
+// runs its DP on one goroutine; results here are combined in the reference's iteration order, so
+// the thread count never changes a tie-break.
+class WorkerPool {
+ public:
+  explicit WorkerPool(int n) {
+    for (int i = 1; i < n; ++i) workers_.emplace_back([this] { loop(); });
+  }
+  ~WorkerPool() {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      stop_ = true;
+      ++gen_;
+    }
+    cv_.notify_all();
+    for (auto& t : workers_) t.join();
+  }
+  int size() const { return (int)workers_.size() + 1; }
+  // f(item, worker) for item in [0, n); dynamic scheduling; returns when all items are done
+  void run(int n, const std::function<void(int, int)>& f) {
+    if (workers_.empty() || n <= 1) {
+      for (int i = 0; i < n; ++i) f(i, 0);
+      return;
+    }
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      fn_ = &f;
+      n_ = n;
+      next_.store(0);
+      pending_ = (int)workers_.size();
+      ++gen_;
+    }
+    cv_.notify_all();
+    for (int i; (i = next_.fetch_add(1)) < n;) f(i, 0);
+    std::unique_lock<std::mutex> lk(mu_);
+    done_.wait(lk, [this] { return pending_ == 0; });
+    fn_ = nullptr;
+  }
+
+ private:
+  void loop() {
+    static std::atomic<int> ids{1};
+    const int me = ids.fetch_add(1);
+    uint64_t seen = 0;
+    for (;;) {
+      const std::function<void(int, int)>* f;
+      int n;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return gen_ != seen; });
+        seen = gen_;
+        if (stop_) return;
+        f = fn_;
+        n = n_;
+      }
+      if (f)
+        for (int i; (i = next_.fetch_add(1)) < n;) (*f)(i, me);
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (--pending_ == 0) done_.notify_one();
+      }
+    }
+  }
+  std::vector<std::thread> workers_;
+  std::mutex mu_;
+  std::condition_variable cv_, done_;
+  const std::function<void(int, int)>* fn_ = nullptr;
+  int n_ = 0, pending_ = 0;
+  std::atomic<int> next_{0};
+  uint64_t gen_ = 0;
+  bool stop_ = false;
+};
+
 struct DPResults {
   std::vector<std::vector<Branch>> branches;  // per k = 1..m
   std::vector<double> qsat;
@@ -181,9 +258,17 @@ struct DPResults {
 template <class Scorer>
 class DP {
   using S = typename Scorer::S;
+  // best (u -> w) of one across-scan as a plain value: score, nodes, the four split indices
+  struct Desc {
+    bool ok = false;
+    S score{};
+    int u = 0, w = 0;
+    int idx[4] = {0, 0, 0, 0};
+  };
 
  public:
-  DP(const TreeData& td, const Scorer& sc) : td_(td), sc_(sc), n_(td.n()), dp_(n_), tb_(n_) {}
+  DP(const TreeData& td, const Scorer& sc, int nthreads = 1)
+      : td_(td), sc_(sc), n_(td.n()), dp_(n_), tb_(n_), pool_(std::max(1, nthreads)) {}
 
   void run() {  // RunDP, main_dp.go:90-104 (gotree PostOrder = children in order, then node)
     std::vector<int> order;
@@ -214,9 +299,12 @@ class DP {
   std::vector<std::vector<S>> dp_;
   std::vector<std::vector<int>> tb_;
   TraceArena arena_;
+  WorkerPool pool_;
   // cycleDP of the vertex being solved (main_dp.go:30-34)
   std::vector<std::vector<S>> cs_;
   std::vector<std::vector<int>> ct_;
+  std::vector<std::pair<int, int>> items_;  // (u, other subtree) in the reference's visiting order
+  std::vector<Desc> descs_;
 
   void post_order(int v, std::vector<int>& out) const {
     std::vector<std::pair<int, int>> st{{v, 0}};
@@ -292,29 +380,42 @@ class DP {
     return best;
   }
 
-  Cand score_edges_across(int u, int sub, int prevK) {  // main_dp.go:247-287
-    Cand best;
-    subtree_pre(sub, [&](int w) {
+  // scoreEdgesAcross (main_dp.go:247-287) without side effects: the best w for this u as a plain
+  // descriptor; the trace is materialised by the caller only for a candidate it accepts.
+  Desc score_edges_across(int u, int sub, int prevK) const {
+    Desc best;
+    const int end = td_.subtree_end[sub];
+    for (int w = sub; w < end; ++w) {  // SubtreePreOrder(sub): ids are preorder
       S edge = sc_.calc(u, w);
       const std::vector<S>* lists[4] = {&cs_[w], &cs_[u], &dp_[w], &dp_[u]};
       int idx[4];
-      if (!four_way_best_split(lists, prevK, idx)) return;
+      if (!four_way_best_split(lists, prevK, idx)) continue;
       S score = edge + cs_[w][idx[0]] + cs_[u][idx[1]] + dp_[w][idx[2]] + dp_[u][idx[3]];
       if (score > best.score || !best.ok) {
-        TraceArena::Trace t;
-        t.cycle = true;
-        t.pathW = ct_[w][idx[0]];
-        t.pathU = ct_[u][idx[1]];
-        t.wDown = tb_[w][idx[2]];
-        t.uDown = tb_[u][idx[3]];
-        t.branch = {u, w};
-        best.trace = arena_.add(t);
-        best.br = t.branch;
-        best.score = score;
         best.ok = true;
+        best.score = score;
+        best.u = u;
+        best.w = w;
+        for (int i = 0; i < 4; ++i) best.idx[i] = idx[i];
       }
-    });
+    }
     return best;
+  }
+  Cand materialise(const Desc& d) {
+    Cand c;
+    if (!d.ok) return c;
+    TraceArena::Trace t;
+    t.cycle = true;
+    t.pathW = ct_[d.w][d.idx[0]];
+    t.pathU = ct_[d.u][d.idx[1]];
+    t.wDown = tb_[d.w][d.idx[2]];
+    t.uDown = tb_[d.u][d.idx[3]];
+    t.branch = {d.u, d.w};
+    c.trace = arena_.add(t);
+    c.br = t.branch;
+    c.score = d.score;
+    c.ok = true;
+    return c;
   }
 
   Cand score_add_edge_k(int v, int k) {  // main_dp.go:178-216
@@ -334,9 +435,36 @@ class DP {
       if (td_.tip(c)) continue;
       consider(score_edges_down(v, prevK));
     }
+    // SubtreePostOrder(v, ...) (helpers.go:9-24): every u of the first child's subtree in post-order
+    // against the second child's subtree, then the other way round. The per-u scans are
+    // independent, so they run on the pool; acceptance below replays the reference's order.
     int c0 = td_.children[v][0], c1 = td_.children[v][1];
-    subtree_post_helper(c0, c1, [&](int u, int other) { consider(score_edges_across(u, other, prevK)); });
-    subtree_post_helper(c1, c0, [&](int u, int other) { consider(score_edges_across(u, other, prevK)); });
+    items_.clear();
+    {
+      std::vector<int> order;
+      post_order(c0, order);
+      for (int u : order) items_.push_back({u, c1});
+      order.clear();
+      post_order(c1, order);
+      for (int u : order) items_.push_back({u, c0});
+    }
+    descs_.assign(items_.size(), Desc{});
+    const size_t work = (size_t)(td_.subtree_end[c0] - c0) * (size_t)(td_.subtree_end[c1] - c1) * (size_t)(prevK + 1);
+    auto body = [&](int i, int) { descs_[i] = score_edges_across(items_[i].first, items_[i].second, prevK); };
+    if (work > 20000 && pool_.size() > 1) {
+      pool_.run((int)items_.size(), body);
+    } else {
+      for (int i = 0; i < (int)items_.size(); ++i) body(i, 0);
+    }
+    for (const Desc& d : descs_) {
+      if (!d.ok) continue;
+      // same acceptance test as consider(), evaluated before the trace is allocated
+      int len = cycle_length(d.u, d.w, td_);
+      if (d.score > best.score || !best.ok || (d.score == best.score && len <= bestLen)) {
+        best = materialise(d);
+        bestLen = len;
+      }
+    }
     return best;
   }
 
@@ -433,7 +561,9 @@ enum class ScoreMode : int { Max = 0, Norm = 1, Sym = 2 };
 
 // infer.Infer after Preprocess + Scorer.Init (infer.go:79-95) and DP.collateResults
 // (main_dp.go:106-127): run the DP over precomputed tables.
-inline DPResults run_dp(const TreeData& td, const ScoreTables& tabs, ScoreMode mode, int n_gtrees, double alpha) {
+inline DPResults run_dp(const TreeData& td, const ScoreTables& tabs, ScoreMode mode, int n_gtrees, double alpha,
+                        int nthreads = 0) {
+  if (nthreads <= 0) nthreads = (int)std::max(1u, std::thread::hardware_concurrency());
   DPResults res;
   auto collate = [&](auto& dp) {
     const auto& rs = dp.root_scores();
@@ -449,17 +579,17 @@ inline DPResults run_dp(const TreeData& td, const ScoreTables& tabs, ScoreMode m
   };
   if (mode == ScoreMode::Max) {
     MaximizeScorer sc{&tabs};
-    DP<MaximizeScorer> dp(td, sc);
+    DP<MaximizeScorer> dp(td, sc, nthreads);
     dp.run();
     collate(dp);
   } else if (mode == ScoreMode::Norm) {
     NormalizedScorer sc{&tabs, n_gtrees};
-    DP<NormalizedScorer> dp(td, sc);
+    DP<NormalizedScorer> dp(td, sc, nthreads);
     dp.run();
     collate(dp);
   } else {
     SymDiffScorer sc{&tabs, 0, alpha};  // NGTree is never set for sym (infer.go:84-85)
-    DP<SymDiffScorer> dp(td, sc);
+    DP<SymDiffScorer> dp(td, sc, nthreads);
     dp.run();
     collate(dp);
   }

@@ -106,7 +106,10 @@ int camus_host_run_dp(const camus_host_problem* p, int mode, const uint64_t* tot
     tabs.n_survivors = n_survivors;
     tabs.sum_counts = sum_counts;
     auto r = std::make_unique<camus_host_results>();
-    r->res = run_dp(p->td, tabs, (ScoreMode)mode, n_gtrees, alpha);
+    // CAMUS_HOST_THREADS: worker threads of the DP's across-scan (0 / unset = all cores); the
+    // result does not depend on it
+    const char* e = getenv("CAMUS_HOST_THREADS");
+    r->res = run_dp(p->td, tabs, (ScoreMode)mode, n_gtrees, alpha, e ? atoi(e) : 0);
     for (auto& b : r->res.branches) r->newicks.push_back(make_network_newick(p->td, b));
     *out = r.release();
     return 0;

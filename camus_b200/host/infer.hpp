@@ -210,7 +210,7 @@ inline InferResults Infer(Tree tre, std::vector<Tree>& geneTrees, const InferOpt
   ScorerOpts resolved;
   r.tables = ScorerInit(opts.ScoreModeV, r.tree, opts.NProcs, so, &resolved, log);
   if (log) log("preprocessing finished, beginning dp algorithm");
-  r.dp = run_dp(r.tree.td, r.tables, opts.ScoreModeV, resolved.nGTrees, resolved.alpha);
+  r.dp = run_dp(r.tree.td, r.tables, opts.ScoreModeV, resolved.nGTrees, resolved.alpha, opts.NProcs);
   if (log) {
     log(std::to_string(r.dp.branches.size()) + " edges identified");
     log("beginning traceback");

@@ -215,3 +215,23 @@ def test_fast_equals_literal_on_dataset(large_problem, qmode, thr):
     for as_set in (False, True):
         assert np.array_equal(a.quartet_totals(as_set, True), b.quartet_totals(as_set, False))
     assert a.literal_emissions() > 0
+
+
+def test_dp_is_thread_count_invariant(monkeypatch):
+    """The host DP runs scoreEdgesAcross on a thread pool and replays the reference's visiting
+    order when it accepts candidates: 1 thread and all threads give identical networks."""
+    from camus_b200 import synth
+    s = synth.make(90, 50, 3)
+    prob = Problem(s.constraint, s.genes)
+    o = orc.Oracle().load(prob)
+    ns, sc = o.count_filter(2, 0.5, False)
+    tot, pen = o.quartet_totals(False, False), o.edge_penalties()
+    out = {}
+    for nt in ("1", "3", "0"):
+        monkeypatch.setenv("CAMUS_HOST_THREADS", nt)
+        out[nt] = [prob.run_dp(tot, pen if m != "max" else None, m, False, ns, sc, prob.n_trees, 0.3) for m in ("max", "norm", "sym")]
+    for nt in ("3", "0"):
+        for a, b in zip(out["1"], out[nt]):
+            assert a.newicks == b.newicks and a.branches == b.branches and a.qsat == b.qsat
+            assert [repr(x) for x in a.root_scores] == [repr(x) for x in b.root_scores]
+    assert len(out["1"][0].newicks) >= 3
