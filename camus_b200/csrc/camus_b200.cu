@@ -85,6 +85,7 @@ struct camus_b200 {
   int as_set_hint = 0;       // weight the fused pass of count_filter scores with
   int max_depth = 0;         // deepest node over all gene trees
   bool all_complete = true;  // every gene tree so far holds all taxa and is fully resolved
+  bool all_rooted = true;    // ... and none of them has a trifurcating (unrooted) root
   bool allow_half = true;      // CAMUS_B200_NO_HALF=1 forces the integer plane builder (A/B, tests)
   bool allow_complete = true;  // CAMUS_B200_NO_COMPLETE=1 forces the general kernel (A/B, tests)
 
@@ -304,6 +305,7 @@ int camus_b200_set_constraint(camus_b200* ctx, int32_t n_nodes, int32_t n_taxa, 
   ctx->h_taxon.clear();
   ctx->resolutions = 0;
   ctx->all_complete = true;
+  ctx->all_rooted = true;
   ctx->max_depth = 0;
   ctx->G = 0;
   ctx->genes_dirty = true;
@@ -320,6 +322,7 @@ int camus_b200_clear_gene_trees(camus_b200* ctx) {
   ctx->h_taxon.clear();
   ctx->resolutions = 0;
   ctx->all_complete = true;
+  ctx->all_rooted = true;
   ctx->max_depth = 0;
   ctx->G = 0;
   ctx->genes_dirty = true;
@@ -374,6 +377,7 @@ int camus_b200_add_gene_trees(camus_b200* ctx, int32_t n_trees, const int64_t* n
     for (int64_t i = 0; i < nn && complete; ++i)
       if (n_child[i] != 0 && n_child[i] != 2 && !(i == 0 && n_child[i] == 3)) complete = false;
     if (!complete) ctx->all_complete = false;
+    if (n_child[0] != 2) ctx->all_rooted = false;
   }
   int64_t base = ctx->h_node_off.back() - node_off[0];
   for (int g = 0; g < n_trees; ++g) ctx->h_node_off.push_back(node_off[g + 1] + base);
@@ -430,26 +434,35 @@ int build_planes(camus_b200* ctx, bool do_upload = true) {
                                                             ctx->d_hT.p, npad, ctx->d_nleaf.p);
     CK_LAUNCH();
     size_t dt_group = (size_t)npad * npad * kLanes;  // u16 elements
-    int gb_max = (int)std::max<size_t>(1, std::min<size_t>(ctx->G32, ((size_t)1 << 30) / (dt_group * 2)));
+    // Tree groups go through the depth table in batches of <= 256 MB (measured: running K1 of
+    // the next batch on a second stream under K1b of this one gains nothing, both are issue bound).
+    int gb_max = (int)std::max<size_t>(1, std::min<size_t>(ctx->G32, ((size_t)256 << 20) / (dt_group * 2)));
+    if (const char* e = getenv("CAMUS_B200_PREP_BATCH")) gb_max = std::max(1, std::min(ctx->G32, atoi(e)));  // tuning
     CK(ctx->d_Dt.alloc(dt_group * gb_max));
     const unsigned n_tiles = (unsigned)num_tiles(ctx->M);
     // packed fp16 compares need exact depths: depth + 1 <= 2048 (checked in add_gene_trees)
     const bool half_path = ctx->max_depth + 1 <= 2048 && ctx->allow_half;
+    // rooted triples are all resolved only under a binary root (a trifurcating root resolves
+    // every quartet but leaves the triples across its three subtrees unresolved)
+    const bool complete = ctx->all_complete && ctx->all_rooted && ctx->allow_complete;
+    uint16_t* dt = ctx->d_Dt.p;
     for (int g0 = 0; g0 < ctx->G32; g0 += gb_max) {
       int gb = std::min(gb_max, ctx->G32 - g0);
       // integer depths: 0 = absent; fp16 depths: 0xFFFF = NaN = absent
-      CK(cudaMemsetAsync(ctx->d_Dt.p, half_path ? 0xFF : 0, dt_group * gb * 2, ctx->stream));
+      CK(cudaMemsetAsync(dt, half_path ? 0xFF : 0, dt_group * gb * 2, ctx->stream));
       dim3 blk(kLanes, 8);
       dim3 g1((npad + 7) / 8, gb);
       if (half_path)
-        k_depth_table<true><<<g1, blk, 0, ctx->stream>>>(g0, G, npad, ctx->d_nleaf.p, ctx->d_lrT.p, ctx->d_hT.p, ctx->d_Dt.p);
+        k_depth_table<true><<<g1, blk, 0, ctx->stream>>>(g0, G, npad, ctx->d_nleaf.p, ctx->d_lrT.p, ctx->d_hT.p, dt);
       else
-        k_depth_table<false><<<g1, blk, 0, ctx->stream>>>(g0, G, npad, ctx->d_nleaf.p, ctx->d_lrT.p, ctx->d_hT.p, ctx->d_Dt.p);
+        k_depth_table<false><<<g1, blk, 0, ctx->stream>>>(g0, G, npad, ctx->d_nleaf.p, ctx->d_lrT.p, ctx->d_hT.p, dt);
       CK_LAUNCH();
-      if (half_path)
-        k_triple_planes_h2<<<n_tiles, 256, 0, ctx->stream>>>(g0, gb, G32, npad, ctx->d_Dt.p, ctx->d_tri.p);
+      if (half_path && complete)
+        k_triple_planes_h2<true><<<n_tiles, 256, 0, ctx->stream>>>(g0, gb, G32, G, npad, dt, ctx->d_tri.p);
+      else if (half_path)
+        k_triple_planes_h2<false><<<n_tiles, 256, 0, ctx->stream>>>(g0, gb, G32, G, npad, dt, ctx->d_tri.p);
       else
-        k_triple_planes<<<n_tiles, 256, 0, ctx->stream>>>(g0, gb, G32, npad, ctx->d_Dt.p, ctx->d_tri.p);
+        k_triple_planes<<<n_tiles, 256, 0, ctx->stream>>>(g0, gb, G32, npad, dt, ctx->d_tri.p);
       CK_LAUNCH();
     }
   }

@@ -170,31 +170,69 @@ __global__ void __launch_bounds__(256) k_triple_planes(int grp0, int n_batch, in
 
 // ---------------------------------------------------------------------------------------------
 // K1b, packed form (default): depths are fp16 (exact: the host checks depth + 1 <= 2048), absent
-// pairs are NaN. One setp.gt.f16x2 compares TWO triples (y, y+1) per lane and yields two
-// predicates; NaN makes every comparison false, so no presence test is needed. The integer
-// kernel above spends 6 ALU-pipe instructions per triple (min3, 4 ISETP, SEL) and is bound by that
-// pipe; here the compares run on the FMA pipe and a triple costs ~8 issue slots.
+// pairs are NaN, which makes every comparison false, so no presence test is needed.
+//
+// The transpose "lane = tree" -> "bit = tree" is NOT done with ballots here. A ballot costs one
+// issue slot per 32-bit output word plus the compare, the operand loads and the store of a word
+// that only one lane keeps (~2.8 slots per word in total; the kernel was bound by instruction
+// issue). Instead every thread owns one (x, y) pair of the tile and two z, walks the 32 trees of
+// the group two at a time (set.gt.u32.f16x2 yields a 0xFFFF mask per half) and ORs the masked
+// result into its own accumulator word: 1 HSET2 + 1 LOP3 per two output bits, operands fetched
+// with 128-bit shared loads (8 trees each), D(a,b) of all 32 trees held in registers across z.
+// That is ~1.1 issue slots per output word.
+//
+// Bit order inside a word: tree 2k of the group sits in bit k, tree 2k+1 in bit 16+k. The count
+// kernel only popcounts ANDs of words of the same group, so any fixed permutation is equivalent.
+//
+// Shared rows are 64 B (32 trees x fp16); the 16-byte chunk c of row r is stored at chunk
+// c ^ ((r >> 1) & 3), so that the 8 lanes of a 128-bit load phase (8 consecutive rows) cover all
+// 32 banks.
+//
+// kComplete (every gene tree complete, binary, with a binary root): off the diagonal exactly one
+// of the three planes is set per tree, so the third is ~(w0 | w1) & (trees of the group).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void cmp2_ballot(uint32_t a2, uint32_t b2, uint32_t& lo, uint32_t& hi) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p, q;\n"
-      "setp.gt.f16x2 p|q, %2, %3;\n"
-      "vote.sync.ballot.b32 %0, p, 0xffffffff;\n"
-      "vote.sync.ballot.b32 %1, q, 0xffffffff;\n"
-      "}\n"
-      : "=r"(lo), "=r"(hi)
-      : "r"(a2), "r"(b2));
+__device__ __forceinline__ uint32_t gt2_mask(uint32_t a, uint32_t b) {
+  uint32_t m;
+  asm("set.gt.u32.f16x2 %0, %1, %2;" : "=r"(m) : "r"(a), "r"(b));
+  return m;
 }
 
-__global__ void __launch_bounds__(256) k_triple_planes_h2(int grp0, int n_batch, int n_groups_total, int npad,
+__device__ __forceinline__ const uint4* plane_row_chunk(const uint16_t* rows, int r, int c) {
+  return reinterpret_cast<const uint4*>(rows + r * kLanes + ((c ^ ((r >> 1) & 3)) << 3));
+}
+
+template <bool kDerive>
+__device__ __forceinline__ void triple_words(const uint4 (&ab)[4], const uint16_t* s_ac, int r_ac, const uint16_t* s_bc,
+                                             int r_bc, uint32_t vm, uint32_t (&w)[3]) {
+  w[0] = w[1] = w[2] = 0;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const uint4 ac = *plane_row_chunk(s_ac, r_ac, c);
+    const uint32_t abv[4] = {ab[c].x, ab[c].y, ab[c].z, ab[c].w};
+    const uint32_t acv[4] = {ac.x, ac.y, ac.z, ac.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t bit = 0x00010001u << (c * 4 + j);
+      w[0] |= gt2_mask(abv[j], acv[j]) & bit;  // ab|c : D(a,b) > D(a,c)
+      w[1] |= gt2_mask(acv[j], abv[j]) & bit;  // ac|b : D(a,c) > D(a,b)
+    }
+    if (!kDerive) {
+      const uint4 bc = *plane_row_chunk(s_bc, r_bc, c);
+      const uint32_t bcv[4] = {bc.x, bc.y, bc.z, bc.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) w[2] |= gt2_mask(bcv[j], abv[j]) & (0x00010001u << (c * 4 + j));  // bc|a
+    }
+  }
+  if (kDerive) w[2] = ~(w[0] | w[1]) & vm;
+}
+
+template <bool kComplete>
+__global__ void __launch_bounds__(256, 4) k_triple_planes_h2(int grp0, int n_batch, int n_groups_total, int n_trees, int npad,
                                                           const uint16_t* __restrict__ Dt, uint32_t* __restrict__ Tri) {
-  __shared__ __align__(16) uint16_t s_d[3][64][kLanes];  // [ab | ac | bc][i*8+j][lane], fp16 bits, NaN = absent
-  // Tile image: the 3 planes are padded to 516 words so that lanes 0..2 (one plane each) hit
-  // different banks, and the dummy row the other 29 lanes write to sits 16 banks away.
-  __shared__ __align__(128) uint32_t s_img[3 * kPlanePad + 4 + 8 * 64];
-  uint32_t* const s_out = s_img;
-  uint32_t* const s_scr = s_img + 3 * kPlanePad + 4;
+  // fp16 bits, NaN = absent. Rows: ab[x*8+y], ac[x*8+z], bc[z*8+y] (the index that varies across
+  // the lanes of a load phase is the low one).
+  __shared__ __align__(16) uint16_t s_d[3][64 * kLanes];
+  __shared__ __align__(16) uint32_t s_img[kTileWords];
   __shared__ uint32_t s_seg[3];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint64_t tile = blockIdx.x;
@@ -210,51 +248,55 @@ __global__ void __launch_bounds__(256) k_triple_planes_h2(int grp0, int n_batch,
   }
   __syncthreads();
   const uint32_t a0 = s_seg[0] * 8, b0 = s_seg[1] * 8, c0 = s_seg[2] * 8;
-  const int z = warp;
-  uint32_t* out_lane = lane < 3 ? s_out + lane * kPlanePad + z * 64 : s_scr + warp * 64;
-  const uint32_t m0 = lane == 0 ? 0xFFFFFFFFu : 0u, m01 = lane <= 1 ? 0xFFFFFFFFu : 0u;
+  const bool derive = kComplete && s_seg[0] < s_seg[1] && s_seg[1] < s_seg[2];  // every (x, y, z) is in rank order
+  const int y = tid & 7, x = (tid >> 3) & 7, zh = tid >> 6;
+
+  // staging: per group 3 x 64 rows; a warp copies 8 rows (512 contiguous bytes) per 128-bit access
+  const uint16_t* src[3];
+  uint16_t* dst[3];
+#pragma unroll
+  for (int it = 0; it < 3; ++it) {
+    const int seg = it * 8 + warp;  // 0..23
+    const int which = seg >> 3, i = seg & 7, j = lane >> 2, c = lane & 3;
+    const uint32_t lo = (which == 2 ? b0 : a0) + i;
+    const uint32_t hi = (which == 0 ? b0 : c0) + j;
+    src[it] = lo < hi ? Dt + ((size_t)lo * npad + hi) * kLanes + c * 8 : nullptr;  // null: wrong rank order -> NaN
+    const int r = which == 2 ? j * 8 + i : i * 8 + j;
+    dst[it] = &s_d[which][r * kLanes + ((c ^ ((r >> 1) & 3)) << 3)];
+  }
+  const size_t group_stride = (size_t)npad * npad * kLanes;
+  const uint4 nan4 = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+  uint4 pre[3];
+#pragma unroll
+  for (int it = 0; it < 3; ++it) pre[it] = src[it] ? __ldg(reinterpret_cast<const uint4*>(src[it])) : nan4;
+
   for (int gb = 0; gb < n_batch; ++gb) {
-    if (gb) __syncthreads();
-    const uint16_t* D = Dt + (size_t)gb * npad * npad * kLanes;
-    // stage the 3 x 64 pair rows with warp-wide 128-bit copies (8 rows = 512 contiguous bytes)
 #pragma unroll
-    for (int it = 0; it < 3; ++it) {
-      const int seg = it * 8 + warp;  // 0..23
-      const int which = seg >> 3, i = seg & 7, j = lane >> 2;
-      const uint32_t x = (which == 2 ? b0 : a0) + i;
-      const uint32_t y0 = which == 0 ? b0 : c0;
-      uint4 v = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);  // NaN: wrong rank order
-      if (x < y0 + j) v = *reinterpret_cast<const uint4*>(D + ((size_t)x * npad + y0 + j) * kLanes + (lane & 3) * 8);
-      *reinterpret_cast<uint4*>(&s_d[which][i * 8 + j][(lane & 3) * 8]) = v;
+    for (int it = 0; it < 3; ++it) *reinterpret_cast<uint4*>(dst[it]) = pre[it];
+    __syncthreads();
+    if (gb + 1 < n_batch) {  // next group's rows travel while this one is computed
+#pragma unroll
+      for (int it = 0; it < 3; ++it)
+        pre[it] = src[it] ? __ldg(reinterpret_cast<const uint4*>(src[it] + (size_t)(gb + 1) * group_stride)) : nan4;
+    }
+    const int left = n_trees - (grp0 + gb) * kLanes;  // trees in this group
+    const int n_even = left >= 32 ? 16 : (left > 0 ? (left + 1) >> 1 : 0), n_odd = left >= 32 ? 16 : (left > 0 ? left >> 1 : 0);
+    const uint32_t vm = ((1u << n_even) - 1u) | (((1u << n_odd) - 1u) << 16);
+    uint4 ab[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) ab[c] = *plane_row_chunk(s_d[0], x * 8 + y, c);
+#pragma unroll
+    for (int zz = 0; zz < 2; ++zz) {
+      const int z = 2 * zh + zz;
+      uint32_t w[3];
+      if (derive) triple_words<true>(ab, s_d[1], x * 8 + z, s_d[2], z * 8 + y, vm, w);
+      else triple_words<false>(ab, s_d[1], x * 8 + z, s_d[2], z * 8 + y, vm, w);
+#pragma unroll
+      for (int p = 0; p < 3; ++p) s_img[tile_word(p, x, y, z)] = w[p];
     }
     __syncthreads();
-    uint32_t ac2[8];
-#pragma unroll
-    for (int x = 0; x < 8; ++x) {
-      const uint32_t h = s_d[1][x * 8 + z][lane];
-      ac2[x] = h | (h << 16);
-    }
-#pragma unroll
-    for (int yp = 0; yp < 4; ++yp) {
-      const uint32_t bc2 = (uint32_t)s_d[2][(2 * yp) * 8 + z][lane] | ((uint32_t)s_d[2][(2 * yp + 1) * 8 + z][lane] << 16);
-#pragma unroll
-      for (int x = 0; x < 8; ++x) {
-        const uint32_t ab2 = (uint32_t)s_d[0][x * 8 + 2 * yp][lane] | ((uint32_t)s_d[0][x * 8 + 2 * yp + 1][lane] << 16);
-        uint32_t w0a, w0b, w1a, w1b, w2a, w2b;
-        cmp2_ballot(ab2, ac2[x], w0a, w0b);  // ab|c : D(a,b) > D(a,c)
-        cmp2_ballot(ac2[x], ab2, w1a, w1b);  // ac|b : D(a,c) > D(a,b)
-        cmp2_ballot(bc2, ab2, w2a, w2b);     // bc|a : D(b,c) > D(a,b)
-        const uint32_t sa_ = (((w0a & m0) | (w1a & ~m0)) & m01) | (w2a & ~m01);
-        const uint32_t sb_ = (((w0b & m0) | (w1b & ~m0)) & m01) | (w2b & ~m01);
-        // y = 2*yp and 2*yp+1: tile_word offsets ((y>>1)*4 + (x>>1))*4 + (y&1)*2 + (x&1)
-        out_lane[(yp * 4 + (x >> 1)) * 4 + (x & 1)] = sa_;
-        out_lane[(yp * 4 + (x >> 1)) * 4 + 2 + (x & 1)] = sb_;
-      }
-    }
-    __syncthreads();
-    uint4* dst = reinterpret_cast<uint4*>(Tri + (tile * n_groups_total + (grp0 + gb)) * kTileWords);
-    for (int i = tid; i < kTileWords / 4; i += 256)
-      dst[i] = *reinterpret_cast<const uint4*>(s_out + (i >> 7) * kPlanePad + (i & 127) * 4);
+    uint4* out = reinterpret_cast<uint4*>(Tri + (tile * n_groups_total + (grp0 + gb)) * kTileWords);
+    for (int i = tid; i < kTileWords / 4; i += 256) out[i] = reinterpret_cast<const uint4*>(s_img)[i];
   }
 }
 

@@ -81,7 +81,7 @@ def test_fused_and_table_pipelines_agree(gpu, qmode, thr, monkeypatch):
 
 
 def test_integer_and_fp16_plane_builders_agree(gpu, monkeypatch):
-    """k_triple_planes_h2 (packed fp16 compares, NaN = absent) is the default; trees deeper than
+    """k_triple_planes_h2 (packed fp16 mask compares, NaN = absent) is the default; trees deeper than
     2047 fall back to the integer kernel, forced here with CAMUS_B200_NO_HALF=1."""
     from camus_b200.cabi import CamusB200
     monkeypatch.setenv("CAMUS_B200_NO_HALF", "1")
@@ -98,6 +98,24 @@ def test_integer_and_fp16_plane_builders_agree(gpu, monkeypatch):
                 assert np.array_equal(a, b)
             assert np.array_equal(ctx.quartet_totals(False), o.quartet_totals(False, False))
     integer.close()
+
+
+def _unroot(nwk: str) -> str:
+    """((X,Y),Z); -> (X,Y,Z);  (plain newick without lengths; a leaf first child is rotated away)"""
+    body = nwk.strip().rstrip(";")[1:-1]
+    depth, cut = 0, -1
+    for i, ch in enumerate(body):
+        depth += ch == "("
+        depth -= ch == ")"
+        if ch == "," and depth == 0:
+            cut = i
+            break
+    first, rest = body[:cut], body[cut + 1:]
+    if not first.startswith("("):
+        first, rest = rest, first
+    if not first.startswith("("):
+        return nwk
+    return "(" + first[1:-1] + "," + rest + ");"
 
 
 def test_complete_tree_specialisation(gpu, monkeypatch):
@@ -119,6 +137,20 @@ def test_complete_tree_specialisation(gpu, monkeypatch):
             assert np.array_equal(ctx.quartet_totals(False), o.quartet_totals(False, False))
             for a, b in zip(ctx.export_quartets(raw=True), o.export_raw_counts()):
                 assert np.array_equal(a, b)
+    # unrooted input (trifurcating root): every quartet is still resolved (count kernel stays
+    # specialised) but the rooted triples across the three root subtrees are not (plane builder
+    # must not derive the third plane)
+    lines = [_unroot(l) for l in s.genes.strip().split("\n")]
+    assert sum(l.count("(") == 41 - 2 for l in lines) > 60  # really trifurcating now
+    prob3 = Problem(s.constraint, "\n".join(lines[:40]) + "\n")
+    o3 = orc.Oracle().load(prob3)
+    want = o3.count_filter(2, 0.4, False)
+    for ctx in (gpu, general):
+        ctx.load(prob3)
+        assert ctx.count_filter(2, 0.4) == want
+        assert np.array_equal(ctx.quartet_totals(False), o3.quartet_totals(False, False))
+        for x, y in zip(ctx.export_quartets(raw=True), o3.export_raw_counts()):
+            assert np.array_equal(x, y)
     # add one star tree and one tree with a missing taxon: the specialisation must switch itself off
     labs = prob.tip_names
     extra = "(" + ",".join(labs) + ");\n(" + ",".join(labs[:-1]) + ");\n"
