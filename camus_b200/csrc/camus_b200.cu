@@ -57,6 +57,7 @@ struct camus_b200 {
   std::vector<int32_t> int_of_ref, rank_of_tip_h;
   DevBuf<int32_t> d_parent, d_depth, d_sz, d_rc, d_nleaves, d_firstleaf, d_leafnode, d_tip_of_rank, d_ref_id, d_rank_of_tip;
   DevBuf<uint32_t> d_lcaD;
+  DevBuf<uint8_t> d_seg_uniform;
   ConstraintDev ct{};
 
   // ---- gene trees (host staging until the next count) ----
@@ -88,6 +89,7 @@ struct camus_b200 {
   bool all_rooted = true;    // ... and none of them has a trifurcating (unrooted) root
   bool allow_half = true;      // CAMUS_B200_NO_HALF=1 forces the integer plane builder (A/B, tests)
   bool allow_complete = true;  // CAMUS_B200_NO_COMPLETE=1 forces the general kernel (A/B, tests)
+  bool allow_regular = true;   // CAMUS_B200_NO_REGULAR=1 sends every box through the survivor queue (A/B, tests)
 
   float ms[CAMUS_B200_T_N] = {0};
   uint64_t launches = 0;
@@ -189,6 +191,7 @@ int camus_b200_create(camus_b200** out, int n_gpus, const int* devices) {
   cudaFuncSetAttribute(k_count<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CountCfg<true>::kSmemBytes);
   cudaFuncSetAttribute(k_count<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CountCfg<true>::kSmemBytes);
   if (const char* e = getenv("CAMUS_B200_NO_COMPLETE")) ctx->allow_complete = !(e[0] == '1');
+  if (const char* e = getenv("CAMUS_B200_NO_REGULAR")) ctx->allow_regular = !(e[0] == '1');
   if (const char* e = getenv("CAMUS_B200_NO_HALF")) ctx->allow_half = !(e[0] == '1');
   if (const char* e = getenv("CAMUS_B200_UNFUSED")) ctx->use_fused = !(e[0] == '1');
   *out = ctx;
@@ -293,10 +296,14 @@ int camus_b200_set_constraint(camus_b200* ctx, int32_t n_nodes, int32_t n_taxa, 
       upload(ctx, ctx->d_ref_id, ref_of_int.data(), n) || upload(ctx, ctx->d_rank_of_tip, ctx->rank_of_tip_h.data(), N))
     return CAMUS_B200_ERR_CUDA;
   CK(ctx->d_lcaD.alloc((size_t)N * N));
+  CK(ctx->d_seg_uniform.alloc((size_t)ctx->M * ctx->M));
   ctx->ct = ConstraintDev{n, N, ctx->d_parent.p, ctx->d_depth.p, ctx->d_sz.p, ctx->d_rc.p, ctx->d_nleaves.p,
-                          ctx->d_firstleaf.p, ctx->d_leafnode.p, ctx->d_tip_of_rank.p, ctx->d_ref_id.p, ctx->d_lcaD.p};
+                          ctx->d_firstleaf.p, ctx->d_leafnode.p, ctx->d_tip_of_rank.p, ctx->d_ref_id.p, ctx->d_lcaD.p,
+                          ctx->d_seg_uniform.p, ctx->M};
   dim3 grid((N + 127) / 128, N);
   k_constraint_lca<<<grid, 128, 0, ctx->stream>>>(N, ctx->d_leafnode.p, ctx->d_parent.p, ctx->d_sz.p, ctx->d_depth.p, ctx->d_lcaD.p);
+  CK_LAUNCH();
+  k_segment_pairs<<<(ctx->M * ctx->M + 7) / 8, 256, 0, ctx->stream>>>(N, ctx->M, ctx->d_lcaD.p, ctx->d_seg_uniform.p);
   CK_LAUNCH();
   CK(cudaStreamSynchronize(ctx->stream));
   // taxon numbering changed: gene trees given for an earlier constraint are dropped
@@ -509,7 +516,7 @@ int run_fused(camus_b200* ctx, int qmode, double threshold, int as_set, uint64_t
     uint64_t nbx = std::min(max_grid, mine - b0);
     CountParams prm{ctx->d_tri.p, std::max(ctx->G32, 1), BoxMap{b0, ctx->chunk, (uint32_t)ctx->rank, (uint32_t)ctx->world}, nullptr, ctx->G};
     static const int dbg = getenv("CAMUS_B200_DEBUG") ? atoi(getenv("CAMUS_B200_DEBUG")) : 0;
-    FusedParams fz{qmode, threshold, ctx->d_thr_tab.p, as_set, ctx->d_Z.p, ctx->d_totals.p, rep, (unsigned long long)zn, dbg};
+    FusedParams fz{qmode, threshold, ctx->d_thr_tab.p, as_set, ctx->d_Z.p, ctx->d_totals.p, rep, (unsigned long long)zn, ctx->allow_regular ? 1 : 0, dbg};
     if (use_complete(ctx))
       k_count<true, true><<<(unsigned)nbx, kCountThreads, CountCfg<true>::kSmemBytes, ctx->stream>>>(prm, fz, ctx->ct);
     else

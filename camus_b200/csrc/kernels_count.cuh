@@ -66,6 +66,7 @@ struct FusedParams {
   unsigned long long* totals;  // [0] n_survivors, [1] sum_counts
   int z_rep;                   // number of privatised copies of Z (hot-address spreading), stride z_stride
   unsigned long long z_stride;
+  int regular;                 // 1 = regular boxes take the marginal-sum epilogue (CAMUS_B200_NO_REGULAR=1 clears it)
   int debug;                   // profiling only (CAMUS_B200_DEBUG): 1 = skip the score scatter, 2 = skip the whole epilogue
 };
 
@@ -88,7 +89,7 @@ k_count(CountParams prm, FusedParams fz, ConstraintDev ct) {
   using Cfg = CountCfg<kComplete>;
   extern __shared__ __align__(128) uint32_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kCountStages * Cfg::kStageWords);
-  __shared__ uint32_t s_seg[4];
+  __shared__ uint32_t s_seg[5];  // four segments, [4] = regular box
 
   const int tid = threadIdx.x;
   const int ta = tid & 3, tb = (tid >> 2) & 3, tc = (tid >> 4) & 3, td = tid >> 6;
@@ -100,6 +101,11 @@ k_count(CountParams prm, FusedParams fz, ConstraintDev ct) {
     s_seg[1] = sb;
     s_seg[2] = sc;
     s_seg[3] = sd;
+    if constexpr (kFused) {
+      const uint8_t* U = ct.seg_uniform;
+      const uint32_t S = (uint32_t)ct.n_seg;
+      s_seg[4] = fz.regular && sa < sb && sb < sc && sc < sd && U[sa * S + sb] && U[sb * S + sc] && U[sc * S + sd];
+    }
     for (int s = 0; s < kCountStages; ++s) mbar_init(&bars[s], 1);
     fence_mbar_init();
   }
@@ -230,9 +236,18 @@ k_count(CountParams prm, FusedParams fz, ConstraintDev ct) {
     // Phase 1 (per thread, its 16 cells): filter + constraint removal; survivors are COMPACTED into
     // a queue in the shared memory of the now idle tile ring. Phase 2: the queue is scored with
     // all lanes busy. Survivors are sparse under -q 1/2 (a few % of the cells).
+    //
+    // Regular boxes (the three consecutive segment pairs have one LCA each, ConstraintDev::
+    // seg_uniform; half of all boxes of a random 1000-taxon constraint) skip the queue: junction,
+    // m-node and component of a (bottom taxon, topology) are box constants, so the box's whole
+    // contribution is 4 axes x 2 topologies x 8 marginal sums of the surviving counts (+ their
+    // totals, subtracted at the m-nodes): 72 reductions per box instead of 8 per survivor.
     __shared__ unsigned long long s_red[2][kCountThreads / 32];
     __shared__ uint32_t s_qn;
+    __shared__ uint32_t s_marg[4][2][8];  // [bottom axis a..d][topology slot][coordinate]
     if (tid == 0) s_qn = 0;
+    if (tid < 64) (&s_marg[0][0][0])[tid] = 0;
+    const bool regular = s_seg[4] != 0;
     __syncthreads();  // also: every issued bulk copy has been waited for, the ring can be reused
     static_assert(kCountStages * Cfg::kStageBytes >= kBoxCells * 16, "survivor queue must fit the ring");
     uint4* queue = reinterpret_cast<uint4*>(smem);  // up to kBoxCells entries (64 KB)
@@ -240,6 +255,58 @@ k_count(CountParams prm, FusedParams fz, ConstraintDev ct) {
     const uint32_t a0 = sa * 8 + 2 * ta, b0 = sb * 8 + 2 * tb, c0 = sc * 8 + 2 * tc, d0 = sd * 8 + 2 * td;
     const int lane = tid & 31;
     unsigned long long ns = 0, sum = 0;
+    // packed LCAs of the box's first taxa: THE LCAs of a regular box
+    const uint32_t bg1 = ct.lcaD[(size_t)(sa * 8) * N + sb * 8], bg2 = ct.lcaD[(size_t)(sb * 8) * N + sc * 8],
+                   bg3 = ct.lcaD[(size_t)(sc * 8) * N + sd * 8];
+    const bool kill0 = constraint_topology(bg1, bg2, bg3) == 0;  // the constraint displays ab|cd here (else ad|bc)
+    if (regular) {
+      // slot 0 = ac|bd, slot 1 = the one of ab|cd / ad|bc the constraint does not display
+      uint32_t ma[2][2] = {{0, 0}, {0, 0}}, mb[2][2] = {{0, 0}, {0, 0}}, mc[2][2] = {{0, 0}, {0, 0}}, md[2][2] = {{0, 0}, {0, 0}};
+#pragma unroll
+      for (int ll = 0; ll < 2; ++ll)
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const uint32_t x[4] = {a0 + i, b0 + j, c0 + kk, d0 + ll};
+              uint32_t c[3];
+              counts_of(((ll * 2 + kk) * 2 + j) * 2 + i, c);
+              if (fz.debug == 2) {
+                sum += c[0] + c[1] + c[2];
+                continue;
+              }
+              if (fz.qmode != 0 && (c[0] | c[1] | c[2])) filter_cell(c, x, fz.qmode, fz.threshold, fz.thr_tab, ct.tip_of_rank);
+              uint32_t w0 = c[1], w1 = kill0 ? c[2] : c[0];
+              ns += (w0 != 0) + (w1 != 0);
+              sum += (unsigned long long)w0 + w1;
+              if (fz.as_set) {
+                w0 = w0 != 0;
+                w1 = w1 != 0;
+              }
+              ma[0][i] += w0; mb[0][j] += w0; mc[0][kk] += w0; md[0][ll] += w0;
+              ma[1][i] += w1; mb[1][j] += w1; mc[1][kk] += w1; md[1][ll] += w1;
+            }
+      if (fz.debug == 0) {
+        // warp sums over the lanes that share the coordinate, one shared atomic per (warp, sum)
+        const uint32_t mask_a = 0x11111111u << ta, mask_b = 0x000F000Fu << (4 * tb);
+        const uint32_t mask_c = lane < 16 ? 0x0000FFFFu : 0xFFFF0000u;
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl)
+#pragma unroll
+          for (int par = 0; par < 2; ++par) {
+            uint32_t v = __reduce_add_sync(mask_a, ma[sl][par]);
+            if (lane < 4 && v) atomicAdd(&s_marg[0][sl][2 * ta + par], v);
+            v = __reduce_add_sync(mask_b, mb[sl][par]);
+            if (lane == 4 * tb && v) atomicAdd(&s_marg[1][sl][2 * tb + par], v);
+            v = __reduce_add_sync(mask_c, mc[sl][par]);
+            if ((lane & 15) == 0 && v) atomicAdd(&s_marg[2][sl][2 * tc + par], v);
+            v = __reduce_add_sync(0xFFFFFFFFu, md[sl][par]);
+            if (lane == 0 && v) atomicAdd(&s_marg[3][sl][2 * td + par], v);
+          }
+      }
+    } else {
 #pragma unroll
     for (int ll = 0; ll < 2; ++ll)
 #pragma unroll
@@ -282,6 +349,7 @@ k_count(CountParams prm, FusedParams fz, ConstraintDev ct) {
               }
             }
           }
+    }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
       ns += __shfl_xor_sync(0xFFFFFFFFu, ns, off);
@@ -302,7 +370,42 @@ k_count(CountParams prm, FusedParams fz, ConstraintDev ct) {
       if (t0) red_add_u64(&fz.totals[0], t0);
       if (t1) red_add_u64(&fz.totals[1], t1);
     }
-    if (fz.debug != 1) {
+    if (regular) {
+      if (fz.debug == 0 && tid < 72) {
+        // threads 0..63: one (axis, slot, coordinate) sum, added at the leaf; 64..71: the (axis,
+        // slot) total, subtracted at the m-node. Junction / m / component as in score_cell.
+        const int be = tid < 64 ? tid >> 4 : (tid - 64) >> 1;
+        const int sl = tid < 64 ? (tid >> 3) & 1 : tid & 1;
+        const int t = sl == 0 ? 1 : (kill0 ? 2 : 0);
+        uint32_t h1, h2, m;
+        if (be == 0) {
+          h1 = bg2; h2 = bg3; m = bg1;
+        } else if (be == 1) {
+          h1 = min(bg1, bg2); h2 = bg3; m = max(bg1, bg2);
+        } else if (be == 2) {
+          h1 = bg1; h2 = min(bg2, bg3); m = max(bg2, bg3);
+        } else {
+          h1 = bg1; h2 = bg2; m = bg3;
+        }
+        const bool first = h1 > h2;
+        const uint32_t J = (first ? h1 : h2) & 0xFFFFu;
+        const int p = partner_of(t, be);
+        const int pos = p - (p > be ? 1 : 0);
+        const int comp = first ? pos : (pos + 2) % 3;
+        long long v = 0;
+        size_t row;
+        if (tid < 64) {
+          v = s_marg[be][sl][tid & 7];
+          row = (size_t)ct.leafnode[s_seg[be] * 8 + (tid & 7)];
+        } else {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v -= s_marg[be][sl][k];
+          row = m & 0xFFFFu;
+        }
+        if (v) red_add_u64(fz.Z + (size_t)(blockIdx.x % (unsigned)fz.z_rep) * fz.z_stride + (row * (size_t)ct.n + J) * 3 + comp,
+                           (unsigned long long)v);
+      }
+    } else if (fz.debug != 1) {
       const uint32_t qn = s_qn;
       GlobalAcc acc{fz.Z + (size_t)(blockIdx.x % (unsigned)fz.z_rep) * fz.z_stride};
 #pragma unroll 1

@@ -22,6 +22,8 @@ struct ConstraintDev {
   const int32_t* tip_of_rank; // [n_taxa] gotree tip index of that leaf
   const int32_t* ref_id;      // [n]
   const uint32_t* lcaD;       // [n_taxa][n_taxa] (depth << 16 | node) of the LCA of two leaves
+  const uint8_t* seg_uniform; // [n_seg][n_seg] 1 if every leaf pair of the two 8-leaf segments has the same LCA
+  int n_seg;
 };
 
 struct CellCoords {
@@ -60,6 +62,27 @@ __device__ __forceinline__ int constraint_topology(uint32_t g1, uint32_t g2, uin
 
 // partner of taxon position i (0..3 = a,b,c,d) in topology t (0 ab|cd, 1 ac|bd, 2 ad|bc)
 __device__ __forceinline__ int partner_of(int t, int i) { return t == 0 ? (i ^ 1) : (t == 1 ? (i ^ 2) : (3 - i)); }
+
+// seg_uniform[A][B] (A < B): all 64 leaf pairs of the segments A and B (8 consecutive DFS ranks
+// each) have the same LCA, and both segments are full. A box whose three consecutive segment pairs
+// are uniform ("regular box") has one junction / one m-node / one component per (bottom taxon,
+// topology), which the fused count kernel exploits. One warp per segment pair.
+__global__ void k_segment_pairs(int n_taxa, int n_seg, const uint32_t* __restrict__ lcaD, uint8_t* __restrict__ out) {
+  const int pair = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (pair >= n_seg * n_seg) return;
+  const int A = pair / n_seg, B = pair % n_seg;
+  bool ok = A < B && B * 8 + 8 <= n_taxa;
+  if (ok) {
+    const uint32_t ref = lcaD[(size_t)(A * 8) * n_taxa + B * 8];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int e = lane + 32 * k;
+      ok = ok && lcaD[(size_t)(A * 8 + (e >> 3)) * n_taxa + B * 8 + (e & 7)] == ref;
+    }
+  }
+  ok = __all_sync(0xFFFFFFFFu, ok);
+  if (lane == 0) out[pair] = ok ? 1 : 0;
+}
 
 // prep.filterQuartets + Threshold.Keep for one 4-set (internal/prep/quartetfilter.go:67-96).
 // c[] = counts of ab|cd, ac|bd, ad|bc (DFS order); ti[] = gotree tip indices of a,b,c,d.

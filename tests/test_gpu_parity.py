@@ -100,6 +100,41 @@ def test_integer_and_fp16_plane_builders_agree(gpu, monkeypatch):
     integer.close()
 
 
+def test_regular_box_epilogue(gpu, monkeypatch):
+    """Boxes whose three consecutive segment pairs have one LCA each are scored from marginal sums
+    (kernels_count.cuh, "regular boxes"); CAMUS_B200_NO_REGULAR=1 sends every box through the
+    survivor queue. Both against the oracle, on a balanced constraint (every strict box regular),
+    a random one and a caterpillar (no regular box)."""
+    from camus_b200.cabi import CamusB200
+    monkeypatch.setenv("CAMUS_B200_NO_REGULAR", "1")
+    queue_only = CamusB200(0)
+    monkeypatch.delenv("CAMUS_B200_NO_REGULAR")
+
+    def balanced(lo, hi):
+        if hi - lo == 1:
+            return "t%04d" % lo
+        mid = (lo + hi) // 2
+        return "(" + balanced(lo, mid) + "," + balanced(mid, hi) + ")"
+
+    s = synth.make(64, 70, 21, drop_frac=0.05)
+    cat = "t0000"
+    for i in range(1, 64):
+        cat = "(" + cat + ",t%04d)" % i
+    for constraint in (balanced(0, 64) + ";", s.constraint, cat + ";"):
+        prob = Problem(constraint, s.genes)
+        o = orc.Oracle().load(prob)
+        for qmode, thr in ((0, 0.0), (1, 0.3), (2, 0.5)):
+            want = o.count_filter(qmode, thr, False)
+            for ctx in (gpu, queue_only):
+                ctx.load(prob)
+                for as_set in (False, True):
+                    ctx.set_score_hint(as_set)
+                    assert ctx.count_filter(qmode, thr) == want
+                    assert np.array_equal(ctx.quartet_totals(as_set), o.quartet_totals(as_set, False))
+    gpu.set_score_hint(False)
+    queue_only.close()
+
+
 def _unroot(nwk: str) -> str:
     """((X,Y),Z); -> (X,Y,Z);  (plain newick without lengths; a leaf first child is rotated away)"""
     body = nwk.strip().rstrip(";")[1:-1]
