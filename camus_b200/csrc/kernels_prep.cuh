@@ -197,6 +197,20 @@ __device__ __forceinline__ uint32_t gt2_mask(uint32_t a, uint32_t b) {
   return m;
 }
 
+// The same comparison on the FMA pipe: depths are integers, so sat(a - b) is 1.0 where a > b and
+// 0.0 elsewhere (.sat also flushes NaN to +0). HSET2 and LOP3 both issue on the ALU pipe, which
+// bound the kernel (ncu: alu 70 %, fma 9 %); half of the 32 trees take this route instead.
+__device__ __forceinline__ uint32_t gt2_unit(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("fma.rn.sat.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(b), "r"(0xBC00BC00u), "r"(a));  // b * -1 + a
+  return d;
+}
+__device__ __forceinline__ uint32_t fma2(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+
 __device__ __forceinline__ const uint4* plane_row_chunk(const uint16_t* rows, int r, int c) {
   return reinterpret_cast<const uint4*>(rows + r * kLanes + ((c ^ ((r >> 1) & 3)) << 3));
 }
@@ -205,24 +219,36 @@ template <bool kDerive>
 __device__ __forceinline__ void triple_words(const uint4 (&ab)[4], const uint16_t* s_ac, int r_ac, const uint16_t* s_bc,
                                              int r_bc, uint32_t vm, uint32_t (&w)[3]) {
   w[0] = w[1] = w[2] = 0;
+  // trees 16..31 of the group: fp16 accumulators 1024 + sum of 2^k, exact below 2048; the low 8
+  // mantissa bits of each half are the 8 result bits
+  uint32_t f[3] = {0x64006400u, 0x64006400u, 0x64006400u};
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     const uint4 ac = *plane_row_chunk(s_ac, r_ac, c);
     const uint32_t abv[4] = {ab[c].x, ab[c].y, ab[c].z, ab[c].w};
     const uint32_t acv[4] = {ac.x, ac.y, ac.z, ac.w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const uint32_t bit = 0x00010001u << (c * 4 + j);
-      w[0] |= gt2_mask(abv[j], acv[j]) & bit;  // ab|c : D(a,b) > D(a,c)
-      w[1] |= gt2_mask(acv[j], abv[j]) & bit;  // ac|b : D(a,c) > D(a,b)
-    }
+    uint32_t bcv[4] = {0, 0, 0, 0};
     if (!kDerive) {
       const uint4 bc = *plane_row_chunk(s_bc, r_bc, c);
-      const uint32_t bcv[4] = {bc.x, bc.y, bc.z, bc.w};
+      bcv[0] = bc.x; bcv[1] = bc.y; bcv[2] = bc.z; bcv[3] = bc.w;
+    }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) w[2] |= gt2_mask(bcv[j], abv[j]) & (0x00010001u << (c * 4 + j));  // bc|a
+    for (int j = 0; j < 4; ++j) {
+      if (c < 2) {  // ALU pipe: mask compare + masked OR
+        const uint32_t bit = 0x00010001u << (c * 4 + j);
+        w[0] |= gt2_mask(abv[j], acv[j]) & bit;  // ab|c : D(a,b) > D(a,c)
+        w[1] |= gt2_mask(acv[j], abv[j]) & bit;  // ac|b : D(a,c) > D(a,b)
+        if (!kDerive) w[2] |= gt2_mask(bcv[j], abv[j]) & bit;  // bc|a : D(b,c) > D(a,b)
+      } else {  // FMA pipe: unit compare + weighted accumulate
+        const uint32_t wt = 0x3C003C00u + 0x04000400u * ((c - 2) * 4 + j);  // 2^k in both halves
+        f[0] = fma2(gt2_unit(abv[j], acv[j]), wt, f[0]);
+        f[1] = fma2(gt2_unit(acv[j], abv[j]), wt, f[1]);
+        if (!kDerive) f[2] = fma2(gt2_unit(bcv[j], abv[j]), wt, f[2]);
+      }
     }
   }
+#pragma unroll
+  for (int p = 0; p < (kDerive ? 2 : 3); ++p) w[p] |= (f[p] & 0x00FF00FFu) << 8;
   if (kDerive) w[2] = ~(w[0] | w[1]) & vm;
 }
 

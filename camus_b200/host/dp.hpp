@@ -10,6 +10,7 @@
 #include <atomic>
 #include <cmath>
 #include <condition_variable>
+#include <cstdlib>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -245,6 +246,18 @@ class WorkerPool {
   bool stop_ = false;
 };
 
+// val[i] = max(val[i], c[i] + cu): the inner loop of the integer across-scan below. Cloned per ISA
+// and dispatched at load time (the library is built on one machine and runs on another).
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__)
+__attribute__((target_clones("avx512f", "avx2", "default"), optimize("O3")))
+#endif
+static void maxplus_accumulate(uint64_t* __restrict__ val, const uint64_t* __restrict__ c, uint64_t cu, int n) {
+  for (int i = 0; i < n; ++i) {
+    const uint64_t t = c[i] + cu;
+    val[i] = t > val[i] ? t : val[i];
+  }
+}
+
 struct DPResults {
   std::vector<std::vector<Branch>> branches;  // per k = 1..m
   std::vector<double> qsat;
@@ -300,11 +313,16 @@ class DP {
   std::vector<std::vector<int>> tb_;
   TraceArena arena_;
   WorkerPool pool_;
+  // CAMUS_DP_LITERAL=1: literal FourWayBestSplit scan for integer scores too (A/B, tests)
+  bool fast_enabled_ = !(getenv("CAMUS_DP_LITERAL") && getenv("CAMUS_DP_LITERAL")[0] == '1');
   // cycleDP of the vertex being solved (main_dp.go:30-34)
   std::vector<std::vector<S>> cs_;
   std::vector<std::vector<int>> ct_;
   std::vector<std::pair<int, int>> items_;  // (u, other subtree) in the reference's visiting order
   std::vector<Desc> descs_;
+  // integer scores only: conv_[j][x] = max over i + i' = j of cs_[x][i] + dp_[x][i'] (see fast_across)
+  std::vector<std::vector<S>> conv_;
+  static constexpr bool kIntegerScores = std::is_same_v<S, uint64_t>;
 
   void post_order(int v, std::vector<int>& out) const {
     std::vector<std::pair<int, int>> st{{v, 0}};
@@ -401,9 +419,59 @@ class DP {
     }
     return best;
   }
-  Cand materialise(const Desc& d) {
+  // ---- integer scores: the across-scan as a max-plus product -----------------------------------
+  // FourWayBestSplit maximises cs_w[a] + cs_u[b] + dp_w[c] + dp_u[d] over a + b + c + d = prevK,
+  // pairing (cs_w, cs_u) and (dp_w, dp_u) and re-solving every split for every (u, w, k): O(k^2)
+  // per pair and step. Max-plus convolution is associative, so for exact (integer) scores the
+  // same maximum is max_j conv_w[j] + conv_u[prevK - j] with the per-node conv_x = cs_x (*) dp_x,
+  // of which every step only adds the entry j = prevK: O(k) per pair and step, vectorised over w.
+  // Only the VALUE is taken from this form; the split indices of a candidate the replay accepts
+  // come from the reference's own FourWayBestSplit (materialise), so tie-breaks are untouched.
+  // Float scorers keep the literal scan: their sums are order dependent.
+  void conv_update(int v, int prevK) {
+    if ((int)conv_.size() <= prevK) conv_.resize(prevK + 1);
+    std::vector<S>& c = conv_[prevK];
+    if ((int)c.size() != n_) c.assign(n_, S{});
+    const int end = td_.subtree_end[v];
+    for (int x = v; x < end; ++x) {
+      const std::vector<S>&a = cs_[x], &b = dp_[x];
+      const int lo = std::max(0, prevK - ((int)b.size() - 1)), hi = std::min(prevK, (int)a.size() - 1);
+      S best{};
+      for (int i = lo; i <= hi; ++i) best = std::max(best, a[i] + b[prevK - i]);
+      c[x] = best;
+    }
+  }
+  Desc fast_across(int u, int sub, int prevK) const {
+    Desc best;
+    const int end = td_.subtree_end[sub], len = end - sub;
+    thread_local std::vector<S> val;
+    val.assign(len, S{});
+    for (int j = 0; j <= prevK; ++j)
+      maxplus_accumulate(reinterpret_cast<uint64_t*>(val.data()), reinterpret_cast<const uint64_t*>(conv_[j].data() + sub),
+                         (uint64_t)conv_[prevK - j][u], len);
+    for (int i = 0; i < len; ++i) {
+      const S score = sc_.calc(u, sub + i) + val[i];
+      if (score > best.score || !best.ok) {
+        best.ok = true;
+        best.score = score;
+        best.u = u;
+        best.w = sub + i;
+      }
+    }
+    best.idx[0] = -1;  // split indices are resolved on acceptance
+    return best;
+  }
+
+  Cand materialise(Desc d) {
     Cand c;
     if (!d.ok) return c;
+    if (d.idx[0] < 0) {
+      const std::vector<S>* lists[4] = {&cs_[d.w], &cs_[d.u], &dp_[d.w], &dp_[d.u]};
+      const int prevK = (int)cs_[d.w].size() - 1;
+      if (!four_way_best_split(lists, prevK, d.idx)) throw CamusError(Err::Internal, "fast across-scan: infeasible split");
+      if (sc_.calc(d.u, d.w) + cs_[d.w][d.idx[0]] + cs_[d.u][d.idx[1]] + dp_[d.w][d.idx[2]] + dp_[d.u][d.idx[3]] != d.score)
+        throw CamusError(Err::Internal, "fast across-scan: score mismatch");
+    }
     TraceArena::Trace t;
     t.cycle = true;
     t.pathW = ct_[d.w][d.idx[0]];
@@ -450,7 +518,18 @@ class DP {
     }
     descs_.assign(items_.size(), Desc{});
     const size_t work = (size_t)(td_.subtree_end[c0] - c0) * (size_t)(td_.subtree_end[c1] - c1) * (size_t)(prevK + 1);
-    auto body = [&](int i, int) { descs_[i] = score_edges_across(items_[i].first, items_[i].second, prevK); };
+    bool fast = false;
+    if constexpr (kIntegerScores) fast = fast_enabled_;
+    if (fast) conv_update(v, prevK);
+    auto body = [&](int i, int) {
+      if constexpr (kIntegerScores) {
+        if (fast) {
+          descs_[i] = fast_across(items_[i].first, items_[i].second, prevK);
+          return;
+        }
+      }
+      descs_[i] = score_edges_across(items_[i].first, items_[i].second, prevK);
+    };
     if (work > 20000 && pool_.size() > 1) {
       pool_.run((int)items_.size(), body);
     } else {

@@ -235,3 +235,42 @@ def test_dp_is_thread_count_invariant(monkeypatch):
             assert a.newicks == b.newicks and a.branches == b.branches and a.qsat == b.qsat
             assert [repr(x) for x in a.root_scores] == [repr(x) for x in b.root_scores]
     assert len(out["1"][0].newicks) >= 3
+
+
+@pytest.mark.parametrize("kind", ["oracle", "sparse_small", "dense_ties", "wide"])
+def test_dp_maxplus_scan_equals_literal_scan(monkeypatch, kind):
+    """For integer scores (max mode) the across-scan takes the candidate VALUES from a max-plus
+    product and the split indices from the reference's FourWayBestSplit (dp.hpp, fast_across);
+    CAMUS_DP_LITERAL=1 runs the literal O(k^2) scan. Same branches, same order, same networks: on
+    an oracle table and on synthetic score tables built for ties (the DP accepts any u64 table)."""
+    from camus_b200 import synth
+    rng = np.random.default_rng(11)
+    if kind == "oracle":
+        s = synth.make(64, 20, 5)
+        prob = Problem(s.constraint, s.genes)
+        o = orc.Oracle().load(prob)
+        ns, sc = o.count_filter(0, 0.0, False)
+        tables = [o.quartet_totals(False, False), o.quartet_totals(True, False)]
+    else:
+        s = synth.make({"sparse_small": 120, "dense_ties": 48, "wide": 150}[kind], 1, 9)
+        prob = Problem(s.constraint, s.genes)
+        n = prob.n_nodes
+        ns, sc = 1000, 100000
+        tables = []
+        for rep in range(2):
+            if kind == "sparse_small":  # few scoring edges, tiny equal weights
+                t = (rng.random((n, n)) < 0.02) * rng.integers(1, 3, (n, n))
+            elif kind == "dense_ties":  # every edge scores 0..2
+                t = rng.integers(0, 3, (n, n))
+            else:  # a few heavy edges over a floor of ones
+                t = np.ones((n, n), np.int64) + (rng.random((n, n)) < 0.001) * rng.integers(1, 10**9, (n, n))
+            tables.append(np.ascontiguousarray(t, np.uint64))
+    for tot in tables:
+        out = {}
+        for lit in ("1", "0"):
+            monkeypatch.setenv("CAMUS_DP_LITERAL", lit)
+            out[lit] = prob.run_dp(tot, None, "max", False, ns, sc, 1, 0.3)
+        a, b = out["1"], out["0"]
+        assert a.branches == b.branches and a.newicks == b.newicks and a.qsat == b.qsat
+        assert [repr(x) for x in a.root_scores] == [repr(x) for x in b.root_scores]
+        assert len(a.newicks) >= 3
