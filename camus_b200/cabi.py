@@ -69,13 +69,17 @@ def _p(a: np.ndarray):
 
 
 class CamusB200:
-    """One context on one GPU. Method names and argument meaning follow include/camus_b200.h."""
+    """One context on one GPU (or, with `devices`, on several GPUs of this process). Method names
+    and argument meaning follow include/camus_b200.h."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, devices=None):
+        """devices: list of GPU ordinals for one handle that drives several GPUs of this process
+        (camus_b200_create with n_gpus > 1); default is the single GPU `device`."""
         L = lib()
         h = C.c_void_p()
-        dev = (C.c_int * 1)(device)
-        rc = L.camus_b200_create(C.byref(h), 1, dev)
+        devs = list(devices) if devices is not None else [device]
+        dev = (C.c_int * len(devs))(*devs)
+        rc = L.camus_b200_create(C.byref(h), len(devs), dev)
         if rc != 0:
             raise CamusB200Error(L.camus_b200_last_error(None).decode())
         self._h = h

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "camus_b200.h"
@@ -46,6 +47,14 @@ struct DevBuf {
 }  // namespace
 
 struct camus_b200 {
+  // n_gpus > 1: this handle only fans out to one single-device context per GPU (subs); the 4-set
+  // index space is dealt to them exactly as to the ranks of a multi-process run (BoxMap), and
+  // their partial junction tables are summed on subs[0] over NVLink peer reads.
+  std::vector<camus_b200*> subs;
+  int user_rank = 0, user_world = 1;  // partition of the whole handle (multi-process on top)
+  bool peer_access = false;
+  DevBuf<unsigned long long> d_stage;  // on subs[0]: landing buffer when peer access is unavailable
+
   int device = 0;
   std::string err;
   cudaStream_t stream = nullptr;
@@ -137,6 +146,22 @@ int upload(camus_b200* ctx, DevBuf<T>& buf, const T* src, size_t count) {
   return 0;
 }
 
+// n_gpus > 1: run f(sub, index) on every device at once (the single-device calls block on their
+// own stream), first failure wins.
+template <class F>
+int fan_out(camus_b200* ctx, F f) {
+  const int n = (int)ctx->subs.size();
+  std::vector<int> rc(n, 0);
+  std::vector<std::thread> th;
+  for (int i = 1; i < n; ++i) th.emplace_back([&, i] { rc[i] = f(ctx->subs[i], i); });
+  rc[0] = f(ctx->subs[0], 0);
+  for (auto& t : th) t.join();
+  for (int i = 0; i < n; ++i)
+    if (rc[i]) return ctx->fail(rc[i], "device " + std::to_string(ctx->subs[i]->device) + ": " + ctx->subs[i]->err);
+  return 0;
+}
+int reduce_partials(camus_b200* ctx);
+
 int build_planes(camus_b200* ctx, bool do_upload);
 int run_count(camus_b200* ctx);
 int run_filter(camus_b200* ctx, int qmode, double threshold, uint64_t* ns, uint64_t* sum);
@@ -152,14 +177,8 @@ uint64_t cells_budget_boxes(size_t free_bytes) {
 
 extern "C" {
 
-int camus_b200_create(camus_b200** out, int n_gpus, const int* devices) {
-  if (!out) return CAMUS_B200_ERR_ARG;
+static int create_one(camus_b200** out, int dev) {
   *out = nullptr;
-  if (n_gpus != 1) {
-    g_create_err = "camus_b200_create: n_gpus must be 1 (one process per GPU; see camus_b200_set_partition)";
-    return CAMUS_B200_ERR_ARG;
-  }
-  int dev = devices ? devices[0] : 0;
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
   if (e != cudaSuccess || count == 0) {
@@ -198,8 +217,57 @@ int camus_b200_create(camus_b200** out, int n_gpus, const int* devices) {
   return CAMUS_B200_OK;
 }
 
+int camus_b200_create(camus_b200** out, int n_gpus, const int* devices) {
+  if (!out) return CAMUS_B200_ERR_ARG;
+  *out = nullptr;
+  if (n_gpus < 1 || n_gpus > 64) {
+    g_create_err = "camus_b200_create: n_gpus must be >= 1";
+    return CAMUS_B200_ERR_ARG;
+  }
+  if (n_gpus == 1) return create_one(out, devices ? devices[0] : 0);
+  for (int i = 0; i < n_gpus; ++i)
+    for (int j = i + 1; devices && j < n_gpus; ++j)
+      if (devices[i] == devices[j]) {
+        g_create_err = "camus_b200_create: device listed twice";
+        return CAMUS_B200_ERR_ARG;
+      }
+  camus_b200* ctx = new camus_b200();
+  for (int i = 0; i < n_gpus; ++i) {
+    camus_b200* sub = nullptr;
+    int rc = create_one(&sub, devices ? devices[i] : i);
+    if (rc) {
+      camus_b200_destroy(ctx);
+      return rc;
+    }
+    ctx->subs.push_back(sub);
+    camus_b200_set_partition(sub, i, n_gpus);
+  }
+  // subs[0] sums the partial tables by reading its peers' memory directly
+  ctx->peer_access = true;
+  cudaSetDevice(ctx->subs[0]->device);
+  for (int i = 1; i < n_gpus; ++i) {
+    int can = 0;
+    cudaDeviceCanAccessPeer(&can, ctx->subs[0]->device, ctx->subs[i]->device);
+    if (can) {
+      cudaError_t e = cudaDeviceEnablePeerAccess(ctx->subs[i]->device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) can = 0;
+      cudaGetLastError();
+    }
+    if (!can) ctx->peer_access = false;
+  }
+  *out = ctx;
+  return CAMUS_B200_OK;
+}
+
 void camus_b200_destroy(camus_b200* ctx) {
   if (!ctx) return;
+  if (!ctx->subs.empty()) {
+    cudaSetDevice(ctx->subs[0]->device);
+    ctx->d_stage.release();
+    for (camus_b200* s : ctx->subs) camus_b200_destroy(s);
+    delete ctx;
+    return;
+  }
   cudaSetDevice(ctx->device);
   if (ctx->ev[0]) cudaEventDestroy(ctx->ev[0]);
   if (ctx->ev[1]) cudaEventDestroy(ctx->ev[1]);
@@ -211,6 +279,13 @@ const char* camus_b200_last_error(const camus_b200* ctx) { return ctx ? ctx->err
 
 int camus_b200_set_partition(camus_b200* ctx, int rank, int world) {
   if (!ctx || world < 1 || rank < 0 || rank >= world) return ctx ? ctx->fail(CAMUS_B200_ERR_ARG, "bad partition") : CAMUS_B200_ERR_ARG;
+  if (!ctx->subs.empty()) {  // this process's share is dealt on to its devices
+    const int n = (int)ctx->subs.size();
+    ctx->user_rank = rank;
+    ctx->user_world = world;
+    for (int i = 0; i < n; ++i) camus_b200_set_partition(ctx->subs[i], rank * n + i, world * n);
+    return 0;
+  }
   ctx->rank = rank;
   ctx->world = world;
   ctx->cell_state = camus_b200::NONE;
@@ -225,6 +300,12 @@ int camus_b200_set_constraint(camus_b200* ctx, int32_t n_nodes, int32_t n_taxa, 
   if (!parent || !child0 || !child1 || !tip_index || n_taxa < 2 || n_nodes != 2 * n_taxa - 1)
     return ctx->fail(CAMUS_B200_ERR_ARG, "set_constraint: need a rooted binary tree (n_nodes = 2*n_taxa - 1)");
   if (n_taxa > 32767) return ctx->fail(CAMUS_B200_ERR_ARG, "set_constraint: at most 32767 taxa (15-bit packing, quartet.go:17)");
+  if (!ctx->subs.empty()) {
+    int rc = fan_out(ctx, [&](camus_b200* s, int) { return camus_b200_set_constraint(s, n_nodes, n_taxa, parent, child0, child1, tip_index); });
+    ctx->n = rc ? 0 : n_nodes;
+    ctx->N = rc ? 0 : n_taxa;
+    return rc;
+  }
   CK(cudaSetDevice(ctx->device));
   const int n = n_nodes, N = n_taxa;
   int root = -1;
@@ -324,6 +405,10 @@ int camus_b200_set_constraint(camus_b200* ctx, int32_t n_nodes, int32_t n_taxa, 
 
 int camus_b200_clear_gene_trees(camus_b200* ctx) {
   if (!ctx) return CAMUS_B200_ERR_ARG;
+  if (!ctx->subs.empty()) {
+    for (camus_b200* s : ctx->subs) camus_b200_clear_gene_trees(s);
+    return 0;
+  }
   ctx->h_node_off.assign(1, 0);
   ctx->h_parent.clear();
   ctx->h_taxon.clear();
@@ -343,6 +428,8 @@ int camus_b200_add_gene_trees(camus_b200* ctx, int32_t n_trees, const int64_t* n
                               const int32_t* taxon) {
   if (!ctx) return CAMUS_B200_ERR_ARG;
   if (ctx->n == 0) return ctx->fail(CAMUS_B200_ERR_ARG, "add_gene_trees: set the constraint tree first");
+  if (!ctx->subs.empty())
+    return fan_out(ctx, [&](camus_b200* s, int) { return camus_b200_add_gene_trees(s, n_trees, node_off, parent, taxon); });
   if (n_trees < 0 || !node_off || (n_trees > 0 && (!parent || !taxon))) return ctx->fail(CAMUS_B200_ERR_ARG, "add_gene_trees: null argument");
   std::vector<int> stamp(ctx->N, -1);
   std::vector<char> has_child;
@@ -646,6 +733,53 @@ int run_finish(camus_b200* ctx, uint64_t* out) {
   return 0;
 }
 
+// Sum the devices' partial junction tables into subs[0]'s (copy 0 of its Z). With peer access one
+// kernel on device 0 reads the other tables straight over NVLink; otherwise they are copied in.
+__global__ void k_add_peers(unsigned long long* __restrict__ z, const unsigned long long* const* __restrict__ peers, int n_peers,
+                            size_t zn) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= zn) return;
+  unsigned long long acc = z[i];
+  for (int p = 0; p < n_peers; ++p) acc += peers[p][i];
+  z[i] = acc;
+}
+
+int reduce_partials(camus_b200* wrap) {
+  camus_b200* ctx = wrap->subs[0];  // CK reports into the leader's context
+  const size_t zn = (size_t)ctx->n * ctx->n * 3;
+  for (camus_b200* s : wrap->subs)
+    if (!s->z_valid) return wrap->fail(CAMUS_B200_ERR_ARG, "reduce_partials: a device has no partial table");
+  int rc = [&]() -> int {
+    CK(cudaSetDevice(ctx->device));
+    StageTimer t(ctx, CAMUS_B200_T_FINAL);
+    const int np = (int)wrap->subs.size() - 1;
+    if (wrap->peer_access) {
+      std::vector<const unsigned long long*> h(np);
+      for (int i = 0; i < np; ++i) h[i] = wrap->subs[i + 1]->d_Z.p;
+      CK(wrap->d_stage.alloc(np));
+      CK(cudaMemcpyAsync(wrap->d_stage.p, h.data(), np * sizeof(void*), cudaMemcpyHostToDevice, ctx->stream));
+      k_add_peers<<<(unsigned)((zn + 255) / 256), 256, 0, ctx->stream>>>(
+          ctx->d_Z.p, reinterpret_cast<const unsigned long long* const*>(wrap->d_stage.p), np, zn);
+      CK_LAUNCH();
+      CK(cudaStreamSynchronize(ctx->stream));  // h must outlive the copy
+    } else {
+      CK(wrap->d_stage.alloc(zn + 1));
+      for (int i = 0; i < np; ++i) {
+        const unsigned long long* one = wrap->d_stage.p;
+        CK(cudaMemcpyPeerAsync(wrap->d_stage.p, ctx->device, wrap->subs[i + 1]->d_Z.p, wrap->subs[i + 1]->device, zn * 8, ctx->stream));
+        CK(cudaMemcpyAsync(wrap->d_stage.p + zn, &one, sizeof(void*), cudaMemcpyHostToDevice, ctx->stream));
+        k_add_peers<<<(unsigned)((zn + 255) / 256), 256, 0, ctx->stream>>>(
+            ctx->d_Z.p, reinterpret_cast<const unsigned long long* const*>(wrap->d_stage.p + zn), 1, zn);
+        CK_LAUNCH();
+        CK(cudaStreamSynchronize(ctx->stream));
+      }
+    }
+    if (t.stop()) return CAMUS_B200_ERR_CUDA;
+    return 0;
+  }();
+  return rc ? wrap->fail(rc, ctx->err) : 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -655,6 +789,19 @@ int camus_b200_count_filter(camus_b200* ctx, int qmode, double threshold, uint64
   if (ctx->n == 0) return ctx->fail(CAMUS_B200_ERR_ARG, "count_filter: set the constraint tree first");
   if (qmode < 0 || qmode > 2 || !(threshold >= 0 && threshold <= 1))
     return ctx->fail(CAMUS_B200_ERR_ARG, "count_filter: quartet mode in [0,2] and threshold in [0,1] (quartetfilter.go:41-61)");
+  if (!ctx->subs.empty()) {
+    std::vector<uint64_t> ns(ctx->subs.size(), 0), sc(ctx->subs.size(), 0);
+    int rc = fan_out(ctx, [&](camus_b200* s, int i) { return camus_b200_count_filter(s, qmode, threshold, &ns[i], &sc[i]); });
+    if (rc) return rc;
+    uint64_t a = 0, b = 0;
+    for (size_t i = 0; i < ns.size(); ++i) {
+      a += ns[i];
+      b += sc[i];
+    }
+    if (n_survivors) *n_survivors = a;
+    if (sum_counts) *sum_counts = b;
+    return 0;
+  }
   CK(cudaSetDevice(ctx->device));
   std::memset(ctx->ms, 0, sizeof(ctx->ms));
   ctx->launches = 0;
@@ -669,6 +816,7 @@ int camus_b200_count_filter(camus_b200* ctx, int qmode, double threshold, uint64
 
 int camus_b200_set_score_hint(camus_b200* ctx, int as_set) {
   if (!ctx) return CAMUS_B200_ERR_ARG;
+  for (camus_b200* s : ctx->subs) camus_b200_set_score_hint(s, as_set);
   ctx->as_set_hint = as_set != 0;
   return 0;
 }
@@ -676,6 +824,22 @@ int camus_b200_set_score_hint(camus_b200* ctx, int as_set) {
 int camus_b200_run_resident(camus_b200* ctx, int qmode, double threshold, int as_set, uint64_t* out,
                             uint64_t* n_survivors, uint64_t* sum_counts) {
   if (!ctx) return CAMUS_B200_ERR_ARG;
+  if (!ctx->subs.empty()) {
+    std::vector<uint64_t> ns(ctx->subs.size(), 0), sc(ctx->subs.size(), 0);
+    int rc = fan_out(ctx, [&](camus_b200* s, int i) { return camus_b200_run_resident(s, qmode, threshold, as_set, nullptr, &ns[i], &sc[i]); });
+    if (rc) return rc;
+    uint64_t a = 0, b = 0;
+    for (size_t i = 0; i < ns.size(); ++i) {
+      a += ns[i];
+      b += sc[i];
+    }
+    if (n_survivors) *n_survivors = a;
+    if (sum_counts) *sum_counts = b;
+    if ((rc = reduce_partials(ctx))) return rc;
+    if (!out) return 0;
+    if ((rc = camus_b200_quartet_totals_finish(ctx->subs[0], out))) return ctx->fail(rc, ctx->subs[0]->err);
+    return 0;
+  }
   if (ctx->genes_dirty || ctx->n == 0)
     return ctx->fail(CAMUS_B200_ERR_ARG, "run_resident: the gene trees are not on the device yet (call camus_b200_count_filter once)");
   if (qmode < 0 || qmode > 2 || !(threshold >= 0 && threshold <= 1)) return ctx->fail(CAMUS_B200_ERR_ARG, "run_resident: bad filter options");
@@ -699,12 +863,20 @@ int camus_b200_run_resident(camus_b200* ctx, int qmode, double threshold, int as
 
 int camus_b200_quartet_totals_partial(camus_b200* ctx, int as_set) {
   if (!ctx) return CAMUS_B200_ERR_ARG;
+  if (!ctx->subs.empty()) {
+    int rc = fan_out(ctx, [&](camus_b200* s, int) { return camus_b200_quartet_totals_partial(s, as_set); });
+    return rc ? rc : reduce_partials(ctx);
+  }
   CK(cudaSetDevice(ctx->device));
   return run_score(ctx, as_set != 0);
 }
 
 int camus_b200_partial_buffer(camus_b200* ctx, void** dev_ptr, uint64_t* n_int64) {
   if (!ctx || !dev_ptr || !n_int64) return CAMUS_B200_ERR_ARG;
+  if (!ctx->subs.empty()) {
+    int rc = camus_b200_partial_buffer(ctx->subs[0], dev_ptr, n_int64);
+    return rc ? ctx->fail(rc, ctx->subs[0]->err) : 0;
+  }
   if (!ctx->z_valid) return ctx->fail(CAMUS_B200_ERR_ARG, "partial_buffer: call quartet_totals_partial first");
   *dev_ptr = ctx->d_Z.p;
   *n_int64 = (uint64_t)ctx->n * ctx->n * 3;
@@ -713,12 +885,20 @@ int camus_b200_partial_buffer(camus_b200* ctx, void** dev_ptr, uint64_t* n_int64
 
 int camus_b200_quartet_totals_finish(camus_b200* ctx, uint64_t* out) {
   if (!ctx || !out) return CAMUS_B200_ERR_ARG;
+  if (!ctx->subs.empty()) {
+    int rc = camus_b200_quartet_totals_finish(ctx->subs[0], out);
+    return rc ? ctx->fail(rc, ctx->subs[0]->err) : 0;
+  }
   CK(cudaSetDevice(ctx->device));
   return run_finish(ctx, out);
 }
 
 int camus_b200_quartet_totals(camus_b200* ctx, int as_set, uint64_t* out) {
   if (!ctx || !out) return CAMUS_B200_ERR_ARG;
+  if (!ctx->subs.empty()) {
+    int rc = camus_b200_quartet_totals_partial(ctx, as_set);
+    return rc ? rc : camus_b200_quartet_totals_finish(ctx, out);
+  }
   CK(cudaSetDevice(ctx->device));
   int rc = run_score(ctx, as_set != 0);
   if (rc) return rc;
@@ -728,6 +908,10 @@ int camus_b200_quartet_totals(camus_b200* ctx, int as_set, uint64_t* out) {
 int camus_b200_edge_penalties(camus_b200* ctx, uint64_t* out) {
   if (!ctx || !out) return CAMUS_B200_ERR_ARG;
   if (ctx->n == 0) return ctx->fail(CAMUS_B200_ERR_ARG, "edge_penalties: set the constraint tree first");
+  if (!ctx->subs.empty()) {
+    int rc = camus_b200_edge_penalties(ctx->subs[0], out);
+    return rc ? ctx->fail(rc, ctx->subs[0]->err) : 0;
+  }
   CK(cudaSetDevice(ctx->device));
   const int n = ctx->n;
   CK(ctx->d_out.alloc((size_t)n * n));
@@ -741,6 +925,36 @@ int camus_b200_edge_penalties(camus_b200* ctx, uint64_t* out) {
 
 int camus_b200_export_quartets(camus_b200* ctx, int raw, uint64_t* keys, uint32_t* counts, uint64_t cap, uint64_t* n_out) {
   if (!ctx || !n_out) return CAMUS_B200_ERR_ARG;
+  if (!ctx->subs.empty()) {
+    // every device exports its share; the shares are disjoint, the merged list is sorted by key
+    std::vector<std::vector<uint64_t>> k(ctx->subs.size());
+    std::vector<std::vector<uint32_t>> c(ctx->subs.size());
+    std::vector<uint64_t> cnt(ctx->subs.size(), 0);
+    const bool fetch = keys && counts && cap;
+    int rc = fan_out(ctx, [&](camus_b200* s, int i) {
+      int r = camus_b200_export_quartets(s, raw, nullptr, nullptr, 0, &cnt[i]);
+      if (r || !fetch || !cnt[i]) return r;
+      k[i].resize(cnt[i]);
+      c[i].resize(cnt[i]);
+      return camus_b200_export_quartets(s, raw, k[i].data(), c[i].data(), cnt[i], &cnt[i]);
+    });
+    if (rc) return rc;
+    uint64_t total = 0;
+    for (uint64_t x : cnt) total += x;
+    *n_out = total;
+    if (fetch) {
+      std::vector<std::pair<uint64_t, uint32_t>> all;
+      all.reserve(total);
+      for (size_t i = 0; i < k.size(); ++i)
+        for (size_t j = 0; j < k[i].size(); ++j) all.emplace_back(k[i][j], c[i][j]);
+      std::sort(all.begin(), all.end());
+      for (uint64_t i = 0; i < std::min<uint64_t>(total, cap); ++i) {
+        keys[i] = all[i].first;
+        counts[i] = all[i].second;
+      }
+    }
+    return 0;
+  }
   CK(cudaSetDevice(ctx->device));
   if (!ctx->counted) return ctx->fail(CAMUS_B200_ERR_ARG, "export_quartets: call camus_b200_count_filter first");
   int rc;
@@ -784,6 +998,10 @@ int camus_b200_export_quartets(camus_b200* ctx, int raw, uint64_t* keys, uint32_
 
 int camus_b200_query_cells(camus_b200* ctx, int32_t n_query, const int32_t* quads, uint32_t* counts) {
   if (!ctx || n_query < 0 || (n_query && (!quads || !counts))) return CAMUS_B200_ERR_ARG;
+  if (!ctx->subs.empty()) {  // every device holds all bit-planes
+    int rc = camus_b200_query_cells(ctx->subs[0], n_query, quads, counts);
+    return rc ? ctx->fail(rc, ctx->subs[0]->err) : 0;
+  }
   if (ctx->genes_dirty || ctx->n == 0) return ctx->fail(CAMUS_B200_ERR_ARG, "query_cells: call camus_b200_count_filter first");
   for (int i = 0; i < 4 * n_query; ++i)
     if (quads[i] < 0 || quads[i] >= ctx->N) return ctx->fail(CAMUS_B200_ERR_ARG, "query_cells: tip index out of range");
@@ -808,6 +1026,17 @@ int camus_b200_query_cells(camus_b200* ctx, int32_t n_query, const int32_t* quad
 
 int camus_b200_stage_ms(const camus_b200* ctx, float* ms, uint64_t* n_launches) {
   if (!ctx) return CAMUS_B200_ERR_ARG;
+  if (!ctx->subs.empty()) {  // slowest device per stage, launches of all
+    float m[CAMUS_B200_T_N] = {0};
+    uint64_t l = 0;
+    for (const camus_b200* s : ctx->subs) {
+      for (int i = 0; i < CAMUS_B200_T_N; ++i) m[i] = std::max(m[i], s->ms[i]);
+      l += s->launches;
+    }
+    if (ms) std::memcpy(ms, m, sizeof(m));
+    if (n_launches) *n_launches = l;
+    return 0;
+  }
   if (ms) std::memcpy(ms, ctx->ms, sizeof(ctx->ms));
   if (n_launches) *n_launches = ctx->launches;
   return 0;
@@ -815,6 +1044,7 @@ int camus_b200_stage_ms(const camus_b200* ctx, float* ms, uint64_t* n_launches) 
 
 int camus_b200_workload(const camus_b200* ctx, uint64_t* resolutions, uint64_t* n_cells, uint64_t* n_boxes) {
   if (!ctx) return CAMUS_B200_ERR_ARG;
+  if (!ctx->subs.empty()) return camus_b200_workload(ctx->subs[0], resolutions, n_cells, n_boxes);
   if (resolutions) *resolutions = ctx->resolutions;
   if (n_cells) *n_cells = choose4((uint64_t)ctx->N);
   if (n_boxes) *n_boxes = ctx->n ? num_boxes(ctx->M) : 0;

@@ -197,8 +197,13 @@ int main(int argc, char** argv) {
     Tree tre = read_constraint_text(read_file(pos[0], "reading tree file:"), pos[0]);
     std::string gtext = read_file(pos[1], "opening");
     GeneTrees gts = format == "nexus" ? read_gene_trees_nexus(gtext, pos[1]) : read_gene_trees_newick(gtext, pos[1]);
+    // CAMUS_B200_DEVICE = first CUDA ordinal (default 0), CAMUS_B200_GPUS = how many GPUs from there on
+    // (default 1). The reference CLI has no such flags; the environment keeps its flag set unchanged.
     int ordinal = getenv("CAMUS_B200_DEVICE") ? atoi(getenv("CAMUS_B200_DEVICE")) : 0;
-    auto dev = std::make_shared<Device>(ordinal);
+    int ngpus = getenv("CAMUS_B200_GPUS") ? std::max(1, atoi(getenv("CAMUS_B200_GPUS"))) : 1;
+    std::vector<int> ordinals;
+    for (int i = 0; i < ngpus; ++i) ordinals.push_back(ordinal + i);
+    auto dev = std::make_shared<Device>(ordinals);
     InferResults res = Infer(std::move(tre), gts.trees, opts, dev, logline);
     std::vector<std::string> newicks;
     for (auto& b : res.dp.branches) newicks.push_back(make_network_newick(res.tree.td, b));

@@ -23,9 +23,10 @@ using LogFn = std::function<void(const std::string&)>;
 // ---- device handle (RAII over the C-ABI) ------------------------------------------------------
 class Device {
  public:
-  explicit Device(int ordinal = 0) {
-    int dev = ordinal;
-    if (camus_b200_create(&ctx_, 1, &dev) != 0)
+  explicit Device(int ordinal = 0) : Device(std::vector<int>{ordinal}) {}
+  // one handle over several GPUs of this process (camus_b200_create with n_gpus > 1)
+  explicit Device(const std::vector<int>& ordinals) {
+    if (camus_b200_create(&ctx_, (int)ordinals.size(), ordinals.data()) != 0)
       throw CamusError(Err::Device, std::string("camus_b200: ") + camus_b200_last_error(nullptr));
   }
   ~Device() { camus_b200_destroy(ctx_); }

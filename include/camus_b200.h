@@ -40,8 +40,11 @@ enum {
   CAMUS_B200_ERR_INPUT = 4    /* malformed flat tree */
 };
 
-/* n_gpus must be 1 in this release (one context per process and device; multi-GPU runs use one
- * process per GPU and camus_b200_set_partition). devices[0] = CUDA ordinal, NULL = device 0. */
+/* One handle for n_gpus GPUs of this process (1, 2, 4, 8). devices[i] = CUDA
+ * ordinal, NULL = 0..n_gpus-1. With n_gpus > 1 every call below fans out: each GPU gets all gene
+ * trees and 1/n_gpus of the 4-taxon-set index space, and the partial edge tables are summed on
+ * devices[0] by peer reads over NVLink. Results are bit-identical for any n_gpus. One process per
+ * GPU (n_gpus = 1 each + camus_b200_set_partition + a caller-side all-reduce) is the alternative. */
 int camus_b200_create(camus_b200** out, int n_gpus, const int* devices);
 void camus_b200_destroy(camus_b200* ctx);
 /* ctx may be NULL: returns the last error of a failed camus_b200_create on this thread. */
@@ -51,7 +54,8 @@ const char* camus_b200_last_error(const camus_b200* ctx);
  * only partition `rank` of `world`. Every rank must be given ALL gene trees. After
  * camus_b200_count_filter and camus_b200_quartet_totals_partial the caller sums the partial
  * buffers over ranks (NCCL all-reduce on the device pointers returned below) and then calls
- * camus_b200_quartet_totals_finish. Default is (0, 1). */
+ * camus_b200_quartet_totals_finish. Default is (0, 1). A handle with n_gpus > 1 deals its
+ * partition on to its GPUs (world * n_gpus shares); its partial buffer lives on devices[0]. */
 int camus_b200_set_partition(camus_b200* ctx, int rank, int world);
 
 /* Constraint tree in reference node-id order (preprocess.go:28-30), rooted, binary.

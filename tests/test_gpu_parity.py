@@ -524,3 +524,50 @@ def test_config2_full_size_properties(gpu):
     assert (tot2 <= tot_all).all() and tot2.any()
     mask = np.array([[prob.should_calc_edge(u, w) for w in range(0, prob.n_nodes, 7)] for u in range(0, prob.n_nodes, 7)])
     assert not tot_all[::7, ::7][~mask].any()
+
+
+def _n_devices():
+    import torch
+    return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(_n_devices() < 2, reason="needs two GPUs (gpurun --gpus 2)")
+def test_multi_gpu_handle_matches_single(gpu):
+    """camus_b200_create(n_gpus > 1): one handle, every GPU of the process. Survivors, both edge
+    tables, penalties, exported quartets and probes equal the single-GPU handle's, fused and
+    table pipelines, also with a caller-side partition on top (2 x n_gpus shares)."""
+    from camus_b200.cabi import CamusB200
+    nd = min(_n_devices(), 4)
+    multi = CamusB200(devices=list(range(nd)))
+    for s, ms, qmode, thr in ((synth.make(72, 90, 12, support=True, drop_frac=0.1, nexus=True), 0.5, 1, 0.25),
+                              (synth.make(64, 64, 13), 0.0, 2, 0.5)):
+        prob = Problem(s.constraint, s.genes, s.fmt, ms)
+        gpu.load(prob)
+        multi.load(prob)
+        for as_set in (False, True):
+            gpu.set_score_hint(as_set)
+            multi.set_score_hint(as_set)
+            assert multi.count_filter(qmode, thr) == gpu.count_filter(qmode, thr)
+            assert np.array_equal(multi.quartet_totals(as_set), gpu.quartet_totals(as_set))
+        assert np.array_equal(multi.edge_penalties(), gpu.edge_penalties())
+        for raw in (True, False):
+            for a, b in zip(multi.export_quartets(raw=raw), gpu.export_quartets(raw=raw)):
+                assert np.array_equal(a, b)
+        quads = np.array([[0, 1, 2, 3], [5, 17, 40, 63], [9, 8, 7, 6]], np.int32)
+        assert np.array_equal(multi.query_cells(quads), gpu.query_cells(quads))
+        out, ns, sc = multi.run_resident(qmode, thr, False)
+        assert (ns, sc) == gpu.count_filter(qmode, thr) and np.array_equal(out, gpu.quartet_totals(False))
+        # two such handles as two "processes": shares 0 and 1 of 2, summed by hand
+        parts = []
+        for r in range(2):
+            multi.set_partition(r, 2)
+            ns_r, sc_r = multi.count_filter(qmode, thr)
+            multi.quartet_totals_partial(False)
+            parts.append((ns_r, sc_r, multi.partial_tensor().clone()))
+        assert (parts[0][0] + parts[1][0], parts[0][1] + parts[1][1]) == (ns, sc)
+        multi.partial_tensor().copy_(parts[0][2] + parts[1][2])
+        assert np.array_equal(multi.quartet_totals_finish(), out)
+        multi.set_partition(0, 1)
+    gpu.set_score_hint(False)
+    multi.close()
