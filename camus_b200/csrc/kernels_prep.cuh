@@ -211,8 +211,11 @@ __device__ __forceinline__ uint32_t fma2(uint32_t a, uint32_t b, uint32_t c) {
   return d;
 }
 
-__device__ __forceinline__ const uint4* plane_row_chunk(const uint16_t* rows, int r, int c) {
-  return reinterpret_cast<const uint4*>(rows + r * kLanes + ((c ^ ((r >> 1) & 3)) << 3));
+// u16 offset of chunk c of row r. kPad: 16 B after every 8 rows, for the array whose rows are read
+// at a stride of 8 by the quarter-warps of one load (ac: 4 different x, same z).
+template <bool kPad>
+__device__ __forceinline__ int plane_chunk_off(int r, int c) {
+  return r * kLanes + ((c ^ ((r >> 1) & 3)) << 3) + (kPad ? (r >> 3) << 3 : 0);
 }
 
 template <bool kDerive>
@@ -224,12 +227,12 @@ __device__ __forceinline__ void triple_words(const uint4 (&ab)[4], const uint16_
   uint32_t f[3] = {0x64006400u, 0x64006400u, 0x64006400u};
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
-    const uint4 ac = *plane_row_chunk(s_ac, r_ac, c);
+    const uint4 ac = *reinterpret_cast<const uint4*>(s_ac + plane_chunk_off<true>(r_ac, c));
     const uint32_t abv[4] = {ab[c].x, ab[c].y, ab[c].z, ab[c].w};
     const uint32_t acv[4] = {ac.x, ac.y, ac.z, ac.w};
     uint32_t bcv[4] = {0, 0, 0, 0};
     if (!kDerive) {
-      const uint4 bc = *plane_row_chunk(s_bc, r_bc, c);
+      const uint4 bc = *reinterpret_cast<const uint4*>(s_bc + plane_chunk_off<false>(r_bc, c));
       bcv[0] = bc.x; bcv[1] = bc.y; bcv[2] = bc.z; bcv[3] = bc.w;
     }
 #pragma unroll
@@ -257,7 +260,7 @@ __global__ void __launch_bounds__(256, 4) k_triple_planes_h2(int grp0, int n_bat
                                                           const uint16_t* __restrict__ Dt, uint32_t* __restrict__ Tri) {
   // fp16 bits, NaN = absent. Rows: ab[x*8+y], ac[x*8+z], bc[z*8+y] (the index that varies across
   // the lanes of a load phase is the low one).
-  __shared__ __align__(16) uint16_t s_d[3][64 * kLanes];
+  __shared__ __align__(16) uint16_t s_d[3][64 * kLanes + 64];
   __shared__ __align__(16) uint32_t s_img[kTileWords];
   __shared__ uint32_t s_seg[3];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -288,7 +291,7 @@ __global__ void __launch_bounds__(256, 4) k_triple_planes_h2(int grp0, int n_bat
     const uint32_t hi = (which == 0 ? b0 : c0) + j;
     src[it] = lo < hi ? Dt + ((size_t)lo * npad + hi) * kLanes + c * 8 : nullptr;  // null: wrong rank order -> NaN
     const int r = which == 2 ? j * 8 + i : i * 8 + j;
-    dst[it] = &s_d[which][r * kLanes + ((c ^ ((r >> 1) & 3)) << 3)];
+    dst[it] = &s_d[which][which == 1 ? plane_chunk_off<true>(r, c) : plane_chunk_off<false>(r, c)];
   }
   const size_t group_stride = (size_t)npad * npad * kLanes;
   const uint4 nan4 = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
@@ -310,7 +313,7 @@ __global__ void __launch_bounds__(256, 4) k_triple_planes_h2(int grp0, int n_bat
     const uint32_t vm = ((1u << n_even) - 1u) | (((1u << n_odd) - 1u) << 16);
     uint4 ab[4];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) ab[c] = *plane_row_chunk(s_d[0], x * 8 + y, c);
+    for (int c = 0; c < 4; ++c) ab[c] = *reinterpret_cast<const uint4*>(s_d[0] + plane_chunk_off<false>(x * 8 + y, c));
 #pragma unroll
     for (int zz = 0; zz < 2; ++zz) {
       const int z = 2 * zh + zz;

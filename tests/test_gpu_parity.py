@@ -483,6 +483,24 @@ def test_config3_taxa_scale_properties(gpu):
     tot2 = gpu.quartet_totals(False)
     assert 0 < ns2 < ns_all and sum2 < sum_all and (tot2 <= tot_all).all() and tot2.any()
     assert not tot2[0].any() and not tot2[:, 0].any()
+    # the two scoring epilogues (marginal sums on regular boxes vs survivor queue everywhere) are
+    # independent code paths: identical tables at 1000 taxa, weighted and -asSet
+    import os
+    from camus_b200.cabi import CamusB200
+    os.environ["CAMUS_B200_NO_REGULAR"] = "1"
+    try:
+        queue_only = CamusB200(0)
+    finally:
+        del os.environ["CAMUS_B200_NO_REGULAR"]
+    queue_only.load(prob)
+    assert queue_only.count_filter(2, 0.5) == (ns2, sum2)
+    assert np.array_equal(queue_only.quartet_totals(False), tot2)
+    gpu.set_score_hint(True)
+    queue_only.set_score_hint(True)
+    assert gpu.count_filter(2, 0.5) == queue_only.count_filter(2, 0.5)
+    assert np.array_equal(gpu.quartet_totals(True), queue_only.quartet_totals(True))
+    gpu.set_score_hint(False)
+    queue_only.close()
 
 
 def test_config2_full_size_properties(gpu):
