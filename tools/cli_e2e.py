@@ -17,7 +17,19 @@ if c["min_support"]:
 cmd += [f"{d}/c.nwk", f"{d}/g.{ext}"]
 t0 = time.time()
 r = subprocess.run(cmd, capture_output=True, text=True)
-print("rc", r.returncode, "wall %.2fs" % (time.time() - t0))
+t1 = time.time()
+print("rc", r.returncode, "wall %.2fs" % (t1 - t0))
+# where the wall time goes outside the log's own span: process start-up before the first line,
+# teardown (device memory release) after the last
+import datetime
+stamps = []
+for l in r.stderr.splitlines():
+    try:
+        stamps.append(datetime.datetime.strptime(l[:26], "%Y/%m/%d %H:%M:%S.%f").timestamp())
+    except ValueError:
+        pass
+if stamps:
+    print("start-up %.2fs  logged span %.2fs  teardown %.2fs" % (stamps[0] - t0, stamps[-1] - stamps[0], t1 - stamps[-1]))
 for l in r.stderr.splitlines():
     print(l[:160])
 print(r.stdout[:300].replace("\n", " | "))
