@@ -141,7 +141,7 @@ k_count(CountParams prm, FusedParams fz, ConstraintDev ct) {
   };
 
   if (tid == 0)
-    for (int g = 0; g < kCountStages - 1 && g < G; ++g) issue(g);
+    for (int g = 0; g < kCountStages && g < G; ++g) issue(g);
 
   // general: cnt[c][t] = trees displaying topology t. complete: cnt[c][0] = c(ab|cd) | c(ac|bd) << 16.
   constexpr int kCnt = kComplete ? 1 : 3;
@@ -160,9 +160,15 @@ k_count(CountParams prm, FusedParams fz, ConstraintDev ct) {
 
   for (int g = 0; g < G; ++g) {
     const int s = g % kCountStages;
-    // everyone has finished group g-1, whose stage is the one refilled now
-    __syncthreads();
-    if (tid == 0 && g + kCountStages - 1 < G) issue(g + kCountStages - 1);
+    // One CTA barrier per TWO groups: at even g everyone has finished groups g-2 and g-1, whose
+    // stages are refilled with g+2 and g+3 (the ring holds g .. g+3 in flight or ready).
+    if ((g & 1) == 0 && g > 0) {
+      __syncthreads();
+      if (tid == 0) {
+        if (g + 2 < G) issue(g + 2);
+        if (g + 3 < G) issue(g + 3);
+      }
+    }
     mbar_wait(&bars[s], (uint32_t)((g / kCountStages) & 1));
 
     const uint4* st = reinterpret_cast<const uint4*>(smem + s * Cfg::kStageWords);

@@ -40,9 +40,18 @@ def test_create_without_gpu_fails_loudly(lib):
         cabi.CamusB200(0)
 
 
-def test_create_rejects_multi_gpu_in_one_context(lib):
+def test_create_argument_checks(lib):
+    """n_gpus >= 1, no device listed twice (checked before any CUDA call); a multi-GPU handle on a
+    box without GPUs fails like the single one."""
     h = C.c_void_p()
-    assert lib.camus_b200_create(C.byref(h), 2, None) != 0
+    assert lib.camus_b200_create(C.byref(h), 0, None) == 1 and not h.value
+    assert lib.camus_b200_create(None, 1, None) == 1
+    twice = (C.c_int * 2)(0, 0)
+    assert lib.camus_b200_create(C.byref(h), 2, twice) == 1 and not h.value
+    assert "twice" in lib.camus_b200_last_error(None).decode()
+    import torch
+    if not torch.cuda.is_available():
+        assert lib.camus_b200_create(C.byref(h), 2, None) != 0 and not h.value
 
 
 def test_product_does_not_import_oracle():
