@@ -152,10 +152,12 @@ k_count(CountParams prm, FusedParams fz, ConstraintDev ct) {
     for (int t = 0; t < kCnt; ++t) cnt[c][t] = 0;
 
   // per-thread uint4 offsets inside a plane, (z * 4 + ty) * 4 + tx, hoisted out of the group loop
-  const uint32_t o_abc = ((2 * tc) * 4 + tb) * 4 + ta;  // + 16 per kk
-  const uint32_t o_abd = ((2 * td) * 4 + tb) * 4 + ta;  // + 16 per ll
-  const uint32_t o_acd = ((2 * td) * 4 + tc) * 4 + ta;
-  const uint32_t o_bcd = ((2 * td) * 4 + tc) * 4 + tb;
+  // (made opaque to the compiler, which otherwise re-derives them from tid in every iteration)
+  uint32_t o_abc = ((2 * tc) * 4 + tb) * 4 + ta;  // + 16 per kk
+  uint32_t o_abd = ((2 * td) * 4 + tb) * 4 + ta;  // + 16 per ll
+  uint32_t o_acd = ((2 * td) * 4 + tc) * 4 + ta;
+  uint32_t o_bcd = ((2 * td) * 4 + tc) * 4 + tb;
+  asm volatile("" : "+r"(o_abc), "+r"(o_abd), "+r"(o_acd), "+r"(o_bcd));
   constexpr int kPlaneU4 = kPlaneWords / 4;
 
   for (int g = 0; g < G; ++g) {

@@ -18,6 +18,8 @@
 #include <cstdlib>
 #include <map>
 #include <stdexcept>
+#include <atomic>
+#include <thread>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -363,25 +365,54 @@ struct GeneTrees {
 // prep.readGeneTreesFile newick branch (io.go:133-153): one tree per non-blank line.
 inline GeneTrees read_gene_trees_newick(const std::string& text, const std::string& fname = "<text>") {
   GeneTrees g;
+  // non-blank lines first, then the trees are parsed in parallel (the reference parses serially;
+  // the first bad line in file order is still the one reported)
+  struct Line {
+    size_t begin, end;
+    int lineno;
+  };
+  std::vector<Line> lines;
   size_t start = 0;
   int lineno = 0;
   while (start <= text.size()) {
     size_t nl = text.find('\n', start);
     if (nl == std::string::npos) nl = text.size();
-    std::string line = trim(text.substr(start, nl - start));
-    if (!line.empty()) {
-      try {
-        g.trees.push_back(parse_newick(line));
-      } catch (const CamusError& e) {
-        throw CamusError(Err::InvalidFormat, "invalid format, error reading gene tree on line " +
-                                                 std::to_string(lineno) + " in " + fname + ": " + e.what());
-      }
-    }
+    size_t b = start, e = nl;
+    while (b < e && std::isspace((unsigned char)text[b])) ++b;
+    while (e > b && std::isspace((unsigned char)text[e - 1])) --e;
+    if (e > b) lines.push_back({b, e, lineno});
     ++lineno;
     if (nl == text.size()) break;
     start = nl + 1;
   }
-  if (g.trees.empty()) throw CamusError(Err::InvalidFile, "invalid file, empty gene tree file " + fname);
+  if (lines.empty()) throw CamusError(Err::InvalidFile, "invalid file, empty gene tree file " + fname);
+  g.trees.resize(lines.size());
+  std::vector<std::string> errs(lines.size());
+  std::vector<char> bad(lines.size(), 0);
+  auto work = [&](size_t i) {
+    try {
+      g.trees[i] = parse_newick(text.substr(lines[i].begin, lines[i].end - lines[i].begin));
+    } catch (const CamusError& e) {
+      bad[i] = 1;
+      errs[i] = e.what();
+    }
+  };
+  const size_t nthreads = std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), text.size() > (1u << 18) ? lines.size() : 1);
+  if (nthreads <= 1) {
+    for (size_t i = 0; i < lines.size(); ++i) work(i);
+  } else {
+    std::atomic<size_t> next{0};
+    std::vector<std::thread> th;
+    for (size_t t = 0; t < nthreads; ++t)
+      th.emplace_back([&] {
+        for (size_t i; (i = next.fetch_add(1)) < lines.size();) work(i);
+      });
+    for (auto& t : th) t.join();
+  }
+  for (size_t i = 0; i < lines.size(); ++i)
+    if (bad[i])
+      throw CamusError(Err::InvalidFormat, "invalid format, error reading gene tree on line " + std::to_string(lines[i].lineno) +
+                                               " in " + fname + ": " + errs[i]);
   for (size_t i = 0; i < g.trees.size(); ++i) g.names.push_back(std::to_string(i + 1));
   return g;
 }

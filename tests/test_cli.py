@@ -57,3 +57,22 @@ def test_cli_reproduces_golden_networks(tmp_path, qmode, thr, mode, alpha, nnets
     log = open(prefix + ".log").read()
     assert "1123 gene trees provided, containing %d quartets not in the constraint tree" % (14423 if qmode == 0 else 1150) in log
     assert "%d edges identified" % nnets in log
+
+
+def test_parallel_newick_parse_reports_first_bad_line():
+    """Gene-tree files above 256 KB are parsed on all host threads; results and the error for the
+    FIRST malformed line (io.go:141-147 reports the line index) do not depend on that."""
+    from camus_b200 import synth
+    from camus_b200.hostlib import Problem, CamusError
+    s = synth.make(300, 400, 5)
+    assert len(s.genes) > (1 << 18)
+    whole = Problem(s.constraint, s.genes)
+    lines = s.genes.strip().split("\n")
+    half = Problem(s.constraint, "\n".join(lines[:100]))  # below the threshold: serial parse
+    n100 = int(half.gene_node_off[100])
+    assert whole.n_trees == 400 and half.n_trees == 100
+    assert (whole.gene_parent[:n100] == half.gene_parent).all() and (whole.gene_taxon[:n100] == half.gene_taxon).all()
+    lines[123] = lines[123][:50]
+    lines[300] = "((a,b"
+    with pytest.raises(CamusError, match="line 123"):
+        Problem(s.constraint, "\n".join(lines))
