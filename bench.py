@@ -331,10 +331,15 @@ def run_ours(args):
                          "launch_ms": kern_ms / n_launch,
                          "design_bytes_per_launch": design_bytes / n_launch,
                          "design_achieved": design_bytes / (kern_ms * 1e-3) / 1e9,
+                         # the pipe that actually bounds the kernel: one POPC per (cell, counted topology, 32 trees)
+                         # on the XU pipe, 16 lanes per clock and SM (B300_MICROARCH.md), 148 SMs
+                         "xu_floor_ms": (num_boxes / world) * groups * 4096 * (2 if complete else 3)
+                                        / (16 * 148 * clocks.get("sm_mhz", 1965) * 1e6) * 1e3,
                          "note": "achieved uses the survey's accounting (8 B per resolution); the kernel resolves 32 gene trees per "
-                                 "32-bit word in registers, so it moves ~250x fewer bytes than that model and frac exceeds 1; "
-                                 "design_* = bytes of triple tiles the kernel actually streams (L2 + HBM); it is bound by the "
-                                 "POPC (XU) pipe, see DESIGN.md"},
+                                 "32-bit word in registers, so it moves ~60x fewer bytes than that model and frac exceeds 1; "
+                                 "design_* = bytes of triple tiles the kernel actually streams (L2 + HBM); traffic = its DRAM bytes "
+                                 "(ncu); the binding resource is the POPC (XU) pipe: xu_floor_ms / launch_ms is the fraction of "
+                                 "that floor reached, see DESIGN.md"},
             "roofline_whole_path": {"algorithmic_bytes": b_alg, "achieved": b_alg / dt_res / 1e9, "frac": b_alg / dt_res / 1e9 / peak},
             "result": {"n_survivors": first[0], "sum_counts": first[1]},
         }

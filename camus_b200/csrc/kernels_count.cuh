@@ -67,7 +67,8 @@ struct FusedParams {
   int z_rep;                   // number of privatised copies of Z (hot-address spreading), stride z_stride
   unsigned long long z_stride;
   int regular;                 // 1 = regular boxes take the marginal-sum epilogue (CAMUS_B200_NO_REGULAR=1 clears it)
-  int debug;                   // profiling only (CAMUS_B200_DEBUG): 1 = skip the score scatter, 2 = skip the whole epilogue
+  int debug;                   // profiling only (CAMUS_B200_DEBUG): 1 = skip the score scatter, 2 = skip the whole epilogue,
+                               // 3 = as 2 and no tile traffic after the first four groups
 };
 
 __device__ __forceinline__ uint32_t pick(const uint4& v, int hi, int lo) {
@@ -166,12 +167,13 @@ k_count(CountParams prm, FusedParams fz, ConstraintDev ct) {
     // stages are refilled with g+2 and g+3 (the ring holds g .. g+3 in flight or ready).
     if ((g & 1) == 0 && g > 0) {
       __syncthreads();
-      if (tid == 0) {
+      if (tid == 0 && !(kFused && fz.debug == 3)) {
         if (g + 2 < G) issue(g + 2);
         if (g + 3 < G) issue(g + 3);
       }
     }
-    mbar_wait(&bars[s], (uint32_t)((g / kCountStages) & 1));
+    // debug 3 (timing only): the ring is filled once and re-read, i.e. the loop without tile traffic
+    if (!(kFused && fz.debug == 3 && g >= kCountStages)) mbar_wait(&bars[s], (uint32_t)((g / kCountStages) & 1));
 
     const uint4* st = reinterpret_cast<const uint4*>(smem + s * Cfg::kStageWords);
     auto ld = [&](int role, int plane, uint32_t off) -> uint4 { return st[plane_slot<kComplete>(role, plane) * kPlaneU4 + off]; };
@@ -281,7 +283,7 @@ k_count(CountParams prm, FusedParams fz, ConstraintDev ct) {
               const uint32_t x[4] = {a0 + i, b0 + j, c0 + kk, d0 + ll};
               uint32_t c[3];
               counts_of(((ll * 2 + kk) * 2 + j) * 2 + i, c);
-              if (fz.debug == 2) {
+              if (fz.debug >= 2) {
                 sum += c[0] + c[1] + c[2];
                 continue;
               }
@@ -327,7 +329,7 @@ k_count(CountParams prm, FusedParams fz, ConstraintDev ct) {
             uint32_t c[3];
             counts_of(((ll * 2 + kk) * 2 + j) * 2 + i, c);
             bool live = x[0] < x[1] && x[1] < x[2] && x[2] < x[3] && x[3] < N && (c[0] | c[1] | c[2]);
-            if (fz.debug == 2) {
+            if (fz.debug >= 2) {
               if (live) sum += c[0] + c[1] + c[2];
               continue;
             }
