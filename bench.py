@@ -334,7 +334,7 @@ def run_ours(args):
                          # the pipe that actually bounds the kernel: one POPC per (cell, counted topology, 32 trees)
                          # on the XU pipe, 16 lanes per clock and SM (B300_MICROARCH.md), 148 SMs
                          "xu_floor_ms": (num_boxes / world) * groups * 4096 * (2 if complete else 3)
-                                        / (16 * 148 * clocks.get("sm_mhz", 1965) * 1e6) * 1e3,
+                                        / (16 * 148 * (clocks.get("sm_mhz") or 1965) * 1e6) * 1e3,
                          "note": "achieved uses the survey's accounting (8 B per resolution); the kernel resolves 32 gene trees per "
                                  "32-bit word in registers, so it moves ~60x fewer bytes than that model and frac exceeds 1; "
                                  "design_* = bytes of triple tiles the kernel actually streams (L2 + HBM); traffic = its DRAM bytes "
