@@ -451,6 +451,8 @@ int camus_b200_add_gene_trees(camus_b200* ctx, int32_t n_trees, const int64_t* n
         has_child[p] = 1;
         ++n_child[p];
         depth_h[i] = depth_h[p] + 1;
+        if (depth_h[i] >= 65535)
+          return ctx->fail(CAMUS_B200_ERR_INPUT, "add_gene_trees: tree " + std::to_string(g) + " is deeper than 65534 edges (16-bit depth tables)");
         if (depth_h[i] > ctx->max_depth) ctx->max_depth = depth_h[i];
       }
       int t = taxon[b + i];

@@ -589,3 +589,68 @@ def test_multi_gpu_handle_matches_single(gpu):
         multi.set_partition(0, 1)
     gpu.set_score_hint(False)
     multi.close()
+
+
+def _random_tree_with_chains(rng, n_taxa, chains):
+    """Preorder (parent, taxon) arrays of a random binary tree on all taxa, with unary chains of
+    the given lengths inserted above randomly chosen nodes (the first one above the root)."""
+    kids = {}
+    nodes = list(range(n_taxa))
+    nxt = n_taxa
+    while len(nodes) > 1:
+        a = nodes.pop(rng.integers(len(nodes)))
+        b = nodes.pop(rng.integers(len(nodes)))
+        kids[nxt] = (a, b)
+        nodes.append(nxt)
+        nxt += 1
+    root = nodes[0]
+    above = {root: chains[0]}
+    for length in chains[1:]:
+        above[int(rng.integers(nxt))] = length
+    parent, taxon = [], []
+    stack = [(root, -1)]
+    while stack:
+        x, p = stack.pop()
+        for _ in range(above.get(x, 0)):
+            parent.append(p)
+            taxon.append(-1)
+            p = len(parent) - 1
+        parent.append(p)
+        taxon.append(x if x < n_taxa else -1)
+        me = len(parent) - 1
+        if x >= n_taxa:
+            stack.append((kids[x][1], me))
+            stack.append((kids[x][0], me))
+    return np.array(parent, np.int32), np.array(taxon, np.int32)
+
+
+def test_deep_trees_take_the_integer_plane_builder(gpu):
+    """Unary chains make a gene tree deeper than 2047 edges although it has few taxa: fp16 depths
+    are no longer exact and the library must switch to the integer plane builder by itself
+    (camus_b200.cu, half_path). Raw counts, survivors and scores against the oracle; a tree deeper
+    than the 16-bit depth tables can hold is refused."""
+    rng = np.random.default_rng(3)
+    s = synth.make(14, 1, 2)
+    prob = Problem(s.constraint, s.genes)
+    offs, pars, taxs = [0], [], []
+    for g in range(45):
+        chains = [3000, 40, 7] if g % 3 == 0 else ([5] if g % 3 == 1 else [0])
+        p, t = _random_tree_with_chains(rng, 14, chains)
+        pars.append(p)
+        taxs.append(t)
+        offs.append(offs[-1] + len(p))
+    off, par, tax = np.array(offs, np.int64), np.concatenate(pars), np.concatenate(taxs)
+    o = orc.Oracle()
+    o.set_constraint(prob.parent, prob.child0, prob.child1, prob.tip_index, prob.n_taxa)
+    o.add_gene_trees(off, par, tax)
+    gpu.set_constraint(prob.parent, prob.child0, prob.child1, prob.tip_index, prob.n_taxa)
+    gpu.add_gene_trees(off, par, tax)
+    for qmode, thr in ((0, 0.0), (2, 0.3)):
+        assert gpu.count_filter(qmode, thr) == o.count_filter(qmode, thr, False)
+        assert np.array_equal(gpu.quartet_totals(False), o.quartet_totals(False, False))
+    for a, b in zip(gpu.export_quartets(raw=True), o.export_raw_counts()):
+        assert np.array_equal(a, b)
+    from camus_b200.cabi import CamusB200Error
+    p, t = _random_tree_with_chains(rng, 14, [70000])
+    with pytest.raises(CamusB200Error, match="deeper|nodes"):
+        gpu.add_gene_trees(np.array([0, len(p)], np.int64), p, t)
