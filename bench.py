@@ -219,7 +219,11 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     prob, c = make_problem(args.config, args.taxa, args.trees)
-    gpu = CamusB200(local)
+    # Launched under torchrun: one process per GPU. Launched as a plain process with --gpus N > 1:
+    # ONE handle drives the N GPUs (camus_b200_create n_gpus = N), no torch.distributed involved.
+    n_dev = args.gpus if world == 1 and args.gpus > 1 else 1
+    gpu = CamusB200(devices=list(range(n_dev))) if n_dev > 1 else CamusB200(local)
+    shares = world * n_dev
     gpu.set_partition(rank, world)
     gpu.load(prob)
     n = prob.n_nodes
@@ -294,19 +298,21 @@ def run_ours(args):
         # Algorithmic bytes per launch, SURVEY.md 8(d) convention: 8 B per resolution (one count
         # cell read + written per (gene tree, 4-set)) + 16 B per cell (one 128-bit cell read by
         # filter / score), for the share of the 4-set space this rank owns.
-        alg_bytes_kernel = (8 * R + 16 * cells) / world
+        alg_bytes_kernel = (8 * R + 16 * cells) / shares
         kern_ms = stage_ms["count"]
-        n_launch = max(1, -(-num_boxes // world // (1 << 30)))
+        n_launch = max(1, -(-num_boxes // shares // (1 << 30)))
         achieved = alg_bytes_kernel / (kern_ms * 1e-3) / 1e9
         b_alg = 8 * R + 16 * cells + 24 * n * n
         # Bytes the kernel's own design has to move per launch: four 6 KB triple tiles per
         # (box, tree group), read once each (HBM or L2), and one pass over the junction tables.
         groups = -(-prob.n_trees // 32)
-        design_bytes = (num_boxes / world) * groups * 4 * 6144
+        design_bytes = (num_boxes / shares) * groups * 4 * 6144
         traffic = None
         tf = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tf):
             traffic = json.load(open(tf)).get(f"config{args.config}_k_count_dram_bytes_per_launch")
+        if shares > 1:
+            traffic = None  # the captures are single-GPU launches
         h2d = int(prob.gene_node_off.nbytes + prob.gene_parent.nbytes + prob.gene_taxon.nbytes)
         # complete binary gene trees take the 8-plane kernel variant (2/3 of the tile bytes)
         nl = np.diff(np.concatenate([[0], np.cumsum(prob.gene_taxon >= 0)[prob.gene_node_off[1:] - 1]]))
@@ -314,13 +320,15 @@ def run_ours(args):
         if complete:
             design_bytes *= 2.0 / 3.0
         line = {
-            "metric": METRIC, "value": R / dt_res, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": METRIC, "value": R / dt_res, "unit": UNIT, "n_gpus": shares, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dt_res * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u32", "data": "synthetic",
             "config": {"workload": workload_name(args.config, c), "resolutions_per_step": R, "cells": cells, "boxes": num_boxes,
-                       "sharding": f"4-taxon-set index space / {world}, all trees on every rank, one NCCL all-reduce of the junction table",
+                       "sharding": f"4-taxon-set index space / {shares}, all trees on every GPU, " +
+                                   ("one NCCL all-reduce of the junction table" if n_dev == 1 else
+                                    "one process and one handle for all GPUs, junction tables summed by NVLink peer reads"),
                        "l2": "no explicit flush: the rooted-triple bit-planes streamed by every step "
-                             f"({design_bytes * world / 1e9:.1f} GB of tile reads over a {groups * 6144 * num_tiles / 1e9:.2f} GB table) exceed the 126 MB L2 many times over"},
+                             f"({design_bytes * shares / 1e9:.1f} GB of tile reads over a {groups * 6144 * num_tiles / 1e9:.2f} GB table) exceed the 126 MB L2 many times over"},
             "clocks": clocks,
             "e2e": {"value": R / dt_e2e, "unit": UNIT, "ms_per_step": dt_e2e * 1e3, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": int(out.nbytes + 16)},
@@ -334,7 +342,7 @@ def run_ours(args):
                          "design_achieved": design_bytes / (kern_ms * 1e-3) / 1e9,
                          # the pipe that actually bounds the kernel: one POPC per (cell, counted topology, 32 trees)
                          # on the XU pipe, 16 lanes per clock and SM (B300_MICROARCH.md), 148 SMs
-                         "xu_floor_ms": (num_boxes / world) * groups * 4096 * (2 if complete else 3)
+                         "xu_floor_ms": (num_boxes / shares) * groups * 4096 * (2 if complete else 3)
                                         / (16 * 148 * (clocks.get("sm_mhz") or 1965) * 1e6) * 1e3,
                          "note": "achieved uses the survey's accounting (8 B per resolution); the kernel resolves 32 gene trees per "
                                  "32-bit word in registers, so it moves ~60x fewer bytes than that model and frac exceeds 1; "
