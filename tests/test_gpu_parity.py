@@ -654,3 +654,38 @@ def test_deep_trees_take_the_integer_plane_builder(gpu):
     p, t = _random_tree_with_chains(rng, 14, [70000])
     with pytest.raises(CamusB200Error, match="deeper|nodes"):
         gpu.add_gene_trees(np.array([0, len(p)], np.int64), p, t)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_randomized_instances(gpu, seed):
+    """Seeded sweep over shapes and options: taxa 9..75 (around the 8-taxon segment and 32-taxon
+    box boundaries), 1..130 trees (around the 32-tree word), complete / missing taxa / collapsed
+    edges / unrooted input, all filter modes, weighted and -asSet scores. Everything the C-ABI
+    returns against the oracle, bit for bit."""
+    rng = np.random.default_rng(1000 + seed)
+    n_taxa = int(rng.choice([9, 15, 16, 17, 31, 32, 33, 40, 47, 64, 65, 75]))
+    n_trees = int(rng.choice([1, 2, 31, 32, 33, 50, 64, 65, 96, 130]))
+    kind = seed % 4
+    s = synth.make(n_taxa, n_trees, 500 + seed, support=(kind == 2), drop_frac=(0.15 if kind in (1, 2) else 0.0),
+                   nni_rate=float(rng.choice([0.5, 3.0, 12.0])))
+    genes = s.genes
+    if kind == 3:
+        genes = "\n".join(_unroot(l) for l in genes.strip().split("\n")) + "\n"
+    prob = Problem(s.constraint, genes, s.fmt, 0.6 if kind == 2 else 0.0)
+    o = orc.Oracle().load(prob)
+    gpu.load(prob)
+    qmode = int(rng.integers(0, 3))
+    thr = float(rng.choice([0.0, 0.1, 1.0 / 3.0, 0.5, 0.9, 1.0]))
+    as_set = bool(rng.integers(0, 2))
+    gpu.set_score_hint(as_set)
+    try:
+        assert gpu.count_filter(qmode, thr) == o.count_filter(qmode, thr, False)
+        assert np.array_equal(gpu.quartet_totals(as_set), o.quartet_totals(as_set, False))
+        assert np.array_equal(gpu.quartet_totals(not as_set), o.quartet_totals(not as_set, False))
+        for a, b in zip(gpu.export_quartets(), o.export_quartets()):
+            assert np.array_equal(a, b)
+        for a, b in zip(gpu.export_quartets(raw=True), o.export_raw_counts()):
+            assert np.array_equal(a, b)
+        assert np.array_equal(gpu.edge_penalties(), o.edge_penalties())
+    finally:
+        gpu.set_score_hint(False)
