@@ -85,6 +85,13 @@ struct camus_b200 {
   DevBuf<unsigned long long> d_Z, d_E, d_out, d_totals, d_keys, d_nout;
   DevBuf<uint32_t> d_counts, d_thr_tab;
   uint64_t n_local = 0, chunk = 1;  // this rank's share of the boxes (BoxMap)
+  // class-scheme partition (layout.cuh): explicit local box list + the tiles this rank builds
+  bool class_scheme = false;
+  DevBuf<uint32_t> d_box_list, d_tile_list;
+  uint64_t n_tiles_local = 0;
+  int list_key[3] = {-1, -1, -1};  // (segments, rank, world) the lists were built for
+  uint32_t tri_mask = 0;           // segment classes whose tiles the bit-planes hold (0xF = every tile)
+  bool want_all_tiles = false;     // camus_b200_query_cells reads arbitrary tiles
   enum CellState { NONE, RAW, FILTERED } cell_state = NONE;
   int last_qmode = 0;
   double last_threshold = 0;
@@ -163,6 +170,7 @@ int fan_out(camus_b200* ctx, F f) {
 int reduce_partials(camus_b200* ctx);
 
 int build_planes(camus_b200* ctx, bool do_upload);
+int set_box_range(camus_b200* ctx);
 int run_count(camus_b200* ctx);
 int run_filter(camus_b200* ctx, int qmode, double threshold, uint64_t* ns, uint64_t* sum);
 
@@ -498,6 +506,10 @@ int build_planes(camus_b200* ctx, bool do_upload = true) {
   const int G = ctx->G, npad = ctx->npad;
   ctx->G32 = (G + kLanes - 1) / kLanes;
   const int G32 = std::max(ctx->G32, 1);
+  if (int rc = set_box_range(ctx)) return rc;
+  // class-scheme partitions read, and therefore build, only the tiles led by their classes
+  const bool partial = ctx->class_scheme && !ctx->want_all_tiles;
+  const uint32_t* tile_list = partial ? ctx->d_tile_list.p : nullptr;
   if (do_upload) {
     StageTimer t(ctx, CAMUS_B200_T_UPLOAD);
     if (upload(ctx, ctx->d_node_off, ctx->h_node_off.data(), ctx->h_node_off.size()) ||
@@ -525,9 +537,20 @@ int build_planes(camus_b200* ctx, bool do_upload = true) {
   CK(ctx->d_tri.alloc(tri_words));
   if (G == 0) CK(cudaMemsetAsync(ctx->d_tri.p, 0, tri_words * 4, ctx->stream));
   if (G > 0) {
-    k_tree_prepare<<<(G + 127) / 128, 128, 0, ctx->stream>>>(G, ctx->d_node_off.p, ctx->d_gparent.p, ctx->d_gtaxon.p,
-                                                            ctx->d_rank_of_tip.p, ctx->d_depth_tmp.p, ctx->d_lrT.p,
-                                                            ctx->d_hT.p, npad, ctx->d_nleaf.p);
+    int max_nodes = 1;
+    for (int g = 0; g < G; ++g) max_nodes = std::max<int>(max_nodes, (int)(ctx->h_node_off[g + 1] - ctx->h_node_off[g]));
+    static const bool serial_prepare = getenv("CAMUS_B200_SERIAL_PREPARE") && getenv("CAMUS_B200_SERIAL_PREPARE")[0] == '1';  // A/B, tests
+    if (max_nodes <= kTreePrepareMaxNodes && !serial_prepare) {
+      const size_t smem = (size_t)max_nodes * 4;
+      if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_tree_prepare_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_tree_prepare_warp<<<G, 32, smem, ctx->stream>>>(G, ctx->d_node_off.p, ctx->d_gparent.p, ctx->d_gtaxon.p,
+                                                         ctx->d_rank_of_tip.p, ctx->d_lrT.p, ctx->d_hT.p, npad, ctx->d_nleaf.p,
+                                                         max_nodes);
+    } else {
+      k_tree_prepare<<<(G + 127) / 128, 128, 0, ctx->stream>>>(G, ctx->d_node_off.p, ctx->d_gparent.p, ctx->d_gtaxon.p,
+                                                              ctx->d_rank_of_tip.p, ctx->d_depth_tmp.p, ctx->d_lrT.p,
+                                                              ctx->d_hT.p, npad, ctx->d_nleaf.p);
+    }
     CK_LAUNCH();
     size_t dt_group = (size_t)npad * npad * kLanes;  // u16 elements
     // Tree groups go through the depth table in batches of <= 256 MB (measured: running K1 of
@@ -535,7 +558,7 @@ int build_planes(camus_b200* ctx, bool do_upload = true) {
     int gb_max = (int)std::max<size_t>(1, std::min<size_t>(ctx->G32, ((size_t)256 << 20) / (dt_group * 2)));
     if (const char* e = getenv("CAMUS_B200_PREP_BATCH")) gb_max = std::max(1, std::min(ctx->G32, atoi(e)));  // tuning
     CK(ctx->d_Dt.alloc(dt_group * gb_max));
-    const unsigned n_tiles = (unsigned)num_tiles(ctx->M);
+    const unsigned n_tiles = partial ? (unsigned)ctx->n_tiles_local : (unsigned)num_tiles(ctx->M);
     // packed fp16 compares need exact depths: depth + 1 <= 2048 (checked in add_gene_trees)
     const bool half_path = ctx->max_depth + 1 <= 2048 && ctx->allow_half;
     // rooted triples are all resolved only under a binary root (a trifurcating root resolves
@@ -553,18 +576,27 @@ int build_planes(camus_b200* ctx, bool do_upload = true) {
       else
         k_depth_table<false><<<g1, blk, 0, ctx->stream>>>(g0, G, npad, ctx->d_nleaf.p, ctx->d_lrT.p, ctx->d_hT.p, dt);
       CK_LAUNCH();
+      if (n_tiles == 0) continue;  // a share without boxes
       if (half_path && complete)
-        k_triple_planes_h2<true><<<n_tiles, 256, 0, ctx->stream>>>(g0, gb, G32, G, npad, dt, ctx->d_tri.p);
+        k_triple_planes_h2<true><<<n_tiles, 256, 0, ctx->stream>>>(g0, gb, G32, G, npad, dt, ctx->d_tri.p, tile_list);
       else if (half_path)
-        k_triple_planes_h2<false><<<n_tiles, 256, 0, ctx->stream>>>(g0, gb, G32, G, npad, dt, ctx->d_tri.p);
+        k_triple_planes_h2<false><<<n_tiles, 256, 0, ctx->stream>>>(g0, gb, G32, G, npad, dt, ctx->d_tri.p, tile_list);
       else
-        k_triple_planes<<<n_tiles, 256, 0, ctx->stream>>>(g0, gb, G32, npad, dt, ctx->d_tri.p);
+        k_triple_planes<<<n_tiles, 256, 0, ctx->stream>>>(g0, gb, G32, npad, dt, ctx->d_tri.p, tile_list);
       CK_LAUNCH();
     }
   }
   if (t.stop()) return CAMUS_B200_ERR_CUDA;
   ctx->genes_dirty = false;
+  ctx->tri_mask = partial ? class_need_mask(ctx->rank, ctx->world) : 0xFu;
   return 0;
+}
+
+// do the bit-planes in HBM hold every tile the current partition reads?
+bool planes_cover(camus_b200* ctx) {
+  if (set_box_range(ctx)) return false;
+  const uint32_t need = ctx->class_scheme ? class_need_mask(ctx->rank, ctx->world) : 0xFu;
+  return (need & ~ctx->tri_mask) == 0;
 }
 
 // the complete-tree kernel packs two 16-bit counters per register
@@ -578,16 +610,76 @@ int make_thr_table(camus_b200* ctx, double threshold) {
   return 0;
 }
 
-void set_box_range(camus_b200* ctx) {
-  uint64_t nb = num_boxes(ctx->M);
-  ctx->chunk = partition_chunk(nb, (uint32_t)ctx->world);
-  ctx->n_local = local_box_count(nb, ctx->chunk, (uint32_t)ctx->rank, (uint32_t)ctx->world);
+// Which split of the box index space (layout.cuh): the class scheme for 4 or 8 shares of a
+// constraint with 32..256 segments, else chunks. CAMUS_B200_PARTITION=chunk|class overrides
+// (class still needs 4 or 8 shares). camus_b200/partition.py mirrors the rule.
+bool use_class_scheme(const camus_b200* ctx) {
+  if (ctx->world != 4 && ctx->world != 8) return false;
+  if (const char* e = getenv("CAMUS_B200_PARTITION")) {
+    if (!strcmp(e, "chunk")) return false;
+    if (!strcmp(e, "class")) return ctx->M <= 256;
+  }
+  return ctx->M >= 32 && ctx->M <= 256;
+}
+
+BoxMap box_map(const camus_b200* ctx, uint64_t b0) {
+  return BoxMap{b0, ctx->chunk, (uint32_t)ctx->rank, (uint32_t)ctx->world, ctx->class_scheme ? ctx->d_box_list.p : nullptr};
+}
+
+int set_box_range(camus_b200* ctx) {
+  const uint64_t nb = num_boxes(ctx->M);
+  if (!use_class_scheme(ctx)) {
+    ctx->class_scheme = false;
+    ctx->chunk = partition_chunk(nb, (uint32_t)ctx->world);
+    ctx->n_local = local_box_count(nb, ctx->chunk, (uint32_t)ctx->rank, (uint32_t)ctx->world);
+    return 0;
+  }
+  ctx->class_scheme = true;
+  ctx->chunk = 1;
+  if (ctx->list_key[0] == ctx->M && ctx->list_key[1] == ctx->rank && ctx->list_key[2] == ctx->world) return 0;
+  // host-built lists, colex order (= the order of the unpartitioned kernel, filtered)
+  const uint32_t S = (uint32_t)ctx->M;
+  const int world = ctx->world, rank = ctx->rank;
+  const uint32_t thr = class_threshold(S, world), need = class_need_mask(rank, world);
+  std::vector<uint8_t> cls(S);
+  for (uint32_t s = 0; s < S; ++s) cls[s] = (uint8_t)seg_class(s);
+  std::vector<uint32_t> boxes, tiles;
+  boxes.reserve((size_t)(nb / world + nb / (8 * (uint64_t)world) + 64));
+  uint32_t idx = 0;
+  for (uint32_t sd = 0; sd < S; ++sd)
+    for (uint32_t sc = 0; sc <= sd; ++sc) {
+      const uint32_t h = class_hash(sc, sd);
+      bool allow[4][4];
+      for (uint32_t i = 0; i < 4; ++i)
+        for (uint32_t j = 0; j < 4; ++j) allow[i][j] = class_owner(i, j, h, world, thr) == rank;
+      for (uint32_t sb = 0; sb <= sc; ++sb) {
+        const bool* row = allow[cls[sb]];
+        for (uint32_t sa = 0; sa <= sb; ++sa, ++idx)
+          if (row[cls[sa]]) boxes.push_back(idx);
+      }
+    }
+  idx = 0;
+  for (uint32_t s2 = 0; s2 < S; ++s2)
+    for (uint32_t s1 = 0; s1 <= s2; ++s1)
+      for (uint32_t s0 = 0; s0 <= s1; ++s0, ++idx)
+        if ((need >> cls[s0]) & 1u) tiles.push_back(idx);
+  CK(ctx->d_box_list.alloc(std::max<size_t>(boxes.size(), 1)));
+  CK(ctx->d_tile_list.alloc(std::max<size_t>(tiles.size(), 1)));
+  if (!boxes.empty()) CK(cudaMemcpyAsync(ctx->d_box_list.p, boxes.data(), boxes.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+  if (!tiles.empty()) CK(cudaMemcpyAsync(ctx->d_tile_list.p, tiles.data(), tiles.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));  // the host vectors go away
+  ctx->n_local = boxes.size();
+  ctx->n_tiles_local = tiles.size();
+  ctx->list_key[0] = ctx->M;
+  ctx->list_key[1] = ctx->rank;
+  ctx->list_key[2] = ctx->world;
+  return 0;
 }
 
 // Fused K2+K3+K4 over this rank's box range: counts stay in registers, survivors are scored
 // straight into the junction table Z. No cell table.
 int run_fused(camus_b200* ctx, int qmode, double threshold, int as_set, uint64_t* ns, uint64_t* sum) {
-  set_box_range(ctx);
+  if (int rc = set_box_range(ctx)) return rc;
   uint64_t mine = ctx->n_local;
   size_t zn = (size_t)ctx->n * ctx->n * 3;
   static const int rep_env = getenv("CAMUS_B200_ZREP") ? atoi(getenv("CAMUS_B200_ZREP")) : 0;
@@ -614,7 +706,7 @@ int run_fused(camus_b200* ctx, int qmode, double threshold, int as_set, uint64_t
   const uint64_t max_grid = 1u << 30;
   for (uint64_t b0 = 0; b0 < mine; b0 += max_grid) {
     uint64_t nbx = std::min(max_grid, mine - b0);
-    CountParams prm{ctx->d_tri.p, std::max(ctx->G32, 1), BoxMap{b0, ctx->chunk, (uint32_t)ctx->rank, (uint32_t)ctx->world}, nullptr, ctx->G};
+    CountParams prm{ctx->d_tri.p, std::max(ctx->G32, 1), box_map(ctx, b0), nullptr, ctx->G};
     static const int dbg = getenv("CAMUS_B200_DEBUG") ? atoi(getenv("CAMUS_B200_DEBUG")) : 0;
     FusedParams fz{qmode, threshold, ctx->d_thr_tab.p, as_set, ctx->d_Z.p, ctx->d_totals.p, rep, (unsigned long long)zn, ctx->allow_regular ? 1 : 0, dbg};
     if (use_complete(ctx))
@@ -642,7 +734,7 @@ int run_fused(camus_b200* ctx, int qmode, double threshold, int as_set, uint64_t
 
 // K2 (table mode) over this rank's box range (whole range resident in d_cells).
 int run_count(camus_b200* ctx) {
-  set_box_range(ctx);
+  if (int rc = set_box_range(ctx)) return rc;
   uint64_t mine = ctx->n_local;
   if (ctx->d_cells.n < mine * kBoxCells) {
     size_t free_b = 0, total_b = 0;
@@ -656,7 +748,7 @@ int run_count(camus_b200* ctx) {
   const uint64_t max_grid = 1u << 30;
   for (uint64_t b0 = 0; b0 < mine; b0 += max_grid) {
     uint64_t nbx = std::min(max_grid, mine - b0);
-    CountParams prm{ctx->d_tri.p, std::max(ctx->G32, 1), BoxMap{b0, ctx->chunk, (uint32_t)ctx->rank, (uint32_t)ctx->world}, ctx->d_cells.p + b0 * kBoxCells, ctx->G};
+    CountParams prm{ctx->d_tri.p, std::max(ctx->G32, 1), box_map(ctx, b0), ctx->d_cells.p + b0 * kBoxCells, ctx->G};
     if (use_complete(ctx))
       k_count<false, true><<<(unsigned)nbx, kCountThreads, CountCfg<true>::kSmemBytes, ctx->stream>>>(prm, FusedParams{}, ctx->ct);
     else
@@ -677,7 +769,7 @@ int run_filter(camus_b200* ctx, int qmode, double threshold, uint64_t* ns, uint6
   const uint64_t max_boxes = 1u << 26;
   for (uint64_t b0 = 0; b0 < mine; b0 += max_boxes) {
     uint64_t nbx = std::min(max_boxes, mine - b0);
-    FilterParams prm{ctx->d_cells.p + b0 * kBoxCells, BoxMap{b0, ctx->chunk, (uint32_t)ctx->rank, (uint32_t)ctx->world}, qmode, threshold, ctx->d_thr_tab.p, ctx->d_totals.p};
+    FilterParams prm{ctx->d_cells.p + b0 * kBoxCells, box_map(ctx, b0), qmode, threshold, ctx->d_thr_tab.p, ctx->d_totals.p};
     k_filter<<<(unsigned)(nbx * 16), 256, 0, ctx->stream>>>(prm, ctx->ct);
     CK_LAUNCH();
   }
@@ -715,7 +807,7 @@ int run_score(camus_b200* ctx, int as_set) {
   const uint64_t max_boxes = 1u << 26;
   for (uint64_t b0 = 0; b0 < mine; b0 += max_boxes) {
     uint64_t nbx = std::min(max_boxes, mine - b0);
-    ScoreParams prm{ctx->d_cells.p + b0 * kBoxCells, BoxMap{b0, ctx->chunk, (uint32_t)ctx->rank, (uint32_t)ctx->world}, as_set, ctx->d_Z.p};
+    ScoreParams prm{ctx->d_cells.p + b0 * kBoxCells, box_map(ctx, b0), as_set, ctx->d_Z.p};
     k_score<<<(unsigned)(nbx * 16), 256, 0, ctx->stream>>>(prm, ctx->ct);
     CK_LAUNCH();
   }
@@ -819,7 +911,11 @@ int camus_b200_count_filter(camus_b200* ctx, int qmode, double threshold, uint64
   std::memset(ctx->ms, 0, sizeof(ctx->ms));
   ctx->launches = 0;
   int rc;
-  if (ctx->genes_dirty && (rc = build_planes(ctx, true))) return rc;
+  if (ctx->genes_dirty) {
+    if ((rc = build_planes(ctx, true))) return rc;
+  } else if (!planes_cover(ctx) && (rc = build_planes(ctx, false))) {  // the partition changed under resident trees
+    return rc;
+  }
   ctx->cell_state = camus_b200::NONE;
   ctx->z_valid = false;
   if (ctx->use_fused) return run_fused(ctx, qmode, threshold, ctx->as_set_hint, n_survivors, sum_counts);
@@ -984,7 +1080,7 @@ int camus_b200_export_quartets(camus_b200* ctx, int raw, uint64_t* keys, uint32_
   const uint64_t max_boxes = 1u << 26;
   for (uint64_t b0 = 0; b0 < mine; b0 += max_boxes) {
     uint64_t nbx = std::min(max_boxes, mine - b0);
-    ExportParams prm{ctx->d_cells.p + b0 * kBoxCells, BoxMap{b0, ctx->chunk, (uint32_t)ctx->rank, (uint32_t)ctx->world}, ctx->d_keys.p, ctx->d_counts.p, cap, ctx->d_nout.p};
+    ExportParams prm{ctx->d_cells.p + b0 * kBoxCells, box_map(ctx, b0), ctx->d_keys.p, ctx->d_counts.p, cap, ctx->d_nout.p};
     k_export<<<(unsigned)(nbx * 16), 256, 0, ctx->stream>>>(prm, ctx->ct);
     CK_LAUNCH();
   }
@@ -1024,6 +1120,10 @@ int camus_b200_query_cells(camus_b200* ctx, int32_t n_query, const int32_t* quad
         if (quads[4 * q + i] == quads[4 * q + j]) return ctx->fail(CAMUS_B200_ERR_ARG, "query_cells: repeated taxon in a 4-set");
   if (n_query == 0) return 0;
   CK(cudaSetDevice(ctx->device));
+  if (ctx->tri_mask != 0xFu) {  // a class-scheme partition built only its own tiles
+    ctx->want_all_tiles = true;
+    if (int rc = build_planes(ctx, false)) return rc;
+  }
   DevBuf<int32_t> dq;
   DevBuf<uint32_t> dc;
   CK(dq.alloc((size_t)4 * n_query));

@@ -53,6 +53,48 @@ __global__ void k_tree_prepare(int n_trees, const int64_t* __restrict__ node_off
   nleaf[g] = pos;
 }
 
+// K0, staged form (default): one warp per gene tree. The parent array is staged in shared memory
+// (u16 local indices), lane 0 resolves the depths there (the serial form above pays two dependent
+// L2 round trips per node), then all lanes emit lr / h with a ballot prefix over the leaves.
+// Dynamic shared memory: 4 bytes per node of the largest tree (the host falls back to the serial
+// kernel above kTreePrepareMaxNodes).
+constexpr int kTreePrepareMaxNodes = 24576;
+__global__ void __launch_bounds__(32) k_tree_prepare_warp(int n_trees, const int64_t* __restrict__ node_off,
+                                                          const int32_t* __restrict__ parent, const int32_t* __restrict__ taxon,
+                                                          const int32_t* __restrict__ rank_of_tip, uint16_t* __restrict__ lrT,
+                                                          uint16_t* __restrict__ hT, int npad, int32_t* __restrict__ nleaf,
+                                                          int max_nodes) {
+  extern __shared__ uint16_t s_tree[];
+  uint16_t* s_par = s_tree;
+  uint16_t* s_dep = s_tree + max_nodes;
+  const int g = blockIdx.x, lane = threadIdx.x;
+  if (g >= n_trees) return;
+  const int64_t base = node_off[g];
+  const int nn = (int)(node_off[g + 1] - base);
+  for (int i = lane; i < nn; i += 32) s_par[i] = (uint16_t)parent[base + i];  // root: 0xFFFF, never read
+  __syncwarp();
+  if (lane == 0) {
+    s_dep[0] = 0;
+    for (int i = 1; i < nn; ++i) s_dep[i] = (uint16_t)(s_dep[s_par[i]] + 1);
+  }
+  __syncwarp();
+  const size_t row0 = (size_t)(g >> 5) * npad;
+  const int gl = g & 31;
+  int pos = 0;
+  for (int i0 = 0; i0 < nn; i0 += 32) {
+    const int i = i0 + lane;
+    const int t = i < nn ? taxon[base + i] : -1;
+    const uint32_t m = __ballot_sync(0xFFFFFFFFu, t >= 0);
+    if (t >= 0) {
+      const int k = pos + __popc(m & ((1u << lane) - 1u));
+      lrT[(row0 + k) * kLanes + gl] = (uint16_t)rank_of_tip[t];
+      if (i + 1 < nn) hT[(row0 + k) * kLanes + gl] = s_dep[i + 1];  // node after a leaf hangs off LCA(leaf, next leaf)
+    }
+    pos += __popc(m);
+  }
+  if (lane == 0) nleaf[g] = pos;
+}
+
 // ---------------------------------------------------------------------------------------------
 // K1: LCA-depth table of every tree of a group batch, in constraint DFS-rank coordinates:
 //   Dt[gb][lo][hi][lane] = 1 + depth of LCA(lo, hi) in tree (grp0+gb)*32+lane, 0 if absent.
@@ -96,8 +138,10 @@ __global__ void k_depth_table(int grp0, int n_trees, int npad, const int32_t* __
 // needs are staged in shared memory (coalesced 64 B rows of Dt), 8 warps x 64 triples ballot into
 // a shared 6 KB image of the tile, which is then written to HBM with 128-bit coalesced stores.
 // Every word of every tile is written, so Tri needs no memset.
+// tile_list: class-scheme partitions build only the tiles this rank reads (layout.cuh); nullptr = all.
 __global__ void __launch_bounds__(256) k_triple_planes(int grp0, int n_batch, int n_groups_total, int npad,
-                                                       const uint16_t* __restrict__ Dt, uint32_t* __restrict__ Tri) {
+                                                       const uint16_t* __restrict__ Dt, uint32_t* __restrict__ Tri,
+                                                       const uint32_t* __restrict__ tile_list) {
   __shared__ __align__(16) uint16_t s_d[3][64][kLanes];  // [ab | ac | bc][i*8+j][lane]
   // Tile image: the 3 planes are padded to 516 words so that lanes 0..2 (one plane each) hit
   // different banks, and the dummy row the other 29 lanes write to sits 16 banks away.
@@ -106,7 +150,7 @@ __global__ void __launch_bounds__(256) k_triple_planes(int grp0, int n_batch, in
   uint32_t* const s_scr = s_img + 3 * kPlanePad + 4;
   __shared__ uint32_t s_seg[3];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint64_t tile = blockIdx.x;
+  const uint64_t tile = tile_list ? tile_list[blockIdx.x] : blockIdx.x;
   if (tid == 0) {
     uint64_t r = tile;
     uint32_t s2 = unrank3(r);
@@ -257,14 +301,15 @@ __device__ __forceinline__ void triple_words(const uint4 (&ab)[4], const uint16_
 
 template <bool kComplete>
 __global__ void __launch_bounds__(256, 4) k_triple_planes_h2(int grp0, int n_batch, int n_groups_total, int n_trees, int npad,
-                                                          const uint16_t* __restrict__ Dt, uint32_t* __restrict__ Tri) {
+                                                          const uint16_t* __restrict__ Dt, uint32_t* __restrict__ Tri,
+                                                          const uint32_t* __restrict__ tile_list) {
   // fp16 bits, NaN = absent. Rows: ab[x*8+y], ac[x*8+z], bc[z*8+y] (the index that varies across
   // the lanes of a load phase is the low one).
   __shared__ __align__(16) uint16_t s_d[3][64 * kLanes + 64];
   __shared__ __align__(16) uint32_t s_img[kTileWords];
   __shared__ uint32_t s_seg[3];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint64_t tile = blockIdx.x;
+  const uint64_t tile = tile_list ? tile_list[blockIdx.x] : blockIdx.x;
   if (tid == 0) {
     uint64_t r = tile;
     uint32_t s2 = unrank3(r);

@@ -83,19 +83,89 @@ CAMUS_HD void pair_unrank(uint64_t r, uint32_t& a, uint32_t& b) {
   a = (uint32_t)(r - choose2((uint64_t)s));
 }
 
-// Multi-rank split of the box index space: boxes are dealt to ranks in chunks, round-robin
-// (rank r owns chunks r, r+world, ...), which balances the ranks (score-scatter cost varies
-// along the index space) while neighbouring CTAs still share triple tiles in L2.
+// Multi-rank split of the box index space, two schemes.
+//
+// Chunk scheme (any world): boxes are dealt to ranks in chunks, round-robin (rank r owns chunks
+// r, r+world, ...), which balances the ranks (score-scatter cost varies along the index space)
+// while neighbouring CTAs still share triple tiles in L2. Every rank reads every triple tile.
+//
+// Class scheme (world 4 or 8, see class_owner below): ranks own boxes by the CLASSES of their
+// first two segments, so that a rank only reads -- and therefore only builds -- the triple tiles
+// whose first segment falls in 2 (or 3) of the 4 classes. The local -> global box map is then an
+// explicit list (`list`, colex order) built on the host.
+//
 // Local box index l of a rank <-> global box rank. Mirrored by camus_b200/partition.py.
 struct BoxMap {
   uint64_t first;  // local index of blockIdx 0 of this launch
   uint64_t chunk;  // boxes per chunk
   uint32_t rank, world;
-  CAMUS_HD uint64_t global(uint64_t i) const {
+  const uint32_t* list;  // class scheme: global box rank of every local box; nullptr = chunk scheme
+#if defined(__CUDACC__)
+  __device__ __forceinline__ uint64_t global(uint64_t i) const {
     uint64_t l = first + i;
+    if (list) return list[l];
     return ((l / chunk) * world + rank) * chunk + l % chunk;
   }
+#endif
 };
+
+// ---- class scheme ----
+// A box (sa <= sb <= sc <= sd) reads the tiles (sa,sb,sc), (sa,sb,sd), (sa,sc,sd), (sb,sc,sd):
+// their FIRST segments are sa and sb only. Segments are coloured with 4 classes (a reflected
+// pattern, so that every class sees the same mix of low and high segments); a rank that owns the
+// boxes of the unordered class pair {i, j} needs the tiles led by classes i and j = half of the
+// table. The 6 mixed pairs weigh 2, the 4 pure pairs (i, i) weigh 1:
+//   world 8: ranks 0..5 own the mixed pairs (0,1) (0,2) (0,3) (1,2) (1,3) (2,3), rank 6 owns
+//            (0,0) + (1,1), rank 7 owns (2,2) + (3,3): every rank builds 1/2 of the tiles;
+//   world 4: rank 0 owns everything inside {0,1}, rank 1 everything inside {2,3} (1/2 of the
+//            tiles), rank 2 owns (0,2) (0,3), rank 3 owns (1,2) (1,3) (3/4 of the tiles).
+// The pure pairs are slightly heavier than half a mixed pair (they hold the sa == sb boxes); a
+// fraction t/256 of them, picked by a hash of (sc, sd), is donated to ranks that need the class
+// anyway (class_threshold evens the box counts out).
+CAMUS_HD uint32_t seg_class(uint32_t s) {
+  uint32_t r = s & 7u;
+  return r < 4 ? r : 7 - r;
+}
+CAMUS_HD int class_pair_rank(uint32_t lo, uint32_t hi) { return lo == 0 ? (int)hi - 1 : (lo == 1 ? (int)hi + 1 : 5); }
+CAMUS_HD uint32_t class_hash(uint32_t sc, uint32_t sd) { return (sc * 7u + sd * 13u) & 255u; }
+CAMUS_HD int class_owner(uint32_t ca, uint32_t cb, uint32_t h, int world, uint32_t t) {
+  const uint32_t lo = ca < cb ? ca : cb, hi = ca < cb ? cb : ca;
+  if (world == 8) {
+    if (lo != hi) return class_pair_rank(lo, hi);
+    if (h < 3 * t) {
+      const uint32_t k = h / t, o = k < lo ? k : k + 1;  // k-th of the three other classes
+      return class_pair_rank(o < lo ? o : lo, o < lo ? lo : o);
+    }
+    return lo < 2 ? 6 : 7;
+  }
+  // world == 4
+  if (lo != hi) return hi < 2 ? 0 : (lo >= 2 ? 1 : (lo == 0 ? 2 : 3));
+  if (h < t) return (lo == 0 || lo == 2) ? 2 : 3;
+  return lo < 2 ? 0 : 1;
+}
+// classes (bit mask) whose tiles rank `rank` reads
+CAMUS_HD uint32_t class_need_mask(int rank, int world) {
+  if (world == 8) {
+    const uint32_t m[8] = {0x3, 0x5, 0x9, 0x6, 0xA, 0xC, 0x3, 0xC};
+    return m[rank & 7];
+  }
+  const uint32_t m[4] = {0x3, 0xC, 0xD, 0xE};
+  return m[rank & 3];
+}
+// donation threshold (of 256) that evens out the box counts of the ranks for m segments
+inline uint32_t class_threshold(uint32_t m, int world) {
+  uint64_t D = 0, O = 0;  // boxes of pure / mixed class pairs
+  for (uint32_t sa = 0; sa < m; ++sa)
+    for (uint32_t sb = sa; sb < m; ++sb) {
+      uint64_t k = (uint64_t)(m - sb) * (m - sb + 1) / 2;
+      (seg_class(sa) == seg_class(sb) ? D : O) += k;
+    }
+  if (D == 0 || 3 * D <= O) return 0;
+  uint64_t scale = world == 8 ? 64 : 128;
+  uint64_t t = (scale * (3 * D - O) + (3 * D) / 2) / (3 * D);
+  uint64_t cap = world == 8 ? 85 : 255;
+  return (uint32_t)(t > cap ? cap : t);
+}
 CAMUS_HD uint64_t partition_chunk(uint64_t nb, uint32_t world) {
   uint64_t c = nb / ((uint64_t)world * 64);
   return c < 1 ? 1 : (c > 2048 ? 2048 : c);

@@ -426,6 +426,82 @@ def test_partitions_on_one_gpu(gpu, world):
         gpu.set_partition(0, 1)
 
 
+@pytest.mark.parametrize("world", [4, 8])
+def test_class_partitions_on_one_gpu(gpu, world, monkeypatch):
+    """The class scheme of camus_b200_set_partition (4 and 8 shares; forced here below its default
+    size): every share, run one after the other on this GPU with ONLY its own tile classes built,
+    yields the survivors the mirror assigns to it, and the partial tables add up to the oracle's.
+    query_cells afterwards rebuilds every tile."""
+    import torch
+    from camus_b200 import partition as part
+    monkeypatch.setenv("CAMUS_B200_PARTITION", "class")
+    s = synth.make(100, 60, 23, drop_frac=0.05)
+    prob = Problem(s.constraint, s.genes)
+    o = orc.Oracle().load(prob)
+    o.count_filter(2, 0.3, False)
+    keys, counts = o.export_quartets()
+    want_tot = o.quartet_totals(False, False)
+    owner = part.owner_of_quartets(keys, part.dfs_rank_of_tip(prob.parent, prob.child0, prob.child1, prob.tip_index), world)
+    assert len(set(owner.tolist())) == world
+    acc = None
+    try:
+        for r in range(world):
+            gpu.set_partition(r, world)
+            if r % 2 == 0:
+                gpu.load(prob)  # odd shares reuse the resident trees: the planes are rebuilt for the new classes
+            ns, sc = gpu.count_filter(2, 0.3)
+            assert (ns, sc) == (int((owner == r).sum()), int(counts[owner == r].sum()))
+            if r in (0, world - 1):
+                gk, gc = gpu.export_quartets()
+                assert np.array_equal(gk, keys[owner == r]) and np.array_equal(gc, counts[owner == r])
+            gpu.quartet_totals_partial(False)
+            z = gpu.partial_tensor().clone()
+            acc = z if acc is None else acc + z
+        gpu.partial_tensor().copy_(acc)
+        torch.cuda.synchronize()
+        assert np.array_equal(gpu.quartet_totals_finish(), want_tot)
+        quads = np.array([[0, 1, 2, 3], [5, 17, 40, 63], [99, 8, 57, 6], [90, 91, 92, 93]], np.int32)
+        got = gpu.query_cells(quads)
+        gpu.set_partition(0, 1)
+        gpu.load(prob)
+        gpu.count_filter(2, 0.3)
+        assert np.array_equal(got, gpu.query_cells(quads))
+    finally:
+        gpu.set_partition(0, 1)
+
+
+def test_default_class_scheme_shares_sum_to_the_whole(gpu, monkeypatch):
+    """264 taxa = 33 segments: 8 shares take the class scheme by default (complete binary trees,
+    the complete-tree kernels). Shares run one after the other through run_resident; scalars and
+    junction tables add up to the unpartitioned run's."""
+    import torch
+    from camus_b200 import partition as part
+    monkeypatch.delenv("CAMUS_B200_PARTITION", raising=False)
+    assert part.use_class_scheme(264, 8)
+    s = synth.make(264, 40, 29)
+    prob = Problem(s.constraint, s.genes)
+    gpu.set_partition(0, 1)
+    gpu.load(prob)
+    want = gpu.count_filter(2, 0.5)
+    want_tot = gpu.quartet_totals(False)
+    acc, ns, sc = None, 0, 0
+    try:
+        for r in range(8):
+            gpu.set_partition(r, 8)
+            if r == 0:
+                gpu.count_filter(2, 0.5)
+            _, a, b = gpu.run_resident(2, 0.5, False, partial_only=True)
+            ns, sc = ns + a, sc + b
+            z = gpu.partial_tensor().clone()
+            acc = z if acc is None else acc + z
+        assert (ns, sc) == want
+        gpu.partial_tensor().copy_(acc)
+        torch.cuda.synchronize()
+        assert np.array_equal(gpu.quartet_totals_finish(), want_tot)
+    finally:
+        gpu.set_partition(0, 1)
+
+
 # ------------------------------------------------- mid / full size: oracle + size-free properties
 def test_mid_size_vs_oracle(gpu):
     s = synth.make(96, 100, 11)

@@ -25,8 +25,10 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, scheme=None):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    if scheme:
+        os.environ["CAMUS_B200_PARTITION"] = scheme
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         s = synth.make(26, 40, 77, drop_frac=0.1)
@@ -50,12 +52,12 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_partial_tables_sum_to_the_full_table(world):
+@pytest.mark.parametrize("world,scheme", [(2, None), (3, None), (4, "class")])
+def test_partial_tables_sum_to_the_full_table(world, scheme):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, scheme)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
@@ -79,3 +81,35 @@ def test_box_ranges_cover_the_index_space():
     m = 5
     seen = sorted(part.box_index(a, b, c, d) for d in range(m) for c in range(d + 1) for b in range(c + 1) for a in range(b + 1))
     assert seen == list(range(part.choose(m + 3, 4)))
+
+
+@pytest.mark.parametrize("world", [4, 8])
+def test_class_scheme_is_a_cover_and_ranks_read_only_their_tile_classes(world):
+    """Class scheme (layout.cuh class_owner): every box has one owner; the four triple tiles of a
+    box are led by its first two segments, whose classes must be in the owner's tile mask (the
+    rank builds no other tiles); box counts are even; half (3/4 for two ranks of 4) of the tiles
+    are built per rank."""
+    for m in (7, 33, 40):
+        sa, sb, sc, sd = part.all_boxes(m)
+        own = part.class_owner(sa, sb, sc, sd, m, world)
+        assert own.min() >= 0 and own.max() < world and len(own) == part.choose(m + 3, 4)
+        for r in range(world):
+            need = part.class_need_mask(r, world)
+            sel = own == r
+            assert np.all((need >> part.seg_class(sa[sel])) & 1) and np.all((need >> part.seg_class(sb[sel])) & 1)
+        if m >= 33:
+            cnt = np.bincount(own, minlength=world) * world / len(own)
+            assert cnt.max() < 1.06 and cnt.min() > 0.94
+            lead = part.seg_class(np.array([a for c in range(m) for b in range(c + 1) for a in range(b + 1)]))
+            frac = [float((((part.class_need_mask(r, world) >> lead) & 1) != 0).mean()) for r in range(world)]
+            assert max(frac) < (0.78 if world == 4 else 0.53)
+
+
+def test_scheme_rule(monkeypatch):
+    monkeypatch.delenv("CAMUS_B200_PARTITION", raising=False)
+    assert part.use_class_scheme(1000, 8) and part.use_class_scheme(1000, 4) and part.use_class_scheme(256, 8)
+    assert not part.use_class_scheme(1000, 2) and not part.use_class_scheme(200, 8) and not part.use_class_scheme(1000, 1)
+    monkeypatch.setenv("CAMUS_B200_PARTITION", "chunk")
+    assert not part.use_class_scheme(1000, 8)
+    monkeypatch.setenv("CAMUS_B200_PARTITION", "class")
+    assert part.use_class_scheme(40, 8) and not part.use_class_scheme(40, 3)
