@@ -319,12 +319,17 @@ def run_ours(args):
         complete = bool((nl == prob.n_taxa).all()) and not c.get("support", False)
         if complete:
             design_bytes *= 2.0 / 3.0
+        from camus_b200 import partition as part
+        scheme = "one share" if shares == 1 else (
+            "class scheme: a rank owns boxes by the classes of their first two segments and builds only the "
+            f"{'1/2' if shares == 8 else '1/2 or 3/4'} of the bit-planes it reads" if part.use_class_scheme(prob.n_taxa, shares)
+            else "chunk scheme: chunks of boxes round-robin, every rank builds every bit-plane")
         line = {
             "metric": METRIC, "value": R / dt_res, "unit": UNIT, "n_gpus": shares, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dt_res * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u32", "data": "synthetic",
             "config": {"workload": workload_name(args.config, c), "resolutions_per_step": R, "cells": cells, "boxes": num_boxes,
-                       "sharding": f"4-taxon-set index space / {shares}, all trees on every GPU, " +
+                       "sharding": f"4-taxon-set index space / {shares} ({scheme}), all trees on every GPU, " +
                                    ("one NCCL all-reduce of the junction table" if n_dev == 1 else
                                     "one process and one handle for all GPUs, junction tables summed by NVLink peer reads"),
                        "l2": "no explicit flush: the rooted-triple bit-planes streamed by every step "
