@@ -51,6 +51,7 @@ def lib() -> C.CDLL:
         L.camus_b200_run_resident.argtypes = [vp, C.c_int, C.c_double, C.c_int, vp, u64p, u64p]
         L.camus_b200_stage_ms.argtypes = [vp, C.POINTER(C.c_float), u64p]
         L.camus_b200_workload.argtypes = [vp, u64p, u64p, u64p]
+        L.camus_b200_reticulation_counts.argtypes = [vp, C.c_int32, C.c_int32, vp, C.c_int32, vp, vp, vp, vp, vp]
         _lib = L
     return _lib
 
@@ -61,6 +62,7 @@ EXPORTED = [
     "camus_b200_set_score_hint", "camus_b200_count_filter", "camus_b200_quartet_totals", "camus_b200_edge_penalties",
     "camus_b200_export_quartets", "camus_b200_query_cells", "camus_b200_quartet_totals_partial", "camus_b200_partial_buffer",
     "camus_b200_quartet_totals_finish", "camus_b200_run_resident", "camus_b200_stage_ms", "camus_b200_workload",
+    "camus_b200_reticulation_counts",
 ]
 
 
@@ -156,6 +158,16 @@ class CamusB200:
         out = np.zeros((len(quads), 3), np.uint32)
         self._ck(lib().camus_b200_query_cells(self._h, len(quads), _p(quads), _p(out)))
         return out
+
+    def reticulation_counts(self, net):
+        """score.ReticulationScore's per-gene-tree loop (score.go:31-60) for a hostlib.NetworkProblem:
+        (totals, supported), uint64 [n_trees, n_ret]."""
+        tot = np.zeros((net.n_trees, net.n_ret), np.uint64)
+        sup = np.zeros((net.n_trees, net.n_ret), np.uint64)
+        a = [np.ascontiguousarray(x) for x in (net.records, net.gene_node_off, net.gene_parent, net.gene_taxon)]
+        self._ck(lib().camus_b200_reticulation_counts(self._h, net.n_tips, net.n_ret, _p(a[0]), net.n_trees, _p(a[1]), _p(a[2]),
+                                                      _p(a[3]), _p(tot), _p(sup)))
+        return tot, sup
 
     # ---- split form for multi-process runs ----
     def quartet_totals_partial(self, as_set: bool = False):

@@ -12,6 +12,7 @@
 #include "camus_b200.h"
 #include "kernels_count.cuh"
 #include "kernels_prep.cuh"
+#include "kernels_retic.cuh"
 #include "kernels_score.cuh"
 
 using namespace camus_dev;
@@ -1133,6 +1134,102 @@ int camus_b200_query_cells(camus_b200* ctx, int32_t n_query, const int32_t* quad
                                                                 ctx->d_rank_of_tip.p, ctx->d_tip_of_rank.p);
   CK_LAUNCH();
   CK(cudaMemcpyAsync(counts, dc.p, (size_t)12 * n_query, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int camus_b200_reticulation_counts(camus_b200* ctx, int32_t n_tips, int32_t n_ret, const uint32_t* records,
+                                   int32_t n_trees, const int64_t* node_off, const int32_t* parent,
+                                   const int32_t* taxon, uint64_t* totals, uint64_t* supported) {
+  if (!ctx) return CAMUS_B200_ERR_ARG;
+  if (!ctx->subs.empty()) {
+    int rc = camus_b200_reticulation_counts(ctx->subs[0], n_tips, n_ret, records, n_trees, node_off, parent, taxon, totals, supported);
+    return rc ? ctx->fail(rc, ctx->subs[0]->err) : 0;
+  }
+  if (n_tips < 1 || n_tips > 32767 || n_ret < 1 || n_ret > kRetMax || n_trees < 0 || !records || !node_off || !totals || !supported ||
+      (n_trees > 0 && (!parent || !taxon)))
+    return ctx->fail(CAMUS_B200_ERR_ARG, "reticulation_counts: bad argument (1..32767 tips, 1..64 reticulations)");
+  // the flat trees are validated like camus_b200_add_gene_trees does
+  int max_nodes = 1;
+  std::vector<int> stamp(n_tips, -1), depth_h;
+  std::vector<char> has_child;
+  for (int g = 0; g < n_trees; ++g) {
+    const int64_t b = node_off[g], nn = node_off[g + 1] - b;
+    if (nn <= 0 || nn > 24576)
+      return ctx->fail(CAMUS_B200_ERR_INPUT, "reticulation_counts: tree " + std::to_string(g) + " has " + std::to_string(nn) + " nodes (1..24576 supported)");
+    max_nodes = std::max<int>(max_nodes, (int)nn);
+    has_child.assign(nn, 0);
+    depth_h.assign(nn, 0);
+    for (int64_t i = 0; i < nn; ++i) {
+      const int p = parent[b + i];
+      if ((i == 0) != (p < 0) || p >= i)
+        return ctx->fail(CAMUS_B200_ERR_INPUT, "reticulation_counts: tree " + std::to_string(g) + " is not in preorder");
+      if (p >= 0) {
+        has_child[p] = 1;
+        depth_h[i] = depth_h[p] + 1;
+      }
+      const int t = taxon[b + i];
+      if (t >= n_tips) return ctx->fail(CAMUS_B200_ERR_INPUT, "reticulation_counts: taxon index out of range");
+      if (t >= 0) {
+        if (stamp[t] == g) return ctx->fail(CAMUS_B200_ERR_INPUT, "reticulation_counts: tree " + std::to_string(g) + " contains a taxon twice");
+        stamp[t] = g;
+      }
+    }
+    for (int64_t i = 0; i < nn; ++i)
+      if ((taxon[b + i] >= 0) == (has_child[i] != 0))
+        return ctx->fail(CAMUS_B200_ERR_INPUT, "reticulation_counts: tree " + std::to_string(g) + ": taxon set on an internal node or missing on a leaf");
+  }
+  const size_t n_out = (size_t)n_trees * n_ret;
+  if (n_trees == 0) return 0;
+  CK(cudaSetDevice(ctx->device));
+  const uint64_t n_sets = choose4((uint64_t)n_tips);
+  if (n_sets == 0) {
+    std::memset(totals, 0, n_out * 8);
+    std::memset(supported, 0, n_out * 8);
+    return 0;
+  }
+  if ((n_sets + kRetThreads - 1) / kRetThreads > 0x7FFFFFFFull)
+    return ctx->fail(CAMUS_B200_ERR_NOMEM, "reticulation_counts: too many 4-taxon sets for one launch");
+  const size_t total_nodes = (size_t)(node_off[n_trees] - node_off[0]);
+  DevBuf<int64_t> d_off;
+  DevBuf<int32_t> d_par, d_tax;
+  DevBuf<uint32_t> d_rec;
+  DevBuf<uint16_t> d_D;
+  DevBuf<uint8_t> d_rb;
+  DevBuf<unsigned long long> d_tot, d_sup;
+  // depth tables of a batch of trees: <= 1 GiB, <= 65535 trees (grid.y)
+  const size_t per_tree = (size_t)n_tips * n_tips;
+  const int batch = (int)std::max<size_t>(1, std::min<size_t>({(size_t)n_trees, (size_t)65535, ((size_t)1 << 29) / per_tree}));
+  std::vector<int64_t> off0(node_off, node_off + n_trees + 1);
+  for (auto& o : off0) o -= node_off[0];
+  CK(d_off.alloc(n_trees + 1));
+  CK(d_par.alloc(total_nodes));
+  CK(d_tax.alloc(total_nodes));
+  CK(d_rec.alloc((size_t)n_ret * n_tips * 4));
+  CK(d_D.alloc(per_tree * batch));
+  CK(d_rb.alloc(n_trees));
+  CK(d_tot.alloc(n_out));
+  CK(d_sup.alloc(n_out));
+  CK(cudaMemcpyAsync(d_off.p, off0.data(), (n_trees + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_par.p, parent + node_off[0], total_nodes * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_tax.p, taxon + node_off[0], total_nodes * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_rec.p, records, (size_t)n_ret * n_tips * 16, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemsetAsync(d_tot.p, 0, n_out * 8, ctx->stream));
+  CK(cudaMemsetAsync(d_sup.p, 0, n_out * 8, ctx->stream));
+  const size_t smem = (size_t)max_nodes * 8;
+  if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_ret_depths, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  for (int g0 = 0; g0 < n_trees; g0 += batch) {
+    const int nb = std::min(batch, n_trees - g0);
+    CK(cudaMemsetAsync(d_D.p, 0, per_tree * nb * 2, ctx->stream));
+    k_ret_depths<<<nb, kRetThreads, smem, ctx->stream>>>(d_off.p + g0, d_par.p, d_tax.p, n_tips, max_nodes, d_D.p, d_rb.p + g0);
+    CK_LAUNCH();
+    k_ret_score<<<dim3((unsigned)((n_sets + kRetThreads - 1) / kRetThreads), nb), kRetThreads, 0, ctx->stream>>>(
+        n_tips, n_ret, n_sets, reinterpret_cast<const uint4*>(d_rec.p), d_D.p, d_rb.p + g0, 0,
+        d_tot.p + (size_t)g0 * n_ret, d_sup.p + (size_t)g0 * n_ret);
+    CK_LAUNCH();
+  }
+  CK(cudaMemcpyAsync(totals, d_tot.p, n_out * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(supported, d_sup.p, n_out * 8, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return 0;
 }

@@ -6,6 +6,7 @@
 #include <memory>
 
 #include "dp.hpp"
+#include "retic.hpp"
 
 using namespace camus;
 
@@ -25,6 +26,16 @@ struct camus_host_problem {
   bool warned_missing = false;
   double pct_no_support = 0;
   std::string constraint_newick;
+};
+
+// score.ReticulationScore inputs (internal/score/score.go:25-72), flattened for
+// camus_b200_reticulation_counts
+struct camus_host_network {
+  NetworkData nd;
+  std::vector<uint32_t> records;
+  RetGeneFlat gf;
+  std::vector<int32_t> net_parent, net_tip_index, uwvs;
+  std::string fmt;
 };
 
 struct camus_host_results {
@@ -135,5 +146,65 @@ int camus_host_results_branches(const camus_host_results* r, int k, int32_t* uw)
 double camus_host_results_qsat(const camus_host_results* r, int k) { return r->res.qsat[k - 1]; }
 double camus_host_results_root_score(const camus_host_results* r, int k) { return r->res.root_scores_f[k]; }
 const char* camus_host_results_newick(const camus_host_results* r, int k) { return r->newicks[k - 1].c_str(); }
+
+// ---- score.ReticulationScore: host half (network parsing, level-1 check, per-tip records) ----
+// Returns 0, a camus::Err code, 11 (ErrNoReticulations) or 12 (ErrNotLevel1).
+int camus_host_network_load(const char* network_text, const char* gene_text, int gene_format, camus_host_network** out) {
+  try {
+    auto p = std::make_unique<camus_host_network>();
+    p->nd = make_network_data(read_constraint_text(network_text));
+    p->records = reticulation_records(p->nd);
+    GeneTrees gts;
+    if (gene_text && *gene_text)
+      gts = gene_format == 1 ? read_gene_trees_nexus(gene_text) : read_gene_trees_newick(gene_text);
+    p->gf = flatten_gene_trees_for_network(gts.trees, p->nd);
+    for (int i = 0; i < p->nd.n; ++i) {
+      p->net_parent.push_back(p->nd.parent[i]);
+      const Node& x = p->nd.tree.nodes[p->nd.node_of_id[i]];
+      p->net_tip_index.push_back(x.tip() ? x.tip_index : -1);
+    }
+    for (size_t r = 0; r < p->nd.labels.size(); ++r) {
+      p->uwvs.push_back(p->nd.u[r]);
+      p->uwvs.push_back(p->nd.w[r]);
+      p->uwvs.push_back(p->nd.v[r]);
+      p->uwvs.push_back(p->nd.wsub[r]);
+    }
+    *out = p.release();
+    return 0;
+  } catch (const RetError& e) {
+    g_err = e.what();
+    return e.code;
+  } catch (const CamusError& e) {
+    return fail(e);
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return (int)Err::Internal;
+  }
+}
+void camus_host_network_free(camus_host_network* p) { delete p; }
+void camus_host_network_dims(const camus_host_network* p, int32_t* n_nodes, int32_t* n_tips, int32_t* n_ret, int32_t* n_trees,
+                             int64_t* total_gene_nodes) {
+  *n_nodes = p->nd.n;
+  *n_tips = p->nd.n_tips;
+  *n_ret = (int32_t)p->nd.labels.size();
+  *n_trees = (int32_t)p->gf.node_off.size() - 1;
+  *total_gene_nodes = (int64_t)p->gf.parent.size();
+}
+const uint32_t* camus_host_network_records(const camus_host_network* p) { return p->records.data(); }
+const int64_t* camus_host_network_gene_node_off(const camus_host_network* p) { return p->gf.node_off.data(); }
+const int32_t* camus_host_network_gene_parent(const camus_host_network* p) { return p->gf.parent.data(); }
+const int32_t* camus_host_network_gene_taxon(const camus_host_network* p) { return p->gf.taxon.data(); }
+const int32_t* camus_host_network_parent(const camus_host_network* p) { return p->net_parent.data(); }
+const int32_t* camus_host_network_tip_index(const camus_host_network* p) { return p->net_tip_index.data(); }
+const int32_t* camus_host_network_uwvs(const camus_host_network* p) { return p->uwvs.data(); }  // 4 ints per label: u, w, v, wSub
+const char* camus_host_network_label(const camus_host_network* p, int r) { return p->nd.labels[r].c_str(); }
+const char* camus_host_network_node_name(const camus_host_network* p, int id) {
+  return (id >= 0 && id < p->nd.n) ? p->nd.tree.nodes[p->nd.node_of_id[id]].name.c_str() : "";
+}
+// strconv.FormatFloat(supported / total, 'f', -1, 64) as prep.WriteRetScoresToCSV prints it (io.go:315-340)
+const char* camus_host_format_ratio(camus_host_network* p, uint64_t supported, uint64_t total) {
+  p->fmt = format_ratio(supported, total);
+  return p->fmt.c_str();
+}
 
 }  // extern "C"

@@ -18,7 +18,7 @@ from . import build
 ERR_NAMES = {
     1: "ErrUnrooted", 2: "ErrNonBinary", 3: "ErrMulTree", 4: "ErrTipNameMismatch",
     5: "ErrInvalidFile", 6: "ErrInvalidFormat", 7: "ErrTypeOutRange", 8: "ErrInvalidScorerOption",
-    9: "ErrDevice", 10: "ErrInternal",
+    9: "ErrDevice", 10: "ErrInternal", 11: "ErrNoReticulations", 12: "ErrNotLevel1",
 }
 
 
@@ -71,6 +71,24 @@ def lib() -> C.CDLL:
         L.camus_host_results_root_score.restype = C.c_double
         L.camus_host_results_newick.argtypes = [C.c_void_p, C.c_int]
         L.camus_host_results_newick.restype = C.c_char_p
+        vp = C.c_void_p
+        L.camus_host_network_load.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.POINTER(vp)]
+        L.camus_host_network_free.argtypes = [vp]
+        L.camus_host_network_dims.argtypes = [vp] + [C.POINTER(C.c_int32)] * 4 + [C.POINTER(C.c_int64)]
+        L.camus_host_network_records.argtypes = [vp]
+        L.camus_host_network_records.restype = C.POINTER(C.c_uint32)
+        L.camus_host_network_gene_node_off.argtypes = [vp]
+        L.camus_host_network_gene_node_off.restype = C.POINTER(C.c_int64)
+        for nm in ("gene_parent", "gene_taxon", "parent", "tip_index", "uwvs"):
+            f = getattr(L, "camus_host_network_" + nm)
+            f.argtypes = [vp]
+            f.restype = C.POINTER(C.c_int32)
+        L.camus_host_network_label.argtypes = [vp, C.c_int]
+        L.camus_host_network_label.restype = C.c_char_p
+        L.camus_host_network_node_name.argtypes = [vp, C.c_int]
+        L.camus_host_network_node_name.restype = C.c_char_p
+        L.camus_host_format_ratio.argtypes = [vp, C.c_uint64, C.c_uint64]
+        L.camus_host_format_ratio.restype = C.c_char_p
         _lib = L
     return _lib
 
@@ -178,3 +196,60 @@ class Problem:
             return DPResult(branches, qsat, roots, newicks)
         finally:
             L.camus_host_results_free(r)
+
+
+class NetworkProblem:
+    """Inputs of score.ReticulationScore (internal/score/score.go:25-72), parsed and flattened: the
+    level-1 network (prep.ConvertToNetwork, io.go:173-236) reduced to one 16-byte record per
+    (reticulation, network tip), and the gene trees as CSR with NETWORK tip indices. What the Go
+    side would hand to camus_b200_reticulation_counts."""
+
+    def __init__(self, network_text: str, gene_text: str, fmt: str = "newick"):
+        L = lib()
+        h = C.c_void_p()
+        rc = L.camus_host_network_load(network_text.encode(), gene_text.encode(), 1 if fmt == "nexus" else 0, C.byref(h))
+        if rc != 0:
+            raise CamusError(rc, L.camus_host_last_error().decode())
+        self._h = h
+        nn, nt, nr, ng = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+        tot = C.c_int64()
+        L.camus_host_network_dims(h, C.byref(nn), C.byref(nt), C.byref(nr), C.byref(ng), C.byref(tot))
+        self.n_nodes, self.n_tips, self.n_ret, self.n_trees, self.total_gene_nodes = nn.value, nt.value, nr.value, ng.value, tot.value
+
+        def arr(fn, n, dt):
+            if n == 0:
+                return np.zeros(0, dt)
+            return np.ctypeslib.as_array(fn(h), shape=(n,)).astype(dt, copy=True)
+
+        self.records = arr(L.camus_host_network_records, self.n_ret * self.n_tips * 4, np.uint32).reshape(self.n_ret, self.n_tips, 4)
+        self.gene_node_off = arr(L.camus_host_network_gene_node_off, self.n_trees + 1, np.int64)
+        self.gene_parent = arr(L.camus_host_network_gene_parent, self.total_gene_nodes, np.int32)
+        self.gene_taxon = arr(L.camus_host_network_gene_taxon, self.total_gene_nodes, np.int32)
+        self.parent = arr(L.camus_host_network_parent, self.n_nodes, np.int32)
+        self.tip_index = arr(L.camus_host_network_tip_index, self.n_nodes, np.int32)
+        self.uwvs = arr(L.camus_host_network_uwvs, 4 * self.n_ret, np.int32).reshape(self.n_ret, 4)
+        self.labels = [L.camus_host_network_label(h, r).decode() for r in range(self.n_ret)]
+        self.node_names = [L.camus_host_network_node_name(h, i).decode() for i in range(self.n_nodes)]
+
+    @classmethod
+    def from_files(cls, network_file: str, gene_file: str, fmt: str = "newick"):
+        return cls(read_text(network_file), read_text(gene_file), fmt)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().camus_host_network_free(self._h)
+            self._h = None
+
+    def scores(self, totals: np.ndarray, supported: np.ndarray) -> np.ndarray:
+        """float64(supported) / float64(totals), NaN where nothing was comparable (score.go:62-68)."""
+        with np.errstate(invalid="ignore", divide="ignore"):
+            return np.where(totals == 0, np.nan, supported.astype(np.float64) / totals.astype(np.float64))
+
+    def csv(self, totals: np.ndarray, supported: np.ndarray, names=None) -> str:
+        """prep.WriteRetScoresToCSV (io.go:315-340)."""
+        L = lib()
+        rows = ["gene," + ",".join(self.labels)]
+        for g in range(self.n_trees):
+            cells = [L.camus_host_format_ratio(self._h, int(supported[g, r]), int(totals[g, r])).decode() for r in range(self.n_ret)]
+            rows.append(",".join([str(names[g] if names else g + 1)] + cells))
+        return "\n".join(rows)

@@ -14,6 +14,8 @@
  *                                  (+ graphs.mapQuartetsToVertices     internal/graphs/treedata.go:197-222)
  *   camus_b200_edge_penalties   <- score.CalculateEdgePenalties        internal/score/penalty.go:11-29
  *   camus_b200_export_quartets  <- the map[Quartet]uint32 itself       internal/graphs/quartet.go:11-31
+ *   camus_b200_reticulation_counts <- the per-gene-tree loop of score.ReticulationScore
+ *                                                                       internal/score/score.go:31-60
  *
  * Conventions: plain pointers + sizes, host memory, valid for the duration of the call only (cgo
  * rule: no pointer is kept after return). All functions return 0 on success, non-zero on failure
@@ -103,6 +105,25 @@ int camus_b200_export_quartets(camus_b200* ctx, int raw, uint64_t* keys, uint32_
  * quads = 4 distinct constraint tip indices per query; counts = 3 per query, in the reference's
  * topology order for the taxa sorted by tip index (0b1100, 0b1010, 0b0110; quartet.go:23-25). */
 int camus_b200_query_cells(camus_b200* ctx, int32_t n_query, const int32_t* quads, uint32_t* counts);
+
+/* score.ReticulationScore (internal/score/score.go:25-72): for every gene tree and every
+ * reticulation of a given level-1 network, how many emissions of the quartet enumerator
+ * (gtre.Quartets(false, ..) after gtre.UnRoot(), duplicates included, score.go:38-43) are comparable
+ * with the reticulation (QuartetScore != Qdiff -> totals) and how many agree with it (== Qeq ->
+ * supported). The Go side keeps ConvertToNetwork, MakeTreeData, the Level1 check and
+ * getReticulationNodes, flattens what QuartetScore reads about the network into one record per
+ * (reticulation r, network tip t) and divides supported / totals in float64 afterwards:
+ *   records[(r * n_tips + t) * 4 + 0] = node id of LCA(w_r, t)      (quartettotals.go:121)
+ *                                 + 1 = node id of LCA(u_r, t)      (quartettotals.go:123)
+ *                                 + 2 = depth of the first | depth of the second << 16
+ *                                 + 3 = bit 0: t under w_r, 1: under v_r, 2: under wSub_r, 3: under u_r
+ * with node id 0 = the root. Gene trees: CSR as in camus_b200_add_gene_trees, taxon = tip index in
+ * the NETWORK tree (its #H tips included, graphs.MapIDsFromConstTree against ntw.NetTree). The call
+ * is independent of the constraint / gene trees loaded into ctx; n_ret <= 64. Outputs are
+ * [n_trees * n_ret], row-major by gene tree. */
+int camus_b200_reticulation_counts(camus_b200* ctx, int32_t n_tips, int32_t n_ret, const uint32_t* records,
+                                   int32_t n_trees, const int64_t* node_off, const int32_t* parent,
+                                   const int32_t* taxon, uint64_t* totals, uint64_t* supported);
 
 /* ---- split form of quartet_totals for multi-process runs ---- */
 int camus_b200_quartet_totals_partial(camus_b200* ctx, int as_set);

@@ -859,4 +859,63 @@ uint64_t oracle_pack_quartet(int t0, int t1, int t2, int t3) {
 }
 int oracle_threshold_keep(double t, uint32_t c0, uint32_t c1, uint32_t c2) { return threshold_keep(t, c0, c1, c2); }
 
+// score.ReticulationScore (score.go:25-72), literal: MakeTreeData on the network tree as parsed
+// (general arity: #H tips and the unary #H nodes stay in), then per gene tree every EMISSION of
+// gotree's enumerator -- duplicates included, the reference does not dedupe here (score.go:43) --
+// is scored against every reticulation (u, w, v, wSub). Node ids: parents before children, 0 = root.
+// totals[g * n_ret + r] = emissions with QuartetScore != Qdiff, supported = those == Qeq.
+int oracle_reticulation_counts(int32_t n_nodes, const int32_t* net_parent, const int32_t* net_tip_index, int32_t n_tips,
+                               int32_t n_ret, const int32_t* uwvs, int32_t n_trees, const int64_t* node_off,
+                               const int32_t* parent, const int32_t* taxon, uint64_t* totals, uint64_t* supported) {
+  Ctx c;
+  c.n = n_nodes;
+  c.n_taxa = n_tips;  // td.NLeaves (treedata.go:49)
+  c.parent.assign(net_parent, net_parent + n_nodes);
+  c.depth.assign(n_nodes, 0);
+  int words = (n_tips + 63) / 64;
+  c.leafset.assign(n_nodes, std::vector<uint64_t>(words, 0));
+  c.tip_to_node.assign(n_tips, -1);
+  for (int i = 1; i < n_nodes; i++) {
+    if (net_parent[i] < 0 || net_parent[i] >= i) return 1;
+    c.depth[i] = c.depth[net_parent[i]] + 1;
+  }
+  for (int i = n_nodes - 1; i >= 0; i--) {
+    int t = net_tip_index[i];
+    if (t >= 0) {
+      c.leafset[i][t >> 6] |= 1ull << (t & 63);
+      c.tip_to_node[t] = i;
+    }
+    if (i > 0)
+      for (int w = 0; w < words; w++) c.leafset[net_parent[i]][w] |= c.leafset[i][w];
+  }
+  c.lca.assign(n_nodes, std::vector<int>(n_nodes, 0));
+  for (int a = 0; a < n_nodes; a++)
+    for (int b = 0; b < n_nodes; b++) {
+      int x = a, y = b;
+      while (x != y) {
+        if (c.depth[x] >= c.depth[y]) x = c.parent[x];
+        else y = c.parent[y];
+      }
+      c.lca[a][b] = x;
+    }
+  for (int g = 0; g < n_trees; g++) {
+    FlatTree t;
+    t.n = int(node_off[g + 1] - node_off[g]);
+    t.parent.assign(parent + node_off[g], parent + node_off[g + 1]);
+    t.taxon.assign(taxon + node_off[g], taxon + node_off[g + 1]);
+    t.build();
+    uint64_t* tot = totals + (size_t)g * n_ret;
+    uint64_t* sup = supported + (size_t)g * n_ret;
+    for (int r = 0; r < n_ret; r++) tot[r] = sup[r] = 0;
+    enumerate_quartets_literal(t, [&](Quartet q) {
+      for (int r = 0; r < n_ret; r++) {
+        int comp = quartet_score(c, q, uwvs[4 * r], uwvs[4 * r + 1], uwvs[4 * r + 2], uwvs[4 * r + 3]);
+        if (comp != Qdiff) tot[r]++;
+        if (comp == Qeq) sup[r]++;
+      }
+    });
+  }
+  return 0;
+}
+
 }  // extern "C"

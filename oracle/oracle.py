@@ -59,6 +59,7 @@ def lib() -> C.CDLL:
         L.oracle_pack_quartet.argtypes = [C.c_int] * 4
         L.oracle_pack_quartet.restype = C.c_uint64
         L.oracle_threshold_keep.argtypes = [C.c_double, C.c_uint32, C.c_uint32, C.c_uint32]
+        L.oracle_reticulation_counts.argtypes = [C.c_int32, vp, vp, C.c_int32, C.c_int32, vp, C.c_int32, vp, vp, vp, vp, vp]
         _lib = L
     return _lib
 
@@ -90,6 +91,18 @@ def tree_quartets(parent: np.ndarray, taxon: np.ndarray, literal: bool = True) -
     keys = np.zeros(n.value, np.uint64)
     lib().oracle_tree_quartets(len(parent), _p(parent), _p(taxon), int(literal), _p(keys), n.value, C.byref(n))
     return keys
+
+
+def reticulation_counts(net):
+    """score.ReticulationScore (score.go:25-72), literal, for a camus_b200.hostlib.NetworkProblem:
+    (totals, supported) as uint64 [n_trees, n_ret]."""
+    tot = np.zeros((net.n_trees, net.n_ret), np.uint64)
+    sup = np.zeros((net.n_trees, net.n_ret), np.uint64)
+    a = [np.ascontiguousarray(x) for x in (net.parent, net.tip_index, net.uwvs, net.gene_node_off, net.gene_parent, net.gene_taxon)]
+    rc = lib().oracle_reticulation_counts(net.n_nodes, _p(a[0]), _p(a[1]), net.n_tips, net.n_ret, _p(a[2]), net.n_trees,
+                                          _p(a[3]), _p(a[4]), _p(a[5]), _p(tot), _p(sup))
+    assert rc == 0
+    return tot, sup
 
 
 class Oracle:
