@@ -1,0 +1,9 @@
+set -x
+cd $GRAFT_REPO_ROOT
+mkdir -p gpurun_out
+( time timeout 600 python -m pytest tests/test_reticulation_score.py -m gpu -x -q ) > gpurun_out/r2_pytest_retic.log 2>&1
+tail -5 gpurun_out/r2_pytest_retic.log
+timeout 600 python tools/retic_times.py --config 2 --cpu-trees 1 > gpurun_out/r2_retic_config2.log 2>&1
+tail -2 gpurun_out/r2_retic_config2.log
+timeout 300 python tools/retic_times.py --config 1 --cpu-trees 20 > gpurun_out/r2_retic_config1.log 2>&1
+tail -2 gpurun_out/r2_retic_config1.log
