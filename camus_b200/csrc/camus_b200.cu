@@ -1196,7 +1196,12 @@ int camus_b200_reticulation_counts(camus_b200* ctx, int32_t n_tips, int32_t n_re
   DevBuf<uint32_t> d_rec;
   DevBuf<uint16_t> d_D;
   DevBuf<uint8_t> d_rb;
-  DevBuf<unsigned long long> d_tot, d_sup;
+  DevBuf<unsigned long long> d_tot, d_sup, d_uw;
+  // per tip: bit r = the tip is under w of reticulation r (bit 0 of the record's flag word)
+  std::vector<unsigned long long> under_w(n_tips, 0);
+  for (int r = 0; r < n_ret; ++r)
+    for (int t = 0; t < n_tips; ++t)
+      if (records[((size_t)r * n_tips + t) * 4 + 3] & 1u) under_w[t] |= 1ull << r;
   // depth tables of a batch of trees: <= 1 GiB, <= 65535 trees (grid.y)
   const size_t per_tree = (size_t)n_tips * n_tips;
   const int batch = (int)std::max<size_t>(1, std::min<size_t>({(size_t)n_trees, (size_t)65535, ((size_t)1 << 29) / per_tree}));
@@ -1210,6 +1215,8 @@ int camus_b200_reticulation_counts(camus_b200* ctx, int32_t n_tips, int32_t n_re
   CK(d_rb.alloc(n_trees));
   CK(d_tot.alloc(n_out));
   CK(d_sup.alloc(n_out));
+  CK(d_uw.alloc(n_tips));
+  CK(cudaMemcpyAsync(d_uw.p, under_w.data(), (size_t)n_tips * 8, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(d_off.p, off0.data(), (n_trees + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(d_par.p, parent + node_off[0], total_nodes * 4, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(d_tax.p, taxon + node_off[0], total_nodes * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -1224,7 +1231,7 @@ int camus_b200_reticulation_counts(camus_b200* ctx, int32_t n_tips, int32_t n_re
     k_ret_depths<<<nb, kRetThreads, smem, ctx->stream>>>(d_off.p + g0, d_par.p, d_tax.p, n_tips, max_nodes, d_D.p, d_rb.p + g0);
     CK_LAUNCH();
     k_ret_score<<<dim3((unsigned)((n_sets + kRetThreads - 1) / kRetThreads), nb), kRetThreads, 0, ctx->stream>>>(
-        n_tips, n_ret, n_sets, reinterpret_cast<const uint4*>(d_rec.p), d_D.p, d_rb.p + g0, 0,
+        n_tips, n_ret, n_sets, reinterpret_cast<const uint4*>(d_rec.p), d_uw.p, d_D.p, d_rb.p + g0,
         d_tot.p + (size_t)g0 * n_ret, d_sup.p + (size_t)g0 * n_ret);
     CK_LAUNCH();
   }

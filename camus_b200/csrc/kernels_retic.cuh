@@ -21,7 +21,8 @@ constexpr int kRetMax = 64;        // reticulations per call (level-1 networks h
 constexpr int kRetThreads = 256;
 
 // R1: per gene tree (one CTA), LCA-depth table over NETWORK tip indices:
-//   D[g][a][b] (a < b) = 1 + depth(LCA(a, b)), 0 = a taxon is absent from the tree.
+//   D[g][b][a] (a < b) = 1 + depth(LCA(a, b)), 0 = a taxon is absent from the tree (lower triangle:
+//   the score kernel's threads differ in their smallest taxon, which is then the contiguous index).
 // Dynamic shared memory: 4 B per node (parent, depth as u16) + 4 B per leaf (tip, gap as u16).
 __global__ void __launch_bounds__(kRetThreads) k_ret_depths(const int64_t* __restrict__ node_off, const int32_t* __restrict__ parent,
                                                             const int32_t* __restrict__ taxon, int n_tips, int max_nodes,
@@ -63,7 +64,7 @@ __global__ void __launch_bounds__(kRetThreads) k_ret_depths(const int64_t* __res
     for (int q = p + 1; q < nl; ++q) {
       m = min(m, (uint32_t)s_gap[q - 1]);
       const uint32_t b = s_tip[q];
-      Dg[(size_t)min(a, b) * n_tips + max(a, b)] = (uint16_t)m;
+      Dg[(size_t)max(a, b) * n_tips + min(a, b)] = (uint16_t)m;
     }
   }
 }
@@ -71,7 +72,7 @@ __global__ void __launch_bounds__(kRetThreads) k_ret_depths(const int64_t* __res
 // QuartetScore (quartettotals.go:107-157) for taxa x[0] < x[1] < x[2] < x[3] (network tip
 // indices) whose tree displays x[p0] x[p1] | the other two. rec = records of ONE reticulation.
 // Returns 0 = Qdiff, 1 = Qneq, 2 = Qeq.
-__device__ __forceinline__ int ret_quartet_score(const uint4* __restrict__ rec, const uint32_t x[4], int pair_of[4],
+__device__ __forceinline__ int ret_quartet_score(const uint4* __restrict__ rec, const uint32_t x[4], const int pair_of[4],
                                                  uint32_t n_leaves) {
   uint4 r[4];
 #pragma unroll
@@ -125,67 +126,62 @@ __device__ __forceinline__ int ret_quartet_score(const uint4* __restrict__ rec, 
   return best == neighbor ? 2 : 1;
 }
 
-// R2: grid = (chunks of 4-taxon sets, gene tree). One thread per 4-set of network tips; per
-// reticulation the block's (total, supported) emission counts go through warp sums into shared
-// counters and one global add per (block, reticulation).
+// R2: grid = (chunks of 4-taxon sets, gene tree). One thread per 4-set of network tips. Most
+// (4-set, reticulation) pairs are Qdiff because QuartetScore wants exactly one of the four taxa under
+// w (quartettotals.go:160-171): under_w[t] holds that flag for all reticulations of tip t as a bit
+// mask, so a thread only evaluates the reticulations that pass. Emission counts go to shared
+// counters (a block adds at most 256 * 65535 per counter) and once per block to the global table.
 __global__ void __launch_bounds__(kRetThreads) k_ret_score(int n_tips, int n_ret, uint64_t n_sets, const uint4* __restrict__ rec,
+                                                           const unsigned long long* __restrict__ under_w,
                                                            const uint16_t* __restrict__ D, const uint8_t* __restrict__ root_binary,
-                                                           int g0, unsigned long long* __restrict__ totals,
+                                                           unsigned long long* __restrict__ totals,
                                                            unsigned long long* __restrict__ supported) {
-  __shared__ unsigned long long s_tot[kRetMax], s_sup[kRetMax];
-  const int tid = threadIdx.x, g = g0 + blockIdx.y;
+  __shared__ uint32_t s_tot[kRetMax], s_sup[kRetMax];
+  const int tid = threadIdx.x, g = blockIdx.y;
   if (tid < kRetMax) s_tot[tid] = s_sup[tid] = 0;
   __syncthreads();
   const uint64_t idx = (uint64_t)blockIdx.x * kRetThreads + tid;
-  uint32_t x[4] = {0, 1, 2, 3};
-  uint32_t mult = 0;
-  int pair_of[4] = {0, 0, 0, 0};
   if (idx < n_sets) {
     uint64_t r = idx;  // colex rank of a < b < c < d
-    const uint32_t d = unrank4(r) + 3;
-    r -= choose4(d);
-    const uint32_t c = unrank3(r) + 2;
-    r -= choose3(c);
-    const uint32_t b = unrank2(r) + 1;
-    r -= choose2(b);
-    x[0] = (uint32_t)r; x[1] = b; x[2] = c; x[3] = d;
-    const uint16_t* Dg = D + (size_t)g * n_tips * n_tips;
-    const uint32_t ab = Dg[x[0] * n_tips + x[1]], ac = Dg[x[0] * n_tips + x[2]], ad = Dg[x[0] * n_tips + x[3]];
-    const uint32_t bc = Dg[x[1] * n_tips + x[2]], bd = Dg[x[1] * n_tips + x[3]], cd = Dg[x[2] * n_tips + x[3]];
-    if (ab && ac && ad && bc && bd && cd) {
+    uint32_t x[4];
+    x[3] = unrank4(r) + 3;
+    r -= choose4(x[3]);
+    x[2] = unrank3(r) + 2;
+    r -= choose3(x[2]);
+    x[1] = unrank2(r) + 1;
+    r -= choose2(x[1]);
+    x[0] = (uint32_t)r;
+    const unsigned long long wa = under_w[x[0]], wb = under_w[x[1]], wc = under_w[x[2]], wd = under_w[x[3]];
+    unsigned long long todo = (wa | wb | wc | wd) & ~((wa & wb) | (wa & wc) | (wa & wd) | (wb & wc) | (wb & wd) | (wc & wd));
+    if (todo) {
+      const uint16_t* Dg = D + (size_t)g * n_tips * n_tips;
+      const uint32_t ab = Dg[x[1] * n_tips + x[0]], ac = Dg[x[2] * n_tips + x[0]], ad = Dg[x[3] * n_tips + x[0]];
+      const uint32_t bc = Dg[x[2] * n_tips + x[1]], bd = Dg[x[3] * n_tips + x[1]], cd = Dg[x[3] * n_tips + x[2]];
       const uint32_t s1 = ab + cd, s2 = ac + bd, s3 = ad + bc;
       const uint32_t mx = max(s1, max(s2, s3));
-      if ((s1 == mx) + (s2 == mx) + (s3 == mx) == 1) {
+      if (ab && ac && ad && bc && bd && cd && (s1 == mx) + (s2 == mx) + (s3 == mx) == 1) {
         const uint32_t lo = min(s1, min(s2, s3));  // the two smaller sums are equal in a tree
         // emissions = edges between the two cherries; a binary root on that path (both cross LCAs
         // are the root: depth sums 1 + 1) loses one edge to UnRoot
-        mult = mx - lo - ((root_binary[g] && lo == 2) ? 1u : 0u);
+        const uint32_t mult = mx - lo - ((root_binary[g] && lo == 2) ? 1u : 0u);
+        int pair_of[4];
         if (s1 == mx) { pair_of[0] = 1; pair_of[1] = 0; pair_of[2] = 3; pair_of[3] = 2; }
         else if (s2 == mx) { pair_of[0] = 2; pair_of[2] = 0; pair_of[1] = 3; pair_of[3] = 1; }
         else { pair_of[0] = 3; pair_of[3] = 0; pair_of[1] = 2; pair_of[2] = 1; }
+        while (todo) {
+          const int rr = __ffsll((long long)todo) - 1;
+          todo &= todo - 1;
+          const int comp = ret_quartet_score(rec + (size_t)rr * n_tips, x, pair_of, (uint32_t)n_tips);
+          if (comp) atomicAdd(&s_tot[rr], mult);
+          if (comp == 2) atomicAdd(&s_sup[rr], mult);
+        }
       }
-    }
-  }
-  const bool any = __syncthreads_or(mult != 0);
-  if (!any) return;
-  for (int rr = 0; rr < n_ret; ++rr) {
-    uint32_t t = 0, s = 0;
-    if (mult) {
-      const int comp = ret_quartet_score(rec + (size_t)rr * n_tips, x, pair_of, (uint32_t)n_tips);
-      t = comp ? mult : 0;
-      s = comp == 2 ? mult : 0;
-    }
-    t = __reduce_add_sync(0xFFFFFFFFu, t);
-    s = __reduce_add_sync(0xFFFFFFFFu, s);
-    if ((tid & 31) == 0) {
-      if (t) atomicAdd(&s_tot[rr], (unsigned long long)t);
-      if (s) atomicAdd(&s_sup[rr], (unsigned long long)s);
     }
   }
   __syncthreads();
   if (tid < n_ret) {
-    if (s_tot[tid]) atomicAdd(&totals[(size_t)g * n_ret + tid], s_tot[tid]);
-    if (s_sup[tid]) atomicAdd(&supported[(size_t)g * n_ret + tid], s_sup[tid]);
+    if (s_tot[tid]) atomicAdd(&totals[(size_t)g * n_ret + tid], (unsigned long long)s_tot[tid]);
+    if (s_sup[tid]) atomicAdd(&supported[(size_t)g * n_ret + tid], (unsigned long long)s_sup[tid]);
   }
 }
 
