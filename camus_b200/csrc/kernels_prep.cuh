@@ -299,8 +299,11 @@ __device__ __forceinline__ void triple_words(const uint4 (&ab)[4], const uint16_
   if (kDerive) w[2] = ~(w[0] | w[1]) & vm;
 }
 
+#ifndef CAMUS_PLANES_MINB
+#define CAMUS_PLANES_MINB 4  // CTAs per SM the packed plane builder is compiled for (A/B builds: -DCAMUS_PLANES_MINB=n)
+#endif
 template <bool kComplete>
-__global__ void __launch_bounds__(256, 4) k_triple_planes_h2(int grp0, int n_batch, int n_groups_total, int n_trees, int npad,
+__global__ void __launch_bounds__(256, CAMUS_PLANES_MINB) k_triple_planes_h2(int grp0, int n_batch, int n_groups_total, int n_trees, int npad,
                                                           const uint16_t* __restrict__ Dt, uint32_t* __restrict__ Tri,
                                                           const uint32_t* __restrict__ tile_list) {
   // fp16 bits, NaN = absent. Rows: ab[x*8+y], ac[x*8+z], bc[z*8+y] (the index that varies across

@@ -667,6 +667,31 @@ def test_multi_gpu_handle_matches_single(gpu):
     multi.close()
 
 
+@pytest.mark.gpu
+@pytest.mark.skipif(_n_devices() < 4, reason="needs four GPUs (gpurun --gpus 4)")
+def test_four_gpu_handle_with_the_class_scheme(gpu, monkeypatch):
+    """One handle over 4 GPUs with the class-scheme split forced: every device builds only its own
+    tile classes; survivors, edge table and exported quartets equal the single-GPU handle's."""
+    from camus_b200.cabi import CamusB200
+    monkeypatch.setenv("CAMUS_B200_PARTITION", "class")
+    multi = CamusB200(devices=[0, 1, 2, 3])
+    try:
+        s = synth.make(88, 70, 31, drop_frac=0.05)
+        prob = Problem(s.constraint, s.genes)
+        gpu.load(prob)
+        multi.load(prob)
+        assert multi.count_filter(2, 0.4) == gpu.count_filter(2, 0.4)
+        assert np.array_equal(multi.quartet_totals(False), gpu.quartet_totals(False))
+        for a, b in zip(multi.export_quartets(), gpu.export_quartets()):
+            assert np.array_equal(a, b)
+        quads = np.array([[0, 1, 2, 3], [5, 17, 40, 63], [80, 8, 57, 6]], np.int32)
+        assert np.array_equal(multi.query_cells(quads), gpu.query_cells(quads))
+        out, ns, sc = multi.run_resident(2, 0.4, False)
+        assert (ns, sc) == gpu.count_filter(2, 0.4) and np.array_equal(out, gpu.quartet_totals(False))
+    finally:
+        multi.close()
+
+
 def _random_tree_with_chains(rng, n_taxa, chains):
     """Preorder (parent, taxon) arrays of a random binary tree on all taxa, with unary chains of
     the given lengths inserted above randomly chosen nodes (the first one above the root)."""
