@@ -152,7 +152,11 @@ CAMUS_HD uint32_t class_need_mask(int rank, int world) {
   const uint32_t m[4] = {0x3, 0xC, 0xD, 0xE};
   return m[rank & 3];
 }
-// donation threshold (of 256) that evens out the box counts of the ranks for m segments
+// donation threshold (of 256) for m segments. World 8: every rank builds half of the tiles, so
+// the box counts are evened out. World 4: ranks 2 and 3 build 3/4 of the tiles against 1/2 for
+// ranks 0 and 1; a tile costs about as much to build (per tree group) as a box costs to count
+// (3.5 ns vs 2.8 ns at 1000 taxa with the complete-tree kernels, 2.8 vs 4.2 with the general
+// ones), so ranks 2 and 3 are given T/4 boxes FEWER than ranks 0 and 1, T = number of tiles.
 inline uint32_t class_threshold(uint32_t m, int world) {
   uint64_t D = 0, O = 0;  // boxes of pure / mixed class pairs
   for (uint32_t sa = 0; sa < m; ++sa)
@@ -161,10 +165,16 @@ inline uint32_t class_threshold(uint32_t m, int world) {
       (seg_class(sa) == seg_class(sb) ? D : O) += k;
     }
   if (D == 0 || 3 * D <= O) return 0;
-  uint64_t scale = world == 8 ? 64 : 128;
-  uint64_t t = (scale * (3 * D - O) + (3 * D) / 2) / (3 * D);
-  uint64_t cap = world == 8 ? 85 : 255;
-  return (uint32_t)(t > cap ? cap : t);
+  if (world == 8) {
+    uint64_t t = (64 * (3 * D - O) + (3 * D) / 2) / (3 * D);
+    return (uint32_t)(t > 85 ? 85 : t);
+  }
+  // world 4: boxes(rank 0) - boxes(rank 2) = D/2 - O/6 - (t/256) * 3D/4, wanted = T/4
+  const uint64_t T = num_tiles(m);
+  const uint64_t have6 = 3 * D - O, want6 = 3 * T / 2;  // both sides times 6
+  if (have6 <= want6) return 0;
+  uint64_t t = (256 * 2 * (have6 - want6) + (9 * D) / 2) / (9 * D);
+  return (uint32_t)(t > 255 ? 255 : t);
 }
 CAMUS_HD uint64_t partition_chunk(uint64_t nb, uint32_t world) {
   uint64_t c = nb / ((uint64_t)world * 64);

@@ -79,8 +79,14 @@ def class_threshold(m: int, world: int) -> int:
     O = int(k[valid & ~same].sum())
     if D == 0 or 3 * D <= O:
         return 0
-    scale, cap = (64, 85) if world == 8 else (128, 255)
-    return min(cap, (scale * (3 * D - O) + (3 * D) // 2) // (3 * D))
+    if world == 8:
+        return min(85, (64 * (3 * D - O) + (3 * D) // 2) // (3 * D))
+    # world 4: ranks 2 and 3 build 3/4 of the tiles, ranks 0 and 1 half: they get T/4 boxes fewer
+    T = choose(m + 2, 3)
+    have6, want6 = 3 * D - O, 3 * T // 2
+    if have6 <= want6:
+        return 0
+    return min(255, (512 * (have6 - want6) + (9 * D) // 2) // (9 * D))
 
 
 def _pair_rank(lo, hi):

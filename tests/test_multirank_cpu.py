@@ -99,7 +99,12 @@ def test_class_scheme_is_a_cover_and_ranks_read_only_their_tile_classes(world):
             assert np.all((need >> part.seg_class(sa[sel])) & 1) and np.all((need >> part.seg_class(sb[sel])) & 1)
         if m >= 33:
             cnt = np.bincount(own, minlength=world) * world / len(own)
-            assert cnt.max() < 1.06 and cnt.min() > 0.94
+            if world == 8:  # every rank builds half of the tiles: even box counts
+                assert cnt.max() < 1.06 and cnt.min() > 0.94
+            else:  # ranks 2, 3 build 3/4 of the tiles instead of 1/2 and get T/4 boxes fewer for it
+                quarter_tiles = part.choose(m + 2, 3) / 4 * world / len(own)
+                assert abs(cnt[0] - cnt[1]) < 0.03 and abs(cnt[2] - cnt[3]) < 0.03
+                assert abs((cnt[0] + cnt[1] - cnt[2] - cnt[3]) / 2 - quarter_tiles) < 0.04
             lead = part.seg_class(np.array([a for c in range(m) for b in range(c + 1) for a in range(b + 1)]))
             frac = [float((((part.class_need_mask(r, world) >> lead) & 1) != 0).mean()) for r in range(world)]
             assert max(frac) < (0.78 if world == 4 else 0.53)
