@@ -1188,8 +1188,8 @@ int camus_b200_reticulation_counts(camus_b200* ctx, int32_t n_tips, int32_t n_re
     std::memset(supported, 0, n_out * 8);
     return 0;
   }
-  if ((n_sets + kRetThreads - 1) / kRetThreads > 0x7FFFFFFFull)
-    return ctx->fail(CAMUS_B200_ERR_NOMEM, "reticulation_counts: too many 4-taxon sets for one launch");
+  const size_t smem_rows = (size_t)n_tips * 4;  // two u16 depth rows per block
+  if (smem_rows > 200 * 1024) return ctx->fail(CAMUS_B200_ERR_NOMEM, "reticulation_counts: network too large for the row-staged kernel");
   const size_t total_nodes = (size_t)(node_off[n_trees] - node_off[0]);
   DevBuf<int64_t> d_off;
   DevBuf<int32_t> d_par, d_tax;
@@ -1225,13 +1225,14 @@ int camus_b200_reticulation_counts(camus_b200* ctx, int32_t n_tips, int32_t n_re
   CK(cudaMemsetAsync(d_sup.p, 0, n_out * 8, ctx->stream));
   const size_t smem = (size_t)max_nodes * 8;
   if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_ret_depths, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (smem_rows > 48 * 1024) CK(cudaFuncSetAttribute(k_ret_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
   for (int g0 = 0; g0 < n_trees; g0 += batch) {
     const int nb = std::min(batch, n_trees - g0);
     CK(cudaMemsetAsync(d_D.p, 0, per_tree * nb * 2, ctx->stream));
     k_ret_depths<<<nb, kRetThreads, smem, ctx->stream>>>(d_off.p + g0, d_par.p, d_tax.p, n_tips, max_nodes, d_D.p, d_rb.p + g0);
     CK_LAUNCH();
-    k_ret_score<<<dim3((unsigned)((n_sets + kRetThreads - 1) / kRetThreads), nb), kRetThreads, 0, ctx->stream>>>(
-        n_tips, n_ret, n_sets, reinterpret_cast<const uint4*>(d_rec.p), d_uw.p, d_D.p, d_rb.p + g0,
+    k_ret_score<<<dim3((unsigned)choose2((uint64_t)n_tips), nb), kRetThreads, smem_rows, ctx->stream>>>(
+        n_tips, n_ret, reinterpret_cast<const uint4*>(d_rec.p), d_uw.p, d_D.p, d_rb.p + g0,
         d_tot.p + (size_t)g0 * n_ret, d_sup.p + (size_t)g0 * n_ret);
     CK_LAUNCH();
   }

@@ -126,62 +126,73 @@ __device__ __forceinline__ int ret_quartet_score(const uint4* __restrict__ rec, 
   return best == neighbor ? 2 : 1;
 }
 
-// R2: grid = (chunks of 4-taxon sets, gene tree). One thread per 4-set of network tips. Most
-// (4-set, reticulation) pairs are Qdiff because QuartetScore wants exactly one of the four taxa under
-// w (quartettotals.go:160-171): under_w[t] holds that flag for all reticulations of tip t as a bit
+// R2: grid = (pairs c < d of network tips, gene tree). The block stages the two depth rows D[c][.]
+// and D[d][.] in shared memory and its threads walk the pairs a < b below c, so a 4-set costs one
+// gathered global load (D[b][a], contiguous in a) and a cheap 32-bit pair unranking. Most (4-set,
+// reticulation) pairs are Qdiff because QuartetScore wants exactly one of the four taxa under w
+// (quartettotals.go:160-171): under_w[t] holds that flag for all reticulations of tip t as a bit
 // mask, so a thread only evaluates the reticulations that pass. Emission counts go to shared
-// counters (a block adds at most 256 * 65535 per counter) and once per block to the global table.
-__global__ void __launch_bounds__(kRetThreads) k_ret_score(int n_tips, int n_ret, uint64_t n_sets, const uint4* __restrict__ rec,
+// counters (64-bit: a block sees up to C(c, 2) sets) and once per block to the global table.
+__global__ void __launch_bounds__(kRetThreads) k_ret_score(int n_tips, int n_ret, const uint4* __restrict__ rec,
                                                            const unsigned long long* __restrict__ under_w,
                                                            const uint16_t* __restrict__ D, const uint8_t* __restrict__ root_binary,
                                                            unsigned long long* __restrict__ totals,
                                                            unsigned long long* __restrict__ supported) {
-  __shared__ uint32_t s_tot[kRetMax], s_sup[kRetMax];
+  extern __shared__ uint16_t s_rows[];  // [2][n_tips]
+  __shared__ unsigned long long s_tot[kRetMax], s_sup[kRetMax];
   const int tid = threadIdx.x, g = blockIdx.y;
+  uint32_t c, d;
+  pair_unrank(blockIdx.x, c, d);
+  if (c < 2) return;
+  const uint16_t* Dg = D + (size_t)g * n_tips * n_tips;
+  const uint32_t cd = Dg[(size_t)d * n_tips + c];
+  if (cd == 0) return;  // c or d is not in this tree
+  uint16_t* rowc = s_rows;
+  uint16_t* rowd = s_rows + n_tips;
+  for (uint32_t i = tid; i < c; i += kRetThreads) {
+    rowc[i] = Dg[(size_t)c * n_tips + i];
+    rowd[i] = Dg[(size_t)d * n_tips + i];
+  }
   if (tid < kRetMax) s_tot[tid] = s_sup[tid] = 0;
   __syncthreads();
-  const uint64_t idx = (uint64_t)blockIdx.x * kRetThreads + tid;
-  if (idx < n_sets) {
-    uint64_t r = idx;  // colex rank of a < b < c < d
-    uint32_t x[4];
-    x[3] = unrank4(r) + 3;
-    r -= choose4(x[3]);
-    x[2] = unrank3(r) + 2;
-    r -= choose3(x[2]);
-    x[1] = unrank2(r) + 1;
-    r -= choose2(x[1]);
-    x[0] = (uint32_t)r;
-    const unsigned long long wa = under_w[x[0]], wb = under_w[x[1]], wc = under_w[x[2]], wd = under_w[x[3]];
-    unsigned long long todo = (wa | wb | wc | wd) & ~((wa & wb) | (wa & wc) | (wa & wd) | (wb & wc) | (wb & wd) | (wc & wd));
-    if (todo) {
-      const uint16_t* Dg = D + (size_t)g * n_tips * n_tips;
-      const uint32_t ab = Dg[x[1] * n_tips + x[0]], ac = Dg[x[2] * n_tips + x[0]], ad = Dg[x[3] * n_tips + x[0]];
-      const uint32_t bc = Dg[x[2] * n_tips + x[1]], bd = Dg[x[3] * n_tips + x[1]], cd = Dg[x[3] * n_tips + x[2]];
-      const uint32_t s1 = ab + cd, s2 = ac + bd, s3 = ad + bc;
-      const uint32_t mx = max(s1, max(s2, s3));
-      if (ab && ac && ad && bc && bd && cd && (s1 == mx) + (s2 == mx) + (s3 == mx) == 1) {
-        const uint32_t lo = min(s1, min(s2, s3));  // the two smaller sums are equal in a tree
-        // emissions = edges between the two cherries; a binary root on that path (both cross LCAs
-        // are the root: depth sums 1 + 1) loses one edge to UnRoot
-        const uint32_t mult = mx - lo - ((root_binary[g] && lo == 2) ? 1u : 0u);
-        int pair_of[4];
-        if (s1 == mx) { pair_of[0] = 1; pair_of[1] = 0; pair_of[2] = 3; pair_of[3] = 2; }
-        else if (s2 == mx) { pair_of[0] = 2; pair_of[2] = 0; pair_of[1] = 3; pair_of[3] = 1; }
-        else { pair_of[0] = 3; pair_of[3] = 0; pair_of[1] = 2; pair_of[2] = 1; }
-        while (todo) {
-          const int rr = __ffsll((long long)todo) - 1;
-          todo &= todo - 1;
-          const int comp = ret_quartet_score(rec + (size_t)rr * n_tips, x, pair_of, (uint32_t)n_tips);
-          if (comp) atomicAdd(&s_tot[rr], mult);
-          if (comp == 2) atomicAdd(&s_sup[rr], mult);
-        }
-      }
+  const unsigned long long wc = under_w[c], wd = under_w[d];
+  const unsigned long long wcd_any = wc | wd, wcd_two = wc & wd;
+  const bool rb = root_binary[g] != 0;
+  const uint32_t n_pairs = c * (c - 1) / 2;
+  for (uint32_t p = tid; p < n_pairs; p += kRetThreads) {
+    // pair (a < b) of rank choose2(b) + a, 32-bit
+    uint32_t b = (uint32_t)((1.0f + sqrtf(1.0f + 8.0f * (float)p)) * 0.5f);
+    while (b * (b - 1) / 2 > p) --b;
+    while ((b + 1) * b / 2 <= p) ++b;
+    const uint32_t a = p - b * (b - 1) / 2;
+    const unsigned long long wa = under_w[a], wb = under_w[b];
+    unsigned long long todo = (wa | wb | wcd_any) & ~((wa & wb) | ((wa | wb) & wcd_any) | wcd_two);
+    if (!todo) continue;
+    const uint32_t ab = Dg[(size_t)b * n_tips + a], ac = rowc[a], bc = rowc[b], ad = rowd[a], bd = rowd[b];
+    const uint32_t s1 = ab + cd, s2 = ac + bd, s3 = ad + bc;
+    const uint32_t mx = max(s1, max(s2, s3));
+    if (!(ab && ac && ad && bc && bd) || (s1 == mx) + (s2 == mx) + (s3 == mx) != 1) continue;
+    const uint32_t lo = min(s1, min(s2, s3));  // the two smaller sums are equal in a tree
+    // emissions = edges between the two cherries; a binary root on that path (both cross LCAs
+    // are the root: depth sums 1 + 1) loses one edge to UnRoot
+    const uint32_t mult = mx - lo - ((rb && lo == 2) ? 1u : 0u);
+    const uint32_t x[4] = {a, b, c, d};
+    int pair_of[4];
+    if (s1 == mx) { pair_of[0] = 1; pair_of[1] = 0; pair_of[2] = 3; pair_of[3] = 2; }
+    else if (s2 == mx) { pair_of[0] = 2; pair_of[2] = 0; pair_of[1] = 3; pair_of[3] = 1; }
+    else { pair_of[0] = 3; pair_of[3] = 0; pair_of[1] = 2; pair_of[2] = 1; }
+    while (todo) {
+      const int rr = __ffsll((long long)todo) - 1;
+      todo &= todo - 1;
+      const int comp = ret_quartet_score(rec + (size_t)rr * n_tips, x, pair_of, (uint32_t)n_tips);
+      if (comp) atomicAdd(&s_tot[rr], (unsigned long long)mult);
+      if (comp == 2) atomicAdd(&s_sup[rr], (unsigned long long)mult);
     }
   }
   __syncthreads();
   if (tid < n_ret) {
-    if (s_tot[tid]) atomicAdd(&totals[(size_t)g * n_ret + tid], (unsigned long long)s_tot[tid]);
-    if (s_sup[tid]) atomicAdd(&supported[(size_t)g * n_ret + tid], (unsigned long long)s_sup[tid]);
+    if (s_tot[tid]) atomicAdd(&totals[(size_t)g * n_ret + tid], s_tot[tid]);
+    if (s_sup[tid]) atomicAdd(&supported[(size_t)g * n_ret + tid], s_sup[tid]);
   }
 }
 
