@@ -440,49 +440,83 @@ int camus_b200_add_gene_trees(camus_b200* ctx, int32_t n_trees, const int64_t* n
   if (!ctx->subs.empty())
     return fan_out(ctx, [&](camus_b200* s, int) { return camus_b200_add_gene_trees(s, n_trees, node_off, parent, taxon); });
   if (n_trees < 0 || !node_off || (n_trees > 0 && (!parent || !taxon))) return ctx->fail(CAMUS_B200_ERR_ARG, "add_gene_trees: null argument");
-  std::vector<int> stamp(ctx->N, -1);
-  std::vector<char> has_child;
-  std::vector<int> n_child, depth_h;
-  uint64_t res = 0;
-  for (int g = 0; g < n_trees; ++g) {
-    int64_t b = node_off[g], e = node_off[g + 1];
-    int64_t nn = e - b;
-    if (nn <= 0 || nn > 65535) return ctx->fail(CAMUS_B200_ERR_INPUT, "add_gene_trees: tree " + std::to_string(g) + " has " + std::to_string(nn) + " nodes (1..65535 supported)");
-    has_child.assign(nn, 0);
-    n_child.assign(nn, 0);
-    depth_h.assign(nn, 0);
-    uint64_t nl = 0;
-    for (int64_t i = 0; i < nn; ++i) {
-      int p = parent[b + i];
-      if ((i == 0) != (p < 0) || p >= i)
-        return ctx->fail(CAMUS_B200_ERR_INPUT, "add_gene_trees: tree " + std::to_string(g) + " is not in preorder (parent before child, single root)");
-      if (p >= 0) {
-        has_child[p] = 1;
-        ++n_child[p];
-        depth_h[i] = depth_h[p] + 1;
-        if (depth_h[i] >= 65535)
-          return ctx->fail(CAMUS_B200_ERR_INPUT, "add_gene_trees: tree " + std::to_string(g) + " is deeper than 65534 edges (16-bit depth tables)");
-        if (depth_h[i] > ctx->max_depth) ctx->max_depth = depth_h[i];
+  // Validation is per tree and independent: large batches are checked on several host threads
+  // (16 MB of nodes at 1000 x 1000 took ~10 ms on one). The first failing tree (lowest index) wins.
+  struct Part {
+    uint64_t res = 0;
+    int max_depth = 0, bad_tree = -1;
+    bool all_complete = true, all_rooted = true;
+    std::string msg;
+  };
+  const int N = ctx->N;
+  auto validate = [&](int g_lo, int g_hi, Part& pt) {
+    std::vector<int> stamp(N, -1);
+    std::vector<char> has_child;
+    std::vector<int> n_child, depth_h;
+    auto bad = [&](int g, const std::string& m) {
+      pt.bad_tree = g;
+      pt.msg = m;
+    };
+    for (int g = g_lo; g < g_hi; ++g) {
+      int64_t b = node_off[g], e = node_off[g + 1];
+      int64_t nn = e - b;
+      if (nn <= 0 || nn > 65535) return bad(g, "add_gene_trees: tree " + std::to_string(g) + " has " + std::to_string(nn) + " nodes (1..65535 supported)");
+      has_child.assign(nn, 0);
+      n_child.assign(nn, 0);
+      depth_h.assign(nn, 0);
+      uint64_t nl = 0;
+      for (int64_t i = 0; i < nn; ++i) {
+        int p = parent[b + i];
+        if ((i == 0) != (p < 0) || p >= i)
+          return bad(g, "add_gene_trees: tree " + std::to_string(g) + " is not in preorder (parent before child, single root)");
+        if (p >= 0) {
+          has_child[p] = 1;
+          ++n_child[p];
+          depth_h[i] = depth_h[p] + 1;
+          if (depth_h[i] >= 65535)
+            return bad(g, "add_gene_trees: tree " + std::to_string(g) + " is deeper than 65534 edges (16-bit depth tables)");
+          if (depth_h[i] > pt.max_depth) pt.max_depth = depth_h[i];
+        }
+        int t = taxon[b + i];
+        if (t >= N) return bad(g, "add_gene_trees: taxon index out of range");
+        if (t >= 0) {
+          if (stamp[t] == g) return bad(g, "add_gene_trees: tree " + std::to_string(g) + " contains a taxon twice");
+          stamp[t] = g;
+          ++nl;
+        }
       }
-      int t = taxon[b + i];
-      if (t >= ctx->N) return ctx->fail(CAMUS_B200_ERR_INPUT, "add_gene_trees: taxon index out of range");
-      if (t >= 0) {
-        if (stamp[t] == g) return ctx->fail(CAMUS_B200_ERR_INPUT, "add_gene_trees: tree " + std::to_string(g) + " contains a taxon twice");
-        stamp[t] = g;
-        ++nl;
-      }
+      for (int64_t i = 0; i < nn; ++i)
+        if ((taxon[b + i] >= 0) == (has_child[i] != 0))
+          return bad(g, "add_gene_trees: tree " + std::to_string(g) + ": taxon set on an internal node or missing on a leaf");
+      pt.res += choose4(nl);
+      // complete + fully resolved: all taxa present, every internal node binary (the root may be a
+      // trifurcation, i.e. the unrooted form of a binary tree)
+      bool complete = nl == (uint64_t)N;
+      for (int64_t i = 0; i < nn && complete; ++i)
+        if (n_child[i] != 0 && n_child[i] != 2 && !(i == 0 && n_child[i] == 3)) complete = false;
+      if (!complete) pt.all_complete = false;
+      if (n_child[0] != 2) pt.all_rooted = false;
     }
-    for (int64_t i = 0; i < nn; ++i)
-      if ((taxon[b + i] >= 0) == (has_child[i] != 0))
-        return ctx->fail(CAMUS_B200_ERR_INPUT, "add_gene_trees: tree " + std::to_string(g) + ": taxon set on an internal node or missing on a leaf");
-    res += choose4(nl);
-    // complete + fully resolved: all taxa present, every internal node binary (the root may be a
-    // trifurcation, i.e. the unrooted form of a binary tree)
-    bool complete = nl == (uint64_t)ctx->N;
-    for (int64_t i = 0; i < nn && complete; ++i)
-      if (n_child[i] != 0 && n_child[i] != 2 && !(i == 0 && n_child[i] == 3)) complete = false;
-    if (!complete) ctx->all_complete = false;
-    if (n_child[0] != 2) ctx->all_rooted = false;
+  };
+  const int64_t total_nodes = n_trees ? node_off[n_trees] - node_off[0] : 0;
+  int n_thr = 1;
+  if (total_nodes > (1 << 18)) n_thr = (int)std::max(1u, std::min({std::thread::hardware_concurrency(), 16u, (unsigned)n_trees}));
+  std::vector<Part> parts(n_thr);
+  {
+    std::vector<std::thread> th;
+    for (int k = 1; k < n_thr; ++k)
+      th.emplace_back([&, k] { validate((int)((int64_t)n_trees * k / n_thr), (int)((int64_t)n_trees * (k + 1) / n_thr), parts[k]); });
+    validate(0, (int)((int64_t)n_trees / n_thr), parts[0]);
+    for (auto& t : th) t.join();
+  }
+  uint64_t res = 0;
+  for (const Part& pt : parts)  // chunks are in tree order: the first bad chunk holds the lowest failing tree
+    if (pt.bad_tree >= 0) return ctx->fail(CAMUS_B200_ERR_INPUT, pt.msg);
+  for (const Part& pt : parts) {
+    res += pt.res;
+    ctx->max_depth = std::max(ctx->max_depth, pt.max_depth);
+    if (!pt.all_complete) ctx->all_complete = false;
+    if (!pt.all_rooted) ctx->all_rooted = false;
   }
   int64_t base = ctx->h_node_off.back() - node_off[0];
   for (int g = 0; g < n_trees; ++g) ctx->h_node_off.push_back(node_off[g + 1] + base);
