@@ -57,7 +57,11 @@ const char* camus_b200_last_error(const camus_b200* ctx);
  * camus_b200_count_filter and camus_b200_quartet_totals_partial the caller sums the partial
  * buffers over ranks (NCCL all-reduce on the device pointers returned below) and then calls
  * camus_b200_quartet_totals_finish. Default is (0, 1). A handle with n_gpus > 1 deals its
- * partition on to its GPUs (world * n_gpus shares); its partial buffer lives on devices[0]. */
+ * partition on to its GPUs (world * n_gpus shares); its partial buffer lives on devices[0].
+ * How the boxes of the index space are dealt is the library's business (chunks round-robin, or for
+ * 4 / 8 shares by segment classes so that a share builds only the bit-planes it reads; DESIGN.md 7,
+ * mirrored for tests by camus_b200/partition.py); the union of the shares is always the whole space
+ * and the summed results do not depend on it. */
 int camus_b200_set_partition(camus_b200* ctx, int rank, int world);
 
 /* Constraint tree in reference node-id order (preprocess.go:28-30), rooted, binary.
