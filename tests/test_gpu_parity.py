@@ -470,6 +470,35 @@ def test_class_partitions_on_one_gpu(gpu, world, monkeypatch):
         gpu.set_partition(0, 1)
 
 
+@pytest.mark.parametrize("n_taxa", [6, 17, 41])
+def test_class_partition_tiny_inputs(gpu, n_taxa, monkeypatch):
+    """Class scheme forced on inputs with 1, 3 and 6 segments: some of the 8 shares own no box (and
+    build no tile) at all; the shares still add up to the oracle's table and survivors."""
+    import torch
+    monkeypatch.setenv("CAMUS_B200_PARTITION", "class")
+    s = synth.make(n_taxa, 30, 100 + n_taxa, drop_frac=0.1)
+    prob = Problem(s.constraint, s.genes)
+    o = orc.Oracle().load(prob)
+    want = o.count_filter(1, 0.2, False)
+    want_tot = o.quartet_totals(True, False)
+    acc, ns, sc = None, 0, 0
+    try:
+        for r in range(8):
+            gpu.set_partition(r, 8)
+            gpu.load(prob)
+            a, b = gpu.count_filter(1, 0.2)
+            ns, sc = ns + a, sc + b
+            gpu.quartet_totals_partial(True)
+            z = gpu.partial_tensor().clone()
+            acc = z if acc is None else acc + z
+        assert (ns, sc) == want
+        gpu.partial_tensor().copy_(acc)
+        torch.cuda.synchronize()
+        assert np.array_equal(gpu.quartet_totals_finish(), want_tot)
+    finally:
+        gpu.set_partition(0, 1)
+
+
 def test_default_class_scheme_shares_sum_to_the_whole(gpu, monkeypatch):
     """264 taxa = 33 segments: 8 shares take the class scheme by default (complete binary trees,
     the complete-tree kernels). Shares run one after the other through run_resident; scalars and
