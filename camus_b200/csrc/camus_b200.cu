@@ -88,7 +88,9 @@ struct camus_b200 {
   uint64_t n_local = 0, chunk = 1;  // this rank's share of the boxes (BoxMap)
   // class-scheme partition (layout.cuh): explicit local box list + the tiles this rank builds
   bool class_scheme = false;
-  DevBuf<uint32_t> d_box_list, d_tile_list;
+  DevBuf<uint32_t> d_box_list, d_tile_list, d_tile_slot;  // tile_slot: tile index -> compact slot (0xFFFFFFFF = not stored)
+  bool tri_compact = false;        // the bit-planes hold only this share's tiles, in tile_list order ...
+  int tri_key[3] = {-1, -1, -1};   // ... of this (segments, rank, world)
   uint64_t n_tiles_local = 0;
   int list_key[3] = {-1, -1, -1};  // (segments, rank, world) the lists were built for
   uint32_t tri_mask = 0;           // segment classes whose tiles the bit-planes hold (0xF = every tile)
@@ -561,7 +563,7 @@ int build_planes(camus_b200* ctx, bool do_upload = true) {
   CK(ctx->d_hT.alloc(per_group * G32));
   CK(cudaMemsetAsync(ctx->d_lrT.p, 0, ctx->d_lrT.bytes(), ctx->stream));
   CK(cudaMemsetAsync(ctx->d_hT.p, 0, ctx->d_hT.bytes(), ctx->stream));
-  size_t tri_words = (size_t)num_tiles(ctx->M) * G32 * kTileWords;
+  size_t tri_words = (size_t)(partial ? ctx->n_tiles_local : num_tiles(ctx->M)) * G32 * kTileWords;
   if (ctx->d_tri.n < tri_words) {  // only query the driver when the table has to grow
     size_t free_b = 0, total_b = 0;
     CK(cudaMemGetInfo(&free_b, &total_b));
@@ -624,15 +626,24 @@ int build_planes(camus_b200* ctx, bool do_upload = true) {
   if (t.stop()) return CAMUS_B200_ERR_CUDA;
   ctx->genes_dirty = false;
   ctx->tri_mask = partial ? class_need_mask(ctx->rank, ctx->world) : 0xFu;
+  ctx->tri_compact = partial;
+  ctx->tri_key[0] = ctx->M;
+  ctx->tri_key[1] = ctx->rank;
+  ctx->tri_key[2] = ctx->world;
   return 0;
 }
 
 // do the bit-planes in HBM hold every tile the current partition reads?
 bool planes_cover(camus_b200* ctx) {
   if (set_box_range(ctx)) return false;
+  // compact storage is laid out for one (segments, rank, world): any change of those needs a rebuild
+  if (ctx->tri_compact && (!ctx->class_scheme || ctx->tri_key[0] != ctx->M || ctx->tri_key[1] != ctx->rank || ctx->tri_key[2] != ctx->world))
+    return false;
   const uint32_t need = ctx->class_scheme ? class_need_mask(ctx->rank, ctx->world) : 0xFu;
   return (need & ~ctx->tri_mask) == 0;
 }
+
+const uint32_t* tile_slots(const camus_b200* ctx) { return ctx->tri_compact ? ctx->d_tile_slot.p : nullptr; }
 
 // the complete-tree kernel packs two 16-bit counters per register
 bool use_complete(const camus_b200* ctx) { return ctx->all_complete && ctx->allow_complete && ctx->G > 0 && ctx->G <= 65535; }
@@ -678,7 +689,7 @@ int set_box_range(camus_b200* ctx) {
   const uint32_t thr = class_threshold(S, world), need = class_need_mask(rank, world);
   std::vector<uint8_t> cls(S);
   for (uint32_t s = 0; s < S; ++s) cls[s] = (uint8_t)seg_class(s);
-  std::vector<uint32_t> boxes, tiles;
+  std::vector<uint32_t> boxes, tiles, slots((size_t)num_tiles(S), 0xFFFFFFFFu);
   boxes.reserve((size_t)(nb / world + nb / (8 * (uint64_t)world) + 64));
   uint32_t idx = 0;
   for (uint32_t sd = 0; sd < S; ++sd)
@@ -697,9 +708,14 @@ int set_box_range(camus_b200* ctx) {
   for (uint32_t s2 = 0; s2 < S; ++s2)
     for (uint32_t s1 = 0; s1 <= s2; ++s1)
       for (uint32_t s0 = 0; s0 <= s1; ++s0, ++idx)
-        if ((need >> cls[s0]) & 1u) tiles.push_back(idx);
+        if ((need >> cls[s0]) & 1u) {
+          slots[idx] = (uint32_t)tiles.size();
+          tiles.push_back(idx);
+        }
   CK(ctx->d_box_list.alloc(std::max<size_t>(boxes.size(), 1)));
   CK(ctx->d_tile_list.alloc(std::max<size_t>(tiles.size(), 1)));
+  CK(ctx->d_tile_slot.alloc(slots.size()));
+  CK(cudaMemcpyAsync(ctx->d_tile_slot.p, slots.data(), slots.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
   if (!boxes.empty()) CK(cudaMemcpyAsync(ctx->d_box_list.p, boxes.data(), boxes.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
   if (!tiles.empty()) CK(cudaMemcpyAsync(ctx->d_tile_list.p, tiles.data(), tiles.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));  // the host vectors go away
@@ -741,7 +757,7 @@ int run_fused(camus_b200* ctx, int qmode, double threshold, int as_set, uint64_t
   const uint64_t max_grid = 1u << 30;
   for (uint64_t b0 = 0; b0 < mine; b0 += max_grid) {
     uint64_t nbx = std::min(max_grid, mine - b0);
-    CountParams prm{ctx->d_tri.p, std::max(ctx->G32, 1), box_map(ctx, b0), nullptr, ctx->G};
+    CountParams prm{ctx->d_tri.p, std::max(ctx->G32, 1), box_map(ctx, b0), nullptr, ctx->G, tile_slots(ctx)};
     static const int dbg = getenv("CAMUS_B200_DEBUG") ? atoi(getenv("CAMUS_B200_DEBUG")) : 0;
     FusedParams fz{qmode, threshold, ctx->d_thr_tab.p, as_set, ctx->d_Z.p, ctx->d_totals.p, rep, (unsigned long long)zn, ctx->allow_regular ? 1 : 0, dbg};
     if (use_complete(ctx))
@@ -783,7 +799,7 @@ int run_count(camus_b200* ctx) {
   const uint64_t max_grid = 1u << 30;
   for (uint64_t b0 = 0; b0 < mine; b0 += max_grid) {
     uint64_t nbx = std::min(max_grid, mine - b0);
-    CountParams prm{ctx->d_tri.p, std::max(ctx->G32, 1), box_map(ctx, b0), ctx->d_cells.p + b0 * kBoxCells, ctx->G};
+    CountParams prm{ctx->d_tri.p, std::max(ctx->G32, 1), box_map(ctx, b0), ctx->d_cells.p + b0 * kBoxCells, ctx->G, tile_slots(ctx)};
     if (use_complete(ctx))
       k_count<false, true><<<(unsigned)nbx, kCountThreads, CountCfg<true>::kSmemBytes, ctx->stream>>>(prm, FusedParams{}, ctx->ct);
     else

@@ -53,6 +53,7 @@ struct CountParams {
   BoxMap bm;       // blockIdx.x -> global box rank
   uint4* cells;    // table mode: [local box][kBoxCells] = (c(ab|cd), c(ac|bd), c(ad|bc), 0)
   int n_trees;
+  const uint32_t* tile_slot;  // class-scheme shares store only the tiles they read: tile index -> slot in tri; nullptr = identity
 };
 
 // Fused mode: the counts never leave the registers. The epilogue applies K3 (filter + constraint
@@ -91,6 +92,7 @@ k_count(CountParams prm, FusedParams fz, ConstraintDev ct) {
   extern __shared__ __align__(128) uint32_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kCountStages * Cfg::kStageWords);
   __shared__ uint32_t s_seg[5];  // four segments, [4] = regular box
+  __shared__ uint64_t s_tile[4];  // slots of the tiles abc, abd, acd, bcd in prm.tri
 
   const int tid = threadIdx.x;
   const int ta = tid & 3, tb = (tid >> 2) & 3, tc = (tid >> 4) & 3, td = tid >> 6;
@@ -102,6 +104,14 @@ k_count(CountParams prm, FusedParams fz, ConstraintDev ct) {
     s_seg[1] = sb;
     s_seg[2] = sc;
     s_seg[3] = sd;
+    auto slot = [&](uint32_t s0, uint32_t s1, uint32_t s2) {
+      const uint64_t t = tile_index(s0, s1, s2);
+      return prm.tile_slot ? (uint64_t)__ldg(prm.tile_slot + t) : t;
+    };
+    s_tile[0] = slot(sa, sb, sc);
+    s_tile[1] = slot(sa, sb, sd);
+    s_tile[2] = slot(sa, sc, sd);
+    s_tile[3] = slot(sb, sc, sd);
     if constexpr (kFused) {
       const uint8_t* U = ct.seg_uniform;
       const uint32_t S = (uint32_t)ct.n_seg;
@@ -115,10 +125,10 @@ k_count(CountParams prm, FusedParams fz, ConstraintDev ct) {
   const int G = prm.n_groups;
   const uint32_t sa = s_seg[0], sb = s_seg[1], sc = s_seg[2], sd = s_seg[3];
   const size_t gstride = (size_t)kTileWords;
-  const uint32_t* src0 = prm.tri + tile_index(sa, sb, sc) * (size_t)G * gstride;  // abc
-  const uint32_t* src1 = prm.tri + tile_index(sa, sb, sd) * (size_t)G * gstride;  // abd
-  const uint32_t* src2 = prm.tri + tile_index(sa, sc, sd) * (size_t)G * gstride;  // acd
-  const uint32_t* src3 = prm.tri + tile_index(sb, sc, sd) * (size_t)G * gstride;  // bcd
+  const uint32_t* src0 = prm.tri + s_tile[0] * (size_t)G * gstride;  // abc
+  const uint32_t* src1 = prm.tri + s_tile[1] * (size_t)G * gstride;  // abd
+  const uint32_t* src2 = prm.tri + s_tile[2] * (size_t)G * gstride;  // acd
+  const uint32_t* src3 = prm.tri + s_tile[3] * (size_t)G * gstride;  // bcd
 
   auto issue = [&](int g) {
     const int s = g % kCountStages;

@@ -138,7 +138,8 @@ __global__ void k_depth_table(int grp0, int n_trees, int npad, const int32_t* __
 // needs are staged in shared memory (coalesced 64 B rows of Dt), 8 warps x 64 triples ballot into
 // a shared 6 KB image of the tile, which is then written to HBM with 128-bit coalesced stores.
 // Every word of every tile is written, so Tri needs no memset.
-// tile_list: class-scheme partitions build only the tiles this rank reads (layout.cuh); nullptr = all.
+// tile_list: class-scheme partitions build only the tiles this rank reads (layout.cuh) and store
+// them compactly, tile tile_list[i] in slot i of Tri; nullptr = all tiles, slot = tile index.
 __global__ void __launch_bounds__(256) k_triple_planes(int grp0, int n_batch, int n_groups_total, int npad,
                                                        const uint16_t* __restrict__ Dt, uint32_t* __restrict__ Tri,
                                                        const uint32_t* __restrict__ tile_list) {
@@ -206,7 +207,7 @@ __global__ void __launch_bounds__(256) k_triple_planes(int grp0, int n_batch, in
     }
   }
   __syncthreads();
-  uint4* dst = reinterpret_cast<uint4*>(Tri + (tile * n_groups_total + (grp0 + gb)) * kTileWords);
+  uint4* dst = reinterpret_cast<uint4*>(Tri + ((tile_list ? (uint64_t)blockIdx.x : tile) * n_groups_total + (grp0 + gb)) * kTileWords);
   for (int i = tid; i < kTileWords / 4; i += 256)
     dst[i] = *reinterpret_cast<const uint4*>(s_out + (i >> 7) * kPlanePad + (i & 127) * 4);
   }
@@ -372,7 +373,7 @@ __global__ void __launch_bounds__(256, CAMUS_PLANES_MINB) k_triple_planes_h2(int
       for (int p = 0; p < 3; ++p) s_img[tile_word(p, x, y, z)] = w[p];
     }
     __syncthreads();
-    uint4* out = reinterpret_cast<uint4*>(Tri + (tile * n_groups_total + (grp0 + gb)) * kTileWords);
+    uint4* out = reinterpret_cast<uint4*>(Tri + ((tile_list ? (uint64_t)blockIdx.x : tile) * n_groups_total + (grp0 + gb)) * kTileWords);
     for (int i = tid; i < kTileWords / 4; i += 256) out[i] = reinterpret_cast<const uint4*>(s_img)[i];
   }
 }

@@ -49,6 +49,12 @@ def run(label):
         if best is None or wall < best["wall_ms"]:
             best = {"share": label, "wall_ms": round(wall, 3), "prep_ms": round(ms["prep"], 3), "count_ms": round(ms["count"], 3),
                     "launches": int(nl), "n_survivors": ns, "sum_counts": sc}
+    try:  # device memory in use by this process (the bit-planes dominate)
+        import torch
+        free_b, total_b = torch.cuda.mem_get_info(0)
+        best["device_used_gb"] = round((total_b - free_b) / 1e9, 2)
+    except Exception:
+        pass
     rows.append(best)
     print(json.dumps(best), flush=True)
     return best
