@@ -961,6 +961,7 @@ int camus_b200_count_filter(camus_b200* ctx, int qmode, double threshold, uint64
   CK(cudaSetDevice(ctx->device));
   std::memset(ctx->ms, 0, sizeof(ctx->ms));
   ctx->launches = 0;
+  ctx->want_all_tiles = false;  // a camus_b200_query_cells probe asks again
   int rc;
   if (ctx->genes_dirty) {
     if ((rc = build_planes(ctx, true))) return rc;
@@ -1006,6 +1007,7 @@ int camus_b200_run_resident(camus_b200* ctx, int qmode, double threshold, int as
   CK(cudaSetDevice(ctx->device));
   std::memset(ctx->ms, 0, sizeof(ctx->ms));
   ctx->launches = 0;
+  ctx->want_all_tiles = false;
   int rc;
   if ((rc = build_planes(ctx, false))) return rc;
   ctx->cell_state = camus_b200::NONE;
