@@ -11,6 +11,7 @@
 #include <cmath>
 #include <condition_variable>
 #include <cstdlib>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -20,6 +21,40 @@
 #include "treedata.hpp"
 
 namespace camus {
+
+// ---- scorer options (score/scorers.go:12-38) ----
+enum class ScoreMode : int { Max = 0, Norm = 1, Sym = 2 };
+struct ScorerOpts {  // scorers.go:25-29
+  int nGTrees = 0;
+  double alpha = 0;
+  bool asSet = false;
+};
+using ScoreOption = std::function<void(ScorerOpts&)>;
+inline ScoreOption AsSet(bool v) {
+  return [v](ScorerOpts& o) { o.asSet = v; };
+}
+inline ScoreOption WithNGtrees(int n) {
+  return [n](ScorerOpts& o) {
+    if (n <= 0) throw CamusError(Err::InvalidScorerOption, "invalid scorer option, number of gene trees must be positive, but is " + std::to_string(n));
+    o.nGTrees = n;
+  };
+}
+inline ScoreOption WithAlpha(double a) {
+  return [a](ScorerOpts& o) {
+    if (a <= 0 || a > 1)
+      throw CamusError(Err::InvalidScorerOption, "invalid scorer option, alpha must be in greater than zero and less than or equal to one, but is " + std::to_string(a));
+    o.alpha = a;
+  };
+}
+
+// score.ParseScorer (scorers.go:12-16)
+inline bool ParseScorer(const std::string& s, ScoreMode& m) {
+  if (s == "max") m = ScoreMode::Max;
+  else if (s == "norm") m = ScoreMode::Norm;
+  else if (s == "sym") m = ScoreMode::Sym;
+  else return false;
+  return true;
+}
 
 struct Branch {
   int u = 0, w = 0;
@@ -636,7 +671,6 @@ inline std::string make_network_newick(const TreeData& td, std::vector<Branch> b
   return nwk;
 }
 
-enum class ScoreMode : int { Max = 0, Norm = 1, Sym = 2 };
 
 // infer.Infer after Preprocess + Scorer.Init (infer.go:79-95) and DP.collateResults
 // (main_dp.go:106-127): run the DP over precomputed tables.

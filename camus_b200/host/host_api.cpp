@@ -25,7 +25,7 @@ struct camus_host_problem {
   int n_gene_trees = 0;
   bool warned_missing = false;
   double pct_no_support = 0;
-  std::string constraint_newick;
+  std::string constraint_newick, constraint_newick_scratch;
 };
 
 // score.ReticulationScore inputs (internal/score/score.go:25-72), flattened for
@@ -146,6 +146,37 @@ int camus_host_results_branches(const camus_host_results* r, int k, int32_t* uw)
 double camus_host_results_qsat(const camus_host_results* r, int k) { return r->res.qsat[k - 1]; }
 double camus_host_results_root_score(const camus_host_results* r, int k) { return r->res.root_scores_f[k]; }
 const char* camus_host_results_newick(const camus_host_results* r, int k) { return r->newicks[k - 1].c_str(); }
+
+// graphs.MakeNetwork(td, branches).Newick() (graphs/net.go:38-101) for k given branches (u0,w0,u1,w1,...).
+const char* camus_host_make_network(camus_host_problem* p, int k, const int32_t* uw) {
+  try {
+    std::vector<Branch> b(k);
+    for (int i = 0; i < k; ++i) {
+      b[i].u = uw[2 * i];
+      b[i].w = uw[2 * i + 1];
+    }
+    p->constraint_newick_scratch = make_network_newick(p->td, b);
+    return p->constraint_newick_scratch.c_str();
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return nullptr;
+  }
+}
+
+// score.ParseScorer + the option funcs infer.Infer passes (infer.go:79-88, scorers.go:12-38):
+// 0 ok, -1 unknown score mode (camus.go reports it), else camus::Err (8 = ErrInvalidScorerOption).
+int camus_host_check_scorer_options(const char* mode, int n_gtrees, double alpha) {
+  try {
+    ScoreMode m;
+    if (!ParseScorer(mode, m)) return -1;
+    ScorerOpts o;
+    if (m == ScoreMode::Norm) WithNGtrees(n_gtrees)(o);
+    if (m == ScoreMode::Sym) WithAlpha(alpha)(o);
+    return 0;
+  } catch (const CamusError& e) {
+    return fail(e);
+  }
+}
 
 // ---- score.ReticulationScore: host half (network parsing, level-1 check, per-tip records) ----
 // Returns 0, a camus::Err code, 11 (ErrNoReticulations) or 12 (ErrNotLevel1).

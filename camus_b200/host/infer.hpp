@@ -97,37 +97,7 @@ inline DeviceTreeData Preprocess(Tree tre, std::vector<Tree>& geneTrees, int /*n
 }
 
 // ---- score ------------------------------------------------------------------------------------
-struct ScorerOpts {  // scorers.go:25-29
-  int nGTrees = 0;
-  double alpha = 0;
-  bool asSet = false;
-};
-using ScoreOption = std::function<void(ScorerOpts&)>;
-inline ScoreOption AsSet(bool v) {
-  return [v](ScorerOpts& o) { o.asSet = v; };
-}
-inline ScoreOption WithNGtrees(int n) {
-  return [n](ScorerOpts& o) {
-    if (n <= 0) throw CamusError(Err::InvalidScorerOption, "invalid scorer option, number of gene trees must be positive, but is " + std::to_string(n));
-    o.nGTrees = n;
-  };
-}
-inline ScoreOption WithAlpha(double a) {
-  return [a](ScorerOpts& o) {
-    if (a <= 0 || a > 1)
-      throw CamusError(Err::InvalidScorerOption, "invalid scorer option, alpha must be in greater than zero and less than or equal to one, but is " + std::to_string(a));
-    o.alpha = a;
-  };
-}
-
-// score.ParseScorer (scorers.go:12-16)
-inline bool ParseScorer(const std::string& s, ScoreMode& m) {
-  if (s == "max") m = ScoreMode::Max;
-  else if (s == "norm") m = ScoreMode::Norm;
-  else if (s == "sym") m = ScoreMode::Sym;
-  else return false;
-  return true;
-}
+// ScorerOpts, AsSet / WithNGtrees / WithAlpha and ParseScorer (scorers.go:12-38) live in dp.hpp
 
 // Scorer.Init for all three scorers (scorers.go:51-60, 82-99, 123-140): fills the integer tables
 // from the device. The float formulas stay in dp.hpp's *Scorer::calc.

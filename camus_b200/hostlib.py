@@ -71,6 +71,9 @@ def lib() -> C.CDLL:
         L.camus_host_results_root_score.restype = C.c_double
         L.camus_host_results_newick.argtypes = [C.c_void_p, C.c_int]
         L.camus_host_results_newick.restype = C.c_char_p
+        L.camus_host_make_network.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int32)]
+        L.camus_host_make_network.restype = C.c_char_p
+        L.camus_host_check_scorer_options.argtypes = [C.c_char_p, C.c_int, C.c_double]
         vp = C.c_void_p
         L.camus_host_network_load.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.POINTER(vp)]
         L.camus_host_network_free.argtypes = [vp]
@@ -166,6 +169,14 @@ class Problem:
     def cycle_length(self, u: int, w: int) -> int:
         return lib().camus_host_cycle_length(self._h, u, w)
 
+    def make_network(self, branches) -> str:
+        """graphs.MakeNetwork(td, branches).Newick() (graphs/net.go:38-101); branches = [(u, w), ...] node ids."""
+        flat = (C.c_int32 * (2 * len(branches)))(*[x for b in branches for x in b])
+        r = lib().camus_host_make_network(self._h, len(branches), flat)
+        if r is None:
+            raise CamusError(10, lib().camus_host_last_error().decode())
+        return r.decode()
+
     def run_dp(self, totals: np.ndarray, penalties: np.ndarray | None = None, mode: str = "max", as_set: bool = False,
                n_survivors: int = 0, sum_counts: int = 0, n_gtrees: int | None = None, alpha: float = 0.1) -> DPResult:
         """infer.Infer after Scorer.Init (infer.go:79-95): DP + traceback + MakeNetwork."""
@@ -196,6 +207,16 @@ class Problem:
             return DPResult(branches, qsat, roots, newicks)
         finally:
             L.camus_host_results_free(r)
+
+
+def check_scorer_options(mode: str, n_gtrees: int = 1, alpha: float = 0.1) -> None:
+    """score.ParseScorer + WithNGtrees / WithAlpha as infer.Infer applies them (infer.go:79-88,
+    scorers.go:12-38). Raises KeyError for an unknown mode, CamusError(ErrInvalidScorerOption) else."""
+    rc = lib().camus_host_check_scorer_options(mode.encode(), int(n_gtrees), float(alpha))
+    if rc == -1:
+        raise KeyError(mode)
+    if rc != 0:
+        raise CamusError(rc, lib().camus_host_last_error().decode())
 
 
 class NetworkProblem:
