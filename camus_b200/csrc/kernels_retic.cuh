@@ -23,7 +23,7 @@ constexpr int kRetThreads = 256;
 // R1: per gene tree (one CTA), LCA-depth table over NETWORK tip indices:
 //   D[g][b][a] (a < b) = 1 + depth(LCA(a, b)), 0 = a taxon is absent from the tree (lower triangle:
 //   the score kernel's threads differ in their smallest taxon, which is then the contiguous index).
-// Dynamic shared memory: 4 B per node (parent, depth as u16) + 4 B per leaf (tip, gap as u16).
+// Dynamic shared memory: 8 B per node of the largest tree (parent, depth, leaf tip, leaf gap, u16 each).
 __global__ void __launch_bounds__(kRetThreads) k_ret_depths(const int64_t* __restrict__ node_off, const int32_t* __restrict__ parent,
                                                             const int32_t* __restrict__ taxon, int n_tips, int max_nodes,
                                                             uint16_t* __restrict__ D, uint8_t* __restrict__ root_binary) {
