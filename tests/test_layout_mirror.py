@@ -1,0 +1,70 @@
+"""camus_b200/partition.py (the Python mirror used by the multi-rank tests) against the index math of
+camus_b200/csrc/layout.cuh itself, compiled for the host with g++ (tests/layout_probe.cpp)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from camus_b200 import partition as part
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def probe(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("layout") / "liblayout_probe.so")
+    subprocess.run(["g++", "-std=c++17", "-O2", "-shared", "-fPIC", "-o", so, os.path.join(HERE, "layout_probe.cpp")], check=True)
+    L = C.CDLL(so)
+    L.probe_box_index.restype = C.c_uint64
+    L.probe_tile_index.restype = C.c_uint64
+    L.probe_partition_chunk.restype = C.c_uint64
+    L.probe_partition_chunk.argtypes = [C.c_uint64, C.c_uint]
+    L.probe_local_box_count.restype = C.c_uint64
+    L.probe_local_box_count.argtypes = [C.c_uint64, C.c_uint, C.c_uint]
+    L.probe_box_unrank.argtypes = [C.c_uint64, C.POINTER(C.c_uint)]
+    return L
+
+
+def test_class_scheme_mirror_is_identical(probe):
+    assert [probe.probe_seg_class(s) for s in range(40)] == part.seg_class(np.arange(40)).tolist()
+    for world in (4, 8):
+        assert [probe.probe_class_need_mask(r, world) for r in range(world)] == [part.class_need_mask(r, world) for r in range(world)]
+        for m in (1, 2, 7, 16, 33, 40, 63, 125, 200, 256):
+            assert probe.probe_class_threshold(m, world) == part.class_threshold(m, world), (m, world)
+        for m in (1, 5, 12, 33):
+            sa, sb, sc, sd = part.all_boxes(m)
+            own = part.class_owner(sa, sb, sc, sd, m, world)
+            got = [probe.probe_class_owner(int(a), int(b), int(c), int(d), m, world) for a, b, c, d in zip(sa, sb, sc, sd)]
+            assert got == own.tolist(), (m, world)
+
+
+def test_box_and_tile_ranks(probe):
+    m = 9
+    sa, sb, sc, sd = part.all_boxes(m)
+    out = (C.c_uint * 4)()
+    for r, (a, b, c, d) in enumerate(zip(sa, sb, sc, sd)):
+        assert probe.probe_box_index(int(a), int(b), int(c), int(d)) == r == part.box_index(int(a), int(b), int(c), int(d))
+        probe.probe_box_unrank(r, out)
+        assert list(out) == [a, b, c, d]
+    # large ranks: the fp32 estimate + integer fix-up of box_unrank stays exact
+    for seg in ((0, 0, 0, 4095), (4095, 4095, 4095, 4095), (17, 900, 901, 2500), (124, 124, 124, 124)):
+        r = probe.probe_box_index(*seg)
+        probe.probe_box_unrank(r, out)
+        assert tuple(out) == seg
+    t = 0
+    for s2 in range(m):
+        for s1 in range(s2 + 1):
+            for s0 in range(s1 + 1):
+                assert probe.probe_tile_index(s0, s1, s2) == t
+                t += 1
+
+
+def test_chunk_scheme_mirror(probe):
+    for n_taxa in (9, 200, 1000):
+        nb = part.num_boxes(n_taxa)
+        for world in (1, 2, 3, 5, 8):
+            assert probe.probe_partition_chunk(nb, world) == part.partition_chunk(nb, world)
+            for r in range(world):
+                assert probe.probe_local_box_count(nb, r, world) == part.local_box_count(nb, r, world)
