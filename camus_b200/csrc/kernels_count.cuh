@@ -27,9 +27,6 @@
 
 namespace camus_dev {
 
-#ifndef CAMUS_COUNT_CSA
-#define CAMUS_COUNT_CSA 0  // 1 = carry-save experiment in the complete-tree count loop (see the main loop)
-#endif
 constexpr int kCountThreads = 256;
 constexpr int kCountStages = 4;
 constexpr int kPlaneWords = kTileWords / 3;  // 512 words = 2 KB: one plane of one tile
@@ -47,7 +44,7 @@ struct CountCfg {
   static constexpr int kStageWords = kPlanes * kPlaneWords;
   static constexpr int kStageBytes = kStageWords * 4;
   static constexpr int kSmemBytes = kCountStages * kStageBytes + 64;  // + mbarriers
-  static constexpr int kMinBlocks = (kComplete && !CAMUS_COUNT_CSA) ? 3 : 2;
+  static constexpr int kMinBlocks = kComplete ? 3 : 2;
 };
 
 struct CountParams {
@@ -174,77 +171,6 @@ k_count(CountParams prm, FusedParams fz, ConstraintDev ct) {
   asm volatile("" : "+r"(o_abc), "+r"(o_abd), "+r"(o_acd), "+r"(o_bcd));
   constexpr int kPlaneU4 = kPlaneWords / 4;
 
-#if CAMUS_COUNT_CSA
-  // EXPERIMENT (-DCAMUS_COUNT_CSA=1, complete-tree variant only; not the shipped build): the POPC
-  // (XU) pipe bounds the loop at 2 POPC per cell and tree group. A 3:2 compressor per (cell,
-  // topology) -- a running "ones" word plus the words of two consecutive groups -> new ones word
-  // + a carry word of weight 2 -- halves the POPCs at the price of 2 LOP3 per saved POPC + add and
-  // of 32 + 32 more registers (2 CTAs/SM instead of 3). See DESIGN.md section 9.
-  if constexpr (kComplete) {
-    uint32_t ones[16][2], held[16][2];
-#pragma unroll
-    for (int c = 0; c < 16; ++c) ones[c][0] = ones[c][1] = 0;
-    auto group_words = [&](int g, auto&& f) {
-      const int s = g % kCountStages;
-      if (!(kFused && fz.debug == 3 && g >= kCountStages)) mbar_wait(&bars[s], (uint32_t)((g / kCountStages) & 1));
-      const uint4* st = reinterpret_cast<const uint4*>(smem + s * Cfg::kStageWords);
-      auto ld = [&](int role, int plane, uint32_t off) -> uint4 { return st[plane_slot<kComplete>(role, plane) * kPlaneU4 + off]; };
-      uint4 abc[2][2];
-#pragma unroll
-      for (int p = 0; p < 2; ++p)
-#pragma unroll
-        for (int kk = 0; kk < 2; ++kk) abc[p][kk] = ld(0, p, o_abc + 16 * kk);
-#pragma unroll
-      for (int ll = 0; ll < 2; ++ll) {
-        const uint4 abd0 = ld(1, 0, o_abd + 16 * ll), abd2 = ld(1, 2, o_abd + 16 * ll);
-        const uint4 acd0 = ld(2, 0, o_acd + 16 * ll), acd2 = ld(2, 2, o_acd + 16 * ll);
-        const uint4 bcd1 = ld(3, 1, o_bcd + 16 * ll), bcd2 = ld(3, 2, o_bcd + 16 * ll);
-#pragma unroll
-        for (int kk = 0; kk < 2; ++kk)
-#pragma unroll
-          for (int j = 0; j < 2; ++j)
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              const int c = ((ll * 2 + kk) * 2 + j) * 2 + i;
-              const uint32_t t0 = (pick(abc[0][kk], j, i) & pick(abd0, j, i)) | (pick(acd2, kk, i) & pick(bcd2, kk, j));  // ab|cd
-              const uint32_t t1 = (pick(abc[1][kk], j, i) & pick(acd0, kk, i)) | (pick(abd2, j, i) & pick(bcd1, kk, j));  // ac|bd
-              f(c, t0, t1);
-            }
-      }
-    };
-    for (int g = 0; g < G; g += 2) {
-      if (g > 0) {
-        __syncthreads();
-        if (tid == 0 && !(kFused && fz.debug == 3)) {
-          if (g + 2 < G) issue(g + 2);
-          if (g + 3 < G) issue(g + 3);
-        }
-      }
-      if (g + 1 < G) {
-        group_words(g, [&](int c, uint32_t t0, uint32_t t1) {
-          held[c][0] = t0;
-          held[c][1] = t1;
-        });
-        group_words(g + 1, [&](int c, uint32_t t0, uint32_t t1) {
-          const uint32_t k0 = (ones[c][0] & held[c][0]) | (t0 & (ones[c][0] | held[c][0]));  // majority
-          const uint32_t k1 = (ones[c][1] & held[c][1]) | (t1 & (ones[c][1] | held[c][1]));
-          ones[c][0] ^= held[c][0] ^ t0;
-          ones[c][1] ^= held[c][1] ^ t1;
-          cnt[c][0] += (__popc(k0) << 1) + (__popc(k1) << 17);
-        });
-      } else {  // odd number of groups: half adder into the ones word
-        group_words(g, [&](int c, uint32_t t0, uint32_t t1) {
-          const uint32_t k0 = ones[c][0] & t0, k1 = ones[c][1] & t1;
-          ones[c][0] ^= t0;
-          ones[c][1] ^= t1;
-          cnt[c][0] += (__popc(k0) << 1) + (__popc(k1) << 17);
-        });
-      }
-    }
-#pragma unroll
-    for (int c = 0; c < 16; ++c) cnt[c][0] += __popc(ones[c][0]) + (__popc(ones[c][1]) << 16);
-  } else
-#endif
   for (int g = 0; g < G; ++g) {
     const int s = g % kCountStages;
     // One CTA barrier per TWO groups: at even g everyone has finished groups g-2 and g-1, whose
