@@ -23,6 +23,7 @@
 #include <atomic>
 #include <cstdint>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -325,8 +326,11 @@ void filter_quartets(QMap& qc, int mode, double thresh) {
   }
 }
 
+struct Dense;  // dense.hpp
+
 struct Ctx {
   std::string err;
+  std::shared_ptr<Dense> dense;  // LCA-depth tables of the dense mode, built on first use
   // constraint tree, ids as given (reference order)
   int n = 0, n_taxa = 0;
   std::vector<int> parent, child0, child1, tip_index, depth, tip_to_node;
@@ -546,58 +550,68 @@ bool ids_are_preorder(const Ctx& c) {
   return true;
 }
 
-void totals_scatter(const Ctx& c, bool asSet, uint64_t* out) {
-  int n = c.n;
-  std::vector<int> sz(n, 1);
-  for (int i = n - 1; i > 0; i--) sz[c.parent[i]] += sz[i];
-  // diff[w][u], u in [0, n]
-  std::vector<int64_t> diff((size_t)n * (n + 1), 0);
+// One surviving quartet's contribution to the difference table diff[w][u] (n rows of n + 1).
+struct ScatterAux {
+  std::vector<int> sz;  // subtree sizes (preorder ids: subtree(x) = [x, x + sz[x]))
+  explicit ScatterAux(const Ctx& c) : sz(c.n, 1) {
+    for (int i = c.n - 1; i > 0; i--) sz[c.parent[i]] += sz[i];
+  }
+};
+// leaf[i] = node of the quartet's i-th taxon (sorted by tip index), Lm[i][j] = LCA node of leaf i
+// and leaf j, topo = the quartet's topology nibble. Preorder node ids (subtree(x) = [x, x + sz[x])).
+inline void scatter_core(const Ctx& c, const ScatterAux& aux, const int leaf[4], const int Lm[4][4], uint8_t topo,
+                         int64_t wgt, int64_t* diff) {
+  const int n = c.n;
+  const std::vector<int>& sz = aux.sz;
   auto deeper = [&](int x, int y) { return c.depth[x] >= c.depth[y] ? x : y; };
-  for (auto kv :c.q) {
-    Quartet q = kv.first;
-    int64_t wgt = asSet ? 1 : (int64_t)kv.second;
-    int leaf[4];
-    for (int i = 0; i < 4; i++) leaf[i] = c.tip_to_node[q_taxon(q, i)];
-    uint8_t topo = q_topology(q);
-    for (int bi = 0; bi < 4; bi++) {
-      int xi = -1;
-      for (int j = 0; j < 4; j++)
-        if (j != bi && ((topo >> j) & 1) == ((topo >> bi) & 1)) xi = j;
-      int o[2], k = 0;
-      for (int j = 0; j < 4; j++)
-        if (j != bi && j != xi) o[k++] = j;
-      int b = leaf[bi], x = leaf[xi], y = leaf[o[0]], z = leaf[o[1]];
-      // m: lowest ancestor of b shared with another quartet taxon
-      int m = deeper(deeper(c.lca[b][x], c.lca[b][y]), c.lca[b][z]);
-      // junction of {x,y,z} and the component holding x
-      int J = deeper(deeper(c.lca[x][y], c.lca[x][z]), c.lca[y][z]);
-      int lo, hi;
-      bool complement = false;
-      if (c.lca[J][x] == J && x != J) {  // x below J: the child subtree of J that holds x
-        int ch = (x >= c.child1[J]) ? c.child1[J] : c.child0[J];
-        lo = ch;
-        hi = ch + sz[ch];
-      } else {  // x outside subtree(J): everything outside, plus J itself
-        complement = true;
-        lo = J + 1;
-        hi = J + sz[J];
-      }
-      for (int s = 0; s < 2; s++) {
-        int wp = s == 0 ? b : m;
-        int64_t v = s == 0 ? wgt : -wgt;
-        int64_t* row = &diff[(size_t)wp * (n + 1)];
-        if (!complement) {
-          row[lo] += v;
-          row[hi] -= v;
-        } else {
-          row[0] += v;
-          row[lo] -= v;
-          row[hi] += v;
-        }
+  for (int bi = 0; bi < 4; bi++) {
+    int xi = -1;
+    for (int j = 0; j < 4; j++)
+      if (j != bi && ((topo >> j) & 1) == ((topo >> bi) & 1)) xi = j;
+    int o[2], k = 0;
+    for (int j = 0; j < 4; j++)
+      if (j != bi && j != xi) o[k++] = j;
+    const int b = leaf[bi], x = leaf[xi];
+    // m: lowest ancestor of b shared with another quartet taxon
+    const int m = deeper(deeper(Lm[bi][xi], Lm[bi][o[0]]), Lm[bi][o[1]]);
+    // junction of {x,y,z} and the component holding x
+    const int J = deeper(deeper(Lm[xi][o[0]], Lm[xi][o[1]]), Lm[o[0]][o[1]]);
+    int lo, hi;
+    bool complement = false;
+    if (x > J && x < J + sz[J]) {  // x below J: the child subtree of J that holds x
+      int ch = (x >= c.child1[J]) ? c.child1[J] : c.child0[J];
+      lo = ch;
+      hi = ch + sz[ch];
+    } else {  // x outside subtree(J): everything outside, plus J itself
+      complement = true;
+      lo = J + 1;
+      hi = J + sz[J];
+    }
+    for (int s = 0; s < 2; s++) {
+      int wp = s == 0 ? b : m;
+      int64_t v = s == 0 ? wgt : -wgt;
+      int64_t* row = &diff[(size_t)wp * (n + 1)];
+      if (!complement) {
+        row[lo] += v;
+        row[hi] -= v;
+      } else {
+        row[0] += v;
+        row[lo] -= v;
+        row[hi] += v;
       }
     }
   }
-  // prefix over u, then subtree sum over w (children have larger ids), then the validity mask
+}
+inline void scatter_quartet(const Ctx& c, const ScatterAux& aux, Quartet q, int64_t wgt, int64_t* diff) {
+  int leaf[4], Lm[4][4];
+  for (int i = 0; i < 4; i++) leaf[i] = c.tip_to_node[q_taxon(q, i)];
+  for (int i = 0; i < 4; i++)
+    for (int j = 0; j < 4; j++) Lm[i][j] = c.lca[leaf[i]][leaf[j]];
+  scatter_core(c, aux, leaf, Lm, q_topology(q), wgt, diff);
+}
+// prefix over u, then subtree sum over w (children have larger ids), then the validity mask
+void scatter_finish(const Ctx& c, const std::vector<int64_t>& diff, uint64_t* out) {
+  const int n = c.n;
   std::vector<int64_t> val((size_t)n * n, 0);
   for (int w = 0; w < n; w++) {
     int64_t acc = 0;
@@ -612,6 +626,13 @@ void totals_scatter(const Ctx& c, bool asSet, uint64_t* out) {
   }
   for (int u = 0; u < n; u++)
     for (int w = 0; w < n; w++) out[(size_t)u * n + w] = should_calc_edge(c, u, w) ? (uint64_t)val[(size_t)w * n + u] : 0;
+}
+
+void totals_scatter(const Ctx& c, bool asSet, uint64_t* out) {
+  ScatterAux aux(c);
+  std::vector<int64_t> diff((size_t)c.n * (c.n + 1), 0);  // diff[w][u], u in [0, n]
+  for (auto kv : c.q) scatter_quartet(c, aux, kv.first, asSet ? 1 : (int64_t)kv.second, diff.data());
+  scatter_finish(c, diff, out);
 }
 
 template <class F>
@@ -633,6 +654,8 @@ void parallel_for(int n, int nthreads, F&& f) {
   for (auto& x : th) x.join();
 }
 
+#include "dense.hpp"
+
 }  // namespace
 
 extern "C" {
@@ -652,6 +675,7 @@ int oracle_set_constraint(oracle_ctx* c, int32_t n_nodes, int32_t n_taxa, const 
   c->child1.assign(child1, child1 + n_nodes);
   c->tip_index.assign(tip_index, tip_index + n_nodes);
   build_tree_tables(*c);
+  c->dense.reset();
   c->genes.clear();
   c->raw.clear();
   c->q.clear();
@@ -669,6 +693,7 @@ int oracle_add_gene_trees(oracle_ctx* c, int32_t n_trees, const int64_t* node_of
     t.build();
     c->genes.push_back(std::move(t));
   }
+  c->dense.reset();
   return 0;
 }
 
@@ -858,6 +883,39 @@ uint64_t oracle_pack_quartet(int t0, int t1, int t2, int t3) {
   return make_quartet(ids, topo);
 }
 int oracle_threshold_keep(double t, uint32_t c0, uint32_t c1, uint32_t c2) { return threshold_keep(t, c0, c1, c2); }
+
+// ---- dense mode (dense.hpp): the whole path without a quartet map, for the large parity cases ----
+// stats[8] = n_survivors, sum_counts, n_raw_keys, sum_raw, hash_raw, hash_surv (0 unless digests), resolutions, cells
+int oracle_dense_run(oracle_ctx* c, int qmode, double threshold, int as_set, int nthreads, int digests, uint64_t* out, uint64_t* stats) {
+  DenseStats s;
+  int rc = dense_run(*c, qmode, threshold, as_set != 0, nthreads, out, &s, digests != 0);
+  if (rc) return rc;
+  const uint64_t v[8] = {s.n_survivors, s.sum_counts, s.n_raw_keys, s.sum_raw, s.hash_raw, s.hash_surv, s.resolutions, s.cells};
+  if (stats) std::memcpy(stats, v, sizeof(v));
+  return 0;
+}
+// literal quartetsTotal (quartettotals.go:78-93) of pairs[(u, w)] that all have LCA v, any input size
+int oracle_dense_literal_at(oracle_ctx* c, int v, int qmode, double threshold, int as_set, int nthreads, int n_pairs,
+                            const int32_t* pairs, uint64_t* out, uint64_t* n_quartets_at_v) {
+  return dense_literal_at(*c, v, qmode, threshold, as_set != 0, nthreads, n_pairs, pairs, out, n_quartets_at_v);
+}
+// filterQuartets on one 4-taxon set, visiting its keys in the given order (a permutation of 0 1 2)
+void oracle_filter_cell(uint32_t* counts, int qmode, double threshold, const int32_t* order) {
+  const int o[3] = {order[0], order[1], order[2]};
+  filter_cell_literal(counts, qmode, threshold, o);
+}
+// prep.filterQuartets (quartetfilter.go:76-96) on an explicit map: keys/counts in, survivors out (sorted by key)
+int oracle_filter_quartets(uint64_t n, const uint64_t* keys, const uint32_t* counts, int qmode, double threshold,
+                           uint64_t* out_keys, uint32_t* out_counts, uint64_t* n_out) {
+  QMap m;
+  for (uint64_t i = 0; i < n; i++) m[keys[i]] = counts[i];
+  filter_quartets(m, qmode, threshold);
+  return export_map(m, out_keys, out_counts, n, n_out);
+}
+// digest of a (key, count) list as dense_run accumulates it
+uint64_t oracle_mix_key(uint64_t key, uint32_t count) { return mix_key(key, count); }
+int oracle_leaves_below(const oracle_ctx* c, int v) { return (int)c->leaves_below[v]; }
+int oracle_depth(const oracle_ctx* c, int v) { return c->depth[v]; }
 
 // score.ReticulationScore (score.go:25-72), literal: MakeTreeData on the network tree as parsed
 // (general arity: #H tips and the unary #H nodes stay in), then per gene tree every EMISSION of

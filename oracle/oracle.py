@@ -59,6 +59,15 @@ def lib() -> C.CDLL:
         L.oracle_pack_quartet.argtypes = [C.c_int] * 4
         L.oracle_pack_quartet.restype = C.c_uint64
         L.oracle_threshold_keep.argtypes = [C.c_double, C.c_uint32, C.c_uint32, C.c_uint32]
+        L.oracle_dense_run.argtypes = [vp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, vp, vp]
+        L.oracle_dense_literal_at.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, vp, vp, u64p]
+        L.oracle_filter_cell.argtypes = [vp, C.c_int, C.c_double, vp]
+        L.oracle_filter_cell.restype = None
+        L.oracle_filter_quartets.argtypes = [C.c_uint64, vp, vp, C.c_int, C.c_double, vp, vp, u64p]
+        L.oracle_mix_key.argtypes = [C.c_uint64, C.c_uint32]
+        L.oracle_mix_key.restype = C.c_uint64
+        L.oracle_leaves_below.argtypes = [vp, C.c_int]
+        L.oracle_depth.argtypes = [vp, C.c_int]
         L.oracle_reticulation_counts.argtypes = [C.c_int32, vp, vp, C.c_int32, C.c_int32, vp, C.c_int32, vp, vp, vp, vp, vp]
         _lib = L
     return _lib
@@ -80,6 +89,35 @@ def unpack_quartet(q: int):
 
 def threshold_keep(t: float, c0: int, c1: int, c2: int) -> bool:
     return bool(lib().oracle_threshold_keep(t, c0, c1, c2))
+
+
+def filter_cell(counts, qmode: int, threshold: float, order=(0, 1, 2)):
+    """prep.filterQuartets on the three topology counts of one 4-taxon set (0 = key absent), visiting
+    the keys in `order`."""
+    c = np.array(counts, np.uint32)
+    o = np.array(order, np.int32)
+    lib().oracle_filter_cell(_p(c), qmode, threshold, _p(o))
+    return tuple(int(x) for x in c)
+
+
+def filter_quartets(keys, counts, qmode: int, threshold: float):
+    """prep.filterQuartets (the map form the literal mode uses) on an explicit (key, count) list."""
+    keys = np.ascontiguousarray(keys, np.uint64)
+    counts = np.ascontiguousarray(counts, np.uint32)
+    ok, oc, n = np.zeros(len(keys), np.uint64), np.zeros(len(keys), np.uint32), C.c_uint64()
+    lib().oracle_filter_quartets(len(keys), _p(keys), _p(counts), qmode, threshold, _p(ok), _p(oc), C.byref(n))
+    return ok[:n.value], oc[:n.value]
+
+
+def digest(keys: np.ndarray, counts: np.ndarray) -> int:
+    """Order-independent 64-bit digest of a (packed quartet, count) list: the sum the oracle's dense
+    mode accumulates over raw / surviving quartets (dense.hpp mix_key)."""
+    with np.errstate(over="ignore"):
+        z = keys.astype(np.uint64) + np.uint64(0x9E3779B97F4A7C15) * (counts.astype(np.uint64) + np.uint64(1))
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+        return int(z.sum(dtype=np.uint64))
 
 
 def tree_quartets(parent: np.ndarray, taxon: np.ndarray, literal: bool = True) -> np.ndarray:
@@ -170,6 +208,36 @@ class Oracle:
         out = np.zeros((len(quads), 3), np.uint32)
         lib().oracle_count_cells(self._h, len(quads), _p(quads), _p(out))
         return out
+
+    def dense_run(self, qmode: int = 0, threshold: float = 0.0, as_set: bool = False, table: bool = True, digests: bool = True):
+        """The whole path in dense mode (oracle/dense.hpp): no quartet map, any size that fits the
+        LCA-depth tables. Returns (stats dict, n x n totals or None)."""
+        out = np.zeros((self.n, self.n), np.uint64) if table else None
+        st = np.zeros(8, np.uint64)
+        rc = lib().oracle_dense_run(self._h, qmode, threshold, int(as_set), self.nthreads, int(digests),
+                                    _p(out) if table else None, _p(st))
+        if rc != 0:
+            raise RuntimeError(lib().oracle_last_error(self._h).decode())
+        names = ("n_survivors", "sum_counts", "n_raw_keys", "sum_raw", "hash_raw", "hash_surv", "resolutions", "cells")
+        return {k: int(v) for k, v in zip(names, st)}, out
+
+    def dense_literal_at(self, v: int, pairs, qmode: int = 0, threshold: float = 0.0, as_set: bool = False):
+        """Literal quartetsTotal (quartettotals.go:78-93) for (u, w) pairs whose LCA is v, at any
+        input size: (values, len(td.Quartets(v)))."""
+        pairs = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
+        out = np.zeros(len(pairs), np.uint64)
+        nq = C.c_uint64()
+        rc = lib().oracle_dense_literal_at(self._h, v, qmode, threshold, int(as_set), self.nthreads, len(pairs), _p(pairs),
+                                           _p(out), C.byref(nq))
+        if rc != 0:
+            raise RuntimeError(lib().oracle_last_error(self._h).decode())
+        return out, nq.value
+
+    def leaves_below(self, v: int) -> int:
+        return lib().oracle_leaves_below(self._h, v)
+
+    def depth(self, v: int) -> int:
+        return lib().oracle_depth(self._h, v)
 
     def quartet_totals(self, as_set: bool = False, literal: bool = True) -> np.ndarray:
         out = np.zeros((self.n, self.n), np.uint64)
