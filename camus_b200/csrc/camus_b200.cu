@@ -14,6 +14,7 @@
 #include "kernels_prep.cuh"
 #include "kernels_retic.cuh"
 #include "kernels_score.cuh"
+#include "kernels_stream.cuh"
 
 using namespace camus_dev;
 
@@ -54,6 +55,7 @@ struct camus_b200 {
   std::vector<camus_b200*> subs;
   int user_rank = 0, user_world = 1;  // partition of the whole handle (multi-process on top)
   bool peer_access = false;
+  bool reduced = false;                // subs[0]'s junction table already holds the sum over all devices
   DevBuf<unsigned long long> d_stage;  // on subs[0]: landing buffer when peer access is unavailable
 
   int device = 0;
@@ -109,6 +111,12 @@ struct camus_b200 {
   bool allow_half = true;      // CAMUS_B200_NO_HALF=1 forces the integer plane builder (A/B, tests)
   bool allow_complete = true;  // CAMUS_B200_NO_COMPLETE=1 forces the general kernel (A/B, tests)
   bool allow_regular = true;   // CAMUS_B200_NO_REGULAR=1 sends every box through the survivor queue (A/B, tests)
+
+  int n_sms = 0;
+  int stream_ctas[2] = {0, 0};  // resident CTAs per SM of k_count_stream<general / complete>
+  bool use_stream = true;       // CAMUS_B200_COUNT_V1=1 selects the one-CTA-per-box kernel (A/B, tests)
+  uint64_t* h_pinned = nullptr;  // pinned staging for the n x n results
+  size_t h_pinned_n = 0;
 
   float ms[CAMUS_B200_T_N] = {0};
   uint64_t launches = 0;
@@ -216,14 +224,32 @@ static int create_one(camus_b200** out, int dev) {
     delete ctx;
     return CAMUS_B200_ERR_CUDA;
   }
-  cudaFuncSetAttribute(k_count<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CountCfg<false>::kSmemBytes);
-  cudaFuncSetAttribute(k_count<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CountCfg<false>::kSmemBytes);
-  cudaFuncSetAttribute(k_count<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CountCfg<true>::kSmemBytes);
-  cudaFuncSetAttribute(k_count<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CountCfg<true>::kSmemBytes);
+  {
+    cudaError_t a = cudaSuccess;
+    auto set = [&](auto kernel, int bytes) {
+      cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+      if (a == cudaSuccess) a = e;
+    };
+    set(k_count<false, false>, CountCfg<false>::kSmemBytes);
+    set(k_count<true, false>, CountCfg<false>::kSmemBytes);
+    set(k_count<false, true>, CountCfg<true>::kSmemBytes);
+    set(k_count<true, true>, CountCfg<true>::kSmemBytes);
+    set(k_count_stream<0>, StreamCfg<0>::kSmemBytes);
+    set(k_count_stream<1>, StreamCfg<1>::kSmemBytes);
+    if (a == cudaSuccess) a = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->stream_ctas[0], k_count_stream<0>, kCountThreads, StreamCfg<0>::kSmemBytes);
+    if (a == cudaSuccess) a = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->stream_ctas[1], k_count_stream<1>, kCountThreads, StreamCfg<1>::kSmemBytes);
+    if (a != cudaSuccess || ctx->stream_ctas[0] < 1 || ctx->stream_ctas[1] < 1) {
+      g_create_err = std::string("camus_b200_create: count kernels do not fit this device (") + cudaGetErrorString(a) + ")";
+      camus_b200_destroy(ctx);
+      return CAMUS_B200_ERR_CUDA;
+    }
+    ctx->n_sms = prop.multiProcessorCount;
+  }
   if (const char* e = getenv("CAMUS_B200_NO_COMPLETE")) ctx->allow_complete = !(e[0] == '1');
   if (const char* e = getenv("CAMUS_B200_NO_REGULAR")) ctx->allow_regular = !(e[0] == '1');
   if (const char* e = getenv("CAMUS_B200_NO_HALF")) ctx->allow_half = !(e[0] == '1');
   if (const char* e = getenv("CAMUS_B200_UNFUSED")) ctx->use_fused = !(e[0] == '1');
+  if (const char* e = getenv("CAMUS_B200_COUNT_V1")) ctx->use_stream = !(e[0] == '1');
   *out = ctx;
   return CAMUS_B200_OK;
 }
@@ -231,8 +257,8 @@ static int create_one(camus_b200** out, int dev) {
 int camus_b200_create(camus_b200** out, int n_gpus, const int* devices) {
   if (!out) return CAMUS_B200_ERR_ARG;
   *out = nullptr;
-  if (n_gpus < 1 || n_gpus > 64) {
-    g_create_err = "camus_b200_create: n_gpus must be >= 1";
+  if (n_gpus < 1 || n_gpus > 16) {
+    g_create_err = "camus_b200_create: n_gpus must be in 1..16 (GPUs of one process)";
     return CAMUS_B200_ERR_ARG;
   }
   if (n_gpus == 1) return create_one(out, devices ? devices[0] : 0);
@@ -283,6 +309,7 @@ void camus_b200_destroy(camus_b200* ctx) {
   if (ctx->ev[0]) cudaEventDestroy(ctx->ev[0]);
   if (ctx->ev[1]) cudaEventDestroy(ctx->ev[1]);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   delete ctx;
 }
 
@@ -294,6 +321,7 @@ int camus_b200_set_partition(camus_b200* ctx, int rank, int world) {
     const int n = (int)ctx->subs.size();
     ctx->user_rank = rank;
     ctx->user_world = world;
+    ctx->reduced = false;
     for (int i = 0; i < n; ++i) camus_b200_set_partition(ctx->subs[i], rank * n + i, world * n);
     return 0;
   }
@@ -312,6 +340,7 @@ int camus_b200_set_constraint(camus_b200* ctx, int32_t n_nodes, int32_t n_taxa, 
     return ctx->fail(CAMUS_B200_ERR_ARG, "set_constraint: need a rooted binary tree (n_nodes = 2*n_taxa - 1)");
   if (n_taxa > 32767) return ctx->fail(CAMUS_B200_ERR_ARG, "set_constraint: at most 32767 taxa (15-bit packing, quartet.go:17)");
   if (!ctx->subs.empty()) {
+    ctx->reduced = false;
     int rc = fan_out(ctx, [&](camus_b200* s, int) { return camus_b200_set_constraint(s, n_nodes, n_taxa, parent, child0, child1, tip_index); });
     ctx->n = rc ? 0 : n_nodes;
     ctx->N = rc ? 0 : n_taxa;
@@ -325,6 +354,7 @@ int camus_b200_set_constraint(camus_b200* ctx, int32_t n_nodes, int32_t n_taxa, 
       if (root >= 0) return ctx->fail(CAMUS_B200_ERR_INPUT, "set_constraint: more than one root");
       root = i;
     }
+    if (parent[i] >= n) return ctx->fail(CAMUS_B200_ERR_INPUT, "set_constraint: parent index out of range");
     bool tip = child0[i] < 0;
     if (tip != (child1[i] < 0) || (tip && (tip_index[i] < 0 || tip_index[i] >= N)) || (!tip && (child0[i] >= n || child1[i] >= n)))
       return ctx->fail(CAMUS_B200_ERR_INPUT, "set_constraint: node is neither a tip nor binary");
@@ -333,19 +363,21 @@ int camus_b200_set_constraint(camus_b200* ctx, int32_t n_nodes, int32_t n_taxa, 
   // internal preorder ids (left child = id + 1), DFS ranks of the leaves
   std::vector<int32_t> ref_of_int, par(n), depth(n), sz(n, 1), rc(n, -1), nleaves(n, 0), firstleaf(n, 0);
   std::vector<int32_t> leafnode(N), tip_of_rank(N);
-  ctx->int_of_ref.assign(n, -1);
-  ctx->rank_of_tip_h.assign(N, -1);
+  // built in locals and moved into the context only when the whole tree has been accepted
+  std::vector<int32_t> int_of_ref(n, -1), rank_of_tip_h(N, -1);
   ref_of_int.reserve(n);
   {
     std::vector<int> st{root};
     while (!st.empty()) {
       int x = st.back();
       st.pop_back();
-      if (ctx->int_of_ref[x] >= 0 || (int)ref_of_int.size() >= n)
+      if (int_of_ref[x] >= 0 || (int)ref_of_int.size() >= n)
         return ctx->fail(CAMUS_B200_ERR_INPUT, "set_constraint: child pointers do not form a tree");
-      ctx->int_of_ref[x] = (int)ref_of_int.size();
+      int_of_ref[x] = (int)ref_of_int.size();
       ref_of_int.push_back(x);
       if (child0[x] >= 0) {
+        if (parent[child0[x]] != x || parent[child1[x]] != x)
+          return ctx->fail(CAMUS_B200_ERR_INPUT, "set_constraint: parent/child arrays disagree");
         st.push_back(child1[x]);
         st.push_back(child0[x]);
       }
@@ -355,16 +387,16 @@ int camus_b200_set_constraint(camus_b200* ctx, int32_t n_nodes, int32_t n_taxa, 
   int nl = 0;
   for (int i = 0; i < n; ++i) {
     int r = ref_of_int[i];
-    par[i] = parent[r] < 0 ? -1 : ctx->int_of_ref[parent[r]];
+    par[i] = parent[r] < 0 ? -1 : int_of_ref[parent[r]];
     if (par[i] >= i) return ctx->fail(CAMUS_B200_ERR_INPUT, "set_constraint: parent/child arrays disagree");
     depth[i] = par[i] < 0 ? 0 : depth[par[i]] + 1;
     if (child0[r] >= 0) {
-      rc[i] = ctx->int_of_ref[child1[r]];
+      rc[i] = int_of_ref[child1[r]];
     } else {
-      if (nl >= N || ctx->rank_of_tip_h[tip_index[r]] >= 0) return ctx->fail(CAMUS_B200_ERR_INPUT, "set_constraint: tip indices are not a permutation");
+      if (nl >= N || rank_of_tip_h[tip_index[r]] >= 0) return ctx->fail(CAMUS_B200_ERR_INPUT, "set_constraint: tip indices are not a permutation");
       leafnode[nl] = i;
       tip_of_rank[nl] = tip_index[r];
-      ctx->rank_of_tip_h[tip_index[r]] = nl;
+      rank_of_tip_h[tip_index[r]] = nl;
       nleaves[i] = 1;
       firstleaf[i] = nl;
       ++nl;
@@ -377,6 +409,8 @@ int camus_b200_set_constraint(camus_b200* ctx, int32_t n_nodes, int32_t n_taxa, 
   }
   for (int i = n - 1; i >= 0; --i)
     if (rc[i] >= 0) firstleaf[i] = firstleaf[i + 1];
+  ctx->int_of_ref = std::move(int_of_ref);
+  ctx->rank_of_tip_h = std::move(rank_of_tip_h);
   ctx->n = n;
   ctx->N = N;
   ctx->npad = (N + kSeg - 1) / kSeg * kSeg;
@@ -417,6 +451,7 @@ int camus_b200_set_constraint(camus_b200* ctx, int32_t n_nodes, int32_t n_taxa, 
 int camus_b200_clear_gene_trees(camus_b200* ctx) {
   if (!ctx) return CAMUS_B200_ERR_ARG;
   if (!ctx->subs.empty()) {
+    ctx->reduced = false;
     for (camus_b200* s : ctx->subs) camus_b200_clear_gene_trees(s);
     return 0;
   }
@@ -439,8 +474,10 @@ int camus_b200_add_gene_trees(camus_b200* ctx, int32_t n_trees, const int64_t* n
                               const int32_t* taxon) {
   if (!ctx) return CAMUS_B200_ERR_ARG;
   if (ctx->n == 0) return ctx->fail(CAMUS_B200_ERR_ARG, "add_gene_trees: set the constraint tree first");
-  if (!ctx->subs.empty())
+  if (!ctx->subs.empty()) {
+    ctx->reduced = false;
     return fan_out(ctx, [&](camus_b200* s, int) { return camus_b200_add_gene_trees(s, n_trees, node_off, parent, taxon); });
+  }
   if (n_trees < 0 || !node_off || (n_trees > 0 && (!parent || !taxon))) return ctx->fail(CAMUS_B200_ERR_ARG, "add_gene_trees: null argument");
   // Validation is per tree and independent: large batches are checked on several host threads
   // (16 MB of nodes at 1000 x 1000 took ~10 ms on one). The first failing tree (lowest index) wins.
@@ -754,17 +791,31 @@ int run_fused(camus_b200* ctx, int qmode, double threshold, int as_set, uint64_t
   if (make_thr_table(ctx, threshold)) return CAMUS_B200_ERR_CUDA;
   CK(cudaMemsetAsync(ctx->d_Z.p, 0, zn * rep * 8, ctx->stream));
   CK(cudaMemsetAsync(ctx->d_totals.p, 0, 16, ctx->stream));
-  const uint64_t max_grid = 1u << 30;
-  for (uint64_t b0 = 0; b0 < mine; b0 += max_grid) {
-    uint64_t nbx = std::min(max_grid, mine - b0);
-    CountParams prm{ctx->d_tri.p, std::max(ctx->G32, 1), box_map(ctx, b0), nullptr, ctx->G, tile_slots(ctx)};
-    static const int dbg = getenv("CAMUS_B200_DEBUG") ? atoi(getenv("CAMUS_B200_DEBUG")) : 0;
-    FusedParams fz{qmode, threshold, ctx->d_thr_tab.p, as_set, ctx->d_Z.p, ctx->d_totals.p, rep, (unsigned long long)zn, ctx->allow_regular ? 1 : 0, dbg};
-    if (use_complete(ctx))
-      k_count<true, true><<<(unsigned)nbx, kCountThreads, CountCfg<true>::kSmemBytes, ctx->stream>>>(prm, fz, ctx->ct);
+  static const int dbg = getenv("CAMUS_B200_DEBUG") ? atoi(getenv("CAMUS_B200_DEBUG")) : 0;
+  FusedParams fz{qmode, threshold, ctx->d_thr_tab.p, as_set, ctx->d_Z.p, ctx->d_totals.p, rep, (unsigned long long)zn, ctx->allow_regular ? 1 : 0, dbg};
+  const bool complete = use_complete(ctx);
+  // streaming kernel: resident CTAs only, every CTA walks its share of the box list
+  const uint64_t per_cta_limit = 1ull << 31;
+  const uint64_t grid_stream = (uint64_t)ctx->n_sms * ctx->stream_ctas[complete ? 1 : 0];
+  if (ctx->use_stream && dbg == 0 && mine > 0 && mine / grid_stream < per_cta_limit) {
+    StreamParams sp{ctx->d_tri.p, std::max(ctx->G32, 1), ctx->G, box_map(ctx, 0), mine, tile_slots(ctx)};
+    const unsigned grid = (unsigned)std::min<uint64_t>(mine, grid_stream);
+    if (complete)
+      k_count_stream<1><<<grid, kCountThreads, StreamCfg<1>::kSmemBytes, ctx->stream>>>(sp, fz, ctx->ct);
     else
-      k_count<true, false><<<(unsigned)nbx, kCountThreads, CountCfg<false>::kSmemBytes, ctx->stream>>>(prm, fz, ctx->ct);
+      k_count_stream<0><<<grid, kCountThreads, StreamCfg<0>::kSmemBytes, ctx->stream>>>(sp, fz, ctx->ct);
     CK_LAUNCH();
+  } else {
+    const uint64_t max_grid = 1u << 30;
+    for (uint64_t b0 = 0; b0 < mine; b0 += max_grid) {
+      uint64_t nbx = std::min(max_grid, mine - b0);
+      CountParams prm{ctx->d_tri.p, std::max(ctx->G32, 1), box_map(ctx, b0), nullptr, ctx->G, tile_slots(ctx)};
+      if (complete)
+        k_count<true, true><<<(unsigned)nbx, kCountThreads, CountCfg<true>::kSmemBytes, ctx->stream>>>(prm, fz, ctx->ct);
+      else
+        k_count<true, false><<<(unsigned)nbx, kCountThreads, CountCfg<false>::kSmemBytes, ctx->stream>>>(prm, fz, ctx->ct);
+      CK_LAUNCH();
+    }
   }
   if (rep > 1) {
     k_sum_replicas<<<(unsigned)((zn + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_Z.p, zn, rep);
@@ -868,6 +919,27 @@ int run_score(camus_b200* ctx, int as_set) {
   return 0;
 }
 
+// d_out -> caller memory through a pinned staging buffer (a direct copy into pageable memory is
+// staged by the driver in small chunks: 32 MB took ~3x longer)
+int copy_out(camus_b200* ctx, uint64_t* out, size_t count) {
+  if (ctx->h_pinned_n < count) {
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    ctx->h_pinned = nullptr;
+    ctx->h_pinned_n = 0;
+    if (cudaMallocHost(&ctx->h_pinned, count * 8) == cudaSuccess) ctx->h_pinned_n = count;
+    else cudaGetLastError();
+  }
+  if (!ctx->h_pinned) {  // no pinned memory to be had: plain copy
+    CK(cudaMemcpyAsync(out, ctx->d_out.p, count * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+  }
+  CK(cudaMemcpyAsync(ctx->h_pinned, ctx->d_out.p, count * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  std::memcpy(out, ctx->h_pinned, count * 8);
+  return 0;
+}
+
 int run_finish(camus_b200* ctx, uint64_t* out) {
   if (!ctx->z_valid) return ctx->fail(CAMUS_B200_ERR_ARG, "quartet_totals_finish: no partial table (call quartet_totals_partial)");
   const int n = ctx->n;
@@ -884,7 +956,7 @@ int run_finish(camus_b200* ctx, uint64_t* out) {
   CK_LAUNCH();
   k_mask_out<<<dim3((n + 127) / 128, n), 128, 0, ctx->stream>>>(ctx->d_E.p, ctx->d_out.p, ctx->ct);
   CK_LAUNCH();
-  CK(cudaMemcpyAsync(out, ctx->d_out.p, (size_t)n * n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (int rc = copy_out(ctx, out, (size_t)n * n)) return rc;
   if (t.stop()) return CAMUS_B200_ERR_CUDA;
   return 0;
 }
@@ -933,7 +1005,9 @@ int reduce_partials(camus_b200* wrap) {
     if (t.stop()) return CAMUS_B200_ERR_CUDA;
     return 0;
   }();
-  return rc ? wrap->fail(rc, ctx->err) : 0;
+  if (rc) return wrap->fail(rc, ctx->err);
+  wrap->reduced = true;
+  return 0;
 }
 
 }  // namespace
@@ -947,6 +1021,7 @@ int camus_b200_count_filter(camus_b200* ctx, int qmode, double threshold, uint64
     return ctx->fail(CAMUS_B200_ERR_ARG, "count_filter: quartet mode in [0,2] and threshold in [0,1] (quartetfilter.go:41-61)");
   if (!ctx->subs.empty()) {
     std::vector<uint64_t> ns(ctx->subs.size(), 0), sc(ctx->subs.size(), 0);
+    ctx->reduced = false;
     int rc = fan_out(ctx, [&](camus_b200* s, int i) { return camus_b200_count_filter(s, qmode, threshold, &ns[i], &sc[i]); });
     if (rc) return rc;
     uint64_t a = 0, b = 0;
@@ -987,6 +1062,7 @@ int camus_b200_run_resident(camus_b200* ctx, int qmode, double threshold, int as
   if (!ctx) return CAMUS_B200_ERR_ARG;
   if (!ctx->subs.empty()) {
     std::vector<uint64_t> ns(ctx->subs.size(), 0), sc(ctx->subs.size(), 0);
+    ctx->reduced = false;
     int rc = fan_out(ctx, [&](camus_b200* s, int i) { return camus_b200_run_resident(s, qmode, threshold, as_set, nullptr, &ns[i], &sc[i]); });
     if (rc) return rc;
     uint64_t a = 0, b = 0;
@@ -1026,6 +1102,11 @@ int camus_b200_run_resident(camus_b200* ctx, int qmode, double threshold, int as
 int camus_b200_quartet_totals_partial(camus_b200* ctx, int as_set) {
   if (!ctx) return CAMUS_B200_ERR_ARG;
   if (!ctx->subs.empty()) {
+    // The sum over the devices lives in subs[0]'s table. It is formed ONCE per scoring pass: a second
+    // call with the same weight (or a finish after a caller-side all-reduce) must not add the peers again.
+    for (camus_b200* s : ctx->subs)
+      if (!(s->z_valid && s->z_as_set == (as_set != 0))) ctx->reduced = false;  // someone rescans: all partial again
+    if (ctx->reduced) return 0;
     int rc = fan_out(ctx, [&](camus_b200* s, int) { return camus_b200_quartet_totals_partial(s, as_set); });
     return rc ? rc : reduce_partials(ctx);
   }
@@ -1048,6 +1129,9 @@ int camus_b200_partial_buffer(camus_b200* ctx, void** dev_ptr, uint64_t* n_int64
 int camus_b200_quartet_totals_finish(camus_b200* ctx, uint64_t* out) {
   if (!ctx || !out) return CAMUS_B200_ERR_ARG;
   if (!ctx->subs.empty()) {
+    if (!ctx->reduced) {  // e.g. straight after a fused count_filter: the devices hold partial tables
+      if (int rc = reduce_partials(ctx)) return rc;
+    }
     int rc = camus_b200_quartet_totals_finish(ctx->subs[0], out);
     return rc ? ctx->fail(rc, ctx->subs[0]->err) : 0;
   }
@@ -1080,7 +1164,7 @@ int camus_b200_edge_penalties(camus_b200* ctx, uint64_t* out) {
   StageTimer t(ctx, CAMUS_B200_T_PENALTY);
   k_penalties<<<dim3((n + 127) / 128, n), 128, 0, ctx->stream>>>(ctx->d_out.p, ctx->ct);
   CK_LAUNCH();
-  CK(cudaMemcpyAsync(out, ctx->d_out.p, (size_t)n * n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (int rc = copy_out(ctx, out, (size_t)n * n)) return rc;
   if (t.stop()) return CAMUS_B200_ERR_CUDA;
   return 0;
 }

@@ -30,11 +30,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n"
       ".reg .pred P1;\n"
-      "LAB_WAIT:\n"
+      "WAIT_%=:\n"
       "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra DONE;\n"
-      "bra LAB_WAIT;\n"
-      "DONE:\n"
+      "@P1 bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
       "}\n" ::"r"(smem_u32(bar)),
       "r"(parity)
       : "memory");

@@ -80,6 +80,32 @@ def test_fused_and_table_pipelines_agree(gpu, qmode, thr, monkeypatch):
     table.close()
 
 
+def test_streaming_and_per_box_count_kernels_agree(gpu, monkeypatch):
+    """k_count_stream (persistent CTAs, default) and k_count (one CTA per box, CAMUS_B200_COUNT_V1=1):
+    same survivors and tables, complete and general trees, every filter mode, few and many tree
+    groups (1 group: the ring runs four boxes ahead), both against the oracle."""
+    from camus_b200.cabi import CamusB200
+    monkeypatch.setenv("CAMUS_B200_COUNT_V1", "1")
+    per_box = CamusB200(0)
+    monkeypatch.delenv("CAMUS_B200_COUNT_V1")
+    cases = [(synth.make(41, 20, 51), 0.0), (synth.make(70, 130, 52), 0.0), (synth.make(66, 300, 53, drop_frac=0.1), 0.0),
+             (synth.make(58, 90, 54, support=True, drop_frac=0.1, nexus=True), 0.7), (synth.make(30, 33, 55), 0.0)]
+    for s, ms in cases:
+        prob = Problem(s.constraint, s.genes, s.fmt, ms)
+        o = orc.Oracle().load(prob)
+        for qmode, thr in ((0, 0.0), (1, 0.3), (2, 0.5)):
+            want = o.count_filter(qmode, thr, False)
+            for as_set in (False, True):
+                ref = o.quartet_totals(as_set, False)
+                for ctx in (gpu, per_box):
+                    ctx.load(prob)
+                    ctx.set_score_hint(as_set)
+                    assert ctx.count_filter(qmode, thr) == want
+                    assert np.array_equal(ctx.quartet_totals(as_set), ref)
+    gpu.set_score_hint(False)
+    per_box.close()
+
+
 def test_integer_and_fp16_plane_builders_agree(gpu, monkeypatch):
     """k_triple_planes_h2 (packed fp16 mask compares, NaN = absent) is the default; trees deeper than
     2047 fall back to the integer kernel, forced here with CAMUS_B200_NO_HALF=1."""
@@ -681,6 +707,16 @@ def test_multi_gpu_handle_matches_single(gpu):
         assert np.array_equal(multi.query_cells(quads), gpu.query_cells(quads))
         out, ns, sc = multi.run_resident(qmode, thr, False)
         assert (ns, sc) == gpu.count_filter(qmode, thr) and np.array_equal(out, gpu.quartet_totals(False))
+        # the sum over the devices is formed once per scoring pass: repeated calls are idempotent
+        assert np.array_equal(multi.quartet_totals(False), out)      # run_resident already reduced
+        assert np.array_equal(multi.quartet_totals(False), out)
+        assert np.array_equal(multi.quartet_totals_finish(), out)
+        multi.set_score_hint(False)
+        assert multi.count_filter(qmode, thr) == (ns, sc)
+        assert np.array_equal(multi.quartet_totals_finish(), out)     # finish straight after a fused count_filter
+        multi.quartet_totals_partial(False)
+        multi.quartet_totals_partial(False)
+        assert np.array_equal(multi.quartet_totals_finish(), out)
         # two such handles as two "processes": shares 0 and 1 of 2, summed by hand
         parts = []
         for r in range(2):
