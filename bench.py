@@ -10,6 +10,12 @@ synthetic gene trees. `value` = gene-tree quartets resolved per second with the 
 in HBM; `e2e` = the same through the C-ABI with HOST buffers (H2D of the trees and D2H of the
 table inside the timed region). With N ranks the 4-taxon-set index space is sharded N ways, every
 rank holds all trees, and the partial junction tables are summed with one NCCL all-reduce.
+
+`--impl reference` times the reference's own algorithm (the oracle's LITERAL mode: bipartition
+enumerator, per-tree set, map merge, filterQuartets, constraint removal, mapQuartetsToVertices and
+the per-(u, w) QuartetScore loop) on the host cores: config 1 in full; for the larger configurations
+a bounded sample (all gene trees induced on 50 of the taxa = the size the reference runs as-is), and
+says so. Both arms print the same `config`.
 """
 from __future__ import annotations
 
@@ -95,6 +101,38 @@ def workload_name(cfg_id, c):
             f"{' -asSet' if c['as_set'] else ''} {c['mode']} mode")
 
 
+def config_dict(cfg_id, c):
+    """The `config` object of the JSON line: identical for both arms (`--impl ours|reference`)."""
+    from math import comb
+    n, g = c["n_taxa"], c["n_trees"]
+    m = -(-n // 8)
+    tiles = (m + 2) * (m + 1) * m // 6
+    boxes = comb(m + 3, 4)
+    groups = -(-g // 32)
+    table = groups * 6144 * tiles
+    l2 = ("explicit flush: 512 MB written before every timed step" if table < (1 << 30) else
+          f"no flush needed: every step streams a {table / 1e9:.2f} GB rooted-triple bit-plane table "
+          f"({boxes * groups * 4 * 4096 / 1e9:.0f} to {boxes * groups * 4 * 6144 / 1e9:.0f} GB of tile reads), far beyond the 126 MB L2")
+    return {"workload": workload_name(cfg_id, c), "taxa": n, "gene_trees": g, "cells": comb(n, 4), "boxes": boxes, "l2": l2}
+
+
+def load_digests(cfg_id, c):
+    p = os.path.join(ROOT, "tests", "golden", "synthetic", "config_digests.json")
+    if not os.path.exists(p):
+        return None
+    d = json.load(open(p))
+    from camus_b200 import synth
+    base = synth.CONFIGS[cfg_id]
+    if c["n_taxa"] != base["n_taxa"] or c["n_trees"] != base["n_trees"]:
+        return None
+    return d.get("config%d" % cfg_id)
+
+
+def table_digest(tab):
+    import zlib
+    return "%08x-%016x" % (zlib.crc32(np.ascontiguousarray(tab).tobytes()), int(tab.sum(dtype=np.uint64)))
+
+
 # ------------------------------------------------------------------------------------------
 def restrict_to_taxa(prob, keep_tips, n_trees):
     """Induced sub-problem on a subset of the taxa (flat arrays only): the constraint tree with
@@ -128,50 +166,96 @@ def restrict_to_taxa(prob, keep_tips, n_trees):
     off, gp, gt = [0], [], []
     for g in range(min(n_trees, prob.n_trees)):
         lo, hi = int(prob.gene_node_off[g]), int(prob.gene_node_off[g + 1])
-        p, t = prob.gene_parent[lo:hi], prob.gene_taxon[lo:hi]
-        kb = np.zeros(hi - lo, np.int64)
-        for i in range(hi - lo - 1, -1, -1):
-            if t[i] >= 0:
-                kb[i] += int(keep[t[i]])
-            if p[i] >= 0:
+        p, t = prob.gene_parent[lo:hi].tolist(), prob.gene_taxon[lo:hi].tolist()
+        m = hi - lo
+        kb = [0] * m   # kept leaves below
+        nk = [0] * m   # children with kept leaves below
+        for i in range(m - 1, -1, -1):
+            if t[i] >= 0 and keep[t[i]]:
+                kb[i] += 1
+            if p[i] >= 0 and kb[i] > 0:
                 kb[p[i]] += kb[i]
-        idx = np.full(hi - lo, -1, np.int64)
+                nk[p[i]] += 1
+        # a node stays if it is a kept leaf or still branches (unifurcations are suppressed, as
+        # gotree does when the reference reads a pruned tree)
+        idx = [-1] * m
+        anc = [-1] * m  # nearest retained ancestor (new index)
         k = 0
-        for i in range(hi - lo):
-            if kb[i] > 0:
+        for i in range(m):
+            up = anc[p[i]] if p[i] >= 0 else -1
+            if kb[i] > 0 and ((t[i] >= 0 and keep[t[i]]) or nk[i] >= 2):
                 idx[i] = k
                 k += 1
-                gp.append(idx[p[i]] if p[i] >= 0 else -1)
-                gt.append(new_tip[t[i]] if t[i] >= 0 else -1)
+                gp.append(up)
+                gt.append(int(new_tip[t[i]]) if t[i] >= 0 else -1)
+                anc[i] = idx[i]
+            else:
+                anc[i] = up
         off.append(len(gp))
     return (par, c0, c1, tip, int(keep.sum())), (np.array(off, np.int64), np.array(gp, np.int32), np.array(gt, np.int32))
 
 
-def cpu_reference_sample(prob, c, n_sample_trees: int, nthreads: int, max_taxa: int = 100):
-    """The reference's own algorithm (oracle literal mode: bipartition enumerator + per-tree set +
-    map merge + filter + constraint removal) on a bounded sample: the first n_sample_trees gene
-    trees, induced on every other taxon when the problem has more than max_taxa taxa (one
-    200-taxon tree alone costs the hash-map algorithm over a minute per core)."""
-    from math import comb
+REF_TAXA = 50  # the reference runs BASELINE.json configs[0] (50 taxa) as-is; larger inputs are sampled at that size
 
-    from oracle import oracle as orc
-    step = max(1, -(-prob.n_taxa // max_taxa))
-    keep = range(0, prob.n_taxa, step)
-    cons, genes = restrict_to_taxa(prob, keep, n_sample_trees)
-    o = orc.Oracle(nthreads)
-    o.set_constraint(*cons[:4], cons[4])
-    o.add_gene_trees(*genes)
-    k = len(genes[0]) - 1
-    res = 0
-    for g in range(k):
-        nl = int((genes[2][genes[0][g]:genes[0][g + 1]] >= 0).sum())
-        res += comb(nl, 4)
-    t0 = time.perf_counter()
-    o.count_filter(c["qmode"], c["threshold"], True)
-    dt = time.perf_counter() - t0
-    desc = (f"first {k} of {prob.n_trees} gene trees induced on {cons[4]} of {prob.n_taxa} taxa (every {step}th tip), "
-            f"{nthreads} threads")
-    return res, dt, desc
+
+class CpuSample:
+    """The reference's own algorithm (oracle LITERAL mode) on a bounded sample of the workload:
+    the whole problem when it has at most REF_TAXA taxa (config 1: in full, nothing extrapolated),
+    else ALL gene trees induced on REF_TAXA of the taxa (every k-th tip). One run = processQuartets
+    + filterQuartets + constraint removal (preprocess.go:44-57), then mapQuartetsToVertices +
+    CalculateQuartetTotals (treedata.go:197-222, quartettotals.go:43-61)."""
+
+    def __init__(self, prob, c, nthreads):
+        from math import comb
+
+        from oracle import oracle as orc
+        self.c, self.nthreads, self.orc = c, nthreads, orc
+        self.full = prob.n_taxa <= REF_TAXA
+        if self.full:
+            self.cons = (prob.parent, prob.child0, prob.child1, prob.tip_index, prob.n_taxa)
+            self.genes = (prob.gene_node_off, prob.gene_parent, prob.gene_taxon)
+            self.desc = f"the whole input ({prob.n_taxa} taxa x {prob.n_trees} gene trees), nothing sampled or extrapolated"
+        else:
+            step = -(-prob.n_taxa // REF_TAXA)
+            self.cons, self.genes = restrict_to_taxa(prob, range(0, prob.n_taxa, step), prob.n_trees)
+            self.desc = (f"all {prob.n_trees} gene trees induced on {self.cons[4]} of the {prob.n_taxa} taxa (every {step}th tip); the "
+                         "literal algorithm gets slower per resolution as taxa grow (duplicate emissions, map size), so this "
+                         "OVERSTATES the reference at the full size, which it cannot run at all above a few hundred taxa")
+        off, tax = self.genes[0], self.genes[2]
+        self.resolutions = 0
+        for g in range(len(off) - 1):
+            self.resolutions += comb(int((tax[off[g]:off[g + 1]] >= 0).sum()), 4)
+
+    def run(self, literal=True):
+        """(seconds count+filter+removal, seconds edge totals)"""
+        o = self.orc.Oracle(self.nthreads)
+        o.set_constraint(*self.cons[:4], self.cons[4])
+        o.add_gene_trees(*self.genes)
+        t0 = time.perf_counter()
+        if literal:
+            o.count_filter(self.c["qmode"], self.c["threshold"], True)
+            t1 = time.perf_counter()
+            o.quartet_totals(self.c["as_set"], True)
+        else:
+            o.dense_run(self.c["qmode"], self.c["threshold"], self.c["as_set"], digests=False)
+            t1 = time.perf_counter()
+        return t1 - t0, time.perf_counter() - t1
+
+    def record(self, n_runs=1):
+        ts = [self.run(True) for _ in range(n_runs)]
+        lit = sum(a + b for a, b in ts) / n_runs
+        fast = sum(self.run(False))
+        return {
+            "value": self.resolutions / lit, "unit": UNIT, "cores": self.nthreads, "kind": "port",
+            "sample": "oracle literal mode (the Go algorithms, function by function) end to end -- processQuartets + filterQuartets + "
+                      "constraint removal + mapQuartetsToVertices + per-(u,w) QuartetScore loop -- on " + self.desc,
+            "sample_resolutions": self.resolutions, "seconds": lit,
+            "seconds_count_filter": sum(a for a, _ in ts) / n_runs, "seconds_edge_totals": sum(b for _, b in ts) / n_runs,
+            "full_size": self.full,
+            "fast_mode": {"value": self.resolutions / fast, "seconds": fast,
+                          "what": "same sample, oracle dense mode (vectorised four-point counting + per-quartet scatter: a "
+                                  "different, faster CPU algorithm than the reference's)"},
+        }
 
 
 def run_reference(args):
@@ -179,23 +263,26 @@ def run_reference(args):
     if rank != 0:
         return
     prob, c = make_problem(args.config, args.taxa, args.trees)
-    cores = os.cpu_count() or 1
-    nthreads = min(cores, args.ref_threads)
-    per_step = max(1, args.ref_trees)
-    times, res = [], 0
+    nthreads = min(os.cpu_count() or 1, args.ref_threads)
+    smp = CpuSample(prob, c, nthreads)
+    times = []
     for i in range(args.warmup + args.steps):
-        res, dt, desc = cpu_reference_sample(prob, c, per_step, nthreads)
+        a, b = smp.run(True)
         if i >= args.warmup:
-            times.append(dt)
+            times.append(a + b)
     dt = sum(times) / len(times)
-    val = res / dt
-    sample = ("literal processQuartets+filterQuartets+constraint removal (oracle port of the Go algorithm) on the " + desc +
-              "; mapQuartetsToVertices and the per-(u,w) QuartetScore loop excluded (~1e12 calls at this size)")
+    val = smp.resolutions / dt
+    fast = sum(smp.run(False))
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "u32", "data": "synthetic", "config": {"workload": workload_name(args.config, c)},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": nthreads, "kind": "port", "sample": sample},
+        "dtype": "u32", "data": "synthetic", "config": config_dict(args.config, c),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": nthreads, "kind": "port",
+                         "sample": "oracle literal mode (the Go algorithms, function by function) end to end -- processQuartets + "
+                                   "filterQuartets + constraint removal + mapQuartetsToVertices + per-(u,w) QuartetScore loop -- on " + smp.desc,
+                         "sample_resolutions": smp.resolutions, "full_size": smp.full,
+                         "fast_mode": {"value": smp.resolutions / fast, "seconds": fast,
+                                       "what": "same sample, oracle dense mode (a different, faster CPU algorithm than the reference's)"}},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -224,7 +311,16 @@ def run_ours(args):
     n_dev = args.gpus if world == 1 and args.gpus > 1 else 1
     gpu = CamusB200(devices=list(range(n_dev))) if n_dev > 1 else CamusB200(local)
     shares = world * n_dev
-    gpu.set_partition(rank, world)
+    # One process per GPU: the collective lives in the library (camus_b200_comm_init: rank 0's NCCL id
+    # is handed round once, then every call returns global results). --collective torch keeps the
+    # round-1 form (set_partition + torch.distributed.all_reduce on the partial table).
+    lib_comm = world > 1 and args.collective == "library"
+    if lib_comm:
+        obj = [CamusB200.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(obj, src=0)
+        gpu.comm_init(obj[0], rank, world)
+    else:
+        gpu.set_partition(rank, world)
     gpu.load(prob)
     n = prob.n_nodes
     out = np.empty((n, n), np.uint64)
@@ -238,7 +334,7 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def reduce_and_finish(ns, sc):
-        if world > 1:
+        if world > 1 and not lib_comm:
             z = gpu.partial_tensor()
             dist.all_reduce(z)
             scal[0], scal[1] = ns, sc
@@ -258,6 +354,9 @@ def run_ours(args):
         return r, ms1, l1
 
     def step_resident():
+        if lib_comm:
+            _, ns, sc = gpu.run_resident(qmode, thr, as_set, out)
+            return ns, sc
         _, ns, sc = gpu.run_resident(qmode, thr, as_set, None, partial_only=True)
         return reduce_and_finish(ns, sc)
 
@@ -265,15 +364,35 @@ def run_ours(args):
     first, _, _ = step_e2e()
     R = gpu.workload()["resolutions"]
 
+    m_seg = -(-prob.n_taxa // 8)
+    num_tiles = (m_seg + 2) * (m_seg + 1) * m_seg // 6
+    groups = -(-prob.n_trees // 32)
+    table_bytes = groups * 6144 * num_tiles
+    # Timing rule: inputs larger than L2, or an explicit flush between steps. The bit-plane table a
+    # step streams is far larger than the 126 MB L2 from config 2 up; for small inputs (config 1)
+    # every step is timed on its own after a 512 MB write.
+    flush = table_bytes < (1 << 30)
+    flush_buf = torch.empty(512 << 20, dtype=torch.uint8, device="cuda") if flush else None
+
     def timed(fn, steps, warmup):
         for _ in range(warmup):
             fn()
         barrier()
-        t0 = time.perf_counter()
-        for _ in range(steps):
-            r = fn()
-        barrier()
-        dt = (time.perf_counter() - t0) / steps
+        if flush:
+            dt = 0.0
+            for _ in range(steps):
+                flush_buf.zero_()
+                barrier()
+                t0 = time.perf_counter()
+                r = fn()
+                torch.cuda.synchronize()
+                dt += (time.perf_counter() - t0) / steps
+        else:
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                r = fn()
+            barrier()
+            dt = (time.perf_counter() - t0) / steps
         if world > 1:
             t = torch.tensor([dt], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -287,38 +406,40 @@ def run_ours(args):
     clocks = sampler.result()
     dt_e2e, r_e2e = timed(lambda: step_e2e()[0], args.steps, max(1, args.warmup // 2))
     assert r_res == first and r_e2e == first, (first, r_res, r_e2e)
+    # the result of the timed steps against the committed digests of this configuration
+    digest_want = load_digests(args.config, c)
+    digest_got = {"n_survivors": first[0], "sum_counts": first[1],
+                  "quartet_totals_as_set" if as_set else "quartet_totals": table_digest(out)}
+    if digest_want is not None and rank == 0:
+        for k, v in digest_got.items():
+            assert digest_want[k] == v, f"result differs from tests/golden/synthetic/config_digests.json: {k} = {v}, expected {digest_want[k]}"
 
     if rank == 0:
         peak, peak_src = load_peaks()
         wl = gpu.workload()
         cells, num_boxes = wl["cells"], wl["boxes"]
-        m_seg = -(-prob.n_taxa // 8)
-        num_tiles = (m_seg + 2) * (m_seg + 1) * m_seg // 6
-        # ---- roofline of the dominant kernel: the fused k_count<true> (count + filter + score) ----
+        # ---- roofline of the dominant kernel: the fused count kernel (count + filter + score) ----
         # Algorithmic bytes per launch, SURVEY.md 8(d) convention: 8 B per resolution (one count
         # cell read + written per (gene tree, 4-set)) + 16 B per cell (one 128-bit cell read by
         # filter / score), for the share of the 4-set space this rank owns.
         alg_bytes_kernel = (8 * R + 16 * cells) / shares
         kern_ms = stage_ms["count"]
-        n_launch = max(1, -(-num_boxes // shares // (1 << 30)))
         achieved = alg_bytes_kernel / (kern_ms * 1e-3) / 1e9
         b_alg = 8 * R + 16 * cells + 24 * n * n
-        # Bytes the kernel's own design has to move per launch: four 6 KB triple tiles per
-        # (box, tree group), read once each (HBM or L2), and one pass over the junction tables.
-        groups = -(-prob.n_trees // 32)
-        design_bytes = (num_boxes / shares) * groups * 4 * 6144
-        traffic = None
-        tf = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tf):
-            traffic = json.load(open(tf)).get(f"config{args.config}_k_count_dram_bytes_per_launch")
-        if shares > 1:
-            traffic = None  # the captures are single-GPU launches
-        h2d = int(prob.gene_node_off.nbytes + prob.gene_parent.nbytes + prob.gene_taxon.nbytes)
-        # complete binary gene trees take the 8-plane kernel variant (2/3 of the tile bytes)
+        # Bytes the kernel's own design has to move per launch: four triple tiles per (box, tree
+        # group), read once each (HBM or L2); 8 of their 12 planes for complete binary trees.
         nl = np.diff(np.concatenate([[0], np.cumsum(prob.gene_taxon >= 0)[prob.gene_node_off[1:] - 1]]))
         complete = bool((nl == prob.n_taxa).all()) and not c.get("support", False)
-        if complete:
-            design_bytes *= 2.0 / 3.0
+        design_bytes = (num_boxes / shares) * groups * 4 * 6144 * (2.0 / 3.0 if complete else 1.0)
+        traffic = None
+        tf = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tf) and shares == 1:  # the captures are single-GPU launches
+            traffic = json.load(open(tf)).get(f"config{args.config}_k_count_dram_bytes_per_launch")
+        h2d = int(prob.gene_node_off.nbytes + prob.gene_parent.nbytes + prob.gene_taxon.nbytes)
+        sm_mhz = clocks.get("sm_mhz") or 1965
+        # the pipe that bounds the kernel: one POPC per (cell, counted topology, 32 trees) on the XU
+        # pipe, 16 lanes per clock and SM, 148 SMs
+        xu_floor_ms = (num_boxes / shares) * groups * 4096 * (2 if complete else 3) / (16 * 148 * sm_mhz * 1e6) * 1e3
         from camus_b200 import partition as part
         scheme = "one share" if shares == 1 else (
             "class scheme: a rank owns boxes by the classes of their first two segments and builds only the "
@@ -328,44 +449,106 @@ def run_ours(args):
             "metric": METRIC, "value": R / dt_res, "unit": UNIT, "n_gpus": shares, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dt_res * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u32", "data": "synthetic",
-            "config": {"workload": workload_name(args.config, c), "resolutions_per_step": R, "cells": cells, "boxes": num_boxes,
-                       "sharding": f"4-taxon-set index space / {shares} ({scheme}), all trees on every GPU, " +
-                                   ("one NCCL all-reduce of the junction table" if n_dev == 1 else
-                                    "one process and one handle for all GPUs, junction tables summed by NVLink peer reads"),
-                       "l2": "no explicit flush: the rooted-triple bit-planes streamed by every step "
-                             f"({design_bytes * shares / 1e9:.1f} GB of tile reads over a {groups * 6144 * num_tiles / 1e9:.2f} GB table) exceed the 126 MB L2 many times over"},
+            "config": config_dict(args.config, c),
+            "sharding": f"4-taxon-set index space / {shares} ({scheme}), all trees on every GPU, " +
+                        (("one ncclAllReduce of the junction table inside the library" if lib_comm else
+                          "one NCCL all-reduce of the junction table (torch.distributed)") if n_dev == 1 else
+                         "one process and one handle for all GPUs, junction tables summed by NVLink peer reads"),
+            "l2_flush": "512 MB write before every timed step (steps timed one by one)" if flush else "none needed (see config.l2)",
+            "resolutions_per_step": R,
             "clocks": clocks,
             "e2e": {"value": R / dt_e2e, "unit": UNIT, "ms_per_step": dt_e2e * 1e3, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": int(out.nbytes + 16)},
             "gpu_launches": int(launches) * args.steps,
             "stage_ms": {k: round(v, 4) for k, v in stage_ms.items()},
-            "roofline": {"bound": "hbm", "kernel": "k_count<fused, %s> (count + filter + score in one launch)" % ("complete" if complete else "general"),
+            "roofline": {"bound": "xu", "binding_pipe": "XU (POPC): 16 lanes per clock and SM; not HBM, not tensor",
+                         "kernel": "k_count_stream<%s> (count + filter + score in one persistent launch)" % ("complete" if complete else "general"),
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes_kernel / n_launch,
-                         "launch_ms": kern_ms / n_launch,
-                         "design_bytes_per_launch": design_bytes / n_launch,
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes_kernel,
+                         "launch_ms": kern_ms,
+                         "xu_floor_ms": xu_floor_ms, "frac_binding": xu_floor_ms / kern_ms,
+                         "design_bytes_per_launch": design_bytes,
                          "design_achieved": design_bytes / (kern_ms * 1e-3) / 1e9,
-                         # the pipe that actually bounds the kernel: one POPC per (cell, counted topology, 32 trees)
-                         # on the XU pipe, 16 lanes per clock and SM (B300_MICROARCH.md), 148 SMs
-                         "xu_floor_ms": (num_boxes / shares) * groups * 4096 * (2 if complete else 3)
-                                        / (16 * 148 * (clocks.get("sm_mhz") or 1965) * 1e6) * 1e3,
-                         "note": "achieved uses the survey's accounting (8 B per resolution); the kernel resolves 32 gene trees per "
-                                 "32-bit word in registers, so it moves ~60x fewer bytes than that model and frac exceeds 1; "
-                                 "design_* = bytes of triple tiles the kernel actually streams (L2 + HBM); traffic = its DRAM bytes "
-                                 "(ncu); the binding resource is the POPC (XU) pipe: xu_floor_ms / launch_ms is the fraction of "
-                                 "that floor reached, see DESIGN.md"},
+                         "hbm_frac_measured": (traffic / (kern_ms * 1e-3) / 1e9 / peak) if traffic else None,
+                         "note": "achieved / frac follow the survey's accounting (8 B per resolution), as the contract asks; the "
+                                 "kernel keeps counts in registers and resolves 32 gene trees per 32-bit word, so it moves ~60x fewer "
+                                 "bytes than that model and frac exceeds 1: it says nothing about efficiency. frac_binding = "
+                                 "xu_floor_ms / launch_ms is the honest figure (fraction of the POPC-pipe floor reached); design_* = "
+                                 "bytes of triple tiles streamed (L2 + HBM); traffic = DRAM bytes per launch from ncu "
+                                 "(profiles/traffic.json), hbm_frac_measured = that over the measured HBM peak"},
             "roofline_whole_path": {"algorithmic_bytes": b_alg, "achieved": b_alg / dt_res / 1e9, "frac": b_alg / dt_res / 1e9 / peak},
-            "result": {"n_survivors": first[0], "sum_counts": first[1]},
+            "result": dict(digest_got, digests_checked=digest_want is not None),
         }
-        if not args.no_cpu:
+        extras = not args.no_extras and shares == 1
+        if extras:
+            # ---- the metric's second half: end-to-end infer seconds (Preprocess + Scorer.Init + RunDP,
+            # infer.go:70-96) from the parsed trees, hot path on the GPU, DP on the host mirror ----
+            t0 = time.perf_counter()
+            gpu.clear_gene_trees()
+            gpu.add_gene_trees(prob.gene_node_off, prob.gene_parent, prob.gene_taxon)
+            ns, sc = gpu.count_filter(qmode, thr)
+            tab = gpu.quartet_totals(as_set)
+            pen = gpu.edge_penalties() if c["mode"] != "max" else None
+            t1 = time.perf_counter()
+            res = prob.run_dp(tab, pen, c["mode"], as_set, ns, sc, prob.n_trees, 0.5)
+            t2 = time.perf_counter()
+            line["infer"] = {"infer_s": t2 - t0, "hot_path_s": t1 - t0, "dp_s": t2 - t1, "score_mode": c["mode"],
+                             "networks": len(res.newicks),
+                             "what": "flat trees -> count/filter -> edge table (GPU, C-ABI) -> DP + traceback + networks (host C++ "
+                                     "mirror of infer/main_dp.go); parsing excluded"}
+        gpu.close()
+        if extras:
+            # ---- the kernel real (incomplete / polytomous) inputs take, on the same workload ----
+            if complete:
+                os.environ["CAMUS_B200_NO_COMPLETE"] = "1"
+                try:
+                    gen = CamusB200(local)
+                finally:
+                    del os.environ["CAMUS_B200_NO_COMPLETE"]
+                gen.load(prob)
+                gen.set_score_hint(as_set)
+                assert gen.count_filter(qmode, thr) == first
+                tg = []
+                for _ in range(2):
+                    t0 = time.perf_counter()
+                    gen.run_resident(qmode, thr, as_set, out)
+                    tg.append(time.perf_counter() - t0)
+                gms, _ = gen.stage_ms()
+                assert digest_got["quartet_totals_as_set" if as_set else "quartet_totals"] == table_digest(out)
+                gen.close()
+                gfloor = num_boxes * groups * 4096 * 3 / (16 * 148 * sm_mhz * 1e6) * 1e3
+                line["general_kernel"] = {"ms_per_step": min(tg) * 1e3, "value": R / min(tg), "count_ms": gms["count"], "prep_ms": gms["prep"],
+                                          "xu_floor_ms": gfloor, "frac_binding": gfloor / gms["count"],
+                                          "what": "same workload with CAMUS_B200_NO_COMPLETE=1: the 12-plane, 3-POPC kernel that gene "
+                                                  "trees with missing taxa or polytomies take; results identical"}
+            # ---- same-size CPU comparison where one exists: BASELINE.json configs[0] in full ----
+            if not args.no_cpu:
+                nthr = min(os.cpu_count() or 1, args.ref_threads)
+                line["cpu_baseline"] = CpuSample(prob, c, nthr).record()
+                if args.config != 1:
+                    p1, c1 = make_problem(1, None, None)
+                    rec1 = CpuSample(p1, c1, nthr).record()
+                    g1 = CamusB200(local)
+                    o1 = np.empty((p1.n_nodes, p1.n_nodes), np.uint64)
+                    ts = []
+                    for _ in range(5):
+                        t0 = time.perf_counter()
+                        g1.load(p1)
+                        g1.set_score_hint(c1["as_set"])
+                        g1.count_filter(c1["qmode"], c1["threshold"])
+                        g1.quartet_totals(c1["as_set"], o1)
+                        ts.append(time.perf_counter() - t0)
+                    g1.close()
+                    line["config1_same_size"] = {
+                        "workload": workload_name(1, c1), "resolutions": rec1["sample_resolutions"],
+                        "gpu_e2e_s": min(ts), "cpu_literal_s": rec1["seconds"], "cpu_fast_mode_s": rec1["fast_mode"]["seconds"], "cores": nthr,
+                        "what": "the one configuration the reference's algorithm runs in full: whole hot path, host buffers in, table out"}
+        elif not args.no_cpu:
             nthr = min(os.cpu_count() or 1, args.ref_threads)
-            res, dtc, desc = cpu_reference_sample(prob, c, args.ref_trees, nthr)
-            line["cpu_baseline"] = {
-                "value": res / dtc, "unit": UNIT, "cores": nthr, "kind": "port",
-                "sample": "literal count+filter+removal (oracle port of the Go algorithm) on the " + desc + "; edge scoring excluded",
-            }
+            line["cpu_baseline"] = CpuSample(prob, c, nthr).record()
         print(json.dumps(line))
-    gpu.close()
+    else:
+        gpu.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -379,9 +562,10 @@ def main():
     ap.add_argument("--config", type=int, default=3, help="BASELINE.json configs[] index + 1 (3 = 1000 taxa x 1000 trees)")
     ap.add_argument("--taxa", type=int, default=None)
     ap.add_argument("--trees", type=int, default=None)
-    ap.add_argument("--ref-trees", type=int, default=8, help="gene trees per CPU-reference sample")
     ap.add_argument("--ref-threads", type=int, default=64)
+    ap.add_argument("--collective", default="library", choices=["library", "torch"])
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the infer / general-kernel / config-1 sub-records")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

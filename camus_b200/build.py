@@ -73,7 +73,7 @@ def build_cuda(force: bool = False, verbose: bool = False) -> str:
     deps = srcs + _sources("csrc", (".cuh", ".h")) + [os.path.join(ROOT, "include", "camus_b200.h")]
     if force or not _newer(CUDA_SO, deps):
         cmd = [nvcc_path(), *NVCCFLAGS, "-I", os.path.join(ROOT, "include"), "-shared", "-o", CUDA_SO, *srcs,
-               "-cudart", "static"]
+               "-cudart", "static", "-ldl"]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         cmd += os.environ.get("CAMUS_NVCC_EXTRA", "").split()

@@ -51,6 +51,9 @@ def lib() -> C.CDLL:
         L.camus_b200_run_resident.argtypes = [vp, C.c_int, C.c_double, C.c_int, vp, u64p, u64p]
         L.camus_b200_stage_ms.argtypes = [vp, C.POINTER(C.c_float), u64p]
         L.camus_b200_workload.argtypes = [vp, u64p, u64p, u64p]
+        L.camus_b200_constraint_tables.argtypes = [vp, vp, vp, vp]
+        L.camus_b200_comm_unique_id.argtypes = [vp]
+        L.camus_b200_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
         L.camus_b200_reticulation_counts.argtypes = [vp, C.c_int32, C.c_int32, vp, C.c_int32, vp, vp, vp, vp, vp]
         _lib = L
     return _lib
@@ -62,7 +65,7 @@ EXPORTED = [
     "camus_b200_set_score_hint", "camus_b200_count_filter", "camus_b200_quartet_totals", "camus_b200_edge_penalties",
     "camus_b200_export_quartets", "camus_b200_query_cells", "camus_b200_quartet_totals_partial", "camus_b200_partial_buffer",
     "camus_b200_quartet_totals_finish", "camus_b200_run_resident", "camus_b200_stage_ms", "camus_b200_workload",
-    "camus_b200_reticulation_counts",
+    "camus_b200_reticulation_counts", "camus_b200_constraint_tables", "camus_b200_comm_unique_id", "camus_b200_comm_init",
 ]
 
 
@@ -151,6 +154,30 @@ class CamusB200:
         if n.value:
             self._ck(lib().camus_b200_export_quartets(self._h, int(raw), _p(keys), _p(counts), n.value, C.byref(n)))
         return keys, counts
+
+    def constraint_tables(self):
+        """(lca [n, n] int32, depth [n] int32, leaves_below [n] uint64): graphs.MakeTreeData's tables
+        (treedata.go:130-194) in the caller's node ids."""
+        lca = np.empty((self.n, self.n), np.int32)
+        depth = np.empty(self.n, np.int32)
+        below = np.empty(self.n, np.uint64)
+        self._ck(lib().camus_b200_constraint_tables(self._h, _p(lca), _p(depth), _p(below)))
+        return lca, depth, below
+
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """Rank 0: the 128-byte NCCL id every rank passes to comm_init."""
+        buf = (C.c_uint8 * 128)()
+        if lib().camus_b200_comm_unique_id(buf) != 0:
+            raise CamusB200Error(lib().camus_b200_last_error(None).decode())
+        return bytes(buf)
+
+    def comm_init(self, uid: bytes, rank: int, world: int):
+        """Attach this context to the library-owned NCCL communicator (collective call); sets the
+        partition (rank, world). Afterwards count_filter / quartet_totals / run_resident return
+        global results on every rank."""
+        buf = (C.c_uint8 * 128).from_buffer_copy(uid)
+        self._ck(lib().camus_b200_comm_init(self._h, buf, rank, world))
 
     def query_cells(self, quads) -> np.ndarray:
         """Raw counts of arbitrary 4-taxon sets (tip indices), reference topology order."""

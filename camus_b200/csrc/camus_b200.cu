@@ -2,9 +2,13 @@
 // kernels in kernels_*.cuh. Host code here only validates and re-indexes the flat trees, plans
 // memory, launches kernels and copies results; every quartet is counted, filtered and scored on
 // the GPU. There is no CPU fallback.
+#include <dlfcn.h>
+#include <nccl.h>
+
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -86,6 +90,7 @@ struct camus_b200 {
   DevBuf<uint32_t> d_tri;
   DevBuf<uint4> d_cells;
   DevBuf<unsigned long long> d_Z, d_E, d_out, d_totals, d_keys, d_nout;
+  DevBuf<unsigned int> d_work;  // box counter of the streaming count kernel
   DevBuf<uint32_t> d_counts, d_thr_tab;
   uint64_t n_local = 0, chunk = 1;  // this rank's share of the boxes (BoxMap)
   // class-scheme partition (layout.cuh): explicit local box list + the tiles this rank builds
@@ -112,11 +117,15 @@ struct camus_b200 {
   bool allow_complete = true;  // CAMUS_B200_NO_COMPLETE=1 forces the general kernel (A/B, tests)
   bool allow_regular = true;   // CAMUS_B200_NO_REGULAR=1 sends every box through the survivor queue (A/B, tests)
 
+  // ---- library-owned collective (camus_b200_comm_init) ----
+  ncclComm_t comm = nullptr;
+  bool z_reduced = false;             // the junction table already holds the sum over all ranks
+  DevBuf<unsigned long long> d_scal;  // the two survivor scalars, all-reduced in place
+  std::vector<int32_t> h_depth, h_nleaves, h_ref_of_int;  // constraint tables in internal ids (constraint_tables)
+
   int n_sms = 0;
   int stream_ctas[2] = {0, 0};  // resident CTAs per SM of k_count_stream<general / complete>
   bool use_stream = true;       // CAMUS_B200_COUNT_V1=1 selects the one-CTA-per-box kernel (A/B, tests)
-  uint64_t* h_pinned = nullptr;  // pinned staging for the n x n results
-  size_t h_pinned_n = 0;
 
   float ms[CAMUS_B200_T_N] = {0};
   uint64_t launches = 0;
@@ -179,6 +188,7 @@ int fan_out(camus_b200* ctx, F f) {
   return 0;
 }
 int reduce_partials(camus_b200* ctx);
+void nccl_api_destroy(ncclComm_t comm);
 
 int build_planes(camus_b200* ctx, bool do_upload);
 int set_box_range(camus_b200* ctx);
@@ -306,10 +316,10 @@ void camus_b200_destroy(camus_b200* ctx) {
     return;
   }
   cudaSetDevice(ctx->device);
+  if (ctx->comm) nccl_api_destroy(ctx->comm);
   if (ctx->ev[0]) cudaEventDestroy(ctx->ev[0]);
   if (ctx->ev[1]) cudaEventDestroy(ctx->ev[1]);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
-  if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   delete ctx;
 }
 
@@ -329,6 +339,7 @@ int camus_b200_set_partition(camus_b200* ctx, int rank, int world) {
   ctx->world = world;
   ctx->cell_state = camus_b200::NONE;
   ctx->z_valid = false;
+  ctx->z_reduced = false;
   ctx->counted = false;
   return 0;
 }
@@ -411,6 +422,9 @@ int camus_b200_set_constraint(camus_b200* ctx, int32_t n_nodes, int32_t n_taxa, 
     if (rc[i] >= 0) firstleaf[i] = firstleaf[i + 1];
   ctx->int_of_ref = std::move(int_of_ref);
   ctx->rank_of_tip_h = std::move(rank_of_tip_h);
+  ctx->h_depth = depth;
+  ctx->h_nleaves = nleaves;
+  ctx->h_ref_of_int = ref_of_int;
   ctx->n = n;
   ctx->N = N;
   ctx->npad = (N + kSeg - 1) / kSeg * kSeg;
@@ -795,11 +809,20 @@ int run_fused(camus_b200* ctx, int qmode, double threshold, int as_set, uint64_t
   FusedParams fz{qmode, threshold, ctx->d_thr_tab.p, as_set, ctx->d_Z.p, ctx->d_totals.p, rep, (unsigned long long)zn, ctx->allow_regular ? 1 : 0, dbg};
   const bool complete = use_complete(ctx);
   // streaming kernel: resident CTAs only, every CTA walks its share of the box list
-  const uint64_t per_cta_limit = 1ull << 31;
-  const uint64_t grid_stream = (uint64_t)ctx->n_sms * ctx->stream_ctas[complete ? 1 : 0];
-  if (ctx->use_stream && dbg == 0 && mine > 0 && mine / grid_stream < per_cta_limit) {
-    StreamParams sp{ctx->d_tri.p, std::max(ctx->G32, 1), ctx->G, box_map(ctx, 0), mine, tile_slots(ctx)};
+  static const int stream_static = getenv("CAMUS_B200_STREAM_STATIC") ? atoi(getenv("CAMUS_B200_STREAM_STATIC")) : 0;    // A/B
+  static const int stream_per_sm = getenv("CAMUS_B200_STREAM_CTAS") ? atoi(getenv("CAMUS_B200_STREAM_CTAS")) : 0;       // A/B
+  static const int verbose = getenv("CAMUS_B200_VERBOSE") ? atoi(getenv("CAMUS_B200_VERBOSE")) : 0;
+  uint64_t grid_stream = (uint64_t)ctx->n_sms * ctx->stream_ctas[complete ? 1 : 0];
+  if (stream_per_sm > 0) grid_stream = (uint64_t)ctx->n_sms * stream_per_sm;
+  if (ctx->use_stream && dbg == 0 && mine > 0 && mine < (1ull << 32) - 4096 && ctx->G < (1 << 24)) {
+    CK(ctx->d_work.alloc(1));
+    CK(cudaMemsetAsync(ctx->d_work.p, 0, 4, ctx->stream));
+    StreamParams sp{ctx->d_tri.p, std::max(ctx->G32, 1), ctx->G, box_map(ctx, 0), mine, stream_static ? nullptr : ctx->d_work.p, tile_slots(ctx)};
     const unsigned grid = (unsigned)std::min<uint64_t>(mine, grid_stream);
+    if (verbose)
+      fprintf(stderr, "[camus_b200] k_count_stream<%d>: %d SMs x %d CTAs (occupancy %d), grid %u, %llu boxes, %d groups, smem %d B\n",
+              complete ? 1 : 0, ctx->n_sms, (int)(grid_stream / ctx->n_sms), ctx->stream_ctas[complete ? 1 : 0], grid,
+              (unsigned long long)mine, ctx->G32, complete ? StreamCfg<1>::kSmemBytes : StreamCfg<0>::kSmemBytes);
     if (complete)
       k_count_stream<1><<<grid, kCountThreads, StreamCfg<1>::kSmemBytes, ctx->stream>>>(sp, fz, ctx->ct);
     else
@@ -829,6 +852,7 @@ int run_fused(camus_b200* ctx, int qmode, double threshold, int as_set, uint64_t
   ctx->last_qmode = qmode;
   ctx->last_threshold = threshold;
   ctx->z_valid = true;
+  ctx->z_reduced = false;
   ctx->z_as_set = as_set;
   ctx->counted = true;
   return 0;
@@ -915,28 +939,82 @@ int run_score(camus_b200* ctx, int as_set) {
   }
   if (t.stop()) return CAMUS_B200_ERR_CUDA;
   ctx->z_valid = true;
+  ctx->z_reduced = false;
   ctx->z_as_set = as_set;
   return 0;
 }
 
-// d_out -> caller memory through a pinned staging buffer (a direct copy into pageable memory is
-// staged by the driver in small chunks: 32 MB took ~3x longer)
-int copy_out(camus_b200* ctx, uint64_t* out, size_t count) {
-  if (ctx->h_pinned_n < count) {
-    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
-    ctx->h_pinned = nullptr;
-    ctx->h_pinned_n = 0;
-    if (cudaMallocHost(&ctx->h_pinned, count * 8) == cudaSuccess) ctx->h_pinned_n = count;
-    else cudaGetLastError();
-  }
-  if (!ctx->h_pinned) {  // no pinned memory to be had: plain copy
-    CK(cudaMemcpyAsync(out, ctx->d_out.p, count * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    return 0;
-  }
-  CK(cudaMemcpyAsync(ctx->h_pinned, ctx->d_out.p, count * 8, cudaMemcpyDeviceToHost, ctx->stream));
+// ---- NCCL, loaded at run time: the library has no link-time dependency on it ----
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  std::string err;
+  bool ok() const { return lib && GetUniqueId && CommInitRank && CommDestroy && AllReduce && GetErrorString; }
+};
+NcclApi& nccl_api() {
+  static NcclApi api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    const char* env = getenv("CAMUS_B200_NCCL_LIB");
+    for (const char* name : {env ? env : "libnccl.so.2", "libnccl.so.2", "libnccl.so"}) {
+      api.lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+      if (api.lib) break;
+    }
+    if (!api.lib) {
+      api.err = std::string("cannot load libnccl.so.2: ") + (dlerror() ? dlerror() : "unknown error");
+      return;
+    }
+    api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(dlsym(api.lib, "ncclGetUniqueId"));
+    api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(api.lib, "ncclCommInitRank"));
+    api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(api.lib, "ncclCommDestroy"));
+    api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(dlsym(api.lib, "ncclAllReduce"));
+    api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(api.lib, "ncclGetErrorString"));
+    if (!api.ok()) api.err = "libnccl.so.2 lacks a required symbol";
+  });
+  return api;
+}
+
+void nccl_api_destroy(ncclComm_t comm) {
+  NcclApi& api = nccl_api();
+  if (api.ok()) api.CommDestroy(comm);
+}
+
+// Sum the partial junction tables of all ranks in place (one all-reduce over NVLink).
+int comm_reduce_table(camus_b200* ctx) {
+  if (!ctx->comm || ctx->z_reduced) return 0;
+  if (!ctx->z_valid) return ctx->fail(CAMUS_B200_ERR_ARG, "no partial table to reduce");
+  NcclApi& api = nccl_api();
+  const size_t zn = (size_t)ctx->n * ctx->n * 3;
+  StageTimer t(ctx, CAMUS_B200_T_FINAL);
+  ncclResult_t r = api.AllReduce(ctx->d_Z.p, ctx->d_Z.p, zn, ncclInt64, ncclSum, ctx->comm, ctx->stream);
+  if (r != ncclSuccess) return ctx->fail(CAMUS_B200_ERR_CUDA, std::string("ncclAllReduce: ") + api.GetErrorString(r));
+  if (t.stop()) return CAMUS_B200_ERR_CUDA;
+  ctx->z_reduced = true;
+  return 0;
+}
+int comm_reduce_scalars(camus_b200* ctx, uint64_t* ns, uint64_t* sum) {
+  if (!ctx->comm) return 0;
+  NcclApi& api = nccl_api();
+  unsigned long long h[2] = {ns ? *ns : 0, sum ? *sum : 0};
+  CK(ctx->d_scal.alloc(2));
+  CK(cudaMemcpyAsync(ctx->d_scal.p, h, 16, cudaMemcpyHostToDevice, ctx->stream));
+  ncclResult_t r = api.AllReduce(ctx->d_scal.p, ctx->d_scal.p, 2, ncclUint64, ncclSum, ctx->comm, ctx->stream);
+  if (r != ncclSuccess) return ctx->fail(CAMUS_B200_ERR_CUDA, std::string("ncclAllReduce: ") + api.GetErrorString(r));
+  CK(cudaMemcpyAsync(h, ctx->d_scal.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
-  std::memcpy(out, ctx->h_pinned, count * 8);
+  if (ns) *ns = h[0];
+  if (sum) *sum = h[1];
+  return 0;
+}
+
+// d_out -> caller memory. Measured at 32 MB (n = 1999): a direct copy into the caller's pageable
+// buffer 2.3 ms; through a pinned staging buffer + memcpy 12.5 ms. So: direct.
+int copy_out(camus_b200* ctx, uint64_t* out, size_t count) {
+  CK(cudaMemcpyAsync(out, ctx->d_out.p, count * 8, cudaMemcpyDeviceToHost, ctx->stream));
   return 0;
 }
 
@@ -1045,9 +1123,17 @@ int camus_b200_count_filter(camus_b200* ctx, int qmode, double threshold, uint64
   }
   ctx->cell_state = camus_b200::NONE;
   ctx->z_valid = false;
-  if (ctx->use_fused) return run_fused(ctx, qmode, threshold, ctx->as_set_hint, n_survivors, sum_counts);
-  if ((rc = run_count(ctx))) return rc;
-  return run_filter(ctx, qmode, threshold, n_survivors, sum_counts);
+  uint64_t ns = 0, sc = 0;
+  if (ctx->use_fused) {
+    if ((rc = run_fused(ctx, qmode, threshold, ctx->as_set_hint, &ns, &sc))) return rc;
+  } else {
+    if ((rc = run_count(ctx))) return rc;
+    if ((rc = run_filter(ctx, qmode, threshold, &ns, &sc))) return rc;
+  }
+  if ((rc = comm_reduce_scalars(ctx, &ns, &sc))) return rc;  // with a communicator: the global values
+  if (n_survivors) *n_survivors = ns;
+  if (sum_counts) *sum_counts = sc;
+  return 0;
 }
 
 int camus_b200_set_score_hint(camus_b200* ctx, int as_set) {
@@ -1088,14 +1174,21 @@ int camus_b200_run_resident(camus_b200* ctx, int qmode, double threshold, int as
   if ((rc = build_planes(ctx, false))) return rc;
   ctx->cell_state = camus_b200::NONE;
   ctx->z_valid = false;
+  uint64_t ns = 0, sc = 0;
   if (ctx->use_fused) {
-    if ((rc = run_fused(ctx, qmode, threshold, as_set != 0, n_survivors, sum_counts))) return rc;
+    if ((rc = run_fused(ctx, qmode, threshold, as_set != 0, &ns, &sc))) return rc;
   } else {
     if ((rc = run_count(ctx))) return rc;
-    if ((rc = run_filter(ctx, qmode, threshold, n_survivors, sum_counts))) return rc;
+    if ((rc = run_filter(ctx, qmode, threshold, &ns, &sc))) return rc;
     if ((rc = run_score(ctx, as_set != 0))) return rc;
   }
-  if (!out) return 0;  // multi-process: the caller all-reduces the partial table, then calls ..._finish
+  if (ctx->comm) {  // library-owned collective: global scalars and table on every rank
+    if ((rc = comm_reduce_scalars(ctx, &ns, &sc))) return rc;
+    if ((rc = comm_reduce_table(ctx))) return rc;
+  }
+  if (n_survivors) *n_survivors = ns;
+  if (sum_counts) *sum_counts = sc;
+  if (!out) return 0;  // caller-side reduction: all-reduce the partial table, then call ..._finish
   return run_finish(ctx, out);
 }
 
@@ -1111,7 +1204,8 @@ int camus_b200_quartet_totals_partial(camus_b200* ctx, int as_set) {
     return rc ? rc : reduce_partials(ctx);
   }
   CK(cudaSetDevice(ctx->device));
-  return run_score(ctx, as_set != 0);
+  if (int rc = run_score(ctx, as_set != 0)) return rc;
+  return comm_reduce_table(ctx);
 }
 
 int camus_b200_partial_buffer(camus_b200* ctx, void** dev_ptr, uint64_t* n_int64) {
@@ -1148,6 +1242,7 @@ int camus_b200_quartet_totals(camus_b200* ctx, int as_set, uint64_t* out) {
   CK(cudaSetDevice(ctx->device));
   int rc = run_score(ctx, as_set != 0);
   if (rc) return rc;
+  if ((rc = comm_reduce_table(ctx))) return rc;
   return run_finish(ctx, out);
 }
 
@@ -1167,6 +1262,68 @@ int camus_b200_edge_penalties(camus_b200* ctx, uint64_t* out) {
   if (int rc = copy_out(ctx, out, (size_t)n * n)) return rc;
   if (t.stop()) return CAMUS_B200_ERR_CUDA;
   return 0;
+}
+
+int camus_b200_constraint_tables(camus_b200* ctx, int32_t* lca, int32_t* depth, uint64_t* leaves_below) {
+  if (!ctx) return CAMUS_B200_ERR_ARG;
+  if (ctx->n == 0) return ctx->fail(CAMUS_B200_ERR_ARG, "constraint_tables: set the constraint tree first");
+  if (!ctx->subs.empty()) {
+    int rc = camus_b200_constraint_tables(ctx->subs[0], lca, depth, leaves_below);
+    return rc ? ctx->fail(rc, ctx->subs[0]->err) : 0;
+  }
+  const int n = ctx->n;
+  for (int i = 0; i < n; ++i) {  // internal preorder id i <-> caller's id
+    const int r = ctx->h_ref_of_int[i];
+    if (depth) depth[r] = ctx->h_depth[i];
+    if (leaves_below) leaves_below[r] = (uint64_t)ctx->h_nleaves[i];
+  }
+  if (!lca) return 0;
+  CK(cudaSetDevice(ctx->device));
+  DevBuf<int32_t> d_lca;
+  CK(d_lca.alloc((size_t)n * n));
+  k_node_lca<<<dim3((n + 127) / 128, n), 128, 0, ctx->stream>>>(d_lca.p, ctx->ct);
+  CK_LAUNCH();
+  CK(cudaMemcpyAsync(lca, d_lca.p, (size_t)n * n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int camus_b200_comm_unique_id(uint8_t id[CAMUS_B200_COMM_ID_BYTES]) {
+  static_assert(sizeof(ncclUniqueId) == CAMUS_B200_COMM_ID_BYTES, "ncclUniqueId is 128 bytes");
+  NcclApi& api = nccl_api();
+  if (!id || !api.ok()) {
+    g_create_err = "camus_b200_comm_unique_id: " + (id ? api.err : std::string("null argument"));
+    return CAMUS_B200_ERR_ARG;
+  }
+  ncclUniqueId u;
+  ncclResult_t r = api.GetUniqueId(&u);
+  if (r != ncclSuccess) {
+    g_create_err = std::string("ncclGetUniqueId: ") + api.GetErrorString(r);
+    return CAMUS_B200_ERR_CUDA;
+  }
+  std::memcpy(id, &u, sizeof(u));
+  return 0;
+}
+
+int camus_b200_comm_init(camus_b200* ctx, const uint8_t id[CAMUS_B200_COMM_ID_BYTES], int rank, int world) {
+  if (!ctx || !id) return CAMUS_B200_ERR_ARG;
+  if (!ctx->subs.empty()) return ctx->fail(CAMUS_B200_ERR_ARG, "comm_init: one GPU per process (create the handle with n_gpus = 1)");
+  if (world < 1 || rank < 0 || rank >= world) return ctx->fail(CAMUS_B200_ERR_ARG, "comm_init: bad rank / world");
+  NcclApi& api = nccl_api();
+  if (!api.ok()) return ctx->fail(CAMUS_B200_ERR_CUDA, "comm_init: " + api.err);
+  CK(cudaSetDevice(ctx->device));
+  if (ctx->comm) {
+    api.CommDestroy(ctx->comm);
+    ctx->comm = nullptr;
+  }
+  ncclUniqueId u;
+  std::memcpy(&u, id, sizeof(u));
+  ncclResult_t r = api.CommInitRank(&ctx->comm, world, u, rank);
+  if (r != ncclSuccess) {
+    ctx->comm = nullptr;
+    return ctx->fail(CAMUS_B200_ERR_CUDA, std::string("ncclCommInitRank: ") + api.GetErrorString(r));
+  }
+  return camus_b200_set_partition(ctx, rank, world);
 }
 
 int camus_b200_export_quartets(camus_b200* ctx, int raw, uint64_t* keys, uint32_t* counts, uint64_t cap, uint64_t* n_out) {

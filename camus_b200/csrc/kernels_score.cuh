@@ -389,6 +389,14 @@ __device__ __forceinline__ bool should_calc_edge(const ConstraintDev& ct, int u,
   return !u_under_w && len > 3 && u != 0 && w != 0;
 }
 
+// graphs.calcLCAs (internal/graphs/treedata.go:130-166) for every node pair, in the caller's ids.
+__global__ void k_node_lca(int32_t* __restrict__ out, ConstraintDev ct) {
+  int w = blockIdx.x * blockDim.x + threadIdx.x;
+  int u = blockIdx.y;
+  if (w >= ct.n) return;
+  out[(size_t)ct.ref_id[u] * ct.n + ct.ref_id[w]] = ct.ref_id[node_lca(ct, u, w)];
+}
+
 // K5d: quartetTotals[u][w] in the caller's node ids, 0 where !ShouldCalcEdge.
 __global__ void k_mask_out(const unsigned long long* __restrict__ E, unsigned long long* __restrict__ out, ConstraintDev ct) {
   int w = blockIdx.x * blockDim.x + threadIdx.x;

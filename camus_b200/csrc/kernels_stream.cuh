@@ -68,13 +68,18 @@ struct StreamParams {
   const uint32_t* tri;  // [tile slot][group][kTileWords]
   int n_groups, n_trees;
   BoxMap bm;                   // local box index -> global box rank
-  unsigned long long n_boxes;  // local boxes of this launch; CTA c takes boxes c, c + gridDim.x, ...
+  unsigned long long n_boxes;  // local boxes of this launch
+  unsigned int* work;          // next unclaimed local box (zeroed before the launch); nullptr = static round-robin
   const uint32_t* tile_slot;   // class-scheme shares: tile index -> slot; nullptr = identity
 };
 
 __device__ __forceinline__ uint32_t atom_add_acq_rel_shared(uint32_t* p, uint32_t v) {
   uint32_t old;
+#if defined(CAMUS_STREAM_RELAXED)  // A/B build: no fence around the counter
+  asm volatile("atom.relaxed.cta.shared::cta.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(p)), "r"(v) : "memory");
+#else
   asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(p)), "r"(v) : "memory");
+#endif
   return old;
 }
 
@@ -160,11 +165,14 @@ k_count_stream(StreamParams prm, FusedParams fz, ConstraintDev ct) {
   const uint32_t N = (uint32_t)ct.n_taxa;
   const bool thr_smem = prm.n_trees + 2 <= kThrTabMax;
 
-  // Boxes are dealt round-robin (CTA c: c, c + grid, ...): the CTAs in flight work on neighbouring
-  // boxes, which share triple tiles in L2, and ~24 000 boxes per CTA even out the epilogue costs.
-  auto fetch_box = [&](uint32_t k) {  // thread 0: describe this CTA's k-th box in slot k
+  // Boxes are claimed from a global counter, in order: the CTAs in flight always work on ~grid
+  // consecutive boxes, which share triple tiles in L2 (a static round-robin lets the CTAs drift
+  // apart over thousands of boxes).
+  auto claim = [&](uint32_t k) -> uint32_t {
+    return prm.work ? atomicAdd(prm.work, 1u) : blockIdx.x + k * gridDim.x;
+  };
+  auto describe = [&](uint32_t k, uint32_t i) {  // thread 0: this CTA's k-th box is local box i
     BoxInfo& b = boxes[k % kBoxRing];
-    const unsigned long long i = blockIdx.x + (unsigned long long)k * gridDim.x;
     if (i >= prm.n_boxes) {
       b.valid = 0;
       return;
@@ -222,7 +230,7 @@ k_count_stream(StreamParams prm, FusedParams fz, ConstraintDev ct) {
     reinterpret_cast<unsigned long long*>(done + 4)[0] = 0;
     reinterpret_cast<unsigned long long*>(done + 4)[1] = 0;
     fence_mbar_init();
-    for (uint32_t k = 0; k <= LA; ++k) fetch_box(k);
+    for (uint32_t k = 0; k <= LA; ++k) describe(k, claim(k));
     for (int s = 0; s < S; ++s) issue(0, (uint32_t)s, s);
   }
   for (int i = tid; i < 3 * 64; i += kCountThreads) marg[i] = 0;
@@ -245,7 +253,10 @@ k_count_stream(StreamParams prm, FusedParams fz, ConstraintDev ct) {
   for (uint32_t k = 0;; ++k) {
     const BoxInfo& bx = boxes[k % kBoxRing];
     if (!bx.valid) break;
-    if (tid == 0) fetch_box(k + LA + 1);
+    // claim the box LA + 1 ahead now, describe it after the count loop (the counter's round trip
+    // stays off the critical path of warp 0)
+    uint32_t claimed = 0;
+    if (tid == 0) claimed = claim(k + LA + 1);
 
     uint32_t cnt[16][Cfg::kCnt];
 #pragma unroll
@@ -300,6 +311,8 @@ k_count_stream(StreamParams prm, FusedParams fz, ConstraintDev ct) {
         if ((old & (kWarps - 1)) == kWarps - 1) issue(k, g + S, s);
       }
     }
+
+    if (tid == 0) describe(k + LA + 1, claimed);
 
     // ------------------------------- epilogue of box k, on registers -------------------------------
     auto counts_of = [&](int ci, uint32_t c[3]) {

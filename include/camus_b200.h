@@ -98,6 +98,15 @@ int camus_b200_quartet_totals(camus_b200* ctx, int as_set, uint64_t* out /*[n*n]
 /* penalties[u][w] (row-major n*n), 0 where !ShouldCalcEdge. Needs only the constraint tree. */
 int camus_b200_edge_penalties(camus_b200* ctx, uint64_t* out /*[n*n]*/);
 
+/* The constraint-tree tables graphs.MakeTreeData builds on the host (internal/graphs/treedata.go:27-51),
+ * so that the Go side can skip calcLCAs -- Theta(n^3), ~8e9 inner iterations at n = 1999
+ * (treedata.go:130-166) -- calcDepths (:169-178) and countLeavesBelow (:181-194):
+ *   lca[u * n + w]   = node id of the lowest common ancestor of u and w (TreeData.lca, symmetric, lca[u][u] = u)
+ *   depth[u]         = edges from the root (TreeData.Depths)
+ *   leaves_below[u]  = tips in the subtree of u (TreeData.NumLeavesBelow)
+ * all in the caller's node ids. Any of the three pointers may be NULL. Needs only set_constraint. */
+int camus_b200_constraint_tables(camus_b200* ctx, int32_t* lca /*[n*n]*/, int32_t* depth /*[n]*/, uint64_t* leaves_below /*[n]*/);
+
 /* Surviving quartets in the reference's packing (quartet.go:11-31), sorted by key. Only available
  * when the whole cell table fits on the device (parity / debug; TreeData.Quartets on small
  * inputs). Call with cap = 0 to query n_out. raw != 0 exports the counts before filter/removal. */
@@ -129,7 +138,19 @@ int camus_b200_reticulation_counts(camus_b200* ctx, int32_t n_tips, int32_t n_re
                                    int32_t n_trees, const int64_t* node_off, const int32_t* parent,
                                    const int32_t* taxon, uint64_t* totals, uint64_t* supported);
 
-/* ---- split form of quartet_totals for multi-process runs ---- */
+/* ---- multi-process runs, collective owned by the library (NCCL over NVLink / NVSwitch) ----
+ * One process per GPU: rank 0 calls camus_b200_comm_unique_id and hands the 128 bytes to the other
+ * processes by its own means; every process then calls camus_b200_comm_init (collective, blocking),
+ * which also sets the partition (rank, world). From then on camus_b200_count_filter returns the
+ * GLOBAL n_survivors / sum_counts and camus_b200_quartet_totals / camus_b200_run_resident the GLOBAL
+ * table on every rank: the partial junction tables are summed with one ncclAllReduce(int64, sum)
+ * on the library's stream, the two scalars with another. libnccl.so.2 is loaded at run time
+ * (dlopen); without it comm_init fails and everything else works as before. Single-GPU handles only. */
+#define CAMUS_B200_COMM_ID_BYTES 128
+int camus_b200_comm_unique_id(uint8_t id[CAMUS_B200_COMM_ID_BYTES]);
+int camus_b200_comm_init(camus_b200* ctx, const uint8_t id[CAMUS_B200_COMM_ID_BYTES], int rank, int world);
+
+/* ---- split form of quartet_totals for multi-process runs with a CALLER-side reduction ---- */
 int camus_b200_quartet_totals_partial(camus_b200* ctx, int as_set);
 /* device pointer + element count of the partial junction table (int64 elements) to be summed */
 int camus_b200_partial_buffer(camus_b200* ctx, void** dev_ptr, uint64_t* n_int64);

@@ -255,6 +255,21 @@ def test_quartets_total_kats(gpu):
         assert (tot > 0).any()
 
 
+def test_constraint_tables_vs_oracle(gpu):
+    """camus_b200_constraint_tables = graphs.calcLCAs / calcDepths / countLeavesBelow
+    (treedata.go:130-194), which the Go side would otherwise compute in Theta(n^3)."""
+    for s in (synth.make(57, 3, 71), synth.make(200, 2, 72), synth.make(9, 2, 73)):
+        prob = Problem(s.constraint, s.genes)
+        o = orc.Oracle().load(prob)
+        gpu.load(prob)
+        lca, depth, below = gpu.constraint_tables()
+        n = prob.n_nodes
+        assert np.array_equal(lca, np.array([[o.lca(u, w) for w in range(n)] for u in range(n)], np.int32))
+        assert [int(x) for x in depth] == [o.depth(v) for v in range(n)]
+        assert [int(x) for x in below] == [o.leaves_below(v) for v in range(n)]
+        assert np.array_equal(lca, lca.T) and (np.diag(lca) == np.arange(n)).all()
+
+
 def test_penalty_kats(gpu):
     prob = Problem(K.PENALTY_TREE, "")
     gpu.load(prob)
