@@ -18,7 +18,6 @@
 #include "kernels_prep.cuh"
 #include "kernels_retic.cuh"
 #include "kernels_score.cuh"
-#include "kernels_stream.cuh"
 
 using namespace camus_dev;
 
@@ -90,7 +89,6 @@ struct camus_b200 {
   DevBuf<uint32_t> d_tri;
   DevBuf<uint4> d_cells;
   DevBuf<unsigned long long> d_Z, d_E, d_out, d_totals, d_keys, d_nout;
-  DevBuf<unsigned int> d_work;  // box counter of the streaming count kernel
   DevBuf<uint32_t> d_counts, d_thr_tab;
   uint64_t n_local = 0, chunk = 1;  // this rank's share of the boxes (BoxMap)
   // class-scheme partition (layout.cuh): explicit local box list + the tiles this rank builds
@@ -123,9 +121,7 @@ struct camus_b200 {
   DevBuf<unsigned long long> d_scal;  // the two survivor scalars, all-reduced in place
   std::vector<int32_t> h_depth, h_nleaves, h_ref_of_int;  // constraint tables in internal ids (constraint_tables)
 
-  int n_sms = 0;
-  int stream_ctas[2] = {0, 0};  // resident CTAs per SM of k_count_stream<general / complete>
-  bool use_stream = true;       // CAMUS_B200_COUNT_V1=1 selects the one-CTA-per-box kernel (A/B, tests)
+  bool allow_packed = true;  // CAMUS_B200_NO_PACKED=1 keeps the 3-register general kernel below 1024 trees (A/B, tests)
 
   float ms[CAMUS_B200_T_N] = {0};
   uint64_t launches = 0;
@@ -240,26 +236,22 @@ static int create_one(camus_b200** out, int dev) {
       cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
       if (a == cudaSuccess) a = e;
     };
-    set(k_count<false, false>, CountCfg<false>::kSmemBytes);
-    set(k_count<true, false>, CountCfg<false>::kSmemBytes);
-    set(k_count<false, true>, CountCfg<true>::kSmemBytes);
-    set(k_count<true, true>, CountCfg<true>::kSmemBytes);
-    set(k_count_stream<0>, StreamCfg<0>::kSmemBytes);
-    set(k_count_stream<1>, StreamCfg<1>::kSmemBytes);
-    if (a == cudaSuccess) a = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->stream_ctas[0], k_count_stream<0>, kCountThreads, StreamCfg<0>::kSmemBytes);
-    if (a == cudaSuccess) a = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->stream_ctas[1], k_count_stream<1>, kCountThreads, StreamCfg<1>::kSmemBytes);
-    if (a != cudaSuccess || ctx->stream_ctas[0] < 1 || ctx->stream_ctas[1] < 1) {
+    set(k_count<false, kModeGeneral>, CountCfg<kModeGeneral>::kSmemBytes);
+    set(k_count<true, kModeGeneral>, CountCfg<kModeGeneral>::kSmemBytes);
+    set(k_count<false, kModeComplete>, CountCfg<kModeComplete>::kSmemBytes);
+    set(k_count<true, kModeComplete>, CountCfg<kModeComplete>::kSmemBytes);
+    set(k_count<true, kModePacked>, CountCfg<kModePacked>::kSmemBytes);
+    if (a != cudaSuccess) {
       g_create_err = std::string("camus_b200_create: count kernels do not fit this device (") + cudaGetErrorString(a) + ")";
       camus_b200_destroy(ctx);
       return CAMUS_B200_ERR_CUDA;
     }
-    ctx->n_sms = prop.multiProcessorCount;
   }
   if (const char* e = getenv("CAMUS_B200_NO_COMPLETE")) ctx->allow_complete = !(e[0] == '1');
   if (const char* e = getenv("CAMUS_B200_NO_REGULAR")) ctx->allow_regular = !(e[0] == '1');
   if (const char* e = getenv("CAMUS_B200_NO_HALF")) ctx->allow_half = !(e[0] == '1');
   if (const char* e = getenv("CAMUS_B200_UNFUSED")) ctx->use_fused = !(e[0] == '1');
-  if (const char* e = getenv("CAMUS_B200_COUNT_V1")) ctx->use_stream = !(e[0] == '1');
+  if (const char* e = getenv("CAMUS_B200_NO_PACKED")) ctx->allow_packed = !(e[0] == '1');
   *out = ctx;
   return CAMUS_B200_OK;
 }
@@ -808,37 +800,19 @@ int run_fused(camus_b200* ctx, int qmode, double threshold, int as_set, uint64_t
   static const int dbg = getenv("CAMUS_B200_DEBUG") ? atoi(getenv("CAMUS_B200_DEBUG")) : 0;
   FusedParams fz{qmode, threshold, ctx->d_thr_tab.p, as_set, ctx->d_Z.p, ctx->d_totals.p, rep, (unsigned long long)zn, ctx->allow_regular ? 1 : 0, dbg};
   const bool complete = use_complete(ctx);
-  // streaming kernel: resident CTAs only, every CTA walks its share of the box list
-  static const int stream_static = getenv("CAMUS_B200_STREAM_STATIC") ? atoi(getenv("CAMUS_B200_STREAM_STATIC")) : 0;    // A/B
-  static const int stream_per_sm = getenv("CAMUS_B200_STREAM_CTAS") ? atoi(getenv("CAMUS_B200_STREAM_CTAS")) : 0;       // A/B
-  static const int verbose = getenv("CAMUS_B200_VERBOSE") ? atoi(getenv("CAMUS_B200_VERBOSE")) : 0;
-  uint64_t grid_stream = (uint64_t)ctx->n_sms * ctx->stream_ctas[complete ? 1 : 0];
-  if (stream_per_sm > 0) grid_stream = (uint64_t)ctx->n_sms * stream_per_sm;
-  if (ctx->use_stream && dbg == 0 && mine > 0 && mine < (1ull << 32) - 4096 && ctx->G < (1 << 24)) {
-    CK(ctx->d_work.alloc(1));
-    CK(cudaMemsetAsync(ctx->d_work.p, 0, 4, ctx->stream));
-    StreamParams sp{ctx->d_tri.p, std::max(ctx->G32, 1), ctx->G, box_map(ctx, 0), mine, stream_static ? nullptr : ctx->d_work.p, tile_slots(ctx)};
-    const unsigned grid = (unsigned)std::min<uint64_t>(mine, grid_stream);
-    if (verbose)
-      fprintf(stderr, "[camus_b200] k_count_stream<%d>: %d SMs x %d CTAs (occupancy %d), grid %u, %llu boxes, %d groups, smem %d B\n",
-              complete ? 1 : 0, ctx->n_sms, (int)(grid_stream / ctx->n_sms), ctx->stream_ctas[complete ? 1 : 0], grid,
-              (unsigned long long)mine, ctx->G32, complete ? StreamCfg<1>::kSmemBytes : StreamCfg<0>::kSmemBytes);
+  // incomplete / polytomous trees: up to 1023 of them fit three 10-bit counters in one register
+  const bool packed = !complete && ctx->allow_packed && ctx->G <= 1023;
+  const uint64_t max_grid = 1u << 30;
+  for (uint64_t b0 = 0; b0 < mine; b0 += max_grid) {
+    uint64_t nbx = std::min(max_grid, mine - b0);
+    CountParams prm{ctx->d_tri.p, std::max(ctx->G32, 1), box_map(ctx, b0), nullptr, ctx->G, tile_slots(ctx)};
     if (complete)
-      k_count_stream<1><<<grid, kCountThreads, StreamCfg<1>::kSmemBytes, ctx->stream>>>(sp, fz, ctx->ct);
+      k_count<true, kModeComplete><<<(unsigned)nbx, kCountThreads, CountCfg<kModeComplete>::kSmemBytes, ctx->stream>>>(prm, fz, ctx->ct);
+    else if (packed)
+      k_count<true, kModePacked><<<(unsigned)nbx, kCountThreads, CountCfg<kModePacked>::kSmemBytes, ctx->stream>>>(prm, fz, ctx->ct);
     else
-      k_count_stream<0><<<grid, kCountThreads, StreamCfg<0>::kSmemBytes, ctx->stream>>>(sp, fz, ctx->ct);
+      k_count<true, kModeGeneral><<<(unsigned)nbx, kCountThreads, CountCfg<kModeGeneral>::kSmemBytes, ctx->stream>>>(prm, fz, ctx->ct);
     CK_LAUNCH();
-  } else {
-    const uint64_t max_grid = 1u << 30;
-    for (uint64_t b0 = 0; b0 < mine; b0 += max_grid) {
-      uint64_t nbx = std::min(max_grid, mine - b0);
-      CountParams prm{ctx->d_tri.p, std::max(ctx->G32, 1), box_map(ctx, b0), nullptr, ctx->G, tile_slots(ctx)};
-      if (complete)
-        k_count<true, true><<<(unsigned)nbx, kCountThreads, CountCfg<true>::kSmemBytes, ctx->stream>>>(prm, fz, ctx->ct);
-      else
-        k_count<true, false><<<(unsigned)nbx, kCountThreads, CountCfg<false>::kSmemBytes, ctx->stream>>>(prm, fz, ctx->ct);
-      CK_LAUNCH();
-    }
   }
   if (rep > 1) {
     k_sum_replicas<<<(unsigned)((zn + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_Z.p, zn, rep);
@@ -876,9 +850,9 @@ int run_count(camus_b200* ctx) {
     uint64_t nbx = std::min(max_grid, mine - b0);
     CountParams prm{ctx->d_tri.p, std::max(ctx->G32, 1), box_map(ctx, b0), ctx->d_cells.p + b0 * kBoxCells, ctx->G, tile_slots(ctx)};
     if (use_complete(ctx))
-      k_count<false, true><<<(unsigned)nbx, kCountThreads, CountCfg<true>::kSmemBytes, ctx->stream>>>(prm, FusedParams{}, ctx->ct);
+      k_count<false, kModeComplete><<<(unsigned)nbx, kCountThreads, CountCfg<kModeComplete>::kSmemBytes, ctx->stream>>>(prm, FusedParams{}, ctx->ct);
     else
-      k_count<false, false><<<(unsigned)nbx, kCountThreads, CountCfg<false>::kSmemBytes, ctx->stream>>>(prm, FusedParams{}, ctx->ct);
+      k_count<false, kModeGeneral><<<(unsigned)nbx, kCountThreads, CountCfg<kModeGeneral>::kSmemBytes, ctx->stream>>>(prm, FusedParams{}, ctx->ct);
     CK_LAUNCH();
   }
   if (t.stop()) return CAMUS_B200_ERR_CUDA;
@@ -1097,6 +1071,7 @@ int camus_b200_count_filter(camus_b200* ctx, int qmode, double threshold, uint64
   if (ctx->n == 0) return ctx->fail(CAMUS_B200_ERR_ARG, "count_filter: set the constraint tree first");
   if (qmode < 0 || qmode > 2 || !(threshold >= 0 && threshold <= 1))
     return ctx->fail(CAMUS_B200_ERR_ARG, "count_filter: quartet mode in [0,2] and threshold in [0,1] (quartetfilter.go:41-61)");
+  if (ctx->G >= (1 << 24)) return ctx->fail(CAMUS_B200_ERR_ARG, "count_filter: at most 16 777 215 gene trees (32-bit per-thread survivor sums)");
   if (!ctx->subs.empty()) {
     std::vector<uint64_t> ns(ctx->subs.size(), 0), sc(ctx->subs.size(), 0);
     ctx->reduced = false;

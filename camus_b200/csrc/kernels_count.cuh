@@ -21,6 +21,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <type_traits>
+
 #include "kernels_score.cuh"
 #include "layout.cuh"
 #include "ptx.cuh"
@@ -28,23 +30,54 @@
 namespace camus_dev {
 
 constexpr int kCountThreads = 256;
-constexpr int kCountStages = 4;
 constexpr int kPlaneWords = kTileWords / 3;  // 512 words = 2 KB: one plane of one tile
+#ifndef CAMUS_COUNT_OCC4
+#define CAMUS_COUNT_OCC4 1  // 0 = A/B build of the round-1 shape of the complete-tree loop (3 CTAs per SM, 4-stage ring)
+#endif
+#ifndef CAMUS_COUNT_NOBAR
+#define CAMUS_COUNT_NOBAR 0  // A/B build: no CTA barrier in the group loop, the last warp out of a stage refills it
+#endif
 
-// kComplete: every gene tree holds every taxon and is fully resolved (host-checked in
-// camus_b200_add_gene_trees) and there are at most 65535 trees. Then each tree resolves each
-// cell, so count(ad|bc) = G - count(ab|cd) - count(ac|bd): the third topology word, its POPC and
-// the four planes only it reads are skipped (8 planes = 16 KB per stage instead of 12 = 24 KB),
-// and the two remaining counters share one register (16 + 16 bits). Fewer registers and less
-// shared memory let 3 CTAs share an SM instead of 2, which matters because the kernel is bound
-// by latency at 16 warps/SM, not by a pipe (profiles/r01_k_count_config3_ncu_full.txt).
-template <bool kComplete>
+__device__ __forceinline__ uint32_t atom_add_shared_relaxed(uint32_t* p, uint32_t v) {
+  uint32_t old;
+  asm volatile("atom.relaxed.cta.shared::cta.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(p)), "r"(v) : "memory");
+  return old;
+}
+
+// Counting modes (template parameter kMode):
+//   kModeGeneral  : any gene trees, any number of them. Three 32-bit counters per cell, 12 planes
+//                   per stage, 128 registers, 2 CTAs per SM.
+//   kModeComplete : every gene tree holds every taxon and is fully resolved (host-checked in
+//                   camus_b200_add_gene_trees), at most 65535 trees. Each tree then resolves each
+//                   cell, so count(ad|bc) = G - count(ab|cd) - count(ac|bd): the third topology
+//                   word, its POPC and the four planes only it reads are skipped (8 planes = 16 KB
+//                   per stage) and the two counters share one register (16 + 16 bits).
+//   kModePacked   : incomplete / polytomous trees, at most 1023 of them: the three counters share
+//                   one register (10 + 10 + 10 bits), which brings the general kernel from 128 to
+//                   <= 80 registers and from 2 to 3 CTAs per SM.
+// The loop is bound by latency (XU = POPC pipe ~65 % busy, issue ~60 %), not by a pipe, so
+// resident warps matter: complete and packed fetch the acd / bcd operands per (c, d) pair instead
+// of holding them across both, and run a 3-stage ring, to fit 4 resp. 3 CTAs per SM
+// (profiles/r02_count_variants.md).
+enum : int { kModeGeneral = 0, kModeComplete = 1, kModePacked = 2 };
+
+template <int kMode>
 struct CountCfg {
+  static constexpr bool kComplete = kMode == kModeComplete;
+  static constexpr bool kPacked = kMode == kModePacked;
+  // narrow = operands fetched per (c, d) pair + 3-stage ring with one CTA barrier per group
+#if CAMUS_COUNT_OCC4
+  static constexpr bool kNarrow = kComplete || kPacked;
+#else
+  static constexpr bool kNarrow = kPacked;
+#endif
+  static constexpr int kStages = kNarrow ? 3 : 4;
   static constexpr int kPlanes = kComplete ? 8 : 12;
   static constexpr int kStageWords = kPlanes * kPlaneWords;
   static constexpr int kStageBytes = kStageWords * 4;
-  static constexpr int kSmemBytes = kCountStages * kStageBytes + 64;  // + mbarriers
-  static constexpr int kMinBlocks = kComplete ? 3 : 2;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 64;  // + mbarriers
+  static constexpr int kMinBlocks = kComplete ? (kNarrow ? 4 : 3) : (kPacked ? 3 : 2);
+  static constexpr int kCnt = kMode == kModeGeneral ? 3 : 1;  // counter registers per cell
 };
 
 struct CountParams {
@@ -85,13 +118,16 @@ __device__ __forceinline__ constexpr int plane_slot(int role, int plane) {
   return role == 0 ? plane : (role == 1 ? 2 + (plane >> 1) : (role == 2 ? 4 + (plane >> 1) : 6 + (plane - 1)));
 }
 
-template <bool kFused, bool kComplete>
-__global__ void __launch_bounds__(kCountThreads, CountCfg<kComplete>::kMinBlocks)
+template <bool kFused, int kMode>
+__global__ void __launch_bounds__(kCountThreads, CountCfg<kMode>::kMinBlocks)
 k_count(CountParams prm, FusedParams fz, ConstraintDev ct) {
-  using Cfg = CountCfg<kComplete>;
+  using Cfg = CountCfg<kMode>;
+  constexpr bool kComplete = Cfg::kComplete, kPacked = Cfg::kPacked;
   extern __shared__ __align__(128) uint32_t smem[];
+  constexpr int kCountStages = Cfg::kStages;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kCountStages * Cfg::kStageWords);
   __shared__ uint32_t s_seg[5];  // four segments, [4] = regular box
+  __shared__ uint32_t s_done[4];  // CAMUS_COUNT_NOBAR: warps that have finished with each ring stage
   __shared__ uint64_t s_tile[4];  // slots of the tiles abc, abd, acd, bcd in prm.tri
 
   const int tid = threadIdx.x;
@@ -117,7 +153,10 @@ k_count(CountParams prm, FusedParams fz, ConstraintDev ct) {
       const uint32_t S = (uint32_t)ct.n_seg;
       s_seg[4] = fz.regular && sa < sb && sb < sc && sc < sd && U[sa * S + sb] && U[sb * S + sc] && U[sc * S + sd];
     }
-    for (int s = 0; s < kCountStages; ++s) mbar_init(&bars[s], 1);
+    for (int s = 0; s < kCountStages; ++s) {
+      mbar_init(&bars[s], 1);
+      s_done[s] = 0;
+    }
     fence_mbar_init();
   }
   __syncthreads();
@@ -152,10 +191,11 @@ k_count(CountParams prm, FusedParams fz, ConstraintDev ct) {
   };
 
   if (tid == 0)
-    for (int g = 0; g < kCountStages && g < G; ++g) issue(g);
+    for (int g = 0; g < Cfg::kStages && g < G; ++g) issue(g);
 
   // general: cnt[c][t] = trees displaying topology t. complete: cnt[c][0] = c(ab|cd) | c(ac|bd) << 16.
-  constexpr int kCnt = kComplete ? 1 : 3;
+  // packed: cnt[c][0] = c(ab|cd) | c(ac|bd) << 10 | c(ad|bc) << 20.
+  constexpr int kCnt = Cfg::kCnt;
   uint32_t cnt[16][kCnt];
 #pragma unroll
   for (int c = 0; c < 16; ++c)
@@ -173,13 +213,23 @@ k_count(CountParams prm, FusedParams fz, ConstraintDev ct) {
 
   for (int g = 0; g < G; ++g) {
     const int s = g % kCountStages;
-    // One CTA barrier per TWO groups: at even g everyone has finished groups g-2 and g-1, whose
-    // stages are refilled with g+2 and g+3 (the ring holds g .. g+3 in flight or ready).
-    if ((g & 1) == 0 && g > 0) {
-      __syncthreads();
-      if (tid == 0 && !(kFused && fz.debug == 3)) {
-        if (g + 2 < G) issue(g + 2);
-        if (g + 3 < G) issue(g + 3);
+    if constexpr (CAMUS_COUNT_NOBAR) {
+      // nothing here: see the end of the loop body
+    } else if constexpr (Cfg::kNarrow) {
+      // 3-stage ring: everyone has finished group g-1, its stage is refilled with g+2
+      if (g > 0) {
+        __syncthreads();
+        if (tid == 0 && g + 2 < G) issue(g + 2);
+      }
+    } else {
+      // One CTA barrier per TWO groups: at even g everyone has finished groups g-2 and g-1, whose
+      // stages are refilled with g+2 and g+3 (the ring holds g .. g+3 in flight or ready).
+      if ((g & 1) == 0 && g > 0) {
+        __syncthreads();
+        if (tid == 0 && !(kFused && fz.debug == 3)) {
+          if (g + 2 < G) issue(g + 2);
+          if (g + 3 < G) issue(g + 3);
+        }
       }
     }
     // debug 3 (timing only): the ring is filled once and re-read, i.e. the loop without tile traffic
@@ -194,6 +244,42 @@ k_count(CountParams prm, FusedParams fz, ConstraintDev ct) {
 #pragma unroll
       for (int kk = 0; kk < 2; ++kk) abc[p][kk] = ld(0, p, o_abc + 16 * kk);
 
+    if constexpr (Cfg::kNarrow) {
+      // 64-bit halves of the acd / bcd words: the pair (c = kk, d = ll) fixes the half
+      auto ld2 = [&](int role, int plane, uint32_t off, int kk) -> uint2 {
+        return reinterpret_cast<const uint2*>(st + plane_slot<kComplete>(role, plane) * kPlaneU4 + off)[kk];
+      };
+#pragma unroll
+      for (int ll = 0; ll < 2; ++ll) {
+        uint4 abd[3];
+#pragma unroll
+        for (int p = 0; p < 3; ++p)
+          if (!kComplete || p != 1) abd[p] = ld(1, p, o_abd + 16 * ll);
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+          uint2 acd[3], bcd[3];
+#pragma unroll
+          for (int p = 0; p < 3; ++p) {
+            if (!kComplete || p != 1) acd[p] = ld2(2, p, o_acd + 16 * ll, kk);
+            if (!kComplete || p != 0) bcd[p] = ld2(3, p, o_bcd + 16 * ll, kk);
+          }
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const int c = ((ll * 2 + kk) * 2 + j) * 2 + i;
+              const uint32_t t0 = (pick(abc[0][kk], j, i) & pick(abd[0], j, i)) | ((i ? acd[2].y : acd[2].x) & (j ? bcd[2].y : bcd[2].x));  // ab|cd
+              const uint32_t t1 = (pick(abc[1][kk], j, i) & (i ? acd[0].y : acd[0].x)) | (pick(abd[2], j, i) & (j ? bcd[1].y : bcd[1].x));  // ac|bd
+              if constexpr (kComplete) {
+                cnt[c][0] += __popc(t0) + (__popc(t1) << 16);
+              } else {
+                const uint32_t t2 = (pick(abd[1], j, i) & (i ? acd[1].y : acd[1].x)) | (pick(abc[2][kk], j, i) & (j ? bcd[0].y : bcd[0].x));  // ad|bc
+                cnt[c][0] += __popc(t0) + (__popc(t1) << 10) + (__popc(t2) << 20);
+              }
+            }
+        }
+      }
+    } else {
 #pragma unroll
     for (int ll = 0; ll < 2; ++ll) {
       uint4 abd[3], acd[3], bcd[3];
@@ -222,6 +308,16 @@ k_count(CountParams prm, FusedParams fz, ConstraintDev ct) {
             }
           }
     }
+    }
+    if constexpr (CAMUS_COUNT_NOBAR) {
+      // release the stage: shared loads of a warp are performed in order ahead of its atomic, and the
+      // last of the 8 warps to get here refills the stage with group g + stages
+      __syncwarp();
+      if ((tid & 31) == 0) {
+        const uint32_t old = atom_add_shared_relaxed(&s_done[s], 1u);
+        if ((old & (kCountThreads / 32 - 1)) == kCountThreads / 32 - 1 && g + kCountStages < G) issue(g + kCountStages);
+      }
+    }
   }
 
   // counts of the three topologies of cell ci
@@ -230,6 +326,10 @@ k_count(CountParams prm, FusedParams fz, ConstraintDev ct) {
       c[0] = cnt[ci][0] & 0xFFFFu;
       c[1] = cnt[ci][0] >> 16;
       c[2] = (uint32_t)prm.n_trees - c[0] - c[1];
+    } else if constexpr (kPacked) {
+      c[0] = cnt[ci][0] & 0x3FFu;
+      c[1] = (cnt[ci][0] >> 10) & 0x3FFu;
+      c[2] = cnt[ci][0] >> 20;
     } else {
       c[0] = cnt[ci][0];
       c[1] = cnt[ci][1];
@@ -253,34 +353,84 @@ k_count(CountParams prm, FusedParams fz, ConstraintDev ct) {
           }
   } else {
     // ---- fused K3 + K4 on the register-resident counts ----
-    // Phase 1 (per thread, its 16 cells): filter + constraint removal; survivors are COMPACTED into
-    // a queue in the shared memory of the now idle tile ring. Phase 2: the queue is scored with
-    // all lanes busy. Survivors are sparse under -q 1/2 (a few % of the cells).
-    //
+    // Round-1 profile: 27 % of the kernel's instructions were in this epilogue (~140 per cell, a
+    // dozen branches each). It is now one branch-free pass per cell (~45 instructions):
+    //   X = count of ac|bd, Y = count of the one of ab|cd / ad|bc the constraint does not display,
+    //   Z = count of the one it does (never a survivor); lo <= mid <= hi their sorted values;
+    //   keep = Keep(lo, mid);  X survives iff keep ? (mode 1 or X != lo) : (X == hi), Y likewise.
+    // The one case this cannot decide -- Keep fails and the two largest counts tie, where the
+    // reference's stable topology order picks the survivor -- is deferred: the cell goes to the
+    // warp's queue with its raw counts and is resolved there by apply_filter.
     // Regular boxes (the three consecutive segment pairs have one LCA each, ConstraintDev::
-    // seg_uniform; half of all boxes of a random 1000-taxon constraint) skip the queue: junction,
-    // m-node and component of a (bottom taxon, topology) are box constants, so the box's whole
-    // contribution is 4 axes x 2 topologies x 8 marginal sums of the surviving counts (+ their
-    // totals, subtracted at the m-nodes): 72 reductions per box instead of 8 per survivor.
-    __shared__ unsigned long long s_red[2][kCountThreads / 32];
-    __shared__ uint32_t s_qn;
+    // seg_uniform; half of all boxes of a random 1000-taxon constraint): junction, m-node and
+    // component of a (bottom taxon, topology) are box constants, so the box contributes 4 axes x
+    // 2 topologies x 8 marginal sums of the surviving weights: 72 reductions per box.
+    // Other boxes: survivors are compacted into a queue PER WARP (its eighth of the idle tile
+    // ring: no shared atomics, no CTA barrier) and scored 32 at a time.
+    __shared__ unsigned long long s_tot[2];
     __shared__ uint32_t s_marg[4][2][8];  // [bottom axis a..d][topology slot][coordinate]
-    if (tid == 0) s_qn = 0;
+    __shared__ uint32_t s_wq[kCountThreads / 32];  // queue fill of the warps of a regular box (deferred ties only)
+    if (tid < 2) s_tot[tid] = 0;
     if (tid < 64) (&s_marg[0][0][0])[tid] = 0;
+    if (tid < kCountThreads / 32) s_wq[tid] = 0;
     const bool regular = s_seg[4] != 0;
     __syncthreads();  // also: every issued bulk copy has been waited for, the ring can be reused
-    static_assert(kCountStages * Cfg::kStageBytes >= kBoxCells * 16, "survivor queue must fit the ring");
-    uint4* queue = reinterpret_cast<uint4*>(smem);  // up to kBoxCells entries (64 KB)
+    constexpr int kWarps = kCountThreads / 32;
+    // queue entry = cell (12 bits) | deferred-tie flag | three counts: 16 bytes, or 8 for complete
+    // / packed mode (counts <= 65535), so that the 512 cells of a warp fit its eighth of even a 48 KB ring
+    constexpr bool kSmallCounts = kComplete || kPacked;
+    using QEntry = typename std::conditional<kSmallCounts, uint2, uint4>::type;
+    static_assert(kCountStages * Cfg::kStageBytes >= kBoxCells * (int)sizeof(QEntry), "the per-warp queues must fit the ring");
+    const int lane = tid & 31, warp = tid >> 5;
+    QEntry* queue = reinterpret_cast<QEntry*>(smem) + warp * (kBoxCells / kWarps);  // 512 entries: every cell of the warp
+    auto q_pack = [](uint32_t local, bool tie, uint32_t k0, uint32_t k1, uint32_t k2) -> QEntry {
+      if constexpr (kSmallCounts) return make_uint2(local | (tie ? 0x1000u : 0u) | (k0 << 13) | (k1 << 29), (k1 >> 3) | (k2 << 13));
+      else return make_uint4(local | (tie ? 0x1000u : 0u), k0, k1, k2);
+    };
+    auto q_unpack = [](const QEntry& q, uint32_t& local, bool& tie, uint32_t c[3]) {
+      local = q.x & 0xFFFu;
+      tie = (q.x & 0x1000u) != 0;
+      if constexpr (kSmallCounts) {
+        c[0] = (q.x >> 13) & 0xFFFFu;
+        c[1] = ((q.x >> 29) | (q.y << 3)) & 0xFFFFu;
+        c[2] = (q.y >> 13) & 0xFFFFu;
+      } else {
+        c[0] = q.y; c[1] = q.z; c[2] = q.w;
+      }
+    };
     const uint32_t N = (uint32_t)ct.n_taxa;
     const uint32_t a0 = sa * 8 + 2 * ta, b0 = sb * 8 + 2 * tb, c0 = sc * 8 + 2 * tc, d0 = sd * 8 + 2 * td;
-    const int lane = tid & 31;
-    unsigned long long ns = 0, sum = 0;
+    const uint32_t Gt = (uint32_t)prm.n_trees;
+    const int qmode = fz.qmode;
+    const uint32_t* __restrict__ thr_tab = fz.thr_tab;
+    uint32_t ns = 0, sum = 0;  // per thread: at most 48 keys, 48 x trees counts (the host keeps trees < 2^24 here)
+    uint32_t qn = 0;           // warp-uniform queue fill (irregular boxes)
     // packed LCAs of the box's first taxa: THE LCAs of a regular box
     const uint32_t bg1 = ct.lcaD[(size_t)(sa * 8) * N + sb * 8], bg2 = ct.lcaD[(size_t)(sb * 8) * N + sc * 8],
                    bg3 = ct.lcaD[(size_t)(sc * 8) * N + sd * 8];
-    const bool kill0 = constraint_topology(bg1, bg2, bg3) == 0;  // the constraint displays ab|cd here (else ad|bc)
+    const bool box_kill0 = constraint_topology(bg1, bg2, bg3) == 0;  // regular box: the constraint displays ab|cd (else ad|bc)
+
+    // one cell: (wx, wy) = surviving counts of ac|bd and of the other non-constraint topology; tie = deferred
+    auto decide = [&](const uint32_t c[3], bool kill0, uint32_t& wx, uint32_t& wy, bool& tie) {
+      const uint32_t X = c[1], Y = kill0 ? c[2] : c[0], Z = kill0 ? c[0] : c[2];
+      tie = false;
+      if (qmode == 0) {
+        wx = X;
+        wy = Y;
+        return;
+      }
+      const uint32_t lo = min(X, min(Y, Z)), hi = max(X, max(Y, Z));
+      const uint32_t mid = (kComplete ? Gt : X + Y + Z) - lo - hi;
+      const bool keep = __ldg(&thr_tab[lo + mid]) < mid - lo;  // Threshold.Keep (quartetfilter.go:67-74)
+      const bool drop_lo = qmode == 2;
+      const bool sx = keep ? (!drop_lo || X != lo) : (X == hi);
+      const bool sy = keep ? (!drop_lo || Y != lo) : (Y == hi);
+      tie = !keep && mid == hi && hi != 0;
+      wx = sx && !tie ? X : 0u;
+      wy = sy && !tie ? Y : 0u;
+    };
+
     if (regular) {
-      // slot 0 = ac|bd, slot 1 = the one of ab|cd / ad|bc the constraint does not display
       uint32_t ma[2][2] = {{0, 0}, {0, 0}}, mb[2][2] = {{0, 0}, {0, 0}}, mc[2][2] = {{0, 0}, {0, 0}}, md[2][2] = {{0, 0}, {0, 0}};
 #pragma unroll
       for (int ll = 0; ll < 2; ++ll)
@@ -290,17 +440,16 @@ k_count(CountParams prm, FusedParams fz, ConstraintDev ct) {
           for (int j = 0; j < 2; ++j)
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
-              const uint32_t x[4] = {a0 + i, b0 + j, c0 + kk, d0 + ll};
-              uint32_t c[3];
+              uint32_t c[3], w0, w1;
+              bool tie;
               counts_of(((ll * 2 + kk) * 2 + j) * 2 + i, c);
-              if (fz.debug >= 2) {
-                sum += c[0] + c[1] + c[2];
-                continue;
+              decide(c, box_kill0, w0, w1, tie);
+              if (tie) {  // rare: resolved in the queue pass below
+                const uint32_t at = atomicAdd(&s_wq[warp], 1u);
+                queue[at] = q_pack(cell_local(2 * ta + i, 2 * tb + j, 2 * tc + kk, 2 * td + ll), true, c[0], c[1], c[2]);
               }
-              if (fz.qmode != 0 && (c[0] | c[1] | c[2])) filter_cell(c, x, fz.qmode, fz.threshold, fz.thr_tab, ct.tip_of_rank);
-              uint32_t w0 = c[1], w1 = kill0 ? c[2] : c[0];
               ns += (w0 != 0) + (w1 != 0);
-              sum += (unsigned long long)w0 + w1;
+              sum += w0 + w1;
               if (fz.as_set) {
                 w0 = w0 != 0;
                 w1 = w1 != 0;
@@ -308,136 +457,151 @@ k_count(CountParams prm, FusedParams fz, ConstraintDev ct) {
               ma[0][i] += w0; mb[0][j] += w0; mc[0][kk] += w0; md[0][ll] += w0;
               ma[1][i] += w1; mb[1][j] += w1; mc[1][kk] += w1; md[1][ll] += w1;
             }
-      if (fz.debug == 0) {
-        // warp sums over the lanes that share the coordinate, one shared atomic per (warp, sum)
-        const uint32_t mask_a = 0x11111111u << ta, mask_b = 0x000F000Fu << (4 * tb);
-        const uint32_t mask_c = lane < 16 ? 0x0000FFFFu : 0xFFFF0000u;
+      // warp sums over the lanes that share the coordinate, one shared atomic per (warp, sum)
+      const uint32_t mask_a = 0x11111111u << ta, mask_b = 0x000F000Fu << (4 * tb);
+      const uint32_t mask_c = lane < 16 ? 0x0000FFFFu : 0xFFFF0000u;
 #pragma unroll
-        for (int sl = 0; sl < 2; ++sl)
+      for (int sl = 0; sl < 2; ++sl)
 #pragma unroll
-          for (int par = 0; par < 2; ++par) {
-            uint32_t v = __reduce_add_sync(mask_a, ma[sl][par]);
-            if (lane < 4 && v) atomicAdd(&s_marg[0][sl][2 * ta + par], v);
-            v = __reduce_add_sync(mask_b, mb[sl][par]);
-            if (lane == 4 * tb && v) atomicAdd(&s_marg[1][sl][2 * tb + par], v);
-            v = __reduce_add_sync(mask_c, mc[sl][par]);
-            if ((lane & 15) == 0 && v) atomicAdd(&s_marg[2][sl][2 * tc + par], v);
-            v = __reduce_add_sync(0xFFFFFFFFu, md[sl][par]);
-            if (lane == 0 && v) atomicAdd(&s_marg[3][sl][2 * td + par], v);
-          }
-      }
+        for (int par = 0; par < 2; ++par) {
+          uint32_t v = __reduce_add_sync(mask_a, ma[sl][par]);
+          if (lane < 4 && v) atomicAdd(&s_marg[0][sl][2 * ta + par], v);
+          v = __reduce_add_sync(mask_b, mb[sl][par]);
+          if (lane == 4 * tb && v) atomicAdd(&s_marg[1][sl][2 * tb + par], v);
+          v = __reduce_add_sync(mask_c, mc[sl][par]);
+          if ((lane & 15) == 0 && v) atomicAdd(&s_marg[2][sl][2 * tc + par], v);
+          v = __reduce_add_sync(0xFFFFFFFFu, md[sl][par]);
+          if (lane == 0 && v) atomicAdd(&s_marg[3][sl][2 * td + par], v);
+        }
+      __syncwarp();
+      qn = s_wq[warp];
     } else {
+      // LCAs of the thread's 2x2 (a,b), (b,c), (c,d) pairs, loaded once (was: three loads per live cell)
+      uint32_t g1[2][2], g2[2][2], g3[2][2];
 #pragma unroll
-    for (int ll = 0; ll < 2; ++ll)
+      for (int u = 0; u < 2; ++u)
 #pragma unroll
-      for (int kk = 0; kk < 2; ++kk)
+        for (int v = 0; v < 2; ++v) {
+          g1[u][v] = ct.lcaD[(size_t)min(a0 + u, N - 1) * N + min(b0 + v, N - 1)];
+          g2[u][v] = ct.lcaD[(size_t)min(b0 + u, N - 1) * N + min(c0 + v, N - 1)];
+          g3[u][v] = ct.lcaD[(size_t)min(c0 + u, N - 1) * N + min(d0 + v, N - 1)];
+        }
 #pragma unroll
-        for (int j = 0; j < 2; ++j)
+      for (int ll = 0; ll < 2; ++ll)
 #pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            const uint32_t x[4] = {a0 + i, b0 + j, c0 + kk, d0 + ll};
-            uint32_t c[3];
-            counts_of(((ll * 2 + kk) * 2 + j) * 2 + i, c);
-            bool live = x[0] < x[1] && x[1] < x[2] && x[2] < x[3] && x[3] < N && (c[0] | c[1] | c[2]);
-            if (fz.debug >= 2) {
-              if (live) sum += c[0] + c[1] + c[2];
-              continue;
-            }
-            if (live && fz.qmode != 0) {
-              filter_cell(c, x, fz.qmode, fz.threshold, fz.thr_tab, ct.tip_of_rank);
-              live = (c[0] | c[1] | c[2]) != 0;
-            }
-            if (live) {
-              const uint32_t g1 = ct.lcaD[(size_t)x[0] * N + x[1]];
-              const uint32_t g2 = ct.lcaD[(size_t)x[1] * N + x[2]];
-              const uint32_t g3 = ct.lcaD[(size_t)x[2] * N + x[3]];
-              if (constraint_topology(g1, g2, g3) == 0) c[0] = 0;
-              else c[2] = 0;
-              live = (c[0] | c[1] | c[2]) != 0;
-            }
-            // warp-aggregated queue push: one shared atomic per warp step
-            const uint32_t m = __ballot_sync(0xFFFFFFFFu, live);
-            if (m) {
-              uint32_t base = 0;
-              if (lane == 0) base = atomicAdd(&s_qn, (uint32_t)__popc(m));
-              base = __shfl_sync(0xFFFFFFFFu, base, 0);
-              if (live) {
-                ns += (c[0] != 0) + (c[1] != 0) + (c[2] != 0);
-                sum += (unsigned long long)c[0] + c[1] + c[2];
-                const uint32_t local = cell_local(2 * ta + i, 2 * tb + j, 2 * tc + kk, 2 * td + ll);
-                queue[base + __popc(m & ((1u << lane) - 1))] = make_uint4(local, c[0], c[1], c[2]);
+        for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              uint32_t c[3], wx, wy;
+              bool tie;
+              counts_of(((ll * 2 + kk) * 2 + j) * 2 + i, c);
+              const bool valid = a0 + i < b0 + j && b0 + j < c0 + kk && c0 + kk < d0 + ll && d0 + ll < N;
+              if (!valid) c[0] = c[1] = c[2] = 0;  // diagonal / padded cells hold garbage (and would index the Keep table with it)
+              const bool kill0 = constraint_topology(g1[i][j], g2[j][kk], g3[kk][ll]) == 0;
+              decide(c, kill0, wx, wy, tie);
+              tie = tie && valid;
+              const bool live = valid && ((wx | wy) != 0 || tie);
+              const uint32_t bal = __ballot_sync(0xFFFFFFFFu, live);
+              if (bal) {  // warp-uniform
+                if (live) {
+                  const uint32_t local = cell_local(2 * ta + i, 2 * tb + j, 2 * tc + kk, 2 * td + ll);
+                  const uint32_t at = qn + __popc(bal & ((1u << lane) - 1));
+                  // decided cells carry their surviving counts, deferred ties the raw ones (+ flag)
+                  queue[at] = tie ? q_pack(local, true, c[0], c[1], c[2]) : q_pack(local, false, kill0 ? 0u : wy, wx, kill0 ? wy : 0u);
+                }
+                qn += __popc(bal);
               }
             }
-          }
+      __syncwarp();
     }
+
+    // queue pass (one copy of this code): survivors of an irregular box, deferred ties of any box
+    if (qn) {
+      unsigned long long* Zrep = fz.Z + (size_t)(blockIdx.x % (unsigned)fz.z_rep) * fz.z_stride;
+      GlobalAcc acc{Zrep};
+#pragma unroll 1
+      for (uint32_t e = lane; e < qn; e += 32) {
+        uint32_t local, c[3];
+        bool was_tie;
+        q_unpack(queue[e], local, was_tie, c);
+        const uint32_t x[4] = {sa * 8 + (local & 7), sb * 8 + ((local >> 3) & 7), sc * 8 + ((local >> 6) & 7), sd * 8 + (local >> 9)};
+        const uint32_t h1 = ct.lcaD[(size_t)x[0] * N + x[1]];
+        const uint32_t h2 = ct.lcaD[(size_t)x[1] * N + x[2]];
+        const uint32_t h3 = ct.lcaD[(size_t)x[2] * N + x[3]];
+        const int kc = constraint_topology(h1, h2, h3);
+        if (was_tie) {  // deferred tie: the reference's stable topology order decides (apply_filter)
+          const int ti[4] = {ct.tip_of_rank[x[0]], ct.tip_of_rank[x[1]], ct.tip_of_rank[x[2]], ct.tip_of_rank[x[3]]};
+          apply_filter(c, ti, qmode, fz.threshold);
+        }
+        if (kc == 0) c[0] = 0;
+        else c[2] = 0;
+        if (!regular || was_tie) {
+          ns += (c[0] != 0) + (c[1] != 0) + (c[2] != 0);
+          sum += c[0] + c[1] + c[2];
+        }
+        if (regular) {  // a deferred tie of a regular box joins the marginal sums
+          const uint32_t w0 = fz.as_set ? (c[1] != 0) : c[1];
+          const uint32_t cy = box_kill0 ? c[2] : c[0];
+          const uint32_t w1 = fz.as_set ? (cy != 0) : cy;
+          const uint32_t co[4] = {local & 7, (local >> 3) & 7, (local >> 6) & 7, local >> 9};
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      ns += __shfl_xor_sync(0xFFFFFFFFu, ns, off);
-      sum += __shfl_xor_sync(0xFFFFFFFFu, sum, off);
+          for (int ax = 0; ax < 4; ++ax) {
+            if (w0) atomicAdd(&s_marg[ax][0][co[ax]], w0);
+            if (w1) atomicAdd(&s_marg[ax][1][co[ax]], w1);
+          }
+        } else {
+          score_cell(c, x, h1, h2, h3, ct, acc, fz.as_set);
+        }
+      }
     }
-    if (lane == 0) {
-      s_red[0][tid >> 5] = ns;
-      s_red[1][tid >> 5] = sum;
+
+    // survivor totals: warp sums -> two shared 64-bit atomics per warp -> two global ones per box
+    ns = __reduce_add_sync(0xFFFFFFFFu, ns);
+    const unsigned long long wsum = (unsigned long long)__reduce_add_sync(0xFFFFFFFFu, sum >> 16) * 65536ull + __reduce_add_sync(0xFFFFFFFFu, sum & 0xFFFFu);
+    if (lane == 0 && ns) {
+      atomicAdd(&s_tot[0], (unsigned long long)ns);
+      atomicAdd(&s_tot[1], wsum);
     }
     __syncthreads();
     if (tid == 0) {
-      unsigned long long t0 = 0, t1 = 0;
-#pragma unroll
-      for (int w = 0; w < kCountThreads / 32; ++w) {
-        t0 += s_red[0][w];
-        t1 += s_red[1][w];
-      }
-      if (t0) red_add_u64(&fz.totals[0], t0);
-      if (t1) red_add_u64(&fz.totals[1], t1);
+      if (s_tot[0]) red_add_u64(&fz.totals[0], s_tot[0]);
+      if (s_tot[1]) red_add_u64(&fz.totals[1], s_tot[1]);
     }
-    if (regular) {
-      if (fz.debug == 0 && tid < 72) {
-        // threads 0..63: one (axis, slot, coordinate) sum, added at the leaf; 64..71: the (axis,
-        // slot) total, subtracted at the m-node. Junction / m / component as in score_cell.
-        const int be = tid < 64 ? tid >> 4 : (tid - 64) >> 1;
-        const int sl = tid < 64 ? (tid >> 3) & 1 : tid & 1;
-        const int t = sl == 0 ? 1 : (kill0 ? 2 : 0);
-        uint32_t h1, h2, m;
-        if (be == 0) {
-          h1 = bg2; h2 = bg3; m = bg1;
-        } else if (be == 1) {
-          h1 = min(bg1, bg2); h2 = bg3; m = max(bg1, bg2);
-        } else if (be == 2) {
-          h1 = bg1; h2 = min(bg2, bg3); m = max(bg2, bg3);
-        } else {
-          h1 = bg1; h2 = bg2; m = bg3;
-        }
-        const bool first = h1 > h2;
-        const uint32_t J = (first ? h1 : h2) & 0xFFFFu;
-        const int p = partner_of(t, be);
-        const int pos = p - (p > be ? 1 : 0);
-        const int comp = first ? pos : (pos + 2) % 3;
-        long long v = 0;
-        size_t row;
-        if (tid < 64) {
-          v = s_marg[be][sl][tid & 7];
-          row = (size_t)ct.leafnode[s_seg[be] * 8 + (tid & 7)];
-        } else {
+    if (regular && tid < 72) {
+      // threads 0..63: one (axis, slot, coordinate) sum, added at the leaf; 64..71: the (axis,
+      // slot) total, subtracted at the m-node. Junction / m / component as in score_cell.
+      const int be = tid < 64 ? tid >> 4 : (tid - 64) >> 1;
+      const int sl = tid < 64 ? (tid >> 3) & 1 : tid & 1;
+      const int t = sl == 0 ? 1 : (box_kill0 ? 2 : 0);
+      uint32_t h1, h2, m;
+      if (be == 0) {
+        h1 = bg2; h2 = bg3; m = bg1;
+      } else if (be == 1) {
+        h1 = min(bg1, bg2); h2 = bg3; m = max(bg1, bg2);
+      } else if (be == 2) {
+        h1 = bg1; h2 = min(bg2, bg3); m = max(bg2, bg3);
+      } else {
+        h1 = bg1; h2 = bg2; m = bg3;
+      }
+      const bool first = h1 > h2;
+      const uint32_t J = (first ? h1 : h2) & 0xFFFFu;
+      const int p = partner_of(t, be);
+      const int pos = p - (p > be ? 1 : 0);
+      const int comp = first ? pos : (pos + 2) % 3;
+      long long v = 0;
+      size_t row;
+      if (tid < 64) {
+        v = s_marg[be][sl][tid & 7];
+        row = (size_t)ct.leafnode[s_seg[be] * 8 + (tid & 7)];
+      } else {
 #pragma unroll
-          for (int k = 0; k < 8; ++k) v -= s_marg[be][sl][k];
-          row = m & 0xFFFFu;
-        }
-        if (v) red_add_u64(fz.Z + (size_t)(blockIdx.x % (unsigned)fz.z_rep) * fz.z_stride + (row * (size_t)ct.n + J) * 3 + comp,
-                           (unsigned long long)v);
+        for (int k = 0; k < 8; ++k) v -= s_marg[be][sl][k];
+        row = m & 0xFFFFu;
       }
-    } else if (fz.debug != 1) {
-      const uint32_t qn = s_qn;
-      GlobalAcc acc{fz.Z + (size_t)(blockIdx.x % (unsigned)fz.z_rep) * fz.z_stride};
-#pragma unroll 1
-      for (uint32_t e = tid; e < qn; e += kCountThreads) {
-        const uint4 q = queue[e];
-        const uint32_t x[4] = {sa * 8 + (q.x & 7), sb * 8 + ((q.x >> 3) & 7), sc * 8 + ((q.x >> 6) & 7), sd * 8 + (q.x >> 9)};
-        const uint32_t c[3] = {q.y, q.z, q.w};
-        const uint32_t g1 = ct.lcaD[(size_t)x[0] * N + x[1]];
-        const uint32_t g2 = ct.lcaD[(size_t)x[1] * N + x[2]];
-        const uint32_t g3 = ct.lcaD[(size_t)x[2] * N + x[3]];
-        score_cell(c, x, g1, g2, g3, ct, acc, fz.as_set);
-      }
+      if (v) red_add_u64(fz.Z + (size_t)(blockIdx.x % (unsigned)fz.z_rep) * fz.z_stride + (row * (size_t)ct.n + J) * 3 + comp,
+                         (unsigned long long)v);
     }
   }
 }

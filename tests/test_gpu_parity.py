@@ -80,16 +80,17 @@ def test_fused_and_table_pipelines_agree(gpu, qmode, thr, monkeypatch):
     table.close()
 
 
-def test_streaming_and_per_box_count_kernels_agree(gpu, monkeypatch):
-    """k_count_stream (persistent CTAs, default) and k_count (one CTA per box, CAMUS_B200_COUNT_V1=1):
-    same survivors and tables, complete and general trees, every filter mode, few and many tree
-    groups (1 group: the ring runs four boxes ahead), both against the oracle."""
+def test_packed_and_three_register_general_kernels_agree(gpu, monkeypatch):
+    """Incomplete / polytomous gene trees: up to 1023 of them take k_count<kModePacked> (three 10-bit
+    counters in one register, 3 CTAs per SM), more -- or CAMUS_B200_NO_PACKED=1 -- the 3-register
+    general kernel. Same survivors and tables from both, every filter mode, against the oracle; and
+    the 1023 / 1024 tree boundary (a count of 1023 must not carry into the next field)."""
     from camus_b200.cabi import CamusB200
-    monkeypatch.setenv("CAMUS_B200_COUNT_V1", "1")
-    per_box = CamusB200(0)
-    monkeypatch.delenv("CAMUS_B200_COUNT_V1")
-    cases = [(synth.make(41, 20, 51), 0.0), (synth.make(70, 130, 52), 0.0), (synth.make(66, 300, 53, drop_frac=0.1), 0.0),
-             (synth.make(58, 90, 54, support=True, drop_frac=0.1, nexus=True), 0.7), (synth.make(30, 33, 55), 0.0)]
+    monkeypatch.setenv("CAMUS_B200_NO_PACKED", "1")
+    wide = CamusB200(0)
+    monkeypatch.delenv("CAMUS_B200_NO_PACKED")
+    cases = [(synth.make(41, 20, 51, drop_frac=0.1), 0.0), (synth.make(66, 300, 53, drop_frac=0.1), 0.0),
+             (synth.make(58, 90, 54, support=True, drop_frac=0.1, nexus=True), 0.7), (synth.make(30, 33, 55, drop_frac=0.2), 0.0)]
     for s, ms in cases:
         prob = Problem(s.constraint, s.genes, s.fmt, ms)
         o = orc.Oracle().load(prob)
@@ -97,13 +98,27 @@ def test_streaming_and_per_box_count_kernels_agree(gpu, monkeypatch):
             want = o.count_filter(qmode, thr, False)
             for as_set in (False, True):
                 ref = o.quartet_totals(as_set, False)
-                for ctx in (gpu, per_box):
+                for ctx in (gpu, wide):
                     ctx.load(prob)
                     ctx.set_score_hint(as_set)
                     assert ctx.count_filter(qmode, thr) == want
                     assert np.array_equal(ctx.quartet_totals(as_set), ref)
     gpu.set_score_hint(False)
-    per_box.close()
+    # boundary: 1023 identical trees + one with a missing taxon (packed), then one more tree (3-register)
+    base = synth.make(20, 1, 56)
+    one = base.genes.strip()
+    dropped = Problem(base.constraint, synth.make(20, 1, 56, drop_frac=0.3).genes)
+    for n_same in (1022, 1023):
+        prob = Problem(base.constraint, "\n".join([one] * n_same) + "\n")
+        for ctx in (gpu, wide):
+            ctx.load(prob)
+            ctx.add_gene_trees(dropped.gene_node_off, dropped.gene_parent, dropped.gene_taxon)
+        got = gpu.count_filter(0, 0.0)
+        assert got == wide.count_filter(0, 0.0)
+        gk, gc = gpu.export_quartets(raw=True)
+        assert int(gc.max()) >= n_same
+        assert np.array_equal(gpu.quartet_totals(False), wide.quartet_totals(False))
+    wide.close()
 
 
 def test_integer_and_fp16_plane_builders_agree(gpu, monkeypatch):
