@@ -98,6 +98,9 @@ struct camus_b200 {
   int tri_key[3] = {-1, -1, -1};   // ... of this (segments, rank, world)
   uint64_t n_tiles_local = 0;
   int list_key[3] = {-1, -1, -1};  // (segments, rank, world) the lists were built for
+  DevBuf<uint2> d_box_desc;        // k_box_desc: segments + regular flag of every local box (fused count kernel)
+  uint64_t desc_key[6] = {0, 0, 0, 0, 0, 0};  // (constraint generation, segments, rank, world, scheme, regular) it was built for
+  uint64_t constraint_gen = 0;     // bumped by set_constraint
   uint32_t tri_mask = 0;           // segment classes whose tiles the bit-planes hold (0xF = every tile)
   bool want_all_tiles = false;     // camus_b200_query_cells reads arbitrary tiles
   enum CellState { NONE, RAW, FILTERED } cell_state = NONE;
@@ -419,6 +422,7 @@ int camus_b200_set_constraint(camus_b200* ctx, int32_t n_nodes, int32_t n_taxa, 
   ctx->h_ref_of_int = ref_of_int;
   ctx->n = n;
   ctx->N = N;
+  ++ctx->constraint_gen;
   ctx->npad = (N + kSeg - 1) / kSeg * kSeg;
   ctx->M = ctx->npad / kSeg;
   if (upload(ctx, ctx->d_parent, par.data(), n) || upload(ctx, ctx->d_depth, depth.data(), n) ||
@@ -799,13 +803,34 @@ int run_fused(camus_b200* ctx, int qmode, double threshold, int as_set, uint64_t
   CK(cudaMemsetAsync(ctx->d_totals.p, 0, 16, ctx->stream));
   static const int dbg = getenv("CAMUS_B200_DEBUG") ? atoi(getenv("CAMUS_B200_DEBUG")) : 0;
   FusedParams fz{qmode, threshold, ctx->d_thr_tab.p, as_set, ctx->d_Z.p, ctx->d_totals.p, rep, (unsigned long long)zn, ctx->allow_regular ? 1 : 0, dbg};
+  // box descriptors (segments + regular flag), rebuilt only when the constraint or the partition changed
+  static const bool no_desc = getenv("CAMUS_B200_NO_BOXDESC") && getenv("CAMUS_B200_NO_BOXDESC")[0] == '1';  // A/B
+  const uint2* desc = nullptr;
+  if (!no_desc && mine > 0 && ctx->M < 4096) {
+    const uint64_t key[6] = {ctx->constraint_gen, (uint64_t)ctx->M, (uint64_t)ctx->rank, (uint64_t)ctx->world,
+                             ctx->class_scheme ? 1u : 0u, ctx->allow_regular ? 1u : 0u};
+    bool have = ctx->d_box_desc.p != nullptr && memcmp(key, ctx->desc_key, sizeof key) == 0;
+    if (!have) {
+      cudaError_t e = ctx->d_box_desc.alloc(mine);
+      if (e == cudaSuccess) {
+        k_box_desc<<<(unsigned)((mine + 255) / 256), 256, 0, ctx->stream>>>(box_map(ctx, 0), mine, ctx->ct, ctx->allow_regular ? 1 : 0, ctx->d_box_desc.p);
+        CK_LAUNCH();
+        memcpy(ctx->desc_key, key, sizeof key);
+        have = true;
+      } else {
+        cudaGetLastError();  // no room: the kernel unranks its box itself
+        memset(ctx->desc_key, 0, sizeof key);
+      }
+    }
+    if (have) desc = ctx->d_box_desc.p;
+  }
   const bool complete = use_complete(ctx);
   // incomplete / polytomous trees: up to 1023 of them fit three 10-bit counters in one register
   const bool packed = !complete && ctx->allow_packed && ctx->G <= 1023;
   const uint64_t max_grid = 1u << 30;
   for (uint64_t b0 = 0; b0 < mine; b0 += max_grid) {
     uint64_t nbx = std::min(max_grid, mine - b0);
-    CountParams prm{ctx->d_tri.p, std::max(ctx->G32, 1), box_map(ctx, b0), nullptr, ctx->G, tile_slots(ctx)};
+    CountParams prm{ctx->d_tri.p, std::max(ctx->G32, 1), box_map(ctx, b0), nullptr, ctx->G, tile_slots(ctx), desc};
     if (complete)
       k_count<true, kModeComplete><<<(unsigned)nbx, kCountThreads, CountCfg<kModeComplete>::kSmemBytes, ctx->stream>>>(prm, fz, ctx->ct);
     else if (packed)
@@ -848,7 +873,7 @@ int run_count(camus_b200* ctx) {
   const uint64_t max_grid = 1u << 30;
   for (uint64_t b0 = 0; b0 < mine; b0 += max_grid) {
     uint64_t nbx = std::min(max_grid, mine - b0);
-    CountParams prm{ctx->d_tri.p, std::max(ctx->G32, 1), box_map(ctx, b0), ctx->d_cells.p + b0 * kBoxCells, ctx->G, tile_slots(ctx)};
+    CountParams prm{ctx->d_tri.p, std::max(ctx->G32, 1), box_map(ctx, b0), ctx->d_cells.p + b0 * kBoxCells, ctx->G, tile_slots(ctx), nullptr};
     if (use_complete(ctx))
       k_count<false, kModeComplete><<<(unsigned)nbx, kCountThreads, CountCfg<kModeComplete>::kSmemBytes, ctx->stream>>>(prm, FusedParams{}, ctx->ct);
     else

@@ -87,7 +87,23 @@ struct CountParams {
   uint4* cells;    // table mode: [local box][kBoxCells] = (c(ab|cd), c(ac|bd), c(ad|bc), 0)
   int n_trees;
   const uint32_t* tile_slot;  // class-scheme shares store only the tiles they read: tile index -> slot in tri; nullptr = identity
+  const uint2* desc;          // per local box: segments + regular flag (k_box_desc); nullptr = unrank in the kernel
 };
+
+// Box descriptor: x = sa | sb << 16, y = sc | sd << 16 | regular << 31 (segments < 4096). Unranking a
+// box costs thread 0 two roots, a dozen 64-bit multiplications and its fix-up loops while 255
+// threads wait at the first barrier (8 % of the warp samples of the round-2 profile); the table is
+// built once per (constraint, partition) and costs 8 B per box.
+__global__ void k_box_desc(BoxMap bm, uint64_t n_boxes, ConstraintDev ct, int regular, uint2* out) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_boxes) return;
+  uint32_t sa, sb, sc, sd;
+  box_unrank(bm.global(i), sa, sb, sc, sd);
+  const uint8_t* U = ct.seg_uniform;
+  const uint32_t S = (uint32_t)ct.n_seg;
+  const bool reg = regular && sa < sb && sb < sc && sc < sd && U[sa * S + sb] && U[sb * S + sc] && U[sc * S + sd];
+  out[i] = make_uint2(sa | (sb << 16), sc | (sd << 16) | (reg ? 0x80000000u : 0u));
+}
 
 // Fused mode: the counts never leave the registers. The epilogue applies K3 (filter + constraint
 // removal + scalars) and K4 (edge-score scatter into Z) per cell; no cell table exists in HBM.
@@ -135,11 +151,28 @@ k_count(CountParams prm, FusedParams fz, ConstraintDev ct) {
 
   if (tid == 0) {
     uint32_t sa, sb, sc, sd;
-    box_unrank(prm.bm.global(blockIdx.x), sa, sb, sc, sd);
+    bool reg;
+    if (prm.desc) {
+      const uint2 d = __ldg(prm.desc + prm.bm.first + blockIdx.x);
+      sa = d.x & 0xFFFFu;
+      sb = d.x >> 16;
+      sc = d.y & 0xFFFFu;
+      sd = (d.y >> 16) & 0x7FFFu;
+      reg = (d.y >> 31) != 0;
+    } else {
+      box_unrank(prm.bm.global(blockIdx.x), sa, sb, sc, sd);
+      reg = false;
+      if constexpr (kFused) {
+        const uint8_t* U = ct.seg_uniform;
+        const uint32_t S = (uint32_t)ct.n_seg;
+        reg = fz.regular && sa < sb && sb < sc && sc < sd && U[sa * S + sb] && U[sb * S + sc] && U[sc * S + sd];
+      }
+    }
     s_seg[0] = sa;
     s_seg[1] = sb;
     s_seg[2] = sc;
     s_seg[3] = sd;
+    s_seg[4] = reg;
     auto slot = [&](uint32_t s0, uint32_t s1, uint32_t s2) {
       const uint64_t t = tile_index(s0, s1, s2);
       return prm.tile_slot ? (uint64_t)__ldg(prm.tile_slot + t) : t;
@@ -148,11 +181,6 @@ k_count(CountParams prm, FusedParams fz, ConstraintDev ct) {
     s_tile[1] = slot(sa, sb, sd);
     s_tile[2] = slot(sa, sc, sd);
     s_tile[3] = slot(sb, sc, sd);
-    if constexpr (kFused) {
-      const uint8_t* U = ct.seg_uniform;
-      const uint32_t S = (uint32_t)ct.n_seg;
-      s_seg[4] = fz.regular && sa < sb && sb < sc && sc < sd && U[sa * S + sb] && U[sb * S + sc] && U[sc * S + sd];
-    }
     for (int s = 0; s < kCountStages; ++s) {
       mbar_init(&bars[s], 1);
       s_done[s] = 0;
@@ -219,7 +247,7 @@ k_count(CountParams prm, FusedParams fz, ConstraintDev ct) {
       // 3-stage ring: everyone has finished group g-1, its stage is refilled with g+2
       if (g > 0) {
         __syncthreads();
-        if (tid == 0 && g + 2 < G) issue(g + 2);
+        if (tid == 0 && g + 2 < G && !(kFused && fz.debug == 3)) issue(g + 2);
       }
     } else {
       // One CTA barrier per TWO groups: at even g everyone has finished groups g-2 and g-1, whose
@@ -352,6 +380,15 @@ k_count(CountParams prm, FusedParams fz, ConstraintDev ct) {
             out[cell_local(2 * ta + i, 2 * tb + j, 2 * tc + kk, 2 * td + ll)] = make_uint4(c[0], c[1], c[2], 0u);
           }
   } else {
+    if (fz.debug >= 2) {  // timing decomposition only: the main loop alone (results are wrong on purpose)
+      uint32_t keep = 0;
+#pragma unroll
+      for (int c = 0; c < 16; ++c)
+#pragma unroll
+        for (int t = 0; t < kCnt; ++t) keep ^= cnt[c][t];
+      if (keep == 0xFFFFFFFFu) fz.totals[0] = keep;  // keeps the counters alive
+      return;
+    }
     // ---- fused K3 + K4 on the register-resident counts ----
     // Round-1 profile: 27 % of the kernel's instructions were in this epilogue (~140 per cell, a
     // dozen branches each). It is now one branch-free pass per cell (~45 instructions):
@@ -518,7 +555,7 @@ k_count(CountParams prm, FusedParams fz, ConstraintDev ct) {
     }
 
     // queue pass (one copy of this code): survivors of an irregular box, deferred ties of any box
-    if (qn) {
+    if (qn && fz.debug != 1) {
       unsigned long long* Zrep = fz.Z + (size_t)(blockIdx.x % (unsigned)fz.z_rep) * fz.z_stride;
       GlobalAcc acc{Zrep};
 #pragma unroll 1
