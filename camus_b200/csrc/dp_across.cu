@@ -1,0 +1,472 @@
+// DP offload: the across-scan of the level-1 network DP on the GPU.
+//
+// Reference: infer/main_dp.go:178-216 (scoreAddEdgeK) visits every u of one child subtree of v in
+// post-order and, for each, every w of the other child subtree in preorder (scoreEdgesAcross,
+// main_dp.go:247-287); per (u, w) it runs FourWayBestSplit (infer/helpers.go:83-110) over the four
+// lists cycleDP.scores[w], cycleDP.scores[u], DP[w], DP[u] -- O(k^2) additions per pair and step, which
+// is where the DP's time goes (float score modes at 1000 taxa: minutes on the host).
+//
+// Here one thread evaluates one (u, w) pair LITERALLY: the same sums in the same order, the same
+// first-maximum tie-breaks (BestSplit, helpers.go:51-72: `cur > best || !found` scanning the left index
+// upwards), the final score as edge + cs_w + cs_u + dp_w + dp_u left to right (main_dp.go:268), so
+// float (norm / sym) scores are bit-identical to Go's. The only shortcut: c1[i] (the best split of
+// cs_w / cs_u into i edges) is computed just for the i the last BestSplit can reach.
+//
+// Reduction, equal to the reference's sequential acceptance when no score is NaN:
+//   inside one u : first maximum over w in preorder (`score > bestScore || traceback == nil`);
+//   across the u : maximum score, then the smallest cycle length, then the LAST u in visiting order
+//                  (`curScore == bestScore && cycleLen <= bestCycleLen`, main_dp.go:206).
+// A NaN score anywhere sets a flag and the caller redoes the step on the host.
+//
+// The DP driver (post-order over v, the k loop, cycleDP.update, traceback) stays with the caller:
+// camus_b200/host/dp.hpp here, unchanged Go in the drop-in.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "camus_b200.h"
+
+namespace {
+
+template <class T>
+struct Buf {
+  T* p = nullptr;
+  size_t n = 0;
+  ~Buf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  cudaError_t alloc(size_t count) {
+    if (count <= n && p) return cudaSuccess;
+    release();
+    if (count == 0) return cudaSuccess;
+    cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+    if (e == cudaSuccess) n = count;
+    return e;
+  }
+};
+
+struct ItemBest {
+  unsigned long long score;  // raw 8 bytes (u64 or f64)
+  int ok, u, w, len;
+  int idx[4];
+};
+
+struct StepOut {
+  ItemBest best;
+  int item;
+  int nan_seen;
+};
+
+template <class S>
+__device__ __forceinline__ S as_score(unsigned long long raw) {
+  if constexpr (sizeof(S) == 8 && !std::is_integral<S>::value) return __longlong_as_double((long long)raw);
+  else return (S)raw;
+}
+template <class S>
+__device__ __forceinline__ unsigned long long raw_of(S v) {
+  if constexpr (sizeof(S) == 8 && !std::is_integral<S>::value) return (unsigned long long)__double_as_longlong(v);
+  else return (unsigned long long)v;
+}
+template <class S>
+__device__ __forceinline__ bool is_nan(S v) {
+  if constexpr (std::is_integral<S>::value) return false;
+  else return v != v;
+}
+
+// pending DP[node] lists -> node-major table
+__global__ void k_dp_scatter(int n_pending, const int* __restrict__ desc /*[3*n_pending]: node, len, offset*/,
+                             const unsigned long long* __restrict__ blob, unsigned long long* dp, int* dplen, int dcap) {
+  const int p = blockIdx.x;
+  if (p >= n_pending) return;
+  const int node = desc[3 * p], len = desc[3 * p + 1], off = desc[3 * p + 2];
+  for (int j = threadIdx.x; j < len; j += blockDim.x) dp[(size_t)node * dcap + j] = blob[off + j];
+  if (threadIdx.x == 0) dplen[node] = len;
+}
+
+__global__ void k_dp_repack(const unsigned long long* __restrict__ src, unsigned long long* dst, int n, int old_cap, int new_cap) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)n * old_cap) return;
+  dst[(i / old_cap) * new_cap + i % old_cap] = src[i];
+}
+
+constexpr int kAcrossThreads = 128;
+
+// One block per item (u, other subtree). cs: [k][n] (column of every path length), dp: [n][dcap].
+template <class S>
+__global__ void __launch_bounds__(kAcrossThreads)
+k_dp_across(int n_items, const int* __restrict__ items /*[2*n_items]: u, sub*/, const int* __restrict__ sub_end,
+            const int* __restrict__ depth, int v, int k, int n, int dcap, const unsigned long long* __restrict__ cs_raw,
+            const unsigned long long* __restrict__ dp_raw, const int* __restrict__ dplen,
+            const unsigned long long* __restrict__ edge_raw, ItemBest* item_best, StepOut* out, unsigned int* counter) {
+  extern __shared__ unsigned long long sh_raw[];
+  S* B = reinterpret_cast<S*>(sh_raw);  // cs_u[0..k]
+  S* D = B + (k + 1);                   // dp_u[0..Ld)
+  __shared__ unsigned long long r_score[kAcrossThreads];
+  __shared__ int r_w[kAcrossThreads], r_ok[kAcrossThreads];
+  __shared__ int r_idx[kAcrossThreads][4];
+  __shared__ int s_last;
+  const S* cs = reinterpret_cast<const S*>(cs_raw);
+  const S* dp = reinterpret_cast<const S*>(dp_raw);
+  const S* edge = reinterpret_cast<const S*>(edge_raw);
+  const int tid = threadIdx.x;
+  const int it = blockIdx.x;
+  const int u = items[2 * it], sub = items[2 * it + 1];
+  const int end = sub_end[sub];
+  const int Ld = dplen[u];
+  for (int j = tid; j <= k; j += kAcrossThreads) B[j] = cs[(size_t)j * n + u];
+  for (int j = tid; j < Ld; j += kAcrossThreads) D[j] = dp[(size_t)u * dcap + j];
+  __syncthreads();
+
+  bool ok = false, nan_seen = false;
+  S best{};
+  int bw = 0, bidx[4] = {0, 0, 0, 0};
+  for (int w = sub + tid; w < end; w += kAcrossThreads) {
+    const S* A = cs + w;                     // A[j] = A[j * n]
+    const S* C = dp + (size_t)w * dcap;
+    const int Lc = dplen[w];
+    // FourWayBestSplit (helpers.go:83-110): lists {cs_w, cs_u, dp_w, dp_u}, both cs lists hold k + 1 entries
+    const int m2 = min(k, Lc + Ld - 2) + 1;  // entries SolveAllSplits(dp_w, dp_u) produces
+    bool found = false;
+    S top{};
+    int ti[4] = {0, 0, 0, 0};
+    for (int i = k - (m2 - 1); i <= k; ++i) {
+      S c1 = A[0] + B[i];  // BestSplit(cs_w, cs_u, i): left index 0..i
+      int a1 = 0;
+      for (int j = 1; j <= i; ++j) {
+        const S cur = A[(size_t)j * n] + B[i - j];
+        if (cur > c1) {
+          c1 = cur;
+          a1 = j;
+        }
+      }
+      const int i2 = k - i;  // BestSplit(dp_w, dp_u, i2)
+      const int lo2 = max(0, i2 - (Ld - 1)), hi2 = min(i2, Lc - 1);
+      S c2 = C[lo2] + D[i2 - lo2];
+      int cc = lo2;
+      for (int j = lo2 + 1; j <= hi2; ++j) {
+        const S cur = C[j] + D[i2 - j];
+        if (cur > c2) {
+          c2 = cur;
+          cc = j;
+        }
+      }
+      const S cur = c1 + c2;
+      if (!found || cur > top) {
+        top = cur;
+        ti[0] = a1;
+        ti[1] = i - a1;
+        ti[2] = cc;
+        ti[3] = i2 - cc;
+        found = true;
+      }
+    }
+    S score = edge[(size_t)u * n + w];  // main_dp.go:268, left to right
+    score = score + A[(size_t)ti[0] * n];
+    score = score + B[ti[1]];
+    score = score + C[ti[2]];
+    score = score + D[ti[3]];
+    nan_seen |= is_nan(score);
+    if (!ok || score > best) {
+      ok = true;
+      best = score;
+      bw = w;
+      for (int q = 0; q < 4; ++q) bidx[q] = ti[q];
+    }
+  }
+  if (nan_seen) atomicOr(&out->nan_seen, 1);
+  r_score[tid] = raw_of<S>(best);
+  r_w[tid] = bw;
+  r_ok[tid] = ok;
+  for (int q = 0; q < 4; ++q) r_idx[tid][q] = bidx[q];
+  __syncthreads();
+  // first maximum over w: larger score, or equal score and smaller w
+  for (int s = kAcrossThreads / 2; s > 0; s >>= 1) {
+    if (tid < s && r_ok[tid + s]) {
+      const S a = as_score<S>(r_score[tid]), b = as_score<S>(r_score[tid + s]);
+      if (!r_ok[tid] || b > a || (b == a && r_w[tid + s] < r_w[tid])) {
+        r_score[tid] = r_score[tid + s];
+        r_w[tid] = r_w[tid + s];
+        r_ok[tid] = 1;
+        for (int q = 0; q < 4; ++q) r_idx[tid][q] = r_idx[tid + s][q];
+      }
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    ItemBest ib;
+    ib.score = r_score[0];
+    ib.ok = r_ok[0];
+    ib.u = u;
+    ib.w = r_w[0];
+    ib.len = ib.ok ? (depth[u] - depth[v]) + (depth[ib.w] - depth[v]) + 1 : 0;  // CycleLength, u not above w
+    for (int q = 0; q < 4; ++q) ib.idx[q] = r_idx[0][q];
+    item_best[it] = ib;
+    __threadfence();
+    s_last = atomicAdd(counter, 1u) == (unsigned)n_items - 1;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // the last block folds the items: max score, then min cycle length, then the last item
+  int mine = -1;
+  ItemBest mb{};
+  for (int i = tid; i < n_items; i += kAcrossThreads) {
+    const ItemBest c = item_best[i];
+    if (!c.ok) continue;
+    bool take = mine < 0;
+    if (!take) {
+      const S a = as_score<S>(mb.score), b = as_score<S>(c.score);
+      take = b > a || (b == a && c.len <= mb.len);  // i increases: equal length -> the later item
+    }
+    if (take) {
+      mb = c;
+      mine = i;
+    }
+  }
+  __shared__ ItemBest f_best[kAcrossThreads];
+  __shared__ int f_item[kAcrossThreads];
+  f_best[tid] = mb;
+  f_item[tid] = mine;
+  __syncthreads();
+  for (int s = kAcrossThreads / 2; s > 0; s >>= 1) {
+    if (tid < s && f_item[tid + s] >= 0) {
+      bool take = f_item[tid] < 0;
+      if (!take) {
+        const S a = as_score<S>(f_best[tid].score), b = as_score<S>(f_best[tid + s].score);
+        take = b > a || (b == a && (f_best[tid + s].len < f_best[tid].len ||
+                                    (f_best[tid + s].len == f_best[tid].len && f_item[tid + s] > f_item[tid])));
+      }
+      if (take) {
+        f_best[tid] = f_best[tid + s];
+        f_item[tid] = f_item[tid + s];
+      }
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    out->best = f_best[0];
+    out->item = f_item[0];
+    if (f_item[0] < 0) out->best.ok = 0;
+    *counter = 0;
+  }
+}
+
+}  // namespace
+
+struct camus_b200_dp {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool f64 = false;
+  int n = 0;
+  int kcap = 0, dcap = 0;
+  Buf<int> d_end, d_depth, d_dplen, d_items, d_desc;
+  Buf<unsigned long long> d_edge, d_cs, d_dp, d_blob;
+  Buf<ItemBest> d_item_best;
+  Buf<StepOut> d_out;
+  Buf<unsigned int> d_counter;
+  StepOut* h_out = nullptr;  // pinned
+  int n_items = 0, cur_v = -1;
+  std::vector<int> pend_desc;
+  std::vector<unsigned long long> pend_blob;
+  std::string err;
+  uint64_t launches = 0;
+  int fail(int code, const std::string& m) {
+    err = m;
+    return code;
+  }
+};
+
+static thread_local std::string g_dp_create_err;
+
+#define DCK(call)                                                                                      \
+  do {                                                                                                 \
+    cudaError_t e_ = (call);                                                                           \
+    if (e_ != cudaSuccess) return dp->fail(CAMUS_B200_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+extern "C" {
+
+int camus_b200_dp_create(camus_b200_dp** out, int device, int score_is_f64, int32_t n_nodes, const int32_t* subtree_end,
+                         const int32_t* depth, const void* edge_scores) {
+  if (!out || !subtree_end || !depth || !edge_scores || n_nodes < 1) {
+    g_dp_create_err = "camus_b200_dp_create: null argument or no nodes";
+    return CAMUS_B200_ERR_ARG;
+  }
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) {
+    g_dp_create_err = "camus_b200_dp_create: no such CUDA device (there is no CPU fallback)";
+    return CAMUS_B200_ERR_CUDA;
+  }
+  auto* dp = new camus_b200_dp();
+  dp->device = device;
+  dp->f64 = score_is_f64 != 0;
+  dp->n = n_nodes;
+  auto bail = [&](const char* what, cudaError_t e) {
+    g_dp_create_err = std::string("camus_b200_dp_create: ") + what + ": " + cudaGetErrorString(e);
+    camus_b200_dp_destroy(dp);
+    return CAMUS_B200_ERR_CUDA;
+  };
+  cudaError_t e;
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
+  if ((e = cudaStreamCreateWithFlags(&dp->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
+  if ((e = cudaMallocHost(&dp->h_out, sizeof(StepOut))) != cudaSuccess) return bail("pinned result", e);
+  const size_t n = (size_t)n_nodes;
+  dp->kcap = 32;
+  dp->dcap = 16;
+  if ((e = dp->d_end.alloc(n)) != cudaSuccess || (e = dp->d_depth.alloc(n)) != cudaSuccess || (e = dp->d_dplen.alloc(n)) != cudaSuccess ||
+      (e = dp->d_edge.alloc(n * n)) != cudaSuccess || (e = dp->d_cs.alloc(n * dp->kcap)) != cudaSuccess ||
+      (e = dp->d_dp.alloc(n * dp->dcap)) != cudaSuccess || (e = dp->d_item_best.alloc(n)) != cudaSuccess ||
+      (e = dp->d_items.alloc(2 * n)) != cudaSuccess || (e = dp->d_out.alloc(1)) != cudaSuccess || (e = dp->d_counter.alloc(1)) != cudaSuccess)
+    return bail("cudaMalloc", e);
+  std::vector<int> ones(n, 1);  // tips: DP[tip] = {0} (main_dp.go:98-100)
+  if ((e = cudaMemcpyAsync(dp->d_end.p, subtree_end, n * 4, cudaMemcpyHostToDevice, dp->stream)) != cudaSuccess ||
+      (e = cudaMemcpyAsync(dp->d_depth.p, depth, n * 4, cudaMemcpyHostToDevice, dp->stream)) != cudaSuccess ||
+      (e = cudaMemcpyAsync(dp->d_dplen.p, ones.data(), n * 4, cudaMemcpyHostToDevice, dp->stream)) != cudaSuccess ||
+      (e = cudaMemcpyAsync(dp->d_edge.p, edge_scores, n * n * 8, cudaMemcpyHostToDevice, dp->stream)) != cudaSuccess ||
+      (e = cudaMemsetAsync(dp->d_dp.p, 0, n * dp->dcap * 8, dp->stream)) != cudaSuccess ||
+      (e = cudaMemsetAsync(dp->d_cs.p, 0, n * dp->kcap * 8, dp->stream)) != cudaSuccess ||
+      (e = cudaMemsetAsync(dp->d_counter.p, 0, 4, dp->stream)) != cudaSuccess || (e = cudaStreamSynchronize(dp->stream)) != cudaSuccess)
+    return bail("upload", e);
+  *out = dp;
+  return CAMUS_B200_OK;
+}
+
+void camus_b200_dp_destroy(camus_b200_dp* dp) {
+  if (!dp) return;
+  cudaSetDevice(dp->device);
+  if (dp->stream) cudaStreamDestroy(dp->stream);
+  if (dp->h_out) cudaFreeHost(dp->h_out);
+  delete dp;
+}
+
+const char* camus_b200_dp_last_error(const camus_b200_dp* dp) { return dp ? dp->err.c_str() : g_dp_create_err.c_str(); }
+
+int camus_b200_dp_set_node(camus_b200_dp* dp, int32_t node, int32_t len, const void* scores) {
+  if (!dp) return CAMUS_B200_ERR_ARG;
+  if (node < 0 || node >= dp->n || len < 1 || !scores) return dp->fail(CAMUS_B200_ERR_ARG, "dp_set_node: node out of range or empty list");
+  dp->pend_desc.push_back(node);
+  dp->pend_desc.push_back(len);
+  dp->pend_desc.push_back((int)dp->pend_blob.size());
+  const auto* v = static_cast<const unsigned long long*>(scores);
+  dp->pend_blob.insert(dp->pend_blob.end(), v, v + len);
+  return CAMUS_B200_OK;
+}
+
+static int flush_nodes(camus_b200_dp* dp) {
+  if (dp->pend_desc.empty()) return CAMUS_B200_OK;
+  int need = dp->dcap;
+  for (size_t i = 0; i < dp->pend_desc.size(); i += 3) need = std::max(need, dp->pend_desc[i + 1]);
+  if (need > dp->dcap) {
+    int cap = dp->dcap;
+    while (cap < need) cap *= 2;
+    Buf<unsigned long long> bigger;
+    DCK(bigger.alloc((size_t)dp->n * cap));
+    DCK(cudaMemsetAsync(bigger.p, 0, (size_t)dp->n * cap * 8, dp->stream));
+    const size_t tot = (size_t)dp->n * dp->dcap;
+    k_dp_repack<<<(unsigned)((tot + 255) / 256), 256, 0, dp->stream>>>(dp->d_dp.p, bigger.p, dp->n, dp->dcap, cap);
+    DCK(cudaGetLastError());
+    DCK(cudaStreamSynchronize(dp->stream));
+    std::swap(dp->d_dp.p, bigger.p);
+    std::swap(dp->d_dp.n, bigger.n);
+    dp->dcap = cap;
+    ++dp->launches;
+  }
+  const int np = (int)(dp->pend_desc.size() / 3);
+  DCK(dp->d_desc.alloc(dp->pend_desc.size()));
+  DCK(dp->d_blob.alloc(dp->pend_blob.size()));
+  DCK(cudaMemcpyAsync(dp->d_desc.p, dp->pend_desc.data(), dp->pend_desc.size() * 4, cudaMemcpyHostToDevice, dp->stream));
+  DCK(cudaMemcpyAsync(dp->d_blob.p, dp->pend_blob.data(), dp->pend_blob.size() * 8, cudaMemcpyHostToDevice, dp->stream));
+  k_dp_scatter<<<np, 32, 0, dp->stream>>>(np, dp->d_desc.p, dp->d_blob.p, dp->d_dp.p, dp->d_dplen.p, dp->dcap);
+  DCK(cudaGetLastError());
+  DCK(cudaStreamSynchronize(dp->stream));  // the host vectors are reused
+  ++dp->launches;
+  dp->pend_desc.clear();
+  dp->pend_blob.clear();
+  return CAMUS_B200_OK;
+}
+
+int camus_b200_dp_set_vertex(camus_b200_dp* dp, int32_t v, int32_t n_items, const int32_t* item_u, const int32_t* item_sub) {
+  if (!dp) return CAMUS_B200_ERR_ARG;
+  if (v < 0 || v >= dp->n || n_items < 0 || n_items > dp->n || (n_items && (!item_u || !item_sub)))
+    return dp->fail(CAMUS_B200_ERR_ARG, "dp_set_vertex: bad vertex or item list");
+  cudaSetDevice(dp->device);
+  std::vector<int> it(2 * (size_t)n_items);
+  for (int i = 0; i < n_items; ++i) {
+    if (item_u[i] < 0 || item_u[i] >= dp->n || item_sub[i] < 0 || item_sub[i] >= dp->n) return dp->fail(CAMUS_B200_ERR_ARG, "dp_set_vertex: node out of range");
+    it[2 * i] = item_u[i];
+    it[2 * i + 1] = item_sub[i];
+  }
+  if (n_items) DCK(cudaMemcpyAsync(dp->d_items.p, it.data(), it.size() * 4, cudaMemcpyHostToDevice, dp->stream));
+  DCK(cudaStreamSynchronize(dp->stream));
+  dp->n_items = n_items;
+  dp->cur_v = v;
+  return CAMUS_B200_OK;
+}
+
+int camus_b200_dp_set_path_columns(camus_b200_dp* dp, int32_t k0, int32_t k1, int32_t first, int32_t count, const void* cols) {
+  if (!dp) return CAMUS_B200_ERR_ARG;
+  if (k0 < 0 || k1 < k0 || first < 0 || count < 0 || first + count > dp->n || (!cols && k1 > k0 && count))
+    return dp->fail(CAMUS_B200_ERR_ARG, "dp_set_path_columns: bad range");
+  cudaSetDevice(dp->device);
+  if (k1 > dp->kcap) {
+    int cap = dp->kcap;
+    while (cap < k1) cap *= 2;
+    Buf<unsigned long long> bigger;
+    DCK(bigger.alloc((size_t)dp->n * cap));
+    DCK(cudaMemsetAsync(bigger.p, 0, (size_t)dp->n * cap * 8, dp->stream));
+    DCK(cudaMemcpyAsync(bigger.p, dp->d_cs.p, (size_t)dp->n * dp->kcap * 8, cudaMemcpyDeviceToDevice, dp->stream));
+    DCK(cudaStreamSynchronize(dp->stream));
+    std::swap(dp->d_cs.p, bigger.p);
+    std::swap(dp->d_cs.n, bigger.n);
+    dp->kcap = cap;
+  }
+  if (k1 > k0 && count)
+    DCK(cudaMemcpy2DAsync(dp->d_cs.p + (size_t)k0 * dp->n + first, (size_t)dp->n * 8, cols, (size_t)count * 8, (size_t)count * 8, (size_t)(k1 - k0),
+                          cudaMemcpyHostToDevice, dp->stream));
+  DCK(cudaStreamSynchronize(dp->stream));  // the caller's buffer is free again
+  return CAMUS_B200_OK;
+}
+
+int camus_b200_dp_across(camus_b200_dp* dp, int32_t prev_k, camus_b200_dp_best* out) {
+  if (!dp || !out) return CAMUS_B200_ERR_ARG;
+  if (dp->cur_v < 0) return dp->fail(CAMUS_B200_ERR_ARG, "dp_across: set the vertex first");
+  if (prev_k < 0 || prev_k >= dp->kcap) return dp->fail(CAMUS_B200_ERR_ARG, "dp_across: path columns 0..prev_k have not been set");
+  cudaSetDevice(dp->device);
+  memset(out, 0, sizeof *out);
+  if (dp->n_items == 0) return CAMUS_B200_OK;
+  if (int rc = flush_nodes(dp)) return rc;
+  DCK(cudaMemsetAsync(dp->d_out.p, 0, sizeof(StepOut), dp->stream));
+  const size_t shm = (size_t)(prev_k + 1 + dp->dcap) * 8;
+  if (dp->f64)
+    k_dp_across<double><<<dp->n_items, kAcrossThreads, shm, dp->stream>>>(dp->n_items, dp->d_items.p, dp->d_end.p, dp->d_depth.p, dp->cur_v, prev_k, dp->n,
+                                                                          dp->dcap, dp->d_cs.p, dp->d_dp.p, dp->d_dplen.p, dp->d_edge.p,
+                                                                          dp->d_item_best.p, dp->d_out.p, dp->d_counter.p);
+  else
+    k_dp_across<unsigned long long><<<dp->n_items, kAcrossThreads, shm, dp->stream>>>(dp->n_items, dp->d_items.p, dp->d_end.p, dp->d_depth.p, dp->cur_v, prev_k,
+                                                                                      dp->n, dp->dcap, dp->d_cs.p, dp->d_dp.p, dp->d_dplen.p, dp->d_edge.p,
+                                                                                      dp->d_item_best.p, dp->d_out.p, dp->d_counter.p);
+  DCK(cudaGetLastError());
+  ++dp->launches;
+  DCK(cudaMemcpyAsync(dp->h_out, dp->d_out.p, sizeof(StepOut), cudaMemcpyDeviceToHost, dp->stream));
+  DCK(cudaStreamSynchronize(dp->stream));
+  const StepOut& r = *dp->h_out;
+  out->found = r.best.ok;
+  out->nan_seen = r.nan_seen;
+  out->score_bits = r.best.score;
+  out->u = r.best.u;
+  out->w = r.best.w;
+  out->cycle_length = r.best.len;
+  for (int q = 0; q < 4; ++q) out->split[q] = r.best.idx[q];
+  return CAMUS_B200_OK;
+}
+
+uint64_t camus_b200_dp_launches(const camus_b200_dp* dp) { return dp ? dp->launches : 0; }
+
+}  // extern "C"

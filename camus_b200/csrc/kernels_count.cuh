@@ -34,6 +34,9 @@ constexpr int kPlaneWords = kTileWords / 3;  // 512 words = 2 KB: one plane of o
 #ifndef CAMUS_COUNT_OCC4
 #define CAMUS_COUNT_OCC4 1  // 0 = A/B build of the round-1 shape of the complete-tree loop (3 CTAs per SM, 4-stage ring)
 #endif
+#ifndef CAMUS_COUNT_LANEMAP
+#define CAMUS_COUNT_LANEMAP 1  // 0 = A/B build of the round-1 lane order (ta ta tb tb tc)
+#endif
 #ifndef CAMUS_COUNT_NOBAR
 #define CAMUS_COUNT_NOBAR 0  // A/B build: no CTA barrier in the group loop, the last warp out of a stage refills it
 #endif
@@ -147,7 +150,15 @@ k_count(CountParams prm, FusedParams fz, ConstraintDev ct) {
   __shared__ uint64_t s_tile[4];  // slots of the tiles abc, abd, acd, bcd in prm.tri
 
   const int tid = threadIdx.x;
+  // Lane order. An LDS.128 costs 4 shared-memory wavefronts, or 2 when the four lanes of every
+  // aligned quad read at most two addresses (measured, tools/lds_probe.cu: the address must not
+  // depend on lane bit 0 or on lane bit 1). With lane bits (a0 b0 a1 b1 c0) the bcd operand ignores
+  // bit 0 and the acd operand bit 1: 48 wavefronts per thread and tree group instead of 56.
+#if CAMUS_COUNT_LANEMAP
+  const int ta = (tid & 1) | ((tid >> 1) & 2), tb = ((tid >> 1) & 1) | ((tid >> 2) & 2), tc = (tid >> 4) & 3, td = tid >> 6;
+#else
   const int ta = tid & 3, tb = (tid >> 2) & 3, tc = (tid >> 4) & 3, td = tid >> 6;
+#endif
 
   if (tid == 0) {
     uint32_t sa, sb, sc, sd;
@@ -495,16 +506,22 @@ k_count(CountParams prm, FusedParams fz, ConstraintDev ct) {
               ma[1][i] += w1; mb[1][j] += w1; mc[1][kk] += w1; md[1][ll] += w1;
             }
       // warp sums over the lanes that share the coordinate, one shared atomic per (warp, sum)
+#if CAMUS_COUNT_LANEMAP
+      const uint32_t mask_a = 0x05050505u << ((ta & 1) + 4 * (ta >> 1)), mask_b = 0x00330033u << (2 * (tb & 1) + 8 * (tb >> 1));
+      const bool lead_a = (lane & 0x1A) == 0, lead_b = (lane & 0x15) == 0;
+#else
       const uint32_t mask_a = 0x11111111u << ta, mask_b = 0x000F000Fu << (4 * tb);
+      const bool lead_a = lane < 4, lead_b = lane == 4 * tb;
+#endif
       const uint32_t mask_c = lane < 16 ? 0x0000FFFFu : 0xFFFF0000u;
 #pragma unroll
       for (int sl = 0; sl < 2; ++sl)
 #pragma unroll
         for (int par = 0; par < 2; ++par) {
           uint32_t v = __reduce_add_sync(mask_a, ma[sl][par]);
-          if (lane < 4 && v) atomicAdd(&s_marg[0][sl][2 * ta + par], v);
+          if (lead_a && v) atomicAdd(&s_marg[0][sl][2 * ta + par], v);
           v = __reduce_add_sync(mask_b, mb[sl][par]);
-          if (lane == 4 * tb && v) atomicAdd(&s_marg[1][sl][2 * tb + par], v);
+          if (lead_b && v) atomicAdd(&s_marg[1][sl][2 * tb + par], v);
           v = __reduce_add_sync(mask_c, mc[sl][par]);
           if ((lane & 15) == 0 && v) atomicAdd(&s_marg[2][sl][2 * tc + par], v);
           v = __reduce_add_sync(0xFFFFFFFFu, md[sl][par]);
