@@ -21,6 +21,20 @@ class CamusB200Error(RuntimeError):
     pass
 
 
+_dp_table = None
+
+
+def dp_accel_table():
+    """The eight camus_b200_dp_* entry points as an array of function pointers, in the order
+    camus_host_run_dp_accel expects (camus_b200/host/dp.hpp DpAccelApi)."""
+    global _dp_table
+    if _dp_table is None:
+        L = lib()
+        names = ("create", "destroy", "last_error", "set_node", "set_vertex", "set_path_columns", "across", "launches")
+        _dp_table = (C.c_void_p * 8)(*[C.cast(getattr(L, "camus_b200_dp_" + n), C.c_void_p).value for n in names])
+    return _dp_table
+
+
 def lib() -> C.CDLL:
     global _lib
     if _lib is None:
@@ -66,6 +80,8 @@ EXPORTED = [
     "camus_b200_export_quartets", "camus_b200_query_cells", "camus_b200_quartet_totals_partial", "camus_b200_partial_buffer",
     "camus_b200_quartet_totals_finish", "camus_b200_run_resident", "camus_b200_stage_ms", "camus_b200_workload",
     "camus_b200_reticulation_counts", "camus_b200_constraint_tables", "camus_b200_comm_unique_id", "camus_b200_comm_init",
+    "camus_b200_dp_create", "camus_b200_dp_destroy", "camus_b200_dp_last_error", "camus_b200_dp_set_node",
+    "camus_b200_dp_set_vertex", "camus_b200_dp_set_path_columns", "camus_b200_dp_across", "camus_b200_dp_launches",
 ]
 
 

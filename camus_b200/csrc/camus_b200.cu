@@ -124,6 +124,11 @@ struct camus_b200 {
   DevBuf<unsigned long long> d_scal;  // the two survivor scalars, all-reduced in place
   std::vector<int32_t> h_depth, h_nleaves, h_ref_of_int;  // constraint tables in internal ids (constraint_tables)
 
+  // ---- inputs beyond the bit-plane budget: the 8 class-scheme shares run one after the other on this GPU ----
+  int z_rep_used = 1;        // private copies of Z the running pass sequence uses
+  int passes = 1;            // 8 while such a run is in progress or was the last one
+  int passes_env = 0;        // CAMUS_B200_PASSES at create: 8 / 1 force the mode on / off (tests, A/B)
+  bool force_class = false;  // passes mode: class scheme whatever the number of segments (<= 256)
   bool allow_packed = true;  // CAMUS_B200_NO_PACKED=1 keeps the 3-register general kernel below 1024 trees (A/B, tests)
 
   float ms[CAMUS_B200_T_N] = {0};
@@ -190,6 +195,9 @@ int reduce_partials(camus_b200* ctx);
 void nccl_api_destroy(ncclComm_t comm);
 
 int build_planes(camus_b200* ctx, bool do_upload);
+bool planes_cover(camus_b200* ctx);
+int wanted_passes(camus_b200* ctx);
+int run_passes(camus_b200* ctx, int passes, int qmode, double threshold, int as_set, bool do_upload, uint64_t* ns, uint64_t* sum);
 int set_box_range(camus_b200* ctx);
 int run_count(camus_b200* ctx);
 int run_filter(camus_b200* ctx, int qmode, double threshold, uint64_t* ns, uint64_t* sum);
@@ -255,6 +263,7 @@ static int create_one(camus_b200** out, int dev) {
   if (const char* e = getenv("CAMUS_B200_NO_HALF")) ctx->allow_half = !(e[0] == '1');
   if (const char* e = getenv("CAMUS_B200_UNFUSED")) ctx->use_fused = !(e[0] == '1');
   if (const char* e = getenv("CAMUS_B200_NO_PACKED")) ctx->allow_packed = !(e[0] == '1');
+  if (const char* e = getenv("CAMUS_B200_PASSES")) ctx->passes_env = atoi(e);
   *out = ctx;
   return CAMUS_B200_OK;
 }
@@ -708,6 +717,7 @@ int make_thr_table(camus_b200* ctx, double threshold) {
 // (class still needs 4 or 8 shares). camus_b200/partition.py mirrors the rule.
 bool use_class_scheme(const camus_b200* ctx) {
   if (ctx->world != 4 && ctx->world != 8) return false;
+  if (ctx->force_class) return ctx->M <= 256;
   if (const char* e = getenv("CAMUS_B200_PARTITION")) {
     if (!strcmp(e, "chunk")) return false;
     if (!strcmp(e, "class")) return ctx->M <= 256;
@@ -776,7 +786,9 @@ int set_box_range(camus_b200* ctx) {
 
 // Fused K2+K3+K4 over this rank's box range: counts stay in registers, survivors are scored
 // straight into the junction table Z. No cell table.
-int run_fused(camus_b200* ctx, int qmode, double threshold, int as_set, uint64_t* ns, uint64_t* sum) {
+// pass_flags (passes mode): bit 0 = add to the junction table and the scalars of the earlier passes,
+// bit 1 = more passes follow (the private copies of Z are summed after the last one only)
+int run_fused(camus_b200* ctx, int qmode, double threshold, int as_set, uint64_t* ns, uint64_t* sum, int pass_flags = 0) {
   if (int rc = set_box_range(ctx)) return rc;
   uint64_t mine = ctx->n_local;
   size_t zn = (size_t)ctx->n * ctx->n * 3;
@@ -799,8 +811,13 @@ int run_fused(camus_b200* ctx, int qmode, double threshold, int as_set, uint64_t
   CK(ctx->d_totals.alloc(2));
   StageTimer t(ctx, CAMUS_B200_T_COUNT);
   if (make_thr_table(ctx, threshold)) return CAMUS_B200_ERR_CUDA;
-  CK(cudaMemsetAsync(ctx->d_Z.p, 0, zn * rep * 8, ctx->stream));
-  CK(cudaMemsetAsync(ctx->d_totals.p, 0, 16, ctx->stream));
+  if (!(pass_flags & 1)) {
+    CK(cudaMemsetAsync(ctx->d_Z.p, 0, zn * rep * 8, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_totals.p, 0, 16, ctx->stream));
+    ctx->z_rep_used = rep;
+  } else {
+    rep = ctx->z_rep_used;  // the copies the first pass zeroed
+  }
   static const int dbg = getenv("CAMUS_B200_DEBUG") ? atoi(getenv("CAMUS_B200_DEBUG")) : 0;
   FusedParams fz{qmode, threshold, ctx->d_thr_tab.p, as_set, ctx->d_Z.p, ctx->d_totals.p, rep, (unsigned long long)zn, ctx->allow_regular ? 1 : 0, dbg};
   // box descriptors (segments + regular flag), rebuilt only when the constraint or the partition changed
@@ -839,7 +856,7 @@ int run_fused(camus_b200* ctx, int qmode, double threshold, int as_set, uint64_t
       k_count<true, kModeGeneral><<<(unsigned)nbx, kCountThreads, CountCfg<kModeGeneral>::kSmemBytes, ctx->stream>>>(prm, fz, ctx->ct);
     CK_LAUNCH();
   }
-  if (rep > 1) {
+  if (rep > 1 && !(pass_flags & 2)) {
     k_sum_replicas<<<(unsigned)((zn + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_Z.p, zn, rep);
     CK_LAUNCH();
   }
@@ -855,6 +872,40 @@ int run_fused(camus_b200* ctx, int qmode, double threshold, int as_set, uint64_t
   ctx->z_as_set = as_set;
   ctx->counted = true;
   return 0;
+}
+
+// Inputs beyond the bit-plane budget (12 * tiles * ceil(G/32) * 512 bytes): the 8 shares of the class
+// scheme (layout.cuh) are run one after the other on this GPU. A share reads, and so builds, only the
+// tiles led by 2 of the 4 segment classes = half of the table; the junction table and the two scalars
+// accumulate over the passes (integer sums: the result is the one-pass result). Chosen automatically
+// when the whole table does not fit beside the junction tables; CAMUS_B200_PASSES=8 / =1 force it.
+int wanted_passes(camus_b200* ctx) {
+  const int env = ctx->passes_env;
+  if (!ctx->use_fused || ctx->world != 1 || !ctx->subs.empty() || ctx->comm || ctx->M > 256 || ctx->want_all_tiles) return 1;
+  if (env == 8 || env == 1) return env;
+  const size_t full = (size_t)num_tiles(ctx->M) * std::max((ctx->G + kLanes - 1) / kLanes, 1) * kTileBytes;
+  const size_t zn = (size_t)ctx->n * ctx->n * 3 * 8;
+  const size_t z = std::min<size_t>(zn * 128, (size_t)16 << 30);
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return 1;
+  const size_t avail = free_b + ctx->d_tri.bytes() + ctx->d_Z.bytes();
+  return full + z + ((size_t)4 << 30) > avail ? 8 : 1;
+}
+
+int run_passes(camus_b200* ctx, int passes, int qmode, double threshold, int as_set, bool do_upload, uint64_t* ns, uint64_t* sum) {
+  ctx->passes = passes;
+  int rc = 0;
+  for (int p = 0; p < passes && !rc; ++p) {
+    ctx->rank = p;
+    ctx->world = passes;
+    ctx->force_class = true;
+    rc = build_planes(ctx, do_upload && p == 0);
+    if (!rc) rc = run_fused(ctx, qmode, threshold, as_set, ns, sum, (p > 0 ? 1 : 0) | (p + 1 < passes ? 2 : 0));
+  }
+  ctx->rank = 0;
+  ctx->world = 1;
+  ctx->force_class = false;
+  return rc;
 }
 
 // K2 (table mode) over this rank's box range (whole range resident in d_cells).
@@ -921,7 +972,13 @@ int ensure_filtered(camus_b200* ctx) {
 int run_score(camus_b200* ctx, int as_set) {
   if (!ctx->counted) return ctx->fail(CAMUS_B200_ERR_ARG, "call camus_b200_count_filter first");
   if (ctx->z_valid && ctx->z_as_set == as_set) return 0;
-  if (ctx->use_fused) return run_fused(ctx, ctx->last_qmode, ctx->last_threshold, as_set, nullptr, nullptr);
+  if (ctx->use_fused) {
+    const int passes = wanted_passes(ctx);
+    if (passes > 1) return run_passes(ctx, passes, ctx->last_qmode, ctx->last_threshold, as_set, false, nullptr, nullptr);
+    if (!planes_cover(ctx))  // the last run went through the passes: its bit-planes are one share's
+      if (int rc = build_planes(ctx, false)) return rc;
+    return run_fused(ctx, ctx->last_qmode, ctx->last_threshold, as_set, nullptr, nullptr);
+  }
   int rc = ensure_filtered(ctx);
   if (rc) return rc;
   size_t zn = (size_t)ctx->n * ctx->n * 3;
@@ -1116,6 +1173,17 @@ int camus_b200_count_filter(camus_b200* ctx, int qmode, double threshold, uint64
   ctx->launches = 0;
   ctx->want_all_tiles = false;  // a camus_b200_query_cells probe asks again
   int rc;
+  const int passes = wanted_passes(ctx);
+  if (passes > 1) {
+    ctx->cell_state = camus_b200::NONE;
+    ctx->z_valid = false;
+    uint64_t pns = 0, psc = 0;
+    if ((rc = run_passes(ctx, passes, qmode, threshold, ctx->as_set_hint, ctx->genes_dirty, &pns, &psc))) return rc;
+    if (n_survivors) *n_survivors = pns;
+    if (sum_counts) *sum_counts = psc;
+    return 0;
+  }
+  ctx->passes = 1;
   if (ctx->genes_dirty) {
     if ((rc = build_planes(ctx, true))) return rc;
   } else if (!planes_cover(ctx) && (rc = build_planes(ctx, false))) {  // the partition changed under resident trees
@@ -1171,10 +1239,21 @@ int camus_b200_run_resident(camus_b200* ctx, int qmode, double threshold, int as
   ctx->launches = 0;
   ctx->want_all_tiles = false;
   int rc;
+  const int passes = wanted_passes(ctx);
+  uint64_t ns = 0, sc = 0;
+  if (passes > 1) {
+    ctx->cell_state = camus_b200::NONE;
+    ctx->z_valid = false;
+    if ((rc = run_passes(ctx, passes, qmode, threshold, as_set != 0, false, &ns, &sc))) return rc;
+    if (n_survivors) *n_survivors = ns;
+    if (sum_counts) *sum_counts = sc;
+    if (!out) return 0;
+    return run_finish(ctx, out);
+  }
+  ctx->passes = 1;
   if ((rc = build_planes(ctx, false))) return rc;
   ctx->cell_state = camus_b200::NONE;
   ctx->z_valid = false;
-  uint64_t ns = 0, sc = 0;
   if (ctx->use_fused) {
     if ((rc = run_fused(ctx, qmode, threshold, as_set != 0, &ns, &sc))) return rc;
   } else {

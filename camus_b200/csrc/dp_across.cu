@@ -16,7 +16,12 @@
 //   inside one u : first maximum over w in preorder (`score > bestScore || traceback == nil`);
 //   across the u : maximum score, then the smallest cycle length, then the LAST u in visiting order
 //                  (`curScore == bestScore && cycleLen <= bestCycleLen`, main_dp.go:206).
-// A NaN score anywhere sets a flag and the caller redoes the step on the host.
+// NaN scores are real in norm mode (0 / 0 for the length-3 cycle between the two children of v,
+// which scoreEdgesAcross does not exclude) and the reference's comparisons give them a definite fate:
+// inside one u a NaN is kept only when it belongs to the FIRST w (then nothing replaces it), across
+// the u a NaN candidate is kept only when nothing was accepted before it (then nothing replaces it
+// either). So the fold above runs over the non-NaN candidates, and item 0's candidate is returned
+// separately when it is NaN: the caller takes it iff it has no candidate of its own (scoreEdgesDown).
 //
 // The DP driver (post-order over v, the k loop, cycleDP.update, traceback) stays with the caller:
 // camus_b200/host/dp.hpp here, unchanged Go in the drop-in.
@@ -26,6 +31,7 @@
 #include <cstdint>
 #include <cstring>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "camus_b200.h"
@@ -59,9 +65,10 @@ struct ItemBest {
 };
 
 struct StepOut {
-  ItemBest best;
+  ItemBest best;   // fold over the items whose score is not NaN
   int item;
-  int nan_seen;
+  int nan_seen;    // statistic: some pair scored NaN
+  ItemBest first;  // item 0 when its score is NaN (first.ok), see the header comment
 };
 
 template <class S>
@@ -96,51 +103,70 @@ __global__ void k_dp_repack(const unsigned long long* __restrict__ src, unsigned
   dst[(i / old_cap) * new_cap + i % old_cap] = src[i];
 }
 
+// path columns [k0, k1) of nodes [first, first + count), as uploaded -> node-major table
+__global__ void k_cs_scatter(const unsigned long long* __restrict__ cols, unsigned long long* cs, int kcap, int k0, int nk, int first, int count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nk * count) return;
+  const int jj = i / count, x = i % count;
+  cs[(size_t)(first + x) * kcap + k0 + jj] = cols[i];
+}
+
 constexpr int kAcrossThreads = 128;
 
-// One block per item (u, other subtree). cs: [k][n] (column of every path length), dp: [n][dcap].
+// One block per (item, chunk of 128 consecutive w): one thread evaluates one (u, w) pair, so the work
+// of a heavy u (long DP[u]: (K_u + K_w) * k additions per pair) is spread over many blocks.
+// cs: [n][kcap], dp: [n][dcap] (node-major: a thread walks its own rows).
+struct ChunkBest {
+  unsigned long long score;
+  int ok, w, stuck;  // stuck: the chunk holds the item's FIRST w and its score is NaN
+  int idx[4];
+};
+
 template <class S>
 __global__ void __launch_bounds__(kAcrossThreads)
-k_dp_across(int n_items, const int* __restrict__ items /*[2*n_items]: u, sub*/, const int* __restrict__ sub_end,
-            const int* __restrict__ depth, int v, int k, int n, int dcap, const unsigned long long* __restrict__ cs_raw,
-            const unsigned long long* __restrict__ dp_raw, const int* __restrict__ dplen,
-            const unsigned long long* __restrict__ edge_raw, ItemBest* item_best, StepOut* out, unsigned int* counter) {
+k_dp_across(int n_items, int n_blocks, const int* __restrict__ items /*[2*n_items]: u, sub*/, const int* __restrict__ blk_item,
+            const int* __restrict__ item_blk0 /*[n_items+1]*/, const int* __restrict__ sub_end, const int* __restrict__ depth, int v, int k, int n,
+            int kcap, int dcap, const unsigned long long* __restrict__ cs_raw, const unsigned long long* __restrict__ dp_raw,
+            const int* __restrict__ dplen, const unsigned long long* __restrict__ edge_raw, ChunkBest* chunk_best, StepOut* out,
+            unsigned int* counter) {
   extern __shared__ unsigned long long sh_raw[];
   S* B = reinterpret_cast<S*>(sh_raw);  // cs_u[0..k]
   S* D = B + (k + 1);                   // dp_u[0..Ld)
   __shared__ unsigned long long r_score[kAcrossThreads];
   __shared__ int r_w[kAcrossThreads], r_ok[kAcrossThreads];
   __shared__ int r_idx[kAcrossThreads][4];
-  __shared__ int s_last;
+  __shared__ int s_last, s_stuck;
   const S* cs = reinterpret_cast<const S*>(cs_raw);
   const S* dp = reinterpret_cast<const S*>(dp_raw);
   const S* edge = reinterpret_cast<const S*>(edge_raw);
   const int tid = threadIdx.x;
-  const int it = blockIdx.x;
+  const int it = blk_item[blockIdx.x];
+  const int chunk = blockIdx.x - item_blk0[it];
   const int u = items[2 * it], sub = items[2 * it + 1];
   const int end = sub_end[sub];
   const int Ld = dplen[u];
-  for (int j = tid; j <= k; j += kAcrossThreads) B[j] = cs[(size_t)j * n + u];
+  for (int j = tid; j <= k; j += kAcrossThreads) B[j] = cs[(size_t)u * kcap + j];
   for (int j = tid; j < Ld; j += kAcrossThreads) D[j] = dp[(size_t)u * dcap + j];
+  if (tid == 0) s_stuck = 0;
   __syncthreads();
 
-  bool ok = false, nan_seen = false;
+  bool ok = false;
   S best{};
-  int bw = 0, bidx[4] = {0, 0, 0, 0};
-  for (int w = sub + tid; w < end; w += kAcrossThreads) {
-    const S* A = cs + w;                     // A[j] = A[j * n]
+  int bidx[4] = {0, 0, 0, 0};
+  const int w = sub + chunk * kAcrossThreads + tid;
+  if (w < end) {
+    const S* A = cs + (size_t)w * kcap;
     const S* C = dp + (size_t)w * dcap;
     const int Lc = dplen[w];
     // FourWayBestSplit (helpers.go:83-110): lists {cs_w, cs_u, dp_w, dp_u}, both cs lists hold k + 1 entries
     const int m2 = min(k, Lc + Ld - 2) + 1;  // entries SolveAllSplits(dp_w, dp_u) produces
     bool found = false;
     S top{};
-    int ti[4] = {0, 0, 0, 0};
     for (int i = k - (m2 - 1); i <= k; ++i) {
       S c1 = A[0] + B[i];  // BestSplit(cs_w, cs_u, i): left index 0..i
       int a1 = 0;
       for (int j = 1; j <= i; ++j) {
-        const S cur = A[(size_t)j * n] + B[i - j];
+        const S cur = A[j] + B[i - j];
         if (cur > c1) {
           c1 = cur;
           a1 = j;
@@ -160,35 +186,35 @@ k_dp_across(int n_items, const int* __restrict__ items /*[2*n_items]: u, sub*/, 
       const S cur = c1 + c2;
       if (!found || cur > top) {
         top = cur;
-        ti[0] = a1;
-        ti[1] = i - a1;
-        ti[2] = cc;
-        ti[3] = i2 - cc;
+        bidx[0] = a1;
+        bidx[1] = i - a1;
+        bidx[2] = cc;
+        bidx[3] = i2 - cc;
         found = true;
       }
     }
     S score = edge[(size_t)u * n + w];  // main_dp.go:268, left to right
-    score = score + A[(size_t)ti[0] * n];
-    score = score + B[ti[1]];
-    score = score + C[ti[2]];
-    score = score + D[ti[3]];
-    nan_seen |= is_nan(score);
-    if (!ok || score > best) {
-      ok = true;
-      best = score;
-      bw = w;
-      for (int q = 0; q < 4; ++q) bidx[q] = ti[q];
+    score = score + A[bidx[0]];
+    score = score + B[bidx[1]];
+    score = score + C[bidx[2]];
+    score = score + D[bidx[3]];
+    best = score;
+    ok = true;
+    if (is_nan(score)) {
+      atomicOr(&out->nan_seen, 1);
+      // `score > bestScore` is false for a NaN: only the item's first w keeps one (and is then never replaced)
+      if (w == sub) s_stuck = 1;
+      else ok = false;
     }
   }
-  if (nan_seen) atomicOr(&out->nan_seen, 1);
   r_score[tid] = raw_of<S>(best);
-  r_w[tid] = bw;
+  r_w[tid] = w;
   r_ok[tid] = ok;
   for (int q = 0; q < 4; ++q) r_idx[tid][q] = bidx[q];
   __syncthreads();
-  // first maximum over w: larger score, or equal score and smaller w
+  // first maximum over w: larger score, or equal score and smaller w; a stuck first w wins outright
   for (int s = kAcrossThreads / 2; s > 0; s >>= 1) {
-    if (tid < s && r_ok[tid + s]) {
+    if (tid < s && r_ok[tid + s] && !s_stuck) {
       const S a = as_score<S>(r_score[tid]), b = as_score<S>(r_score[tid + s]);
       if (!r_ok[tid] || b > a || (b == a && r_w[tid + s] < r_w[tid])) {
         r_score[tid] = r_score[tid + s];
@@ -200,33 +226,51 @@ k_dp_across(int n_items, const int* __restrict__ items /*[2*n_items]: u, sub*/, 
     __syncthreads();
   }
   if (tid == 0) {
-    ItemBest ib;
-    ib.score = r_score[0];
-    ib.ok = r_ok[0];
-    ib.u = u;
-    ib.w = r_w[0];
-    ib.len = ib.ok ? (depth[u] - depth[v]) + (depth[ib.w] - depth[v]) + 1 : 0;  // CycleLength, u not above w
-    for (int q = 0; q < 4; ++q) ib.idx[q] = r_idx[0][q];
-    item_best[it] = ib;
+    ChunkBest cb;
+    cb.score = r_score[0];
+    cb.ok = r_ok[0];
+    cb.w = r_w[0];
+    cb.stuck = s_stuck;
+    for (int q = 0; q < 4; ++q) cb.idx[q] = r_idx[0][q];
+    chunk_best[blockIdx.x] = cb;
     __threadfence();
-    s_last = atomicAdd(counter, 1u) == (unsigned)n_items - 1;
+    s_last = atomicAdd(counter, 1u) == (unsigned)n_blocks - 1;
   }
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  // the last block folds the items: max score, then min cycle length, then the last item
+  // The last block folds. Per item: its chunks in w order (first maximum; a stuck chunk 0 ends it).
+  // Across the items: max score, then min cycle length, then the last item; NaN candidates never win,
+  // item 0's is reported separately.
   int mine = -1;
   ItemBest mb{};
   for (int i = tid; i < n_items; i += kAcrossThreads) {
-    const ItemBest c = item_best[i];
+    const int b0 = item_blk0[i], b1 = item_blk0[i + 1];
+    ChunkBest c = chunk_best[b0];
+    if (!c.stuck)
+      for (int b = b0 + 1; b < b1; ++b) {
+        const ChunkBest d = chunk_best[b];
+        if (d.ok && (!c.ok || as_score<S>(d.score) > as_score<S>(c.score))) c = d;  // later chunks hold larger w: ties keep the earlier
+      }
     if (!c.ok) continue;
+    ItemBest ib;
+    ib.score = c.score;
+    ib.ok = 1;
+    ib.u = items[2 * i];
+    ib.w = c.w;
+    ib.len = (depth[ib.u] - depth[v]) + (depth[ib.w] - depth[v]) + 1;  // CycleLength, u not above w
+    for (int q = 0; q < 4; ++q) ib.idx[q] = c.idx[q];
+    if (is_nan(as_score<S>(ib.score))) {
+      if (i == 0) out->first = ib;
+      continue;
+    }
     bool take = mine < 0;
     if (!take) {
-      const S a = as_score<S>(mb.score), b = as_score<S>(c.score);
-      take = b > a || (b == a && c.len <= mb.len);  // i increases: equal length -> the later item
+      const S a = as_score<S>(mb.score), b = as_score<S>(ib.score);
+      take = b > a || (b == a && ib.len <= mb.len);  // i increases: equal length -> the later item
     }
     if (take) {
-      mb = c;
+      mb = ib;
       mine = i;
     }
   }
@@ -266,9 +310,11 @@ struct camus_b200_dp {
   bool f64 = false;
   int n = 0;
   int kcap = 0, dcap = 0;
-  Buf<int> d_end, d_depth, d_dplen, d_items, d_desc;
-  Buf<unsigned long long> d_edge, d_cs, d_dp, d_blob;
-  Buf<ItemBest> d_item_best;
+  Buf<int> d_end, d_depth, d_dplen, d_items, d_desc, d_blk_item, d_item_blk0;
+  Buf<ChunkBest> d_chunk_best;
+  int n_blocks = 0;
+  std::vector<int> h_end;
+  Buf<unsigned long long> d_edge, d_cs, d_dp, d_blob, d_cols;
   Buf<StepOut> d_out;
   Buf<unsigned int> d_counter;
   StepOut* h_out = nullptr;  // pinned
@@ -322,9 +368,10 @@ int camus_b200_dp_create(camus_b200_dp** out, int device, int score_is_f64, int3
   dp->dcap = 16;
   if ((e = dp->d_end.alloc(n)) != cudaSuccess || (e = dp->d_depth.alloc(n)) != cudaSuccess || (e = dp->d_dplen.alloc(n)) != cudaSuccess ||
       (e = dp->d_edge.alloc(n * n)) != cudaSuccess || (e = dp->d_cs.alloc(n * dp->kcap)) != cudaSuccess ||
-      (e = dp->d_dp.alloc(n * dp->dcap)) != cudaSuccess || (e = dp->d_item_best.alloc(n)) != cudaSuccess ||
+      (e = dp->d_dp.alloc(n * dp->dcap)) != cudaSuccess ||
       (e = dp->d_items.alloc(2 * n)) != cudaSuccess || (e = dp->d_out.alloc(1)) != cudaSuccess || (e = dp->d_counter.alloc(1)) != cudaSuccess)
     return bail("cudaMalloc", e);
+  dp->h_end.assign(subtree_end, subtree_end + n);
   std::vector<int> ones(n, 1);  // tips: DP[tip] = {0} (main_dp.go:98-100)
   if ((e = cudaMemcpyAsync(dp->d_end.p, subtree_end, n * 4, cudaMemcpyHostToDevice, dp->stream)) != cudaSuccess ||
       (e = cudaMemcpyAsync(dp->d_depth.p, depth, n * 4, cudaMemcpyHostToDevice, dp->stream)) != cudaSuccess ||
@@ -397,13 +444,25 @@ int camus_b200_dp_set_vertex(camus_b200_dp* dp, int32_t v, int32_t n_items, cons
   if (v < 0 || v >= dp->n || n_items < 0 || n_items > dp->n || (n_items && (!item_u || !item_sub)))
     return dp->fail(CAMUS_B200_ERR_ARG, "dp_set_vertex: bad vertex or item list");
   cudaSetDevice(dp->device);
-  std::vector<int> it(2 * (size_t)n_items);
+  std::vector<int> it(2 * (size_t)n_items), blk0((size_t)n_items + 1, 0), blk_item;
   for (int i = 0; i < n_items; ++i) {
     if (item_u[i] < 0 || item_u[i] >= dp->n || item_sub[i] < 0 || item_sub[i] >= dp->n) return dp->fail(CAMUS_B200_ERR_ARG, "dp_set_vertex: node out of range");
     it[2 * i] = item_u[i];
     it[2 * i + 1] = item_sub[i];
+    const int nw = dp->h_end[item_sub[i]] - item_sub[i];  // nodes of the other subtree
+    const int chunks = std::max(1, (nw + kAcrossThreads - 1) / kAcrossThreads);
+    blk0[i + 1] = blk0[i] + chunks;
+    blk_item.insert(blk_item.end(), chunks, i);
   }
-  if (n_items) DCK(cudaMemcpyAsync(dp->d_items.p, it.data(), it.size() * 4, cudaMemcpyHostToDevice, dp->stream));
+  dp->n_blocks = blk0[n_items];
+  if (n_items) {
+    DCK(dp->d_blk_item.alloc(blk_item.size()));
+    DCK(dp->d_item_blk0.alloc(blk0.size()));
+    DCK(dp->d_chunk_best.alloc(blk_item.size()));
+    DCK(cudaMemcpyAsync(dp->d_items.p, it.data(), it.size() * 4, cudaMemcpyHostToDevice, dp->stream));
+    DCK(cudaMemcpyAsync(dp->d_blk_item.p, blk_item.data(), blk_item.size() * 4, cudaMemcpyHostToDevice, dp->stream));
+    DCK(cudaMemcpyAsync(dp->d_item_blk0.p, blk0.data(), blk0.size() * 4, cudaMemcpyHostToDevice, dp->stream));
+  }
   DCK(cudaStreamSynchronize(dp->stream));
   dp->n_items = n_items;
   dp->cur_v = v;
@@ -421,15 +480,23 @@ int camus_b200_dp_set_path_columns(camus_b200_dp* dp, int32_t k0, int32_t k1, in
     Buf<unsigned long long> bigger;
     DCK(bigger.alloc((size_t)dp->n * cap));
     DCK(cudaMemsetAsync(bigger.p, 0, (size_t)dp->n * cap * 8, dp->stream));
-    DCK(cudaMemcpyAsync(bigger.p, dp->d_cs.p, (size_t)dp->n * dp->kcap * 8, cudaMemcpyDeviceToDevice, dp->stream));
+    const size_t tot = (size_t)dp->n * dp->kcap;
+    k_dp_repack<<<(unsigned)((tot + 255) / 256), 256, 0, dp->stream>>>(dp->d_cs.p, bigger.p, dp->n, dp->kcap, cap);
+    DCK(cudaGetLastError());
     DCK(cudaStreamSynchronize(dp->stream));
     std::swap(dp->d_cs.p, bigger.p);
     std::swap(dp->d_cs.n, bigger.n);
     dp->kcap = cap;
+    ++dp->launches;
   }
-  if (k1 > k0 && count)
-    DCK(cudaMemcpy2DAsync(dp->d_cs.p + (size_t)k0 * dp->n + first, (size_t)dp->n * 8, cols, (size_t)count * 8, (size_t)count * 8, (size_t)(k1 - k0),
-                          cudaMemcpyHostToDevice, dp->stream));
+  const size_t tot = (size_t)(k1 - k0) * count;
+  if (tot) {
+    DCK(dp->d_cols.alloc(tot));
+    DCK(cudaMemcpyAsync(dp->d_cols.p, cols, tot * 8, cudaMemcpyHostToDevice, dp->stream));
+    k_cs_scatter<<<(unsigned)((tot + 255) / 256), 256, 0, dp->stream>>>(dp->d_cols.p, dp->d_cs.p, dp->kcap, k0, k1 - k0, first, count);
+    DCK(cudaGetLastError());
+    ++dp->launches;
+  }
   DCK(cudaStreamSynchronize(dp->stream));  // the caller's buffer is free again
   return CAMUS_B200_OK;
 }
@@ -445,13 +512,15 @@ int camus_b200_dp_across(camus_b200_dp* dp, int32_t prev_k, camus_b200_dp_best* 
   DCK(cudaMemsetAsync(dp->d_out.p, 0, sizeof(StepOut), dp->stream));
   const size_t shm = (size_t)(prev_k + 1 + dp->dcap) * 8;
   if (dp->f64)
-    k_dp_across<double><<<dp->n_items, kAcrossThreads, shm, dp->stream>>>(dp->n_items, dp->d_items.p, dp->d_end.p, dp->d_depth.p, dp->cur_v, prev_k, dp->n,
-                                                                          dp->dcap, dp->d_cs.p, dp->d_dp.p, dp->d_dplen.p, dp->d_edge.p,
-                                                                          dp->d_item_best.p, dp->d_out.p, dp->d_counter.p);
+    k_dp_across<double><<<dp->n_blocks, kAcrossThreads, shm, dp->stream>>>(dp->n_items, dp->n_blocks, dp->d_items.p, dp->d_blk_item.p, dp->d_item_blk0.p,
+                                                                           dp->d_end.p, dp->d_depth.p, dp->cur_v, prev_k, dp->n, dp->kcap, dp->dcap,
+                                                                           dp->d_cs.p, dp->d_dp.p, dp->d_dplen.p, dp->d_edge.p, dp->d_chunk_best.p,
+                                                                           dp->d_out.p, dp->d_counter.p);
   else
-    k_dp_across<unsigned long long><<<dp->n_items, kAcrossThreads, shm, dp->stream>>>(dp->n_items, dp->d_items.p, dp->d_end.p, dp->d_depth.p, dp->cur_v, prev_k,
-                                                                                      dp->n, dp->dcap, dp->d_cs.p, dp->d_dp.p, dp->d_dplen.p, dp->d_edge.p,
-                                                                                      dp->d_item_best.p, dp->d_out.p, dp->d_counter.p);
+    k_dp_across<unsigned long long><<<dp->n_blocks, kAcrossThreads, shm, dp->stream>>>(dp->n_items, dp->n_blocks, dp->d_items.p, dp->d_blk_item.p,
+                                                                                       dp->d_item_blk0.p, dp->d_end.p, dp->d_depth.p, dp->cur_v, prev_k,
+                                                                                       dp->n, dp->kcap, dp->dcap, dp->d_cs.p, dp->d_dp.p, dp->d_dplen.p,
+                                                                                       dp->d_edge.p, dp->d_chunk_best.p, dp->d_out.p, dp->d_counter.p);
   DCK(cudaGetLastError());
   ++dp->launches;
   DCK(cudaMemcpyAsync(dp->h_out, dp->d_out.p, sizeof(StepOut), cudaMemcpyDeviceToHost, dp->stream));
@@ -459,6 +528,11 @@ int camus_b200_dp_across(camus_b200_dp* dp, int32_t prev_k, camus_b200_dp_best* 
   const StepOut& r = *dp->h_out;
   out->found = r.best.ok;
   out->nan_seen = r.nan_seen;
+  out->first_is_nan = r.first.ok;
+  out->first_u = r.first.u;
+  out->first_w = r.first.w;
+  out->first_score_bits = r.first.score;
+  for (int q = 0; q < 4; ++q) out->first_split[q] = r.first.idx[q];
   out->score_bits = r.best.score;
   out->u = r.best.u;
   out->w = r.best.w;

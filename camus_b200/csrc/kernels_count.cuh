@@ -37,6 +37,15 @@ constexpr int kPlaneWords = kTileWords / 3;  // 512 words = 2 KB: one plane of o
 #ifndef CAMUS_COUNT_LANEMAP
 #define CAMUS_COUNT_LANEMAP 1  // 0 = A/B build of the round-1 lane order (ta ta tb tb tc)
 #endif
+#ifndef CAMUS_COUNT_EXPERIMENT
+#define CAMUS_COUNT_EXPERIMENT 0  // timing experiments only (wrong results): 1 = no POPC (XU pipe idle), 2 = operands loaded once per box (LSU idle),
+                                  // 3 = as 2 and no barrier, no tile copies, no mbarrier wait in the group loop (the bare compute loop)
+#endif
+#if CAMUS_COUNT_EXPERIMENT == 1
+#define CAMUS_POPC(x) (x)
+#else
+#define CAMUS_POPC(x) __popc(x)
+#endif
 #ifndef CAMUS_COUNT_NOBAR
 #define CAMUS_COUNT_NOBAR 0  // A/B build: no CTA barrier in the group loop, the last warp out of a stage refills it
 #endif
@@ -252,7 +261,7 @@ k_count(CountParams prm, FusedParams fz, ConstraintDev ct) {
 
   for (int g = 0; g < G; ++g) {
     const int s = g % kCountStages;
-    if constexpr (CAMUS_COUNT_NOBAR) {
+    if constexpr (CAMUS_COUNT_NOBAR || CAMUS_COUNT_EXPERIMENT == 3) {
       // nothing here: see the end of the loop body
     } else if constexpr (Cfg::kNarrow) {
       // 3-stage ring: everyone has finished group g-1, its stage is refilled with g+2
@@ -272,9 +281,13 @@ k_count(CountParams prm, FusedParams fz, ConstraintDev ct) {
       }
     }
     // debug 3 (timing only): the ring is filled once and re-read, i.e. the loop without tile traffic
-    if (!(kFused && fz.debug == 3 && g >= kCountStages)) mbar_wait(&bars[s], (uint32_t)((g / kCountStages) & 1));
+    if (!(kFused && fz.debug == 3 && g >= kCountStages) && !(CAMUS_COUNT_EXPERIMENT == 3 && g >= kCountStages)) mbar_wait(&bars[s], (uint32_t)((g / kCountStages) & 1));
 
+#if CAMUS_COUNT_EXPERIMENT >= 2
+    const uint4* st = reinterpret_cast<const uint4*>(smem) + ((g & 1) ? 0 : 0);  // loop invariant: the loads are hoisted out of the group loop
+#else
     const uint4* st = reinterpret_cast<const uint4*>(smem + s * Cfg::kStageWords);
+#endif
     auto ld = [&](int role, int plane, uint32_t off) -> uint4 { return st[plane_slot<kComplete>(role, plane) * kPlaneU4 + off]; };
 
     uint4 abc[3][2];
@@ -310,10 +323,10 @@ k_count(CountParams prm, FusedParams fz, ConstraintDev ct) {
               const uint32_t t0 = (pick(abc[0][kk], j, i) & pick(abd[0], j, i)) | ((i ? acd[2].y : acd[2].x) & (j ? bcd[2].y : bcd[2].x));  // ab|cd
               const uint32_t t1 = (pick(abc[1][kk], j, i) & (i ? acd[0].y : acd[0].x)) | (pick(abd[2], j, i) & (j ? bcd[1].y : bcd[1].x));  // ac|bd
               if constexpr (kComplete) {
-                cnt[c][0] += __popc(t0) + (__popc(t1) << 16);
+                cnt[c][0] += CAMUS_POPC(t0) + (CAMUS_POPC(t1) << 16);
               } else {
                 const uint32_t t2 = (pick(abd[1], j, i) & (i ? acd[1].y : acd[1].x)) | (pick(abc[2][kk], j, i) & (j ? bcd[0].y : bcd[0].x));  // ad|bc
-                cnt[c][0] += __popc(t0) + (__popc(t1) << 10) + (__popc(t2) << 20);
+                cnt[c][0] += CAMUS_POPC(t0) + (CAMUS_POPC(t1) << 10) + (CAMUS_POPC(t2) << 20);
               }
             }
         }

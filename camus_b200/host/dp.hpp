@@ -8,9 +8,11 @@
 #pragma once
 #include <array>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <condition_variable>
 #include <cstdlib>
+#include <cstring>
 #include <functional>
 #include <mutex>
 #include <string>
@@ -293,11 +295,48 @@ static void maxplus_accumulate(uint64_t* __restrict__ val, const uint64_t* __res
   }
 }
 
+// Optional GPU offload of the across-scan (include/camus_b200.h, "DP offload"): plain C function
+// pointers into libcamus_b200.so, so that this library does not link CUDA. Field order = the order
+// camus_host_run_dp_accel documents.
+struct DpAccelApi {
+  int (*create)(void** out, int device, int score_is_f64, int32_t n_nodes, const int32_t* subtree_end, const int32_t* depth, const void* edge_scores);
+  void (*destroy)(void* dp);
+  const char* (*last_error)(const void* dp);
+  int (*set_node)(void* dp, int32_t node, int32_t len, const void* scores);
+  int (*set_vertex)(void* dp, int32_t v, int32_t n_items, const int32_t* item_u, const int32_t* item_sub);
+  int (*set_path_columns)(void* dp, int32_t k0, int32_t k1, int32_t first, int32_t count, const void* cols);
+  int (*across)(void* dp, int32_t prev_k, void* best);
+  uint64_t (*launches)(const void* dp);
+};
+struct DpAccelBest {  // = camus_b200_dp_best
+  int32_t found, nan_seen;
+  uint64_t score_bits;
+  int32_t u, w, cycle_length;
+  int32_t split[4];
+  int32_t first_is_nan, first_u, first_w;
+  int32_t first_split[4];
+  uint64_t first_score_bits;
+};
+static_assert(sizeof(DpAccelBest) == 80, "layout of camus_b200_dp_best");
+struct DpAccel {
+  const DpAccelApi* api = nullptr;
+  void* handle = nullptr;
+  uint64_t min_work = 0;   // steps below this many (pairs x list entries) stay on the host
+  bool verify = false;     // CAMUS_DP_VERIFY=1: run the host scan as well and compare the winner
+  uint64_t steps = 0, steps_host = 0, nan_fallbacks = 0;
+  double s_columns = 0, s_across = 0;  // seconds inside set_vertex + set_path_columns / inside across
+  void check(int rc, const char* what) const {
+    if (rc != 0) throw CamusError(Err::Internal, std::string("DP offload: ") + what + ": " + (api->last_error(handle) ? api->last_error(handle) : "?"));
+  }
+};
+
 struct DPResults {
   std::vector<std::vector<Branch>> branches;  // per k = 1..m
   std::vector<double> qsat;
   std::vector<double> root_scores_f;  // DP[root][k] as double (for logging / tests)
   std::vector<uint64_t> root_scores_u;
+  uint64_t accel_steps = 0, accel_steps_host = 0, accel_nan_fallbacks = 0, accel_launches = 0;
+  double accel_s_columns = 0, accel_s_across = 0;
 };
 
 // ------------------------------------------------------------------------------------------
@@ -315,8 +354,8 @@ class DP {
   };
 
  public:
-  DP(const TreeData& td, const Scorer& sc, int nthreads = 1)
-      : td_(td), sc_(sc), n_(td.n()), dp_(n_), tb_(n_), pool_(std::max(1, nthreads)) {}
+  DP(const TreeData& td, const Scorer& sc, int nthreads = 1, DpAccel* accel = nullptr)
+      : td_(td), sc_(sc), n_(td.n()), dp_(n_), tb_(n_), pool_(std::max(1, nthreads)), accel_(accel) {}
 
   void run() {  // RunDP, main_dp.go:90-104 (gotree PostOrder = children in order, then node)
     std::vector<int> order;
@@ -348,6 +387,9 @@ class DP {
   std::vector<std::vector<int>> tb_;
   TraceArena arena_;
   WorkerPool pool_;
+  DpAccel* accel_ = nullptr;
+  int accel_v_ = -1, accel_cols_ = 0;  // vertex whose items are on the device, path columns already there
+  std::vector<uint64_t> col_buf_;
   // CAMUS_DP_LITERAL=1: literal FourWayBestSplit scan for integer scores too (A/B, tests)
   bool fast_enabled_ = !(getenv("CAMUS_DP_LITERAL") && getenv("CAMUS_DP_LITERAL")[0] == '1');
   // cycleDP of the vertex being solved (main_dp.go:30-34)
@@ -521,6 +563,94 @@ class DP {
     return c;
   }
 
+  // ---- GPU offload of the across-scan (DpAccel) ---------------------------------------------------
+  static uint64_t raw_of(S v) {
+    uint64_t r;
+    static_assert(sizeof(S) == 8, "8-byte scores");
+    memcpy(&r, &v, 8);
+    return r;
+  }
+  static S score_of(uint64_t r) {
+    S v;
+    memcpy(&v, &r, 8);
+    return v;
+  }
+  // d = the across-scan's winner over the candidates whose score is not NaN (d.ok = false: none);
+  // first = the first u's candidate when it scores NaN (include/camus_b200.h, camus_b200_dp_across)
+  void accel_across(int v, int prevK, Desc& d, Desc& first) {
+    DpAccel& a = *accel_;
+    const auto t0 = std::chrono::steady_clock::now();
+    const int end = td_.subtree_end[v], cnt = end - v;
+    if (accel_v_ != v) {
+      std::vector<int32_t> iu(items_.size()), is(items_.size());
+      for (size_t i = 0; i < items_.size(); ++i) {
+        iu[i] = items_[i].first;
+        is[i] = items_[i].second;
+      }
+      a.check(a.api->set_vertex(a.handle, v, (int32_t)items_.size(), iu.data(), is.data()), "set_vertex");
+      accel_v_ = v;
+      accel_cols_ = 0;
+    }
+    if (accel_cols_ <= prevK) {
+      const int k0 = accel_cols_, k1 = prevK + 1;
+      col_buf_.resize((size_t)(k1 - k0) * cnt);
+      for (int j = k0; j < k1; ++j)
+        for (int x = v; x < end; ++x) col_buf_[(size_t)(j - k0) * cnt + (x - v)] = raw_of(cs_[x][j]);
+      a.check(a.api->set_path_columns(a.handle, k0, k1, v, cnt, col_buf_.data()), "set_path_columns");
+      accel_cols_ = k1;
+    }
+    DpAccelBest b;
+    const auto t1 = std::chrono::steady_clock::now();
+    a.check(a.api->across(a.handle, prevK, &b), "across");
+    const auto t2 = std::chrono::steady_clock::now();
+    a.s_columns += std::chrono::duration<double>(t1 - t0).count();
+    a.s_across += std::chrono::duration<double>(t2 - t1).count();
+    ++a.steps;
+    if (b.nan_seen) ++a.nan_fallbacks;  // statistic: steps in which some pair scored NaN
+    d = Desc{};
+    d.ok = b.found != 0;
+    if (d.ok) {
+      d.score = score_of(b.score_bits);
+      d.u = b.u;
+      d.w = b.w;
+      for (int i = 0; i < 4; ++i) d.idx[i] = b.split[i];
+    }
+    first = Desc{};
+    first.ok = b.first_is_nan != 0;
+    if (first.ok) {
+      first.score = score_of(b.first_score_bits);
+      first.u = b.first_u;
+      first.w = b.first_w;
+      for (int i = 0; i < 4; ++i) first.idx[i] = b.first_split[i];
+    }
+  }
+  // CAMUS_DP_VERIFY=1: the literal host scan over the same items, folded in the reference's order
+  // from the same starting candidate; the offloaded step must end with the same one
+  Cand host_scan_from(Cand best, int bestLen, int prevK) {
+    for (const auto& it : items_) {
+      Desc c = score_edges_across(it.first, it.second, prevK);
+      if (!c.ok) continue;
+      int len = cycle_length(c.u, c.w, td_);
+      if (c.score > best.score || !best.ok || (c.score == best.score && len <= bestLen)) {
+        best = materialise(c);
+        bestLen = len;
+      }
+    }
+    return best;
+  }
+  void verify_same(const Cand& h, const Cand& g, int v, int prevK) const {
+    bool same = h.ok == g.ok;
+    if (same && h.ok) {
+      const auto &a = arena_.traces[h.trace], &b = arena_.traces[g.trace];
+      same = raw_of(h.score) == raw_of(g.score) && h.br.u == g.br.u && h.br.w == g.br.w && a.pathW == b.pathW && a.pathU == b.pathU &&
+             a.wDown == b.wDown && a.uDown == b.uDown;
+    }
+    if (!same)
+      throw CamusError(Err::Internal, "DP offload: device and host across-scan disagree at v " + std::to_string(v) + " prevK " +
+                                          std::to_string(prevK) + ": host (" + std::to_string(h.br.u) + "," + std::to_string(h.br.w) +
+                                          ") device (" + std::to_string(g.br.u) + "," + std::to_string(g.br.w) + ")");
+  }
+
   Cand score_add_edge_k(int v, int k) {  // main_dp.go:178-216
     int prevK = k - 1;
     Cand best;
@@ -553,6 +683,31 @@ class DP {
     }
     descs_.assign(items_.size(), Desc{});
     const size_t work = (size_t)(td_.subtree_end[c0] - c0) * (size_t)(td_.subtree_end[c1] - c1) * (size_t)(prevK + 1);
+    if (accel_ && !items_.empty()) {
+      // float scores pay (k + 1)^2 additions per pair on the host, integer ones (max-plus form) k + 1
+      const uint64_t cost = kIntegerScores && fast_enabled_ ? (uint64_t)work : (uint64_t)work * (uint64_t)(prevK + 1);
+      if (cost >= accel_->min_work) {
+        Desc d, first;
+        accel_across(v, prevK, d, first);
+        Cand host_best;
+        if (accel_->verify) host_best = host_scan_from(best, bestLen, prevK);
+        if (!best.ok && first.ok) {
+          // the first u's candidate scores NaN and nothing was accepted before it: it is taken
+          // (bestCycleTrace == nil) and no later `>` or `==` against a NaN replaces it
+          best = materialise(first);
+        } else if (d.ok) {
+          int len = cycle_length(d.u, d.w, td_);
+          if (d.score > best.score || !best.ok || (d.score == best.score && len <= bestLen)) {
+            best = materialise(d);
+            bestLen = len;
+          }
+        }
+        if (accel_->verify) verify_same(host_best, best, v, prevK);
+        return best;
+      } else {
+        ++accel_->steps_host;
+      }
+    }
     bool fast = false;
     if constexpr (kIntegerScores) fast = fast_enabled_;
     if (fast) conv_update(v, prevK);
@@ -616,6 +771,10 @@ class DP {
     }
     dp_[v] = std::move(scores);
     tb_[v] = std::move(traces);
+    if (accel_) {
+      static_assert(sizeof(S) == 8, "8-byte scores");
+      accel_->check(accel_->api->set_node(accel_->handle, v, (int32_t)dp_[v].size(), dp_[v].data()), "set_node");
+    }
   }
 };
 
@@ -675,9 +834,36 @@ inline std::string make_network_newick(const TreeData& td, std::vector<Branch> b
 // infer.Infer after Preprocess + Scorer.Init (infer.go:79-95) and DP.collateResults
 // (main_dp.go:106-127): run the DP over precomputed tables.
 inline DPResults run_dp(const TreeData& td, const ScoreTables& tabs, ScoreMode mode, int n_gtrees, double alpha,
-                        int nthreads = 0) {
+                        int nthreads = 0, const DpAccelApi* api = nullptr, int device = 0, int64_t min_work = -1) {
   if (nthreads <= 0) nthreads = (int)std::max(1u, std::thread::hardware_concurrency());
   DPResults res;
+  DpAccel accel;
+  // the across-scan on the GPU: the whole edge-score table goes to the device once
+  auto open_accel = [&](const auto& sc) -> DpAccel* {
+    if (!api) return nullptr;
+    using S = typename std::decay_t<decltype(sc)>::S;
+    const int n = td.n();
+    std::vector<S> edge((size_t)n * n);
+    for (int u = 0; u < n; ++u)
+      for (int w = 0; w < n; ++w) edge[(size_t)u * n + w] = sc.calc(u, w);
+    std::vector<int32_t> end(td.subtree_end.begin(), td.subtree_end.end()), dep(td.depths.begin(), td.depths.end());
+    accel.api = api;
+    int rc = api->create(&accel.handle, device, std::is_same_v<S, double> ? 1 : 0, n, end.data(), dep.data(), edge.data());
+    if (rc != 0) {
+      const char* m = api->last_error(nullptr);
+      throw CamusError(Err::Internal, std::string("DP offload: create: ") + (m ? m : "?"));
+    }
+    accel.min_work = min_work >= 0 ? (uint64_t)min_work : 400000;
+    if (const char* e = getenv("CAMUS_DP_ACCEL_MIN_WORK")) accel.min_work = strtoull(e, nullptr, 10);
+    accel.verify = getenv("CAMUS_DP_VERIFY") && getenv("CAMUS_DP_VERIFY")[0] == '1';
+    return &accel;
+  };
+  struct Closer {
+    DpAccel& a;
+    ~Closer() {
+      if (a.handle) a.api->destroy(a.handle);
+    }
+  } closer{accel};
   auto collate = [&](auto& dp) {
     const auto& rs = dp.root_scores();
     int m = (int)rs.size() - 1;
@@ -692,19 +878,27 @@ inline DPResults run_dp(const TreeData& td, const ScoreTables& tabs, ScoreMode m
   };
   if (mode == ScoreMode::Max) {
     MaximizeScorer sc{&tabs};
-    DP<MaximizeScorer> dp(td, sc, nthreads);
+    DP<MaximizeScorer> dp(td, sc, nthreads, open_accel(sc));
     dp.run();
     collate(dp);
   } else if (mode == ScoreMode::Norm) {
     NormalizedScorer sc{&tabs, n_gtrees};
-    DP<NormalizedScorer> dp(td, sc, nthreads);
+    DP<NormalizedScorer> dp(td, sc, nthreads, open_accel(sc));
     dp.run();
     collate(dp);
   } else {
     SymDiffScorer sc{&tabs, 0, alpha};  // NGTree is never set for sym (infer.go:84-85)
-    DP<SymDiffScorer> dp(td, sc, nthreads);
+    DP<SymDiffScorer> dp(td, sc, nthreads, open_accel(sc));
     dp.run();
     collate(dp);
+  }
+  if (accel.handle) {
+    res.accel_steps = accel.steps;
+    res.accel_steps_host = accel.steps_host;
+    res.accel_nan_fallbacks = accel.nan_fallbacks;
+    res.accel_launches = api->launches(accel.handle);
+    res.accel_s_columns = accel.s_columns;
+    res.accel_s_across = accel.s_across;
   }
   return res;
 }

@@ -101,11 +101,13 @@ const char* camus_host_node_name(const camus_host_problem* p, int id) {
 int camus_host_should_calc_edge(const camus_host_problem* p, int u, int w) { return should_calc_edge(u, w, p->td); }
 int camus_host_cycle_length(const camus_host_problem* p, int u, int w) { return cycle_length(u, w, p->td); }
 
-// infer.Infer after Scorer.Init (infer.go:79-95): DP + traceback + MakeNetwork over the two
-// integer tables the hot path produced. mode: 0 max, 1 norm, 2 sym. penalties may be NULL for max.
-int camus_host_run_dp(const camus_host_problem* p, int mode, const uint64_t* totals, const uint64_t* penalties,
-                      int as_set, uint64_t n_survivors, uint64_t sum_counts, int n_gtrees, double alpha,
-                      camus_host_results** out) {
+// accel != NULL: the DP's across-scan runs on the GPU (include/camus_b200.h "DP offload"). accel =
+// eight function pointers, in this order: camus_b200_dp_create, _destroy, _last_error, _set_node,
+// _set_vertex, _set_path_columns, _across, _launches. min_work < 0 = default threshold below which a
+// step stays on the host.
+int camus_host_run_dp_accel(const camus_host_problem* p, int mode, const uint64_t* totals, const uint64_t* penalties,
+                            int as_set, uint64_t n_survivors, uint64_t sum_counts, int n_gtrees, double alpha,
+                            const void* const* accel, int device, int64_t min_work, camus_host_results** out) {
   try {
     ScoreTables tabs;
     tabs.n = p->td.n();
@@ -120,7 +122,12 @@ int camus_host_run_dp(const camus_host_problem* p, int mode, const uint64_t* tot
     // CAMUS_HOST_THREADS: worker threads of the DP's across-scan (0 / unset = all cores); the
     // result does not depend on it
     const char* e = getenv("CAMUS_HOST_THREADS");
-    r->res = run_dp(p->td, tabs, (ScoreMode)mode, n_gtrees, alpha, e ? atoi(e) : 0);
+    DpAccelApi api{};
+    if (accel) {
+      static_assert(sizeof(DpAccelApi) == 8 * sizeof(void*), "eight function pointers");
+      memcpy(&api, accel, sizeof api);
+    }
+    r->res = run_dp(p->td, tabs, (ScoreMode)mode, n_gtrees, alpha, e ? atoi(e) : 0, accel ? &api : nullptr, device, min_work);
     for (auto& b : r->res.branches) r->newicks.push_back(make_network_newick(p->td, b));
     *out = r.release();
     return 0;
@@ -130,6 +137,23 @@ int camus_host_run_dp(const camus_host_problem* p, int mode, const uint64_t* tot
     g_err = e.what();
     return (int)Err::Internal;
   }
+}
+// infer.Infer after Scorer.Init (infer.go:79-95): DP + traceback + MakeNetwork over the two
+// integer tables the hot path produced. mode: 0 max, 1 norm, 2 sym. penalties may be NULL for max.
+int camus_host_run_dp(const camus_host_problem* p, int mode, const uint64_t* totals, const uint64_t* penalties,
+                      int as_set, uint64_t n_survivors, uint64_t sum_counts, int n_gtrees, double alpha,
+                      camus_host_results** out) {
+  return camus_host_run_dp_accel(p, mode, totals, penalties, as_set, n_survivors, sum_counts, n_gtrees, alpha, nullptr, 0, -1, out);
+}
+// offload statistics of the last run: [0] steps on the device, [1] steps kept on the host, [2] steps that saw a NaN score,
+// [3] kernel launches, [4] microseconds uploading items / path columns, [5] microseconds inside camus_b200_dp_across
+void camus_host_results_accel_stats(const camus_host_results* r, uint64_t* out6) {
+  out6[0] = r->res.accel_steps;
+  out6[1] = r->res.accel_steps_host;
+  out6[2] = r->res.accel_nan_fallbacks;
+  out6[3] = r->res.accel_launches;
+  out6[4] = (uint64_t)(r->res.accel_s_columns * 1e6);
+  out6[5] = (uint64_t)(r->res.accel_s_across * 1e6);
 }
 void camus_host_results_free(camus_host_results* r) { delete r; }
 int camus_host_results_count(const camus_host_results* r) { return (int)r->res.branches.size(); }

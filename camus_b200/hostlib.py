@@ -62,6 +62,11 @@ def lib() -> C.CDLL:
         L.camus_host_cycle_length.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.camus_host_run_dp.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_uint64,
                                         C.c_uint64, C.c_int, C.c_double, C.POINTER(C.c_void_p)]
+        L.camus_host_run_dp_accel.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_uint64,
+                                              C.c_uint64, C.c_int, C.c_double, C.c_void_p, C.c_int, C.c_int64,
+                                              C.POINTER(C.c_void_p)]
+        L.camus_host_results_accel_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+        L.camus_host_results_accel_stats.restype = None
         L.camus_host_results_free.argtypes = [C.c_void_p]
         L.camus_host_results_count.argtypes = [C.c_void_p]
         L.camus_host_results_branches.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int32)]
@@ -110,6 +115,7 @@ class DPResult:
     qsat: list[float]
     root_scores: list[float]               # DP[root][k], k = 0..m
     newicks: list[str]
+    accel: dict | None = None              # DP offload statistics (run_dp(gpu=...))
 
 
 class Problem:
@@ -178,9 +184,16 @@ class Problem:
         return r.decode()
 
     def run_dp(self, totals: np.ndarray, penalties: np.ndarray | None = None, mode: str = "max", as_set: bool = False,
-               n_survivors: int = 0, sum_counts: int = 0, n_gtrees: int | None = None, alpha: float = 0.1) -> DPResult:
-        """infer.Infer after Scorer.Init (infer.go:79-95): DP + traceback + MakeNetwork."""
+               n_survivors: int = 0, sum_counts: int = 0, n_gtrees: int | None = None, alpha: float = 0.1,
+               gpu: int | None = None, min_work: int = -1) -> DPResult:
+        """infer.Infer after Scorer.Init (infer.go:79-95): DP + traceback + MakeNetwork. gpu = device
+        index: the DP's across-scan (main_dp.go:247-287) runs there through the camus_b200_dp_* calls
+        of libcamus_b200.so; None = the host scan."""
         L = lib()
+        accel = None
+        if gpu is not None:
+            from . import cabi
+            accel = cabi.dp_accel_table()
         totals = np.ascontiguousarray(totals, dtype=np.uint64)
         assert totals.size == self.n_nodes * self.n_nodes
         pen_p = None
@@ -188,9 +201,11 @@ class Problem:
             penalties = np.ascontiguousarray(penalties, dtype=np.uint64)
             pen_p = penalties.ctypes.data_as(C.c_void_p)
         r = C.c_void_p()
-        rc = L.camus_host_run_dp(self._h, {"max": 0, "norm": 1, "sym": 2}[mode], totals.ctypes.data_as(C.c_void_p),
-                                 pen_p, int(as_set), int(n_survivors), int(sum_counts),
-                                 int(self.n_trees if n_gtrees is None else n_gtrees), float(alpha), C.byref(r))
+        rc = L.camus_host_run_dp_accel(self._h, {"max": 0, "norm": 1, "sym": 2}[mode], totals.ctypes.data_as(C.c_void_p),
+                                       pen_p, int(as_set), int(n_survivors), int(sum_counts),
+                                       int(self.n_trees if n_gtrees is None else n_gtrees), float(alpha),
+                                       C.cast(accel, C.c_void_p) if accel is not None else None, int(gpu or 0), int(min_work),
+                                       C.byref(r))
         if rc != 0:
             raise CamusError(rc, L.camus_host_last_error().decode())
         try:
@@ -204,7 +219,12 @@ class Problem:
                 qsat.append(L.camus_host_results_qsat(r, k))
                 roots.append(L.camus_host_results_root_score(r, k))
                 newicks.append(L.camus_host_results_newick(r, k).decode())
-            return DPResult(branches, qsat, roots, newicks)
+            res = DPResult(branches, qsat, roots, newicks)
+            st = (C.c_uint64 * 6)()
+            L.camus_host_results_accel_stats(r, st)
+            res.accel = {"device_steps": st[0], "host_steps": st[1], "nan_steps": st[2], "launches": st[3],
+                         "upload_s": st[4] * 1e-6, "across_s": st[5] * 1e-6}
+            return res
         finally:
             L.camus_host_results_free(r)
 

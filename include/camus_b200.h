@@ -16,6 +16,7 @@
  *   camus_b200_export_quartets  <- the map[Quartet]uint32 itself       internal/graphs/quartet.go:11-31
  *   camus_b200_reticulation_counts <- the per-gene-tree loop of score.ReticulationScore
  *                                                                       internal/score/score.go:31-60
+ *   camus_b200_dp_across        <- the scoreEdgesAcross loop of scoreAddEdgeK  internal/infer/main_dp.go:199-214, :247-287
  *
  * Conventions: plain pointers + sizes, host memory, valid for the duration of the call only (cgo
  * rule: no pointer is kept after return). All functions return 0 on success, non-zero on failure
@@ -177,6 +178,53 @@ int camus_b200_run_resident(camus_b200* ctx, int qmode, double threshold, int as
 int camus_b200_stage_ms(const camus_b200* ctx, float* ms /*[CAMUS_B200_T_N]*/, uint64_t* n_launches);
 /* resolutions = sum over gene trees of C(leaves,4): the unit of the throughput metric. */
 int camus_b200_workload(const camus_b200* ctx, uint64_t* resolutions, uint64_t* n_cells, uint64_t* n_boxes);
+
+/* ---- DP offload: the across-scan of the level-1 network DP ----
+ * Replaces the loop body of scoreAddEdgeK that calls scoreEdgesAcross for every u
+ * (internal/infer/main_dp.go:199-214 + :247-287) and, inside it, FourWayBestSplit
+ * (internal/infer/helpers.go:83-110). The DP driver stays with the caller: RunDP's post-order walk,
+ * solve's k loop, cycleDP.update, scoreEdgesDown and the traceback (main_dp.go:40-176, :219-244).
+ * Score type = the Scorer's S: uint64 (max) or float64 (norm, sym), passed as raw 8-byte values;
+ * float results are bit-identical to Go's because every sum is formed in the reference's order.
+ * A separate handle (its own stream, about 8 n^2 bytes of HBM), independent of camus_b200.
+ *
+ *   create        node ids = the constraint tree's preorder ids (root 0); subtree_end[x] = one past
+ *                 the last id of x's subtree; depth = TreeData.Depths; edge_scores[u*n + w] =
+ *                 Scorer.CalcScore(u, w) for EVERY pair (the across-scan does not call ShouldCalcEdge)
+ *   set_node      DP[node] once solve(node) has returned (tips are preset to {0})
+ *   set_vertex    start of solve(v): the (u, other child subtree) pairs in SubtreePostOrder order
+ *   set_path_columns  cycleDP.scores[x][k] for k0 <= k < k1 and first <= x < first + count,
+ *                 cols[(k - k0) * count + (x - first)]; every list holds prev_k + 1 entries when
+ *                 across(prev_k) is called
+ *   across        the candidate the reference's loop over SubtreePostOrder(v) ends with when it
+ *                 starts from an empty best: maximum score, then the smallest CycleLength, then the
+ *                 last u in visiting order; inside one u the first maximum over w in preorder.
+ *                 NaN scores (norm mode: 0 / 0 on the length-3 cycle between v's children) follow
+ *                 the reference's comparisons: they never win the fold above; when the candidate of
+ *                 the FIRST u is NaN it is returned in first_*, and the caller takes it iff it holds
+ *                 no candidate yet (bestCycleTrace == nil, main_dp.go:194). */
+typedef struct camus_b200_dp camus_b200_dp;
+typedef struct {
+  int32_t found;         /* 0: no (u, w) pair at this vertex */
+  int32_t nan_seen;
+  uint64_t score_bits;   /* uint64 score, or the IEEE bits of the float64 score */
+  int32_t u, w;
+  int32_t cycle_length;  /* score.CycleLength(u, w) */
+  int32_t split[4];      /* wPathK, uPathK, wDownK, uDownK (main_dp.go:266) */
+  int32_t first_is_nan;  /* the first u's candidate has a NaN score: first_* describe it */
+  int32_t first_u, first_w;
+  int32_t first_split[4];
+  uint64_t first_score_bits;
+} camus_b200_dp_best;
+int camus_b200_dp_create(camus_b200_dp** out, int device, int score_is_f64, int32_t n_nodes, const int32_t* subtree_end,
+                         const int32_t* depth, const void* edge_scores /*[n*n] 8-byte scores*/);
+void camus_b200_dp_destroy(camus_b200_dp* dp);
+const char* camus_b200_dp_last_error(const camus_b200_dp* dp);
+int camus_b200_dp_set_node(camus_b200_dp* dp, int32_t node, int32_t len, const void* scores /*[len]*/);
+int camus_b200_dp_set_vertex(camus_b200_dp* dp, int32_t v, int32_t n_items, const int32_t* item_u, const int32_t* item_sub);
+int camus_b200_dp_set_path_columns(camus_b200_dp* dp, int32_t k0, int32_t k1, int32_t first, int32_t count, const void* cols);
+int camus_b200_dp_across(camus_b200_dp* dp, int32_t prev_k, camus_b200_dp_best* out);
+uint64_t camus_b200_dp_launches(const camus_b200_dp* dp);
 
 #ifdef __cplusplus
 }

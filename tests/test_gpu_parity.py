@@ -885,3 +885,34 @@ def test_randomized_instances(gpu, seed):
         assert np.array_equal(gpu.edge_penalties(), o.edge_penalties())
     finally:
         gpu.set_score_hint(False)
+
+
+# ----------------------------------------------------------------- inputs beyond the bit-plane budget
+def test_eight_sequential_passes_equal_one_pass(gpu, monkeypatch):
+    """CAMUS_B200_PASSES=8: the 8 class-scheme shares run one after the other on one GPU (what the
+    library does by itself when the bit-plane table does not fit, e.g. 1000 taxa x 4000 trees), each
+    holding half of the bit-planes, junction table and scalars accumulating. Same survivors, both edge
+    tables and a second quartet_totals with the other weight, against the oracle and the one-pass
+    context: complete trees, incomplete trees (packed kernel), every filter mode."""
+    from camus_b200.cabi import CamusB200
+    monkeypatch.setenv("CAMUS_B200_PASSES", "8")
+    multi = CamusB200(0)
+    monkeypatch.delenv("CAMUS_B200_PASSES")
+    cases = [(synth.make(70, 130, 61), 0.0), (synth.make(96, 64, 62, drop_frac=0.1), 0.0), (synth.make(23, 40, 63), 0.0),
+             (synth.make(58, 90, 64, support=True, drop_frac=0.1, nexus=True), 0.7)]
+    for s, ms in cases:
+        prob = Problem(s.constraint, s.genes, s.fmt, ms)
+        o = orc.Oracle().load(prob)
+        for qmode, thr in ((0, 0.0), (2, 0.5), (1, 0.3)):
+            want = o.count_filter(qmode, thr, False)
+            for hint in (False, True):
+                multi.load(prob)
+                multi.set_score_hint(hint)
+                assert multi.count_filter(qmode, thr) == want
+                for as_set in (hint, not hint):
+                    assert np.array_equal(multi.quartet_totals(as_set), o.quartet_totals(as_set, False))
+                _, ns, sc = multi.run_resident(qmode, thr, hint, np.empty((prob.n_nodes, prob.n_nodes), np.uint64))
+                assert (ns, sc) == want
+        gpu.load(prob)
+        assert gpu.count_filter(2, 0.5) == o.count_filter(2, 0.5, False)  # the one-pass context is untouched by the mode
+    multi.close()

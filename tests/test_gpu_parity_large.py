@@ -170,3 +170,35 @@ def test_config3_full_size_vs_literal_quartet_score(gpu):
     got = {"n_survivors": ns, "sum_counts": sc, "quartet_totals": table_digest(tab), "quartet_totals_as_set": table_digest(tab_set)}
     want = json.load(open(DIGESTS))["config3"]
     assert got == want, got
+
+
+def test_beyond_the_bit_plane_budget_1000_taxa_3000_trees(gpu):
+    """1000 taxa x 3000 gene trees need a 197 GB bit-plane table: more than one B200 holds. The
+    library then runs the 8 class-scheme shares one after the other (half of the table resident at
+    a time, camus_b200.cu run_passes). Size-independent checks: with -q 0 the unfiltered edge table
+    and both scalars are LINEAR in the gene trees, so the 3000-tree result must equal the sum over
+    three 1000-tree runs (each of which fits and takes the ordinary one-pass path, itself compared
+    with the oracle elsewhere in this file); and the filtered run must reproduce itself through
+    run_resident."""
+    s = synth.make(1000, 3000, 77)
+    lines = s.genes.strip().split("\n")
+    assert len(lines) == 3000
+    parts = []
+    for b in range(3):
+        prob = Problem(s.constraint, "\n".join(lines[b * 1000:(b + 1) * 1000]) + "\n")
+        gpu.load(prob)
+        ns, sc = gpu.count_filter(0, 0.0)
+        parts.append((ns, sc, gpu.quartet_totals(False)))
+        assert gpu.stage_ms()[0]["count"] > 0
+    prob = Problem(s.constraint, s.genes)
+    gpu.load(prob)
+    ns, sc = gpu.count_filter(0, 0.0)
+    tab = gpu.quartet_totals(False)
+    assert sc == sum(p[1] for p in parts)
+    assert ns >= max(p[0] for p in parts)  # distinct surviving keys: a union, not a sum
+    assert np.array_equal(tab, parts[0][2] + parts[1][2] + parts[2][2])
+    want = gpu.count_filter(2, 0.5)
+    t2 = gpu.quartet_totals(False)
+    out, ns2, sc2 = gpu.run_resident(2, 0.5, False)
+    assert (ns2, sc2) == want and np.array_equal(out, t2)
+    gpu.clear_gene_trees()
