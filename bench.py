@@ -437,15 +437,13 @@ def run_ours(args):
             traffic = json.load(open(tf)).get(f"config{args.config}_k_count_dram_bytes_per_launch")
         h2d = int(prob.gene_node_off.nbytes + prob.gene_parent.nbytes + prob.gene_taxon.nbytes)
         sm_mhz = clocks.get("sm_mhz") or 1965
-        # The kernel's floor: one POPC per (cell, counted topology, 32 trees). Two peaks for it:
-        #  * ncu's XU-pipe model: 16 lanes per clock and SM (sm__inst_executed_pipe_xu reads 100 % at that rate);
-        #  * the best POPC rate a synthetic loop sustains on this GPU, measured with tools/lds_probe.cu
-        #    (profiles/r02_pipe_probe.txt): 25.1 lanes per clock and SM at 32 resident warps.
-        # frac_binding is quoted against the SECOND (higher) peak, i.e. it is the conservative figure.
+        # The kernel's floor: one POPC per (cell, counted topology, 32 trees) on the XU pipe, 16 lanes per clock
+        # and SM (one warp-POPC per 8 clocks and SM sub-partition). The rate was verified on this GPU with a
+        # synthetic POPC loop under ncu (tools/lds_probe.cu, profiles/r02_pipe_probe.txt: 8.1 - 8.3 clocks per
+        # warp-POPC and sub-partition at 8 .. 32 resident warps).
         packed = (not complete) and prob.n_trees <= 1023 and os.environ.get("CAMUS_B200_NO_PACKED", "0") != "1"
         popcs = (num_boxes / shares) * groups * 4096 * (2 if complete else 3)
         xu_floor_ms = popcs / (16 * 148 * sm_mhz * 1e6) * 1e3
-        popc_probe_floor_ms = popcs / (25.1 * 148 * sm_mhz * 1e6) * 1e3
         # shared-memory side of the same loop: wavefronts per thread and tree group (LDS.128 = 4, or 2 when the
         # lanes of a quad share addresses; same probe), 8 warps per box, one wavefront per clock and SM
         wavefronts = 48 if complete else 72
@@ -477,18 +475,17 @@ def run_ours(args):
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes_kernel,
                          "launch_ms": kern_ms,
-                         "xu_floor_ms": xu_floor_ms, "frac_xu_pipe_model": xu_floor_ms / kern_ms,
-                         "popc_probe_floor_ms": popc_probe_floor_ms, "lsu_floor_ms": lsu_floor_ms,
-                         "frac_binding": max(popc_probe_floor_ms, lsu_floor_ms) / kern_ms,
+                         "xu_floor_ms": xu_floor_ms, "lsu_floor_ms": lsu_floor_ms,
+                         "frac_binding": max(xu_floor_ms, lsu_floor_ms) / kern_ms,
                          "design_bytes_per_launch": design_bytes,
                          "design_achieved": design_bytes / (kern_ms * 1e-3) / 1e9,
                          "hbm_frac_measured": (traffic / (kern_ms * 1e-3) / 1e9 / peak) if traffic else None,
                          "note": "achieved / frac follow the survey's accounting (8 B per resolution), as the contract asks; the "
                                  "kernel keeps counts in registers and resolves 32 gene trees per 32-bit word, so it moves ~60x fewer "
                                  "bytes than that model and frac exceeds 1: it says nothing about efficiency. frac_binding = the larger of "
-                                 "two measured floors over launch_ms: POPCs at the best rate a synthetic loop reaches on a B200 (25.1 lanes "
-                                 "per clock and SM, tools/lds_probe.cu) and shared-memory wavefronts at one per clock and SM; "
-                                 "frac_xu_pipe_model uses ncu's own XU peak (16 lanes), which the probe exceeds; design_* = "
+                                 "two floors over launch_ms: POPCs at 16 lanes per clock and SM (xu_floor_ms; rate verified with a "
+                                 "synthetic loop under ncu, profiles/r02_pipe_probe.txt) and shared-memory wavefronts at one per clock "
+                                 "and SM (lsu_floor_ms); design_* = "
                                  "bytes of triple tiles streamed (L2 + HBM); traffic = DRAM bytes per launch from ncu "
                                  "(profiles/traffic.json), hbm_frac_measured = that over the measured HBM peak"},
             "roofline_whole_path": {"algorithmic_bytes": b_alg, "achieved": b_alg / dt_res / 1e9, "frac": b_alg / dt_res / 1e9 / peak},

@@ -53,6 +53,9 @@ def lib() -> C.CDLL:
         L.camus_b200_set_constraint.argtypes = [vp, C.c_int32, C.c_int32, vp, vp, vp, vp]
         L.camus_b200_add_gene_trees.argtypes = [vp, C.c_int32, vp, vp, vp]
         L.camus_b200_clear_gene_trees.argtypes = [vp]
+        L.camus_b200_get_gene_trees.argtypes = [vp, vp, vp, vp, C.c_uint64, C.POINTER(C.c_int32), u64p]
+        L.camus_b200_set_tip_labels.argtypes = [vp, C.c_int32, C.c_char_p, vp]
+        L.camus_b200_add_gene_trees_newick.argtypes = [vp, C.c_char_p, C.c_uint64, C.c_double, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         L.camus_b200_set_score_hint.argtypes = [vp, C.c_int]
         L.camus_b200_count_filter.argtypes = [vp, C.c_int, C.c_double, u64p, u64p]
         L.camus_b200_quartet_totals.argtypes = [vp, C.c_int, vp]
@@ -80,6 +83,7 @@ EXPORTED = [
     "camus_b200_export_quartets", "camus_b200_query_cells", "camus_b200_quartet_totals_partial", "camus_b200_partial_buffer",
     "camus_b200_quartet_totals_finish", "camus_b200_run_resident", "camus_b200_stage_ms", "camus_b200_workload",
     "camus_b200_reticulation_counts", "camus_b200_constraint_tables", "camus_b200_comm_unique_id", "camus_b200_comm_init",
+    "camus_b200_set_tip_labels", "camus_b200_add_gene_trees_newick", "camus_b200_get_gene_trees",
     "camus_b200_dp_create", "camus_b200_dp_destroy", "camus_b200_dp_last_error", "camus_b200_dp_set_node",
     "camus_b200_dp_set_vertex", "camus_b200_dp_set_path_columns", "camus_b200_dp_across", "camus_b200_dp_launches",
 ]
@@ -131,6 +135,44 @@ class CamusB200:
         parent = np.ascontiguousarray(parent, np.int32)
         taxon = np.ascontiguousarray(taxon, np.int32)
         self._ck(lib().camus_b200_add_gene_trees(self._h, len(node_off) - 1, _p(node_off), _p(parent), _p(taxon)))
+
+    def set_tip_labels(self, names):
+        """The constraint's tip names in tip-index order (camus_b200_set_tip_labels)."""
+        enc = [n.encode() for n in names]
+        off = np.zeros(len(enc) + 1, np.int64)
+        off[1:] = np.cumsum([len(e) for e in enc])
+        pool = b"".join(enc) or b"\0"
+        self._ck(lib().camus_b200_set_tip_labels(self._h, len(enc), pool, _p(off)))
+
+    def add_gene_trees_newick(self, text, min_support: float = 0.0):
+        """Newick text -> flat trees on the GPU (camus_b200_add_gene_trees_newick). Returns
+        (n_trees, missing_taxa); raises CamusB200Error with code 5 (fallback) and .bad_tree set when
+        the caller has to parse the text itself."""
+        if isinstance(text, str):
+            text = text.encode()
+        nt, mt, bt = C.c_int32(), C.c_int32(), C.c_int32()
+        rc = lib().camus_b200_add_gene_trees_newick(self._h, text, len(text), float(min_support), C.byref(nt), C.byref(mt), C.byref(bt))
+        if rc != 0:
+            e = CamusB200Error(f"[{rc}] " + lib().camus_b200_last_error(self._h).decode())
+            e.code, e.bad_tree = rc, bt.value
+            raise e
+        return nt.value, bool(mt.value)
+
+    def get_gene_trees(self):
+        """(node_off, parent, taxon) of the flat gene trees the context holds."""
+        nt, nn = C.c_int32(), C.c_uint64()
+        self._ck(lib().camus_b200_get_gene_trees(self._h, None, None, None, 0, C.byref(nt), C.byref(nn)))
+        off = np.zeros(nt.value + 1, np.int64)
+        par = np.zeros(max(nn.value, 1), np.int32)
+        tax = np.zeros(max(nn.value, 1), np.int32)
+        self._ck(lib().camus_b200_get_gene_trees(self._h, _p(off), _p(par), _p(tax), nn.value, C.byref(nt), C.byref(nn)))
+        return off, par[:nn.value], tax[:nn.value]
+
+    def load_newick(self, prob, gene_text, min_support: float = 0.0):
+        """As load(), the gene trees parsed and flattened on the GPU from their newick text."""
+        self.set_constraint(prob.parent, prob.child0, prob.child1, prob.tip_index, prob.n_taxa)
+        self.set_tip_labels(prob.tip_names)
+        return self.add_gene_trees_newick(gene_text, min_support)
 
     def clear_gene_trees(self):
         self._ck(lib().camus_b200_clear_gene_trees(self._h))

@@ -15,6 +15,7 @@
 
 #include "camus_b200.h"
 #include "kernels_count.cuh"
+#include "kernels_ingest.cuh"
 #include "kernels_prep.cuh"
 #include "kernels_retic.cuh"
 #include "kernels_score.cuh"
@@ -124,6 +125,13 @@ struct camus_b200 {
   DevBuf<unsigned long long> d_scal;  // the two survivor scalars, all-reduced in place
   std::vector<int32_t> h_depth, h_nleaves, h_ref_of_int;  // constraint tables in internal ids (constraint_tables)
 
+  // ---- gene-tree ingest on the GPU (camus_b200_add_gene_trees_newick) ----
+  DevBuf<unsigned long long> d_lab_hash;
+  DevBuf<int> d_lab_tip;
+  DevBuf<long long> d_lab_off;
+  DevBuf<char> d_lab_pool;
+  unsigned int lab_mask = 0;
+  uint64_t lab_gen = 0;  // constraint generation the label table belongs to (0 = none)
   // ---- inputs beyond the bit-plane budget: the 8 class-scheme shares run one after the other on this GPU ----
   int z_rep_used = 1;        // private copies of Z the running pass sequence uses
   int passes = 1;            // 8 while such a run is in progress or was the last one
@@ -1201,6 +1209,177 @@ int camus_b200_count_filter(camus_b200* ctx, int qmode, double threshold, uint64
   if ((rc = comm_reduce_scalars(ctx, &ns, &sc))) return rc;  // with a communicator: the global values
   if (n_survivors) *n_survivors = ns;
   if (sum_counts) *sum_counts = sc;
+  return 0;
+}
+
+int camus_b200_set_tip_labels(camus_b200* ctx, int32_t n_taxa, const char* labels, const int64_t* label_off) {
+  if (!ctx) return CAMUS_B200_ERR_ARG;
+  if (!ctx->subs.empty()) return fan_out(ctx, [&](camus_b200* s, int) { return camus_b200_set_tip_labels(s, n_taxa, labels, label_off); });
+  if (ctx->n == 0 || n_taxa != ctx->N) return ctx->fail(CAMUS_B200_ERR_ARG, "set_tip_labels: set the constraint tree first; one label per constraint taxon");
+  if (!labels || !label_off || label_off[0] != 0) return ctx->fail(CAMUS_B200_ERR_ARG, "set_tip_labels: null argument");
+  CK(cudaSetDevice(ctx->device));
+  unsigned int cap = 16;
+  while (cap < 2u * (unsigned)n_taxa) cap <<= 1;
+  std::vector<unsigned long long> hs(cap, 0);
+  std::vector<int> tips(cap, -1);
+  for (int t = 0; t < n_taxa; ++t) {
+    const int64_t b = label_off[t], e = label_off[t + 1];
+    if (e < b) return ctx->fail(CAMUS_B200_ERR_ARG, "set_tip_labels: offsets must not decrease");
+    unsigned long long h = 14695981039346656037ull;  // FNV-1a, as nwk_hash
+    for (int64_t i = b; i < e; ++i) {
+      h ^= (unsigned char)labels[i];
+      h *= 1099511628211ull;
+    }
+    if (!h) h = 1;
+    unsigned int s = (unsigned int)h & (cap - 1);
+    while (hs[s]) {
+      if (hs[s] == h) {
+        const int o = tips[s];
+        if (label_off[o + 1] - label_off[o] == e - b && std::memcmp(labels + label_off[o], labels + b, (size_t)(e - b)) == 0)
+          return ctx->fail(CAMUS_B200_ERR_INPUT, "set_tip_labels: the same label twice");
+      }
+      s = (s + 1) & (cap - 1);
+    }
+    hs[s] = h;
+    tips[s] = t;
+  }
+  std::vector<long long> off(label_off, label_off + n_taxa + 1);
+  if (upload(ctx, ctx->d_lab_hash, hs.data(), hs.size()) || upload(ctx, ctx->d_lab_tip, tips.data(), tips.size()) ||
+      upload(ctx, ctx->d_lab_off, off.data(), off.size()) || upload(ctx, ctx->d_lab_pool, labels, (size_t)std::max<int64_t>(label_off[n_taxa], 1)))
+    return CAMUS_B200_ERR_CUDA;
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->lab_mask = cap - 1;
+  ctx->lab_gen = ctx->constraint_gen;
+  return 0;
+}
+
+int camus_b200_add_gene_trees_newick(camus_b200* ctx, const char* text, uint64_t len, double min_support, int32_t* n_trees_out,
+                                     int32_t* missing_taxa, int32_t* bad_tree) {
+  if (!ctx) return CAMUS_B200_ERR_ARG;
+  if (n_trees_out) *n_trees_out = 0;
+  if (missing_taxa) *missing_taxa = 0;
+  if (bad_tree) *bad_tree = 0;
+  if (!ctx->subs.empty()) {
+    ctx->reduced = false;
+    std::vector<int32_t> nt(ctx->subs.size(), 0), mt(ctx->subs.size(), 0), bt(ctx->subs.size(), 0);
+    int rc = fan_out(ctx, [&](camus_b200* s, int i) { return camus_b200_add_gene_trees_newick(s, text, len, min_support, &nt[i], &mt[i], &bt[i]); });
+    if (n_trees_out) *n_trees_out = nt[0];
+    if (missing_taxa) *missing_taxa = mt[0];
+    if (bad_tree) *bad_tree = bt[0];
+    return rc;
+  }
+  if (ctx->n == 0 || ctx->lab_gen != ctx->constraint_gen)
+    return ctx->fail(CAMUS_B200_ERR_ARG, "add_gene_trees_newick: call camus_b200_set_constraint and camus_b200_set_tip_labels first");
+  if (!text || len == 0 || len > ((uint64_t)1 << 31) - 64) return ctx->fail(CAMUS_B200_ERR_ARG, "add_gene_trees_newick: 1 byte .. 2 GiB of text");
+  if (!(min_support == min_support)) return ctx->fail(CAMUS_B200_ERR_ARG, "add_gene_trees_newick: min_support is NaN");
+  CK(cudaSetDevice(ctx->device));
+  // non-blank lines (io.go:138-152: one tree per line), trimmed; finding them is a memchr walk
+  std::vector<long long> lb, le;
+  for (uint64_t start = 0; start < len;) {
+    const char* nl = (const char*)memchr(text + start, '\n', len - start);
+    uint64_t end = nl ? (uint64_t)(nl - text) : len, b = start, e = end;
+    while (b < e && (unsigned char)text[b] <= ' ') ++b;
+    while (e > b && (unsigned char)text[e - 1] <= ' ') --e;
+    if (e > b) {
+      lb.push_back((long long)b);
+      le.push_back((long long)e);
+    }
+    start = end + 1;
+  }
+  const int G = (int)lb.size();
+  if (G == 0) return ctx->fail(CAMUS_B200_ERR_FALLBACK, "add_gene_trees_newick: no tree in the text");
+  StageTimer t(ctx, CAMUS_B200_T_UPLOAD);
+  DevBuf<char> d_text;
+  DevBuf<long long> d_lb, d_le, d_off;
+  DevBuf<int> d_stack, d_par, d_tax, d_nchild;
+  DevBuf<unsigned char> d_coll;
+  DevBuf<unsigned int> d_seen;
+  DevBuf<NwkTreeInfo> d_info;
+  if (upload(ctx, d_text, text, (size_t)len) || upload(ctx, d_lb, lb.data(), lb.size()) || upload(ctx, d_le, le.data(), le.size())) return CAMUS_B200_ERR_CUDA;
+  CK(d_stack.alloc((size_t)len));
+  CK(d_coll.alloc((size_t)len));
+  CK(d_info.alloc(G));
+  CK(d_off.alloc((size_t)G + 1));
+  const size_t words = (size_t)(ctx->N + 31) / 32;
+  CK(d_seen.alloc((size_t)G * words));
+  CK(cudaMemsetAsync(d_seen.p, 0, (size_t)G * words * 4, ctx->stream));
+  const int tb = 64, gb = (G + tb - 1) / tb;
+  k_nwk_pass1<<<gb, tb, 0, ctx->stream>>>(G, d_text.p, d_lb.p, d_le.p, min_support, d_stack.p, d_coll.p, d_info.p);
+  CK_LAUNCH();
+  const long long base = (long long)ctx->h_node_off.back();
+  k_nwk_offsets<<<1, 1024, 0, ctx->stream>>>(G, d_info.p, base, d_off.p);
+  CK_LAUNCH();
+  long long total_end = 0;
+  CK(cudaMemcpyAsync(&total_end, d_off.p + G, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  const size_t cnt = (size_t)(total_end - base);
+  CK(d_par.alloc(std::max<size_t>(cnt, 1)));
+  CK(d_tax.alloc(std::max<size_t>(cnt, 1)));
+  CK(d_nchild.alloc(std::max<size_t>(cnt, 1)));
+  LabelTable lt{ctx->d_lab_hash.p, ctx->d_lab_tip.p, ctx->d_lab_off.p, ctx->d_lab_pool.p, ctx->lab_mask};
+  k_nwk_pass2<<<gb, tb, 0, ctx->stream>>>(G, d_text.p, d_lb.p, d_le.p, d_coll.p, d_stack.p, lt, ctx->N, d_off.p, base, d_par.p, d_tax.p, d_nchild.p,
+                                         d_seen.p, d_info.p);
+  CK_LAUNCH();
+  std::vector<NwkTreeInfo> info(G);
+  std::vector<long long> off((size_t)G + 1);
+  CK(cudaMemcpyAsync(info.data(), d_info.p, (size_t)G * sizeof(NwkTreeInfo), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(off.data(), d_off.p, ((size_t)G + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  static const char* why[] = {"ok", "not in the plain newick dialect or malformed", "single-quoted label", "support value that is not a plain decimal",
+                              "label that is not in the constraint tree (ErrTipNameMismatch)", "label twice in one tree (ErrMulTree)", "too deep"};
+  uint64_t res = 0;
+  int max_depth = 0;
+  bool all_complete = true, all_rooted = true, missing = false;
+  for (int g = 0; g < G; ++g) {
+    const NwkTreeInfo& ti = info[g];
+    int st = ti.status;
+    if (st == kNwkOk && (ti.n_nodes <= 0 || ti.n_nodes > 65535 || ti.max_depth >= 65535)) st = kNwkTooDeep;
+    if (st != kNwkOk) {
+      if (bad_tree) *bad_tree = g + 1;
+      return ctx->fail(CAMUS_B200_ERR_FALLBACK, "add_gene_trees_newick: gene tree " + std::to_string(g + 1) + ", byte " + std::to_string(ti.err_pos) + ": " +
+                                                    why[st < 7 ? st : 1] + "; nothing was added, parse it on the host");
+    }
+    res += choose4((uint64_t)ti.n_leaves);
+    max_depth = std::max(max_depth, ti.max_depth);
+    if (ti.n_leaves != ctx->N) missing = true;
+    if (ti.n_leaves != ctx->N || !ti.binary) all_complete = false;
+    if (ti.root_children != 2) all_rooted = false;
+  }
+  const size_t old = ctx->h_parent.size();
+  ctx->h_parent.resize(old + cnt);
+  ctx->h_taxon.resize(old + cnt);
+  if (cnt) {
+    CK(cudaMemcpyAsync(ctx->h_parent.data() + old, d_par.p, cnt * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_taxon.data() + old, d_tax.p, cnt * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  if (t.stop()) return CAMUS_B200_ERR_CUDA;
+  for (int g = 0; g < G; ++g) ctx->h_node_off.push_back((int64_t)off[g + 1]);
+  ctx->resolutions += res;
+  ctx->max_depth = std::max(ctx->max_depth, max_depth);
+  if (!all_complete) ctx->all_complete = false;
+  if (!all_rooted) ctx->all_rooted = false;
+  ctx->G = (int)ctx->h_node_off.size() - 1;
+  ctx->genes_dirty = true;
+  ctx->cell_state = camus_b200::NONE;
+  ctx->z_valid = false;
+  ctx->counted = false;
+  if (n_trees_out) *n_trees_out = G;
+  if (missing_taxa) *missing_taxa = missing ? 1 : 0;
+  return 0;
+}
+
+int camus_b200_get_gene_trees(camus_b200* ctx, int64_t* node_off, int32_t* parent, int32_t* taxon, uint64_t cap_nodes, int32_t* n_trees,
+                              uint64_t* n_nodes) {
+  if (!ctx) return CAMUS_B200_ERR_ARG;
+  if (!ctx->subs.empty()) return camus_b200_get_gene_trees(ctx->subs[0], node_off, parent, taxon, cap_nodes, n_trees, n_nodes);
+  const uint64_t nn = ctx->h_parent.size();
+  if (n_trees) *n_trees = (int32_t)ctx->h_node_off.size() - 1;
+  if (n_nodes) *n_nodes = nn;
+  if (node_off) std::copy(ctx->h_node_off.begin(), ctx->h_node_off.end(), node_off);
+  if ((parent || taxon) && cap_nodes < nn) return ctx->fail(CAMUS_B200_ERR_ARG, "get_gene_trees: cap_nodes is smaller than the number of nodes");
+  if (parent) std::copy(ctx->h_parent.begin(), ctx->h_parent.end(), parent);
+  if (taxon) std::copy(ctx->h_taxon.begin(), ctx->h_taxon.end(), taxon);
   return 0;
 }
 

@@ -29,6 +29,7 @@
 
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <type_traits>
@@ -127,15 +128,14 @@ __global__ void __launch_bounds__(kAcrossThreads)
 k_dp_across(int n_items, int n_blocks, const int* __restrict__ items /*[2*n_items]: u, sub*/, const int* __restrict__ blk_item,
             const int* __restrict__ item_blk0 /*[n_items+1]*/, const int* __restrict__ sub_end, const int* __restrict__ depth, int v, int k, int n,
             int kcap, int dcap, const unsigned long long* __restrict__ cs_raw, const unsigned long long* __restrict__ dp_raw,
-            const int* __restrict__ dplen, const unsigned long long* __restrict__ edge_raw, ChunkBest* chunk_best, StepOut* out,
-            unsigned int* counter) {
+            const int* __restrict__ dplen, const unsigned long long* __restrict__ edge_raw, ChunkBest* chunk_best, StepOut* out) {
   extern __shared__ unsigned long long sh_raw[];
   S* B = reinterpret_cast<S*>(sh_raw);  // cs_u[0..k]
   S* D = B + (k + 1);                   // dp_u[0..Ld)
   __shared__ unsigned long long r_score[kAcrossThreads];
   __shared__ int r_w[kAcrossThreads], r_ok[kAcrossThreads];
   __shared__ int r_idx[kAcrossThreads][4];
-  __shared__ int s_last, s_stuck;
+  __shared__ int s_stuck;
   const S* cs = reinterpret_cast<const S*>(cs_raw);
   const S* dp = reinterpret_cast<const S*>(dp_raw);
   const S* edge = reinterpret_cast<const S*>(edge_raw);
@@ -233,18 +233,160 @@ k_dp_across(int n_items, int n_blocks, const int* __restrict__ items /*[2*n_item
     cb.stuck = s_stuck;
     for (int q = 0; q < 4; ++q) cb.idx[q] = r_idx[0][q];
     chunk_best[blockIdx.x] = cb;
-    __threadfence();
-    s_last = atomicAdd(counter, 1u) == (unsigned)n_blocks - 1;
+  }
+}
+
+// Tiled form of k_dp_across: one block = up to kTileU consecutive items that scan the SAME other subtree x one
+// chunk of kTileW consecutive w. The cs / DP rows of the chunk's w (read k times per pair) are staged once
+// in shared memory, transposed so that a warp's lanes read consecutive words, and shared by the kTileU items:
+// the one-thread-per-pair kernel above re-reads them from L1 / L2 with a 32-way scattered access per load,
+// which is what bounded it (0.5 ms per step at the root of a 1000-taxon constraint).
+constexpr int kTileW = 64, kTileU = 8;
+
+template <class S>
+__global__ void __launch_bounds__(kTileW* kTileU)
+k_dp_across_tiled(const int* __restrict__ items, const int* __restrict__ blk_tab /*[3*n_blocks]: first item, items in the tile, chunk*/,
+                  const int* __restrict__ item_cb0, const int* __restrict__ sub_end, int k, int n, int kcap, int dcap, int max_len,
+                  const unsigned long long* __restrict__ cs_raw, const unsigned long long* __restrict__ dp_raw, const int* __restrict__ dplen,
+                  const unsigned long long* __restrict__ edge_raw, ChunkBest* chunk_best, StepOut* out) {
+  extern __shared__ unsigned long long sh_raw[];
+  S* As = reinterpret_cast<S*>(sh_raw);         // [k + 1][kTileW]
+  S* Cs = As + (size_t)(k + 1) * kTileW;        // [max_len][kTileW]
+  S* Bs = Cs + (size_t)max_len * kTileW;        // [kTileU][k + 1]
+  S* Ds = Bs + (size_t)kTileU * (k + 1);        // [kTileU][max_len]
+  unsigned long long* r_score = reinterpret_cast<unsigned long long*>(Ds + (size_t)kTileU * max_len);  // [kTileU][kTileW]
+  int* r_w = reinterpret_cast<int*>(r_score + kTileU * kTileW);
+  int* r_ok = r_w + kTileU * kTileW;
+  int* r_idx = r_ok + kTileU * kTileW;  // [kTileU][kTileW][4]
+  __shared__ int s_ld[kTileU], s_stuck[kTileU];
+  const S* cs = reinterpret_cast<const S*>(cs_raw);
+  const S* dp = reinterpret_cast<const S*>(dp_raw);
+  const S* edge = reinterpret_cast<const S*>(edge_raw);
+  const int wt = threadIdx.x, ui = threadIdx.y, tid = ui * kTileW + wt, nthr = kTileW * kTileU;
+  const int first = blk_tab[3 * blockIdx.x], n_it = blk_tab[3 * blockIdx.x + 1], chunk = blk_tab[3 * blockIdx.x + 2];
+  const int sub = items[2 * first + 1], end = sub_end[sub];
+  const int w0 = sub + chunk * kTileW;
+  // stage: thread order = (j, lane) so that shared stores are conflict free (global reads are strided, once per block)
+  for (int idx = tid; idx < (k + 1) * kTileW; idx += nthr) {
+    const int j = idx / kTileW, r = idx % kTileW;
+    As[idx] = w0 + r < end ? cs[(size_t)(w0 + r) * kcap + j] : S{};
+  }
+  for (int idx = tid; idx < max_len * kTileW; idx += nthr) {
+    const int j = idx / kTileW, r = idx % kTileW;
+    Cs[idx] = w0 + r < end ? dp[(size_t)(w0 + r) * dcap + j] : S{};
+  }
+  for (int idx = tid; idx < kTileU * (k + 1); idx += nthr) {
+    const int q = idx / (k + 1), j = idx % (k + 1);
+    Bs[idx] = q < n_it ? cs[(size_t)items[2 * (first + q)] * kcap + j] : S{};
+  }
+  for (int idx = tid; idx < kTileU * max_len; idx += nthr) {
+    const int q = idx / max_len, j = idx % max_len;
+    Ds[idx] = q < n_it ? dp[(size_t)items[2 * (first + q)] * dcap + j] : S{};
+  }
+  if (tid < kTileU) {
+    s_ld[tid] = tid < n_it ? dplen[items[2 * (first + tid)]] : 1;
+    s_stuck[tid] = 0;
   }
   __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  // The last block folds. Per item: its chunks in w order (first maximum; a stuck chunk 0 ends it).
-  // Across the items: max score, then min cycle length, then the last item; NaN candidates never win,
-  // item 0's is reported separately.
+
+  const int w = w0 + wt;
+  bool ok = false;
+  S best{};
+  int bidx[4] = {0, 0, 0, 0};
+  if (ui < n_it && w < end) {
+    const int u = items[2 * (first + ui)];
+    const S* A = As + wt;  // A[j] = A[j * kTileW]
+    const S* C = Cs + wt;
+    const S* B = Bs + (size_t)ui * (k + 1);
+    const S* D = Ds + (size_t)ui * max_len;
+    const int Lc = dplen[w], Ld = s_ld[ui];
+    const int m2 = min(k, Lc + Ld - 2) + 1;
+    bool found = false;
+    S top{};
+    for (int i = k - (m2 - 1); i <= k; ++i) {
+      S c1 = A[0] + B[i];
+      int a1 = 0;
+      for (int j = 1; j <= i; ++j) {
+        const S cur = A[j * kTileW] + B[i - j];
+        if (cur > c1) {
+          c1 = cur;
+          a1 = j;
+        }
+      }
+      const int i2 = k - i;
+      const int lo2 = max(0, i2 - (Ld - 1)), hi2 = min(i2, Lc - 1);
+      S c2 = C[lo2 * kTileW] + D[i2 - lo2];
+      int cc = lo2;
+      for (int j = lo2 + 1; j <= hi2; ++j) {
+        const S cur = C[j * kTileW] + D[i2 - j];
+        if (cur > c2) {
+          c2 = cur;
+          cc = j;
+        }
+      }
+      const S cur = c1 + c2;
+      if (!found || cur > top) {
+        top = cur;
+        bidx[0] = a1;
+        bidx[1] = i - a1;
+        bidx[2] = cc;
+        bidx[3] = i2 - cc;
+        found = true;
+      }
+    }
+    S score = edge[(size_t)u * n + w];  // main_dp.go:268, left to right
+    score = score + A[bidx[0] * kTileW];
+    score = score + B[bidx[1]];
+    score = score + C[bidx[2] * kTileW];
+    score = score + D[bidx[3]];
+    best = score;
+    ok = true;
+    if (is_nan(score)) {
+      atomicOr(&out->nan_seen, 1);
+      if (w == sub) s_stuck[ui] = 1;
+      else ok = false;
+    }
+  }
+  r_score[tid] = raw_of<S>(best);
+  r_w[tid] = w;
+  r_ok[tid] = ok;
+  for (int q = 0; q < 4; ++q) r_idx[tid * 4 + q] = bidx[q];
+  __syncthreads();
+  for (int s = kTileW / 2; s > 0; s >>= 1) {
+    if (wt < s && r_ok[tid + s] && !s_stuck[ui]) {
+      const S a = as_score<S>(r_score[tid]), b = as_score<S>(r_score[tid + s]);
+      if (!r_ok[tid] || b > a || (b == a && r_w[tid + s] < r_w[tid])) {
+        r_score[tid] = r_score[tid + s];
+        r_w[tid] = r_w[tid + s];
+        r_ok[tid] = 1;
+        for (int q = 0; q < 4; ++q) r_idx[tid * 4 + q] = r_idx[(tid + s) * 4 + q];
+      }
+    }
+    __syncthreads();
+  }
+  if (wt == 0 && ui < n_it) {
+    ChunkBest cb;
+    cb.score = r_score[tid];
+    cb.ok = r_ok[tid];
+    cb.w = r_w[tid];
+    cb.stuck = s_stuck[ui];
+    for (int q = 0; q < 4; ++q) cb.idx[q] = r_idx[tid * 4 + q];
+    chunk_best[item_cb0[first + ui] + chunk] = cb;
+  }
+}
+
+// Fold of one step (one block): per item its chunks in w order (first maximum; a stuck chunk 0 ends
+// it); across the items max score, then min cycle length, then the last item; NaN candidates never
+// win, item 0's is reported separately.
+constexpr int kFoldThreads = 1024;
+template <class S>
+__global__ void __launch_bounds__(kFoldThreads)
+k_dp_fold(int n_items, const int* __restrict__ items, const int* __restrict__ item_blk0, const int* __restrict__ depth, int v,
+          const ChunkBest* __restrict__ chunk_best, StepOut* out) {
+  const int tid = threadIdx.x;
   int mine = -1;
   ItemBest mb{};
-  for (int i = tid; i < n_items; i += kAcrossThreads) {
+  for (int i = tid; i < n_items; i += kFoldThreads) {
     const int b0 = item_blk0[i], b1 = item_blk0[i + 1];
     ChunkBest c = chunk_best[b0];
     if (!c.stuck)
@@ -274,12 +416,12 @@ k_dp_across(int n_items, int n_blocks, const int* __restrict__ items /*[2*n_item
       mine = i;
     }
   }
-  __shared__ ItemBest f_best[kAcrossThreads];
-  __shared__ int f_item[kAcrossThreads];
+  __shared__ ItemBest f_best[kFoldThreads];
+  __shared__ int f_item[kFoldThreads];
   f_best[tid] = mb;
   f_item[tid] = mine;
   __syncthreads();
-  for (int s = kAcrossThreads / 2; s > 0; s >>= 1) {
+  for (int s = kFoldThreads / 2; s > 0; s >>= 1) {
     if (tid < s && f_item[tid + s] >= 0) {
       bool take = f_item[tid] < 0;
       if (!take) {
@@ -298,7 +440,6 @@ k_dp_across(int n_items, int n_blocks, const int* __restrict__ items /*[2*n_item
     out->best = f_best[0];
     out->item = f_item[0];
     if (f_item[0] < 0) out->best.ok = 0;
-    *counter = 0;
   }
 }
 
@@ -312,6 +453,9 @@ struct camus_b200_dp {
   int kcap = 0, dcap = 0;
   Buf<int> d_end, d_depth, d_dplen, d_items, d_desc, d_blk_item, d_item_blk0;
   Buf<ChunkBest> d_chunk_best;
+  Buf<int> d_tile_tab, d_item_cb0;  // tiled kernel: (first item, items, chunk) per block; first chunk slot per item
+  int n_tile_blocks = 0, max_len = 1;
+  bool tiled_ok = false;  // the opt-in shared-memory size was granted
   int n_blocks = 0;
   std::vector<int> h_end;
   Buf<unsigned long long> d_edge, d_cs, d_dp, d_blob, d_cols;
@@ -381,6 +525,9 @@ int camus_b200_dp_create(camus_b200_dp** out, int device, int score_is_f64, int3
       (e = cudaMemsetAsync(dp->d_cs.p, 0, n * dp->kcap * 8, dp->stream)) != cudaSuccess ||
       (e = cudaMemsetAsync(dp->d_counter.p, 0, 4, dp->stream)) != cudaSuccess || (e = cudaStreamSynchronize(dp->stream)) != cudaSuccess)
     return bail("upload", e);
+  dp->tiled_ok = cudaFuncSetAttribute(k_dp_across_tiled<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) == cudaSuccess &&
+                 cudaFuncSetAttribute(k_dp_across_tiled<unsigned long long>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) == cudaSuccess;
+  cudaGetLastError();
   *out = dp;
   return CAMUS_B200_OK;
 }
@@ -398,6 +545,7 @@ const char* camus_b200_dp_last_error(const camus_b200_dp* dp) { return dp ? dp->
 int camus_b200_dp_set_node(camus_b200_dp* dp, int32_t node, int32_t len, const void* scores) {
   if (!dp) return CAMUS_B200_ERR_ARG;
   if (node < 0 || node >= dp->n || len < 1 || !scores) return dp->fail(CAMUS_B200_ERR_ARG, "dp_set_node: node out of range or empty list");
+  dp->max_len = std::max(dp->max_len, (int)len);
   dp->pend_desc.push_back(node);
   dp->pend_desc.push_back(len);
   dp->pend_desc.push_back((int)dp->pend_blob.size());
@@ -455,10 +603,34 @@ int camus_b200_dp_set_vertex(camus_b200_dp* dp, int32_t v, int32_t n_items, cons
     blk_item.insert(blk_item.end(), chunks, i);
   }
   dp->n_blocks = blk0[n_items];
+  // tiled kernel: consecutive items with the same other subtree, kTileU at a time, chunks of kTileW
+  std::vector<int> cb0((size_t)n_items + 1, 0), tab;
+  for (int i = 0; i < n_items; ++i) {
+    const int nw = dp->h_end[item_sub[i]] - item_sub[i];
+    cb0[i + 1] = cb0[i] + std::max(1, (nw + kTileW - 1) / kTileW);
+  }
+  for (int i = 0; i < n_items;) {
+    int j = i + 1;
+    while (j < n_items && j - i < kTileU && item_sub[j] == item_sub[i]) ++j;
+    const int chunks = cb0[i + 1] - cb0[i];
+    for (int c = 0; c < chunks; ++c) {
+      tab.push_back(i);
+      tab.push_back(j - i);
+      tab.push_back(c);
+    }
+    i = j;
+  }
+  dp->n_tile_blocks = (int)(tab.size() / 3);
+  if (n_items) {
+    DCK(dp->d_tile_tab.alloc(tab.size()));
+    DCK(dp->d_item_cb0.alloc(cb0.size()));
+    DCK(cudaMemcpyAsync(dp->d_tile_tab.p, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice, dp->stream));
+    DCK(cudaMemcpyAsync(dp->d_item_cb0.p, cb0.data(), cb0.size() * 4, cudaMemcpyHostToDevice, dp->stream));
+    DCK(dp->d_chunk_best.alloc((size_t)std::max(cb0[n_items], blk0[n_items])));
+  }
   if (n_items) {
     DCK(dp->d_blk_item.alloc(blk_item.size()));
     DCK(dp->d_item_blk0.alloc(blk0.size()));
-    DCK(dp->d_chunk_best.alloc(blk_item.size()));
     DCK(cudaMemcpyAsync(dp->d_items.p, it.data(), it.size() * 4, cudaMemcpyHostToDevice, dp->stream));
     DCK(cudaMemcpyAsync(dp->d_blk_item.p, blk_item.data(), blk_item.size() * 4, cudaMemcpyHostToDevice, dp->stream));
     DCK(cudaMemcpyAsync(dp->d_item_blk0.p, blk0.data(), blk0.size() * 4, cudaMemcpyHostToDevice, dp->stream));
@@ -510,19 +682,41 @@ int camus_b200_dp_across(camus_b200_dp* dp, int32_t prev_k, camus_b200_dp_best* 
   if (dp->n_items == 0) return CAMUS_B200_OK;
   if (int rc = flush_nodes(dp)) return rc;
   DCK(cudaMemsetAsync(dp->d_out.p, 0, sizeof(StepOut), dp->stream));
-  const size_t shm = (size_t)(prev_k + 1 + dp->dcap) * 8;
-  if (dp->f64)
-    k_dp_across<double><<<dp->n_blocks, kAcrossThreads, shm, dp->stream>>>(dp->n_items, dp->n_blocks, dp->d_items.p, dp->d_blk_item.p, dp->d_item_blk0.p,
-                                                                           dp->d_end.p, dp->d_depth.p, dp->cur_v, prev_k, dp->n, dp->kcap, dp->dcap,
-                                                                           dp->d_cs.p, dp->d_dp.p, dp->d_dplen.p, dp->d_edge.p, dp->d_chunk_best.p,
-                                                                           dp->d_out.p, dp->d_counter.p);
-  else
-    k_dp_across<unsigned long long><<<dp->n_blocks, kAcrossThreads, shm, dp->stream>>>(dp->n_items, dp->n_blocks, dp->d_items.p, dp->d_blk_item.p,
-                                                                                       dp->d_item_blk0.p, dp->d_end.p, dp->d_depth.p, dp->cur_v, prev_k,
-                                                                                       dp->n, dp->kcap, dp->dcap, dp->d_cs.p, dp->d_dp.p, dp->d_dplen.p,
-                                                                                       dp->d_edge.p, dp->d_chunk_best.p, dp->d_out.p, dp->d_counter.p);
+  static const bool no_tiled = getenv("CAMUS_DP_NO_TILED") && getenv("CAMUS_DP_NO_TILED")[0] == '1';  // A/B, tests
+  const int ml = std::min(dp->max_len, dp->dcap);
+  const size_t shm_tiled = ((size_t)(prev_k + 1 + ml) * (kTileW + kTileU)) * 8 + (size_t)kTileU * kTileW * (8 + 4 + 4 + 16);
+  const bool tiled = dp->tiled_ok && !no_tiled && shm_tiled <= 200 * 1024;
+  const int* cb0 = tiled ? dp->d_item_cb0.p : dp->d_item_blk0.p;
+  if (tiled) {
+    const dim3 blk(kTileW, kTileU);
+    if (dp->f64)
+      k_dp_across_tiled<double><<<dp->n_tile_blocks, blk, shm_tiled, dp->stream>>>(dp->d_items.p, dp->d_tile_tab.p, dp->d_item_cb0.p, dp->d_end.p, prev_k, dp->n,
+                                                                                   dp->kcap, dp->dcap, ml, dp->d_cs.p, dp->d_dp.p, dp->d_dplen.p, dp->d_edge.p,
+                                                                                   dp->d_chunk_best.p, dp->d_out.p);
+    else
+      k_dp_across_tiled<unsigned long long><<<dp->n_tile_blocks, blk, shm_tiled, dp->stream>>>(dp->d_items.p, dp->d_tile_tab.p, dp->d_item_cb0.p, dp->d_end.p,
+                                                                                               prev_k, dp->n, dp->kcap, dp->dcap, ml, dp->d_cs.p, dp->d_dp.p,
+                                                                                               dp->d_dplen.p, dp->d_edge.p, dp->d_chunk_best.p, dp->d_out.p);
+  } else {
+    const size_t shm = (size_t)(prev_k + 1 + dp->dcap) * 8;
+    if (dp->f64)
+      k_dp_across<double><<<dp->n_blocks, kAcrossThreads, shm, dp->stream>>>(dp->n_items, dp->n_blocks, dp->d_items.p, dp->d_blk_item.p, dp->d_item_blk0.p,
+                                                                             dp->d_end.p, dp->d_depth.p, dp->cur_v, prev_k, dp->n, dp->kcap, dp->dcap,
+                                                                             dp->d_cs.p, dp->d_dp.p, dp->d_dplen.p, dp->d_edge.p, dp->d_chunk_best.p,
+                                                                             dp->d_out.p);
+    else
+      k_dp_across<unsigned long long><<<dp->n_blocks, kAcrossThreads, shm, dp->stream>>>(dp->n_items, dp->n_blocks, dp->d_items.p, dp->d_blk_item.p,
+                                                                                         dp->d_item_blk0.p, dp->d_end.p, dp->d_depth.p, dp->cur_v, prev_k,
+                                                                                         dp->n, dp->kcap, dp->dcap, dp->d_cs.p, dp->d_dp.p, dp->d_dplen.p,
+                                                                                         dp->d_edge.p, dp->d_chunk_best.p, dp->d_out.p);
+  }
   DCK(cudaGetLastError());
-  ++dp->launches;
+  if (dp->f64)
+    k_dp_fold<double><<<1, kFoldThreads, 0, dp->stream>>>(dp->n_items, dp->d_items.p, cb0, dp->d_depth.p, dp->cur_v, dp->d_chunk_best.p, dp->d_out.p);
+  else
+    k_dp_fold<unsigned long long><<<1, kFoldThreads, 0, dp->stream>>>(dp->n_items, dp->d_items.p, cb0, dp->d_depth.p, dp->cur_v, dp->d_chunk_best.p, dp->d_out.p);
+  DCK(cudaGetLastError());
+  dp->launches += 2;
   DCK(cudaMemcpyAsync(dp->h_out, dp->d_out.p, sizeof(StepOut), cudaMemcpyDeviceToHost, dp->stream));
   DCK(cudaStreamSynchronize(dp->stream));
   const StepOut& r = *dp->h_out;

@@ -16,6 +16,7 @@
  *   camus_b200_export_quartets  <- the map[Quartet]uint32 itself       internal/graphs/quartet.go:11-31
  *   camus_b200_reticulation_counts <- the per-gene-tree loop of score.ReticulationScore
  *                                                                       internal/score/score.go:31-60
+ *   camus_b200_add_gene_trees_newick <- readGeneTreesFile's parse loop + per-tree preprocessing  internal/prep/io.go:133-153, preprocess.go:87-100
  *   camus_b200_dp_across        <- the scoreEdgesAcross loop of scoreAddEdgeK  internal/infer/main_dp.go:199-214, :247-287
  *
  * Conventions: plain pointers + sizes, host memory, valid for the duration of the call only (cgo
@@ -40,7 +41,8 @@ enum {
   CAMUS_B200_ERR_ARG = 1,     /* bad argument / call order */
   CAMUS_B200_ERR_CUDA = 2,    /* CUDA runtime failure */
   CAMUS_B200_ERR_NOMEM = 3,   /* problem does not fit the device */
-  CAMUS_B200_ERR_INPUT = 4    /* malformed flat tree */
+  CAMUS_B200_ERR_INPUT = 4,   /* malformed flat tree */
+  CAMUS_B200_ERR_FALLBACK = 5 /* camus_b200_add_gene_trees_newick only: the text needs the caller's own parser (nothing was added) */
 };
 
 /* One handle for n_gpus GPUs of this process (1, 2, 4, 8). devices[i] = CUDA
@@ -178,6 +180,30 @@ int camus_b200_run_resident(camus_b200* ctx, int qmode, double threshold, int as
 int camus_b200_stage_ms(const camus_b200* ctx, float* ms /*[CAMUS_B200_T_N]*/, uint64_t* n_launches);
 /* resolutions = sum over gene trees of C(leaves,4): the unit of the throughput metric. */
 int camus_b200_workload(const camus_b200* ctx, uint64_t* resolutions, uint64_t* n_cells, uint64_t* n_boxes);
+
+/* ---- gene-tree ingest on the GPU ----
+ * For newick gene-tree files: replaces the parse loop of prep.readGeneTreesFile (internal/prep/io.go:133-153),
+ * the per-tree UpdateTipIndex / missing-taxa check / CollapseLowSupport(minSupp, true) of prep.processQuartets
+ * (internal/prep/preprocess.go:87-100), graphs.MapIDsFromConstTree (internal/graphs/quartet.go:131-149) and the
+ * flattening in front of camus_b200_add_gene_trees: the file's bytes go to the device, the flat trees are built
+ * there (csrc/kernels_ingest.cuh) and appended exactly as camus_b200_add_gene_trees would append them.
+ *   set_tip_labels   the constraint tree's tip names in tip-index order (ascending byte order, gotree
+ *                    UpdateTipIndex) as one byte pool + offsets; call after camus_b200_set_constraint
+ *   add_gene_trees_newick   text = the file: one tree per non-blank line. min_support = the -s flag (0 = no
+ *                    collapse). *missing_taxa != 0: some tree lacks a constraint taxon (the reference prints its
+ *                    warning once, preprocess.go:90-97).
+ * Returns CAMUS_B200_ERR_FALLBACK, having added NOTHING, when a line is outside the supported dialect
+ * (single-quoted labels; with -s != 0 support values that are not plain decimals of <= 15 significant
+ * digits), malformed, holds a label the constraint does not have (graphs.ErrTipNameMismatch) or a label
+ * twice (prep.ErrMulTree): *bad_tree = its 1-based index, camus_b200_last_error says why, and the caller runs
+ * its own parser + camus_b200_add_gene_trees, which reports the reference's error text. */
+int camus_b200_set_tip_labels(camus_b200* ctx, int32_t n_taxa, const char* labels, const int64_t* label_off /*[n_taxa+1]*/);
+int camus_b200_add_gene_trees_newick(camus_b200* ctx, const char* text, uint64_t len, double min_support,
+                                     int32_t* n_trees, int32_t* missing_taxa, int32_t* bad_tree);
+/* parity / debug: the flat gene trees the context holds (as passed to, or built by, the calls above). Any of the
+ * arrays may be NULL; *n_trees / *n_nodes are always set. cap_nodes = room in parent[] / taxon[]. */
+int camus_b200_get_gene_trees(camus_b200* ctx, int64_t* node_off /*[n_trees+1]*/, int32_t* parent, int32_t* taxon, uint64_t cap_nodes,
+                              int32_t* n_trees, uint64_t* n_nodes);
 
 /* ---- DP offload: the across-scan of the level-1 network DP ----
  * Replaces the loop body of scoreAddEdgeK that calls scoreEdgesAcross for every u
