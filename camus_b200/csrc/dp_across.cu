@@ -462,6 +462,9 @@ struct camus_b200_dp {
   Buf<StepOut> d_out;
   Buf<unsigned int> d_counter;
   StepOut* h_out = nullptr;  // pinned
+  unsigned long long* h_stage = nullptr;  // pinned staging of the path columns (copied asynchronously)
+  size_t stage_cap = 0;
+  bool stage_busy = false;
   int n_items = 0, cur_v = -1;
   std::vector<int> pend_desc;
   std::vector<unsigned long long> pend_blob;
@@ -507,6 +510,8 @@ int camus_b200_dp_create(camus_b200_dp** out, int device, int score_is_f64, int3
   if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
   if ((e = cudaStreamCreateWithFlags(&dp->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
   if ((e = cudaMallocHost(&dp->h_out, sizeof(StepOut))) != cudaSuccess) return bail("pinned result", e);
+  dp->stage_cap = (size_t)n_nodes * 128;  // path columns of 128 steps at once; grows on demand
+  if ((e = cudaMallocHost(&dp->h_stage, dp->stage_cap * 8)) != cudaSuccess) return bail("pinned staging", e);
   const size_t n = (size_t)n_nodes;
   dp->kcap = 32;
   dp->dcap = 16;
@@ -537,6 +542,7 @@ void camus_b200_dp_destroy(camus_b200_dp* dp) {
   cudaSetDevice(dp->device);
   if (dp->stream) cudaStreamDestroy(dp->stream);
   if (dp->h_out) cudaFreeHost(dp->h_out);
+  if (dp->h_stage) cudaFreeHost(dp->h_stage);
   delete dp;
 }
 
@@ -663,13 +669,26 @@ int camus_b200_dp_set_path_columns(camus_b200_dp* dp, int32_t k0, int32_t k1, in
   }
   const size_t tot = (size_t)(k1 - k0) * count;
   if (tot) {
+    // through a pinned staging buffer, asynchronously: camus_b200_dp_across synchronises once per step
+    if (dp->stage_busy) {
+      DCK(cudaStreamSynchronize(dp->stream));
+      dp->stage_busy = false;
+    }
+    if (tot > dp->stage_cap) {
+      if (dp->h_stage) cudaFreeHost(dp->h_stage);
+      dp->h_stage = nullptr;
+      dp->stage_cap = 0;
+      DCK(cudaMallocHost(&dp->h_stage, tot * 2 * 8));
+      dp->stage_cap = tot * 2;
+    }
+    memcpy(dp->h_stage, cols, tot * 8);
     DCK(dp->d_cols.alloc(tot));
-    DCK(cudaMemcpyAsync(dp->d_cols.p, cols, tot * 8, cudaMemcpyHostToDevice, dp->stream));
+    DCK(cudaMemcpyAsync(dp->d_cols.p, dp->h_stage, tot * 8, cudaMemcpyHostToDevice, dp->stream));
     k_cs_scatter<<<(unsigned)((tot + 255) / 256), 256, 0, dp->stream>>>(dp->d_cols.p, dp->d_cs.p, dp->kcap, k0, k1 - k0, first, count);
     DCK(cudaGetLastError());
     ++dp->launches;
+    dp->stage_busy = true;
   }
-  DCK(cudaStreamSynchronize(dp->stream));  // the caller's buffer is free again
   return CAMUS_B200_OK;
 }
 
@@ -719,6 +738,7 @@ int camus_b200_dp_across(camus_b200_dp* dp, int32_t prev_k, camus_b200_dp_best* 
   dp->launches += 2;
   DCK(cudaMemcpyAsync(dp->h_out, dp->d_out.p, sizeof(StepOut), cudaMemcpyDeviceToHost, dp->stream));
   DCK(cudaStreamSynchronize(dp->stream));
+  dp->stage_busy = false;
   const StepOut& r = *dp->h_out;
   out->found = r.best.ok;
   out->nan_seen = r.nan_seen;

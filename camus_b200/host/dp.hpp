@@ -11,6 +11,7 @@
 #include <chrono>
 #include <cmath>
 #include <condition_variable>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <functional>
@@ -372,6 +373,11 @@ class DP {
     }
   }
 
+  ~DP() {
+    if (profile_)
+      fprintf(stderr, "[dp] cycleDP.update %.3f s, scoreEdgesDown %.3f s, item lists %.3f s, across scan %.3f s, acceptance %.3f s\n", t_update_, t_down_,
+              t_items_, t_scan_, t_accept_);
+  }
   const std::vector<S>& root_scores() const { return dp_[0]; }
   std::vector<Branch> traceback(int k) const {
     std::vector<Branch> out;
@@ -388,6 +394,10 @@ class DP {
   TraceArena arena_;
   WorkerPool pool_;
   DpAccel* accel_ = nullptr;
+  // CAMUS_DP_PROFILE=1: seconds per part of the DP, printed by the destructor
+  bool profile_ = getenv("CAMUS_DP_PROFILE") && getenv("CAMUS_DP_PROFILE")[0] == '1';
+  double t_update_ = 0, t_down_ = 0, t_items_ = 0, t_scan_ = 0, t_accept_ = 0, t_noedge_ = 0;
+  static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
   int accel_v_ = -1, accel_cols_ = 0;  // vertex whose items are on the device, path columns already there
   std::vector<uint64_t> col_buf_;
   // CAMUS_DP_LITERAL=1: literal FourWayBestSplit scan for integer scores too (A/B, tests)
@@ -396,6 +406,7 @@ class DP {
   std::vector<std::vector<S>> cs_;
   std::vector<std::vector<int>> ct_;
   std::vector<std::pair<int, int>> items_;  // (u, other subtree) in the reference's visiting order
+  int items_v_ = -1;                        // vertex items_ was built for
   std::vector<Desc> descs_;
   // integer scores only: conv_[j][x] = max over i + i' = j of cs_[x][i] + dp_[x][i'] (see fast_across)
   std::vector<std::vector<S>> conv_;
@@ -655,7 +666,9 @@ class DP {
     int prevK = k - 1;
     Cand best;
     int bestLen = 0;
+    double t0 = now();
     cdp_update(v, prevK);
+    t_update_ += now() - t0;
     auto consider = [&](const Cand& c) {
       if (!c.ok) return;
       int len = cycle_length(c.br.u, c.br.w, td_);
@@ -664,16 +677,20 @@ class DP {
         bestLen = len;
       }
     };
+    t0 = now();
     for (int c : td_.children[v]) {
       if (td_.tip(c)) continue;
       consider(score_edges_down(v, prevK));
     }
+    t_down_ += now() - t0;
+    t0 = now();
     // SubtreePostOrder(v, ...) (helpers.go:9-24): every u of the first child's subtree in post-order
     // against the second child's subtree, then the other way round. The per-u scans are
     // independent, so they run on the pool; acceptance below replays the reference's order.
     int c0 = td_.children[v][0], c1 = td_.children[v][1];
-    items_.clear();
-    {
+    if (items_v_ != v) {  // the item list depends on v only
+      items_v_ = v;
+      items_.clear();
       std::vector<int> order;
       post_order(c0, order);
       for (int u : order) items_.push_back({u, c1});
@@ -682,6 +699,8 @@ class DP {
       for (int u : order) items_.push_back({u, c0});
     }
     descs_.assign(items_.size(), Desc{});
+    t_items_ += now() - t0;
+    t0 = now();
     const size_t work = (size_t)(td_.subtree_end[c0] - c0) * (size_t)(td_.subtree_end[c1] - c1) * (size_t)(prevK + 1);
     if (accel_ && !items_.empty()) {
       // float scores pay (k + 1)^2 additions per pair on the host, integer ones (max-plus form) k + 1
@@ -703,6 +722,7 @@ class DP {
           }
         }
         if (accel_->verify) verify_same(host_best, best, v, prevK);
+        t_scan_ += now() - t0;
         return best;
       } else {
         ++accel_->steps_host;
@@ -725,15 +745,28 @@ class DP {
     } else {
       for (int i = 0; i < (int)items_.size(); ++i) body(i, 0);
     }
+    t_scan_ += now() - t0;
+    t0 = now();
+    // same acceptance test as consider(), folded over plain descriptors: only the candidate the loop ENDS
+    // with gets its split indices and trace (the reference allocates one per acceptance; the intermediate
+    // ones are unreachable garbage). CycleLength (an LCA walk) only where the test needs it.
+    const Desc* win = nullptr;
+    S top = best.score;
+    bool have = best.ok;
     for (const Desc& d : descs_) {
       if (!d.ok) continue;
-      // same acceptance test as consider(), evaluated before the trace is allocated
+      const bool better = d.score > top || !have;
+      if (!better && !(d.score == top)) continue;
       int len = cycle_length(d.u, d.w, td_);
-      if (d.score > best.score || !best.ok || (d.score == best.score && len <= bestLen)) {
-        best = materialise(d);
+      if (better || len <= bestLen) {
+        win = &d;
+        top = d.score;
+        have = true;
         bestLen = len;
       }
     }
+    if (win) best = materialise(*win);
+    t_accept_ += now() - t0;
     return best;
   }
 
@@ -853,7 +886,7 @@ inline DPResults run_dp(const TreeData& td, const ScoreTables& tabs, ScoreMode m
       const char* m = api->last_error(nullptr);
       throw CamusError(Err::Internal, std::string("DP offload: create: ") + (m ? m : "?"));
     }
-    accel.min_work = min_work >= 0 ? (uint64_t)min_work : 400000;
+    accel.min_work = min_work >= 0 ? (uint64_t)min_work : 30000;  // measured at 1000 taxa: 1e5 .. 8e3 are within 10 % of each other
     if (const char* e = getenv("CAMUS_DP_ACCEL_MIN_WORK")) accel.min_work = strtoull(e, nullptr, 10);
     accel.verify = getenv("CAMUS_DP_VERIFY") && getenv("CAMUS_DP_VERIFY")[0] == '1';
     return &accel;
