@@ -1689,7 +1689,7 @@ int camus_b200_query_cells(camus_b200* ctx, int32_t n_query, const int32_t* quad
   return 0;
 }
 
-int camus_b200_reticulation_counts(camus_b200* ctx, int32_t n_tips, int32_t n_ret, const uint32_t* records,
+static int reticulation_counts_batch(camus_b200* ctx, int32_t n_tips, int32_t n_ret, const uint32_t* records,
                                    int32_t n_trees, const int64_t* node_off, const int32_t* parent,
                                    const int32_t* taxon, uint64_t* totals, uint64_t* supported) {
   if (!ctx) return CAMUS_B200_ERR_ARG;
@@ -1790,6 +1790,28 @@ int camus_b200_reticulation_counts(camus_b200* ctx, int32_t n_tips, int32_t n_re
   CK(cudaMemcpyAsync(totals, d_tot.p, n_out * 8, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaMemcpyAsync(supported, d_sup.p, n_out * 8, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+// More than 64 reticulations (score.ReticulationScore has no limit): batches of 64 on this side of the ABI;
+// the per-reticulation records and outputs are independent.
+int camus_b200_reticulation_counts(camus_b200* ctx, int32_t n_tips, int32_t n_ret, const uint32_t* records, int32_t n_trees,
+                                   const int64_t* node_off, const int32_t* parent, const int32_t* taxon, uint64_t* totals,
+                                   uint64_t* supported) {
+  if (!ctx) return CAMUS_B200_ERR_ARG;
+  if (n_ret <= kRetMax || !records || !totals || !supported || n_trees < 0 || n_tips < 1)
+    return reticulation_counts_batch(ctx, n_tips, n_ret, records, n_trees, node_off, parent, taxon, totals, supported);
+  std::vector<uint64_t> t((size_t)n_trees * kRetMax), s((size_t)n_trees * kRetMax);
+  for (int r0 = 0; r0 < n_ret; r0 += kRetMax) {
+    const int rc_n = std::min<int>(kRetMax, n_ret - r0);
+    int rc = reticulation_counts_batch(ctx, n_tips, rc_n, records + (size_t)r0 * n_tips * 4, n_trees, node_off, parent, taxon, t.data(), s.data());
+    if (rc) return rc;
+    for (int g = 0; g < n_trees; ++g)
+      for (int r = 0; r < rc_n; ++r) {
+        totals[(size_t)g * n_ret + r0 + r] = t[(size_t)g * rc_n + r];
+        supported[(size_t)g * n_ret + r0 + r] = s[(size_t)g * rc_n + r];
+      }
+  }
   return 0;
 }
 

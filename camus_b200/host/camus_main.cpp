@@ -112,6 +112,20 @@ void write_csv(std::ostream& os, const TreeData& td, const std::vector<std::stri
 
 }  // namespace
 
+// Go's flag package rejects trailing garbage ("-q 2x"); stoi / stod alone would accept it
+static int whole_int(const std::string& v) {
+  size_t pos = 0;
+  int r = std::stoi(v, &pos);
+  if (pos != v.size()) throw std::invalid_argument(v);
+  return r;
+}
+static double whole_double(const std::string& v) {
+  size_t pos = 0;
+  double r = std::stod(v, &pos);
+  if (pos != v.size()) throw std::invalid_argument(v);
+  return r;
+}
+
 int main(int argc, char** argv) {
   std::string format = "newick", prefix, scoreMode = "max";
   int qmode = 2, nprocs = 0;
@@ -156,14 +170,16 @@ int main(int argc, char** argv) {
         if (format != "newick" && format != "nexus") parser_error("invalid value \"" + format + "\" for flag -f: \"" + format + "\" is not a valid gene tree file format");
       } else if (name == "o") prefix = need();
       else if (name == "sm") scoreMode = need();
-      else if (name == "q") qmode = std::stoi(need());
-      else if (name == "s") supp = std::stod(need());
-      else if (name == "t") thresh = std::stod(need());
-      else if (name == "a") alpha = std::stod(need());
-      else if (name == "n") nprocs = std::stoi(need());
+      else if (name == "q") qmode = whole_int(need());
+      else if (name == "s") supp = whole_double(need());
+      else if (name == "t") thresh = whole_double(need());
+      else if (name == "a") alpha = whole_double(need());
+      else if (name == "n") nprocs = whole_int(need());
       else parser_error("flag provided but not defined: -" + name);
     } catch (const std::invalid_argument&) {
       parser_error("invalid value for flag -" + name);
+    } catch (const std::out_of_range&) {  // Go's flag package: "value out of range"
+      parser_error("invalid value for flag -" + name + ": value out of range");
     }
   }
   if (pos.size() != 2) parser_error("two positional arguments required: <const_tree> <gene_tree_file>");

@@ -135,7 +135,8 @@ int camus_b200_query_cells(camus_b200* ctx, int32_t n_query, const int32_t* quad
  *                                 + 3 = bit 0: t under w_r, 1: under v_r, 2: under wSub_r, 3: under u_r
  * with node id 0 = the root. Gene trees: CSR as in camus_b200_add_gene_trees, taxon = tip index in
  * the NETWORK tree (its #H tips included, graphs.MapIDsFromConstTree against ntw.NetTree). The call
- * is independent of the constraint / gene trees loaded into ctx; n_ret <= 64. Outputs are
+ * is independent of the constraint / gene trees loaded into ctx; any n_ret (batches of 64 inside); gene trees
+ * of at most 24576 nodes. Outputs are
  * [n_trees * n_ret], row-major by gene tree. */
 int camus_b200_reticulation_counts(camus_b200* ctx, int32_t n_tips, int32_t n_ret, const uint32_t* records,
                                    int32_t n_trees, const int64_t* node_off, const int32_t* parent,

@@ -171,5 +171,17 @@ def test_gpu_argument_checks(gpu, large):
     out = np.zeros(5, np.uint64)
     rc = lib().camus_b200_reticulation_counts(gpu._h, large.n_tips, large.n_ret, _p(rec), 1, _p(off), _p(par), _p(tax), _p(out), _p(out))
     assert rc == 4
-    rc = lib().camus_b200_reticulation_counts(gpu._h, large.n_tips, 65, _p(rec), 1, _p(off), _p(par), _p(tax), _p(out), _p(out))
+    rc = lib().camus_b200_reticulation_counts(gpu._h, large.n_tips, 0, _p(rec), 1, _p(off), _p(par), _p(tax), _p(out), _p(out))
     assert rc == 1
+    # more than 64 reticulations (score.ReticulationScore has no limit): batches of 64 inside the call.
+    # The dataset's 5 reticulations repeated 14 times must give the 5 columns 14 times over.
+    tot5, sup5 = gpu.reticulation_counts(large)
+    reps = 14
+    rec70 = np.ascontiguousarray(np.tile(rec.reshape(large.n_ret, -1), (reps, 1)))
+    a = [np.ascontiguousarray(x) for x in (large.gene_node_off, large.gene_parent, large.gene_taxon)]
+    tot = np.zeros((large.n_trees, large.n_ret * reps), np.uint64)
+    sup = np.zeros_like(tot)
+    rc = lib().camus_b200_reticulation_counts(gpu._h, large.n_tips, large.n_ret * reps, _p(rec70), large.n_trees, _p(a[0]), _p(a[1]), _p(a[2]),
+                                              _p(tot), _p(sup))
+    assert rc == 0
+    assert np.array_equal(tot, np.tile(tot5, (1, reps))) and np.array_equal(sup, np.tile(sup5, (1, reps)))
