@@ -504,15 +504,16 @@ def run_ours(args):
             ns, sc = gpu.count_filter(qmode, thr)
             tab = gpu.quartet_totals(as_set)
             pen = gpu.edge_penalties() if c["mode"] != "max" else None
-            prob.run_dp(tab, pen, c["mode"], as_set, ns, sc, prob.n_trees, 0.5, gpu=local)  # warm-up: loads the DP kernels
             t1 = time.perf_counter()
+            prob.run_dp(tab, pen, c["mode"], as_set, ns, sc, prob.n_trees, 0.5, gpu=local)  # untimed warm-up: loads the DP kernels
+            t1b = time.perf_counter()
             res = prob.run_dp(tab, pen, c["mode"], as_set, ns, sc, prob.n_trees, 0.5, gpu=local)
             t2 = time.perf_counter()
             host = prob.run_dp(tab, pen, c["mode"], as_set, ns, sc, prob.n_trees, 0.5) if c["mode"] == "max" or prob.n_taxa <= 400 else None
             t3 = time.perf_counter()
             if host is not None:
                 assert host.branches == res.branches and host.newicks == res.newicks and host.root_scores == res.root_scores
-            line["infer"] = {"infer_s": t2 - t0, "hot_path_s": t1 - t0, "dp_s": t2 - t1, "score_mode": c["mode"],
+            line["infer"] = {"infer_s": (t1 - t0) + (t2 - t1b), "hot_path_s": t1 - t0, "dp_s": t2 - t1b, "dp_first_call_s": t1b - t1, "score_mode": c["mode"],
                              "networks": len(res.newicks), "dp_offload": res.accel,
                              "dp_host_only_s": (t3 - t2) if host is not None else None,
                              "what": "flat trees -> count/filter -> edge table (GPU, C-ABI) -> DP: post-order driver, cycleDP.update and "
