@@ -77,7 +77,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(nm)
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(0.1)  # NVML queries take a driver lock: 50 per second delayed the launches of small configurations by milliseconds
 
     def result(self):
         self.stop_flag = True
