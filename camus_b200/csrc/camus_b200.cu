@@ -132,6 +132,12 @@ struct camus_b200 {
   DevBuf<char> d_lab_pool;
   unsigned int lab_mask = 0;
   uint64_t lab_gen = 0;  // constraint generation the label table belongs to (0 = none)
+  DevBuf<char> nwk_text;  // scratch of add_gene_trees_newick, kept between calls
+  DevBuf<long long> nwk_lb, nwk_le, nwk_off;
+  DevBuf<int> nwk_stack, nwk_par, nwk_tax, nwk_nchild;
+  DevBuf<unsigned char> nwk_coll;
+  DevBuf<unsigned int> nwk_seen;
+  DevBuf<NwkTreeInfo> nwk_info;
   // ---- inputs beyond the bit-plane budget: the 8 class-scheme shares run one after the other on this GPU ----
   int z_rep_used = 1;        // private copies of Z the running pass sequence uses
   int passes = 1;            // 8 while such a run is in progress or was the last one
@@ -1289,12 +1295,13 @@ int camus_b200_add_gene_trees_newick(camus_b200* ctx, const char* text, uint64_t
   const int G = (int)lb.size();
   if (G == 0) return ctx->fail(CAMUS_B200_ERR_FALLBACK, "add_gene_trees_newick: no tree in the text");
   StageTimer t(ctx, CAMUS_B200_T_UPLOAD);
-  DevBuf<char> d_text;
-  DevBuf<long long> d_lb, d_le, d_off;
-  DevBuf<int> d_stack, d_par, d_tax, d_nchild;
-  DevBuf<unsigned char> d_coll;
-  DevBuf<unsigned int> d_seen;
-  DevBuf<NwkTreeInfo> d_info;
+  // scratch lives in the context: cudaMalloc / cudaFree per call cost more than the two kernels
+  DevBuf<char>& d_text = ctx->nwk_text;
+  DevBuf<long long>&d_lb = ctx->nwk_lb, &d_le = ctx->nwk_le, &d_off = ctx->nwk_off;
+  DevBuf<int>&d_stack = ctx->nwk_stack, &d_par = ctx->nwk_par, &d_tax = ctx->nwk_tax, &d_nchild = ctx->nwk_nchild;
+  DevBuf<unsigned char>& d_coll = ctx->nwk_coll;
+  DevBuf<unsigned int>& d_seen = ctx->nwk_seen;
+  DevBuf<NwkTreeInfo>& d_info = ctx->nwk_info;
   if (upload(ctx, d_text, text, (size_t)len) || upload(ctx, d_lb, lb.data(), lb.size()) || upload(ctx, d_le, le.data(), le.size())) return CAMUS_B200_ERR_CUDA;
   CK(d_stack.alloc((size_t)len));
   CK(d_coll.alloc((size_t)len));
