@@ -924,6 +924,9 @@ int run_passes(camus_b200* ctx, int passes, int qmode, double threshold, int as_
 
 // K2 (table mode) over this rank's box range (whole range resident in d_cells).
 int run_count(camus_b200* ctx) {
+  // the bit-planes may belong to one share of a passes run (or to another partition): the table pipeline needs this partition's
+  if (!planes_cover(ctx))
+    if (int rc = build_planes(ctx, false)) return rc;
   if (int rc = set_box_range(ctx)) return rc;
   uint64_t mine = ctx->n_local;
   if (ctx->d_cells.n < mine * kBoxCells) {

@@ -913,6 +913,10 @@ def test_eight_sequential_passes_equal_one_pass(gpu, monkeypatch):
                     assert np.array_equal(multi.quartet_totals(as_set), o.quartet_totals(as_set, False))
                 _, ns, sc = multi.run_resident(qmode, thr, hint, np.empty((prob.n_nodes, prob.n_nodes), np.uint64))
                 assert (ns, sc) == want
+            # the table pipeline after a passes run: the bit-planes in HBM are one share's, export rebuilds the whole table
+            for a, b in zip(multi.export_quartets(), o.export_quartets()):
+                assert np.array_equal(a, b)
+            assert np.array_equal(multi.quartet_totals(False), o.quartet_totals(False, False))
         gpu.load(prob)
         assert gpu.count_filter(2, 0.5) == o.count_filter(2, 0.5, False)  # the one-pass context is untouched by the mode
     multi.close()
