@@ -241,18 +241,19 @@ k_dp_across(int n_items, int n_blocks, const int* __restrict__ items /*[2*n_item
 // in shared memory, transposed so that a warp's lanes read consecutive words, and shared by the kTileU items:
 // the one-thread-per-pair kernel above re-reads them from L1 / L2 with a 32-way scattered access per load,
 // which is what bounded it (0.5 ms per step at the root of a 1000-taxon constraint).
-constexpr int kTileW = 64, kTileU = 8;
+constexpr int kTileW = 64, kTileU = 8, kTileLd = kTileW + 1;
 
 template <class S>
 __global__ void __launch_bounds__(kTileW* kTileU)
-k_dp_across_tiled(const int* __restrict__ items, const int* __restrict__ blk_tab /*[3*n_blocks]: first item, items in the tile, chunk*/,
-                  const int* __restrict__ item_cb0, const int* __restrict__ sub_end, int k, int n, int kcap, int dcap, int max_len,
+k_dp_across_tiled(const int* __restrict__ items, const int* __restrict__ blk_tab /*[4*n_blocks]: first item, items in the tile, chunk, offset into perm*/,
+                  const int* __restrict__ perm /*the other subtree's nodes, longest DP list first*/, const int* __restrict__ item_cb0,
+                  const int* __restrict__ sub_end, int k, int n, int kcap, int dcap, int max_len,
                   const unsigned long long* __restrict__ cs_raw, const unsigned long long* __restrict__ dp_raw, const int* __restrict__ dplen,
                   const unsigned long long* __restrict__ edge_raw, ChunkBest* chunk_best, StepOut* out) {
   extern __shared__ unsigned long long sh_raw[];
-  S* As = reinterpret_cast<S*>(sh_raw);         // [k + 1][kTileW]
-  S* Cs = As + (size_t)(k + 1) * kTileW;        // [max_len][kTileW]
-  S* Bs = Cs + (size_t)max_len * kTileW;        // [kTileU][k + 1]
+  S* As = reinterpret_cast<S*>(sh_raw);         // [k + 1][kTileLd]
+  S* Cs = As + (size_t)(k + 1) * kTileLd;       // [max_len][kTileLd]
+  S* Bs = Cs + (size_t)max_len * kTileLd;       // [kTileU][k + 1]
   S* Ds = Bs + (size_t)kTileU * (k + 1);        // [kTileU][max_len]
   unsigned long long* r_score = reinterpret_cast<unsigned long long*>(Ds + (size_t)kTileU * max_len);  // [kTileU][kTileW]
   int* r_w = reinterpret_cast<int*>(r_score + kTileU * kTileW);
@@ -263,17 +264,22 @@ k_dp_across_tiled(const int* __restrict__ items, const int* __restrict__ blk_tab
   const S* dp = reinterpret_cast<const S*>(dp_raw);
   const S* edge = reinterpret_cast<const S*>(edge_raw);
   const int wt = threadIdx.x, ui = threadIdx.y, tid = ui * kTileW + wt, nthr = kTileW * kTileU;
-  const int first = blk_tab[3 * blockIdx.x], n_it = blk_tab[3 * blockIdx.x + 1], chunk = blk_tab[3 * blockIdx.x + 2];
+  const int first = blk_tab[4 * blockIdx.x], n_it = blk_tab[4 * blockIdx.x + 1], chunk = blk_tab[4 * blockIdx.x + 2];
   const int sub = items[2 * first + 1], end = sub_end[sub];
-  const int w0 = sub + chunk * kTileW;
-  // stage: thread order = (j, lane) so that shared stores are conflict free (global reads are strided, once per block)
+  // The w of a chunk come from a list sorted by the length of DP[w]: the work of a pair grows with that length, and
+  // 32 consecutive preorder ids mix leaves with their heavy ancestors (ncu: 5x more warp instructions than useful ones)
+  const int* pw = perm + blk_tab[4 * blockIdx.x + 3] + chunk * kTileW;
+  const int n_w = min(kTileW, (end - sub) - chunk * kTileW);  // valid entries of pw
+  // stage: the rows are node-major in HBM, so consecutive threads read consecutive j of one row (coalesced;
+  // reading them column-wise cost 4x the bytes in 32-byte sectors and bounded the kernel); the transposed
+  // shared rows are padded to kTileLd so that those stores spread over the banks
   for (int idx = tid; idx < (k + 1) * kTileW; idx += nthr) {
-    const int j = idx / kTileW, r = idx % kTileW;
-    As[idx] = w0 + r < end ? cs[(size_t)(w0 + r) * kcap + j] : S{};
+    const int r = idx / (k + 1), j = idx % (k + 1);
+    As[j * kTileLd + r] = r < n_w ? cs[(size_t)pw[r] * kcap + j] : S{};
   }
   for (int idx = tid; idx < max_len * kTileW; idx += nthr) {
-    const int j = idx / kTileW, r = idx % kTileW;
-    Cs[idx] = w0 + r < end ? dp[(size_t)(w0 + r) * dcap + j] : S{};
+    const int r = idx / max_len, j = idx % max_len;
+    Cs[j * kTileLd + r] = r < n_w ? dp[(size_t)pw[r] * dcap + j] : S{};
   }
   for (int idx = tid; idx < kTileU * (k + 1); idx += nthr) {
     const int q = idx / (k + 1), j = idx % (k + 1);
@@ -289,11 +295,11 @@ k_dp_across_tiled(const int* __restrict__ items, const int* __restrict__ blk_tab
   }
   __syncthreads();
 
-  const int w = w0 + wt;
+  const int w = wt < n_w ? pw[wt] : 0x7FFFFFFF;
   bool ok = false;
   S best{};
   int bidx[4] = {0, 0, 0, 0};
-  if (ui < n_it && w < end) {
+  if (ui < n_it && wt < n_w) {
     const int u = items[2 * (first + ui)];
     const S* A = As + wt;  // A[j] = A[j * kTileW]
     const S* C = Cs + wt;
@@ -307,7 +313,7 @@ k_dp_across_tiled(const int* __restrict__ items, const int* __restrict__ blk_tab
       S c1 = A[0] + B[i];
       int a1 = 0;
       for (int j = 1; j <= i; ++j) {
-        const S cur = A[j * kTileW] + B[i - j];
+        const S cur = A[j * kTileLd] + B[i - j];
         if (cur > c1) {
           c1 = cur;
           a1 = j;
@@ -315,10 +321,10 @@ k_dp_across_tiled(const int* __restrict__ items, const int* __restrict__ blk_tab
       }
       const int i2 = k - i;
       const int lo2 = max(0, i2 - (Ld - 1)), hi2 = min(i2, Lc - 1);
-      S c2 = C[lo2 * kTileW] + D[i2 - lo2];
+      S c2 = C[lo2 * kTileLd] + D[i2 - lo2];
       int cc = lo2;
       for (int j = lo2 + 1; j <= hi2; ++j) {
-        const S cur = C[j * kTileW] + D[i2 - j];
+        const S cur = C[j * kTileLd] + D[i2 - j];
         if (cur > c2) {
           c2 = cur;
           cc = j;
@@ -335,15 +341,15 @@ k_dp_across_tiled(const int* __restrict__ items, const int* __restrict__ blk_tab
       }
     }
     S score = edge[(size_t)u * n + w];  // main_dp.go:268, left to right
-    score = score + A[bidx[0] * kTileW];
+    score = score + A[bidx[0] * kTileLd];
     score = score + B[bidx[1]];
-    score = score + C[bidx[2] * kTileW];
+    score = score + C[bidx[2] * kTileLd];
     score = score + D[bidx[3]];
     best = score;
     ok = true;
     if (is_nan(score)) {
       atomicOr(&out->nan_seen, 1);
-      if (w == sub) s_stuck[ui] = 1;
+      if (w == sub) s_stuck[ui] = 1 + wt;  // the item's first w in preorder: its NaN stays (any lane: the w are sorted by DP length)
       else ok = false;
     }
   }
@@ -365,12 +371,13 @@ k_dp_across_tiled(const int* __restrict__ items, const int* __restrict__ blk_tab
     __syncthreads();
   }
   if (wt == 0 && ui < n_it) {
+    const int src = s_stuck[ui] ? ui * kTileW + s_stuck[ui] - 1 : tid;  // a stuck first w wins outright (nothing was merged)
     ChunkBest cb;
-    cb.score = r_score[tid];
-    cb.ok = r_ok[tid];
-    cb.w = r_w[tid];
-    cb.stuck = s_stuck[ui];
-    for (int q = 0; q < 4; ++q) cb.idx[q] = r_idx[tid * 4 + q];
+    cb.score = r_score[src];
+    cb.ok = r_ok[src];
+    cb.w = r_w[src];
+    cb.stuck = s_stuck[ui] != 0;
+    for (int q = 0; q < 4; ++q) cb.idx[q] = r_idx[src * 4 + q];
     chunk_best[item_cb0[first + ui] + chunk] = cb;
   }
 }
@@ -389,11 +396,15 @@ k_dp_fold(int n_items, const int* __restrict__ items, const int* __restrict__ it
   for (int i = tid; i < n_items; i += kFoldThreads) {
     const int b0 = item_blk0[i], b1 = item_blk0[i + 1];
     ChunkBest c = chunk_best[b0];
-    if (!c.stuck)
-      for (int b = b0 + 1; b < b1; ++b) {
-        const ChunkBest d = chunk_best[b];
-        if (d.ok && (!c.ok || as_score<S>(d.score) > as_score<S>(c.score))) c = d;  // later chunks hold larger w: ties keep the earlier
+    for (int b = b0 + 1; b < b1 && !c.stuck; ++b) {  // chunks in any w order: first maximum = larger score, then smaller w
+      const ChunkBest d = chunk_best[b];
+      if (d.stuck) {
+        c = d;  // the item's first w scored NaN: nothing replaces it
+      } else if (d.ok) {
+        const S a = as_score<S>(c.score), e = as_score<S>(d.score);
+        if (!c.ok || e > a || (e == a && d.w < c.w)) c = d;
       }
+    }
     if (!c.ok) continue;
     ItemBest ib;
     ib.score = c.score;
@@ -453,7 +464,8 @@ struct camus_b200_dp {
   int kcap = 0, dcap = 0;
   Buf<int> d_end, d_depth, d_dplen, d_items, d_desc, d_blk_item, d_item_blk0;
   Buf<ChunkBest> d_chunk_best;
-  Buf<int> d_tile_tab, d_item_cb0;  // tiled kernel: (first item, items, chunk) per block; first chunk slot per item
+  Buf<int> d_tile_tab, d_item_cb0, d_perm;
+  std::vector<int> h_dplen;  // host copy of the DP list lengths (set_node)  // tiled kernel: (first item, items, chunk) per block; first chunk slot per item
   int n_tile_blocks = 0, max_len = 1;
   bool tiled_ok = false;  // the opt-in shared-memory size was granted
   int n_blocks = 0;
@@ -521,6 +533,7 @@ int camus_b200_dp_create(camus_b200_dp** out, int device, int score_is_f64, int3
       (e = dp->d_items.alloc(2 * n)) != cudaSuccess || (e = dp->d_out.alloc(1)) != cudaSuccess || (e = dp->d_counter.alloc(1)) != cudaSuccess)
     return bail("cudaMalloc", e);
   dp->h_end.assign(subtree_end, subtree_end + n);
+  dp->h_dplen.assign(n, 1);
   std::vector<int> ones(n, 1);  // tips: DP[tip] = {0} (main_dp.go:98-100)
   if ((e = cudaMemcpyAsync(dp->d_end.p, subtree_end, n * 4, cudaMemcpyHostToDevice, dp->stream)) != cudaSuccess ||
       (e = cudaMemcpyAsync(dp->d_depth.p, depth, n * 4, cudaMemcpyHostToDevice, dp->stream)) != cudaSuccess ||
@@ -552,6 +565,7 @@ int camus_b200_dp_set_node(camus_b200_dp* dp, int32_t node, int32_t len, const v
   if (!dp) return CAMUS_B200_ERR_ARG;
   if (node < 0 || node >= dp->n || len < 1 || !scores) return dp->fail(CAMUS_B200_ERR_ARG, "dp_set_node: node out of range or empty list");
   dp->max_len = std::max(dp->max_len, (int)len);
+  dp->h_dplen[node] = len;
   dp->pend_desc.push_back(node);
   dp->pend_desc.push_back(len);
   dp->pend_desc.push_back((int)dp->pend_blob.size());
@@ -615,21 +629,36 @@ int camus_b200_dp_set_vertex(camus_b200_dp* dp, int32_t v, int32_t n_items, cons
     const int nw = dp->h_end[item_sub[i]] - item_sub[i];
     cb0[i + 1] = cb0[i] + std::max(1, (nw + kTileW - 1) / kTileW);
   }
+  // per distinct other subtree: its nodes sorted by the length of their DP list, longest first (stable)
+  std::vector<int> perm;
+  std::vector<std::pair<int, int>> perm_of;  // (sub, offset into perm)
+  auto perm_offset = [&](int sub) {
+    for (auto& po : perm_of)
+      if (po.first == sub) return po.second;
+    const int off = (int)perm.size(), e = dp->h_end[sub];
+    for (int x = sub; x < e; ++x) perm.push_back(x);
+    std::stable_sort(perm.begin() + off, perm.end(), [&](int a, int b) { return dp->h_dplen[a] > dp->h_dplen[b]; });
+    perm_of.push_back({sub, off});
+    return off;
+  };
   for (int i = 0; i < n_items;) {
     int j = i + 1;
     while (j < n_items && j - i < kTileU && item_sub[j] == item_sub[i]) ++j;
-    const int chunks = cb0[i + 1] - cb0[i];
+    const int chunks = cb0[i + 1] - cb0[i], poff = perm_offset(item_sub[i]);
     for (int c = 0; c < chunks; ++c) {
       tab.push_back(i);
       tab.push_back(j - i);
       tab.push_back(c);
+      tab.push_back(poff);
     }
     i = j;
   }
-  dp->n_tile_blocks = (int)(tab.size() / 3);
+  dp->n_tile_blocks = (int)(tab.size() / 4);
   if (n_items) {
     DCK(dp->d_tile_tab.alloc(tab.size()));
     DCK(dp->d_item_cb0.alloc(cb0.size()));
+    DCK(dp->d_perm.alloc(std::max<size_t>(perm.size(), 1)));
+    DCK(cudaMemcpyAsync(dp->d_perm.p, perm.data(), perm.size() * 4, cudaMemcpyHostToDevice, dp->stream));
     DCK(cudaMemcpyAsync(dp->d_tile_tab.p, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice, dp->stream));
     DCK(cudaMemcpyAsync(dp->d_item_cb0.p, cb0.data(), cb0.size() * 4, cudaMemcpyHostToDevice, dp->stream));
     DCK(dp->d_chunk_best.alloc((size_t)std::max(cb0[n_items], blk0[n_items])));
@@ -703,17 +732,17 @@ int camus_b200_dp_across(camus_b200_dp* dp, int32_t prev_k, camus_b200_dp_best* 
   DCK(cudaMemsetAsync(dp->d_out.p, 0, sizeof(StepOut), dp->stream));
   static const bool no_tiled = getenv("CAMUS_DP_NO_TILED") && getenv("CAMUS_DP_NO_TILED")[0] == '1';  // A/B, tests
   const int ml = std::min(dp->max_len, dp->dcap);
-  const size_t shm_tiled = ((size_t)(prev_k + 1 + ml) * (kTileW + kTileU)) * 8 + (size_t)kTileU * kTileW * (8 + 4 + 4 + 16);
+  const size_t shm_tiled = ((size_t)(prev_k + 1 + ml) * (kTileLd + kTileU)) * 8 + (size_t)kTileU * kTileW * (8 + 4 + 4 + 16);
   const bool tiled = dp->tiled_ok && !no_tiled && shm_tiled <= 200 * 1024;
   const int* cb0 = tiled ? dp->d_item_cb0.p : dp->d_item_blk0.p;
   if (tiled) {
     const dim3 blk(kTileW, kTileU);
     if (dp->f64)
-      k_dp_across_tiled<double><<<dp->n_tile_blocks, blk, shm_tiled, dp->stream>>>(dp->d_items.p, dp->d_tile_tab.p, dp->d_item_cb0.p, dp->d_end.p, prev_k, dp->n,
+      k_dp_across_tiled<double><<<dp->n_tile_blocks, blk, shm_tiled, dp->stream>>>(dp->d_items.p, dp->d_tile_tab.p, dp->d_perm.p, dp->d_item_cb0.p, dp->d_end.p, prev_k, dp->n,
                                                                                    dp->kcap, dp->dcap, ml, dp->d_cs.p, dp->d_dp.p, dp->d_dplen.p, dp->d_edge.p,
                                                                                    dp->d_chunk_best.p, dp->d_out.p);
     else
-      k_dp_across_tiled<unsigned long long><<<dp->n_tile_blocks, blk, shm_tiled, dp->stream>>>(dp->d_items.p, dp->d_tile_tab.p, dp->d_item_cb0.p, dp->d_end.p,
+      k_dp_across_tiled<unsigned long long><<<dp->n_tile_blocks, blk, shm_tiled, dp->stream>>>(dp->d_items.p, dp->d_tile_tab.p, dp->d_perm.p, dp->d_item_cb0.p, dp->d_end.p,
                                                                                                prev_k, dp->n, dp->kcap, dp->dcap, ml, dp->d_cs.p, dp->d_dp.p,
                                                                                                dp->d_dplen.p, dp->d_edge.p, dp->d_chunk_best.p, dp->d_out.p);
   } else {

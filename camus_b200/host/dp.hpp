@@ -326,6 +326,7 @@ struct DpAccel {
   bool verify = false;     // CAMUS_DP_VERIFY=1: run the host scan as well and compare the winner
   uint64_t steps = 0, steps_host = 0, nan_fallbacks = 0;
   double s_columns = 0, s_across = 0;  // seconds inside set_vertex + set_path_columns / inside across
+  double s_create = 0;                 // edge table + camus_b200_dp_create
   void check(int rc, const char* what) const {
     if (rc != 0) throw CamusError(Err::Internal, std::string("DP offload: ") + what + ": " + (api->last_error(handle) ? api->last_error(handle) : "?"));
   }
@@ -337,7 +338,7 @@ struct DPResults {
   std::vector<double> root_scores_f;  // DP[root][k] as double (for logging / tests)
   std::vector<uint64_t> root_scores_u;
   uint64_t accel_steps = 0, accel_steps_host = 0, accel_nan_fallbacks = 0, accel_launches = 0;
-  double accel_s_columns = 0, accel_s_across = 0;
+  double accel_s_columns = 0, accel_s_across = 0, accel_s_create = 0, accel_s_destroy = 0;
 };
 
 // ------------------------------------------------------------------------------------------
@@ -874,6 +875,7 @@ inline DPResults run_dp(const TreeData& td, const ScoreTables& tabs, ScoreMode m
   // the across-scan on the GPU: the whole edge-score table goes to the device once
   auto open_accel = [&](const auto& sc) -> DpAccel* {
     if (!api) return nullptr;
+    const auto tc0 = std::chrono::steady_clock::now();
     using S = typename std::decay_t<decltype(sc)>::S;
     const int n = td.n();
     std::vector<S> edge((size_t)n * n);
@@ -886,6 +888,7 @@ inline DPResults run_dp(const TreeData& td, const ScoreTables& tabs, ScoreMode m
       const char* m = api->last_error(nullptr);
       throw CamusError(Err::Internal, std::string("DP offload: create: ") + (m ? m : "?"));
     }
+    accel.s_create = std::chrono::duration<double>(std::chrono::steady_clock::now() - tc0).count();
     accel.min_work = min_work >= 0 ? (uint64_t)min_work : 30000;  // measured at 1000 taxa: 1e5 .. 8e3 are within 10 % of each other
     if (const char* e = getenv("CAMUS_DP_ACCEL_MIN_WORK")) accel.min_work = strtoull(e, nullptr, 10);
     accel.verify = getenv("CAMUS_DP_VERIFY") && getenv("CAMUS_DP_VERIFY")[0] == '1';
@@ -893,9 +896,11 @@ inline DPResults run_dp(const TreeData& td, const ScoreTables& tabs, ScoreMode m
   };
   struct Closer {
     DpAccel& a;
-    ~Closer() {
+    void close() {
       if (a.handle) a.api->destroy(a.handle);
+      a.handle = nullptr;
     }
+    ~Closer() { close(); }
   } closer{accel};
   auto collate = [&](auto& dp) {
     const auto& rs = dp.root_scores();
@@ -932,6 +937,10 @@ inline DPResults run_dp(const TreeData& td, const ScoreTables& tabs, ScoreMode m
     res.accel_launches = api->launches(accel.handle);
     res.accel_s_columns = accel.s_columns;
     res.accel_s_across = accel.s_across;
+    res.accel_s_create = accel.s_create;
+    const auto td0 = std::chrono::steady_clock::now();
+    closer.close();
+    res.accel_s_destroy = std::chrono::duration<double>(std::chrono::steady_clock::now() - td0).count();
   }
   return res;
 }

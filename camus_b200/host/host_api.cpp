@@ -146,7 +146,8 @@ int camus_host_run_dp(const camus_host_problem* p, int mode, const uint64_t* tot
   return camus_host_run_dp_accel(p, mode, totals, penalties, as_set, n_survivors, sum_counts, n_gtrees, alpha, nullptr, 0, -1, out);
 }
 // offload statistics of the last run: [0] steps on the device, [1] steps kept on the host, [2] steps that saw a NaN score,
-// [3] kernel launches, [4] microseconds uploading items / path columns, [5] microseconds inside camus_b200_dp_across
+// [3] kernel launches, [4] microseconds uploading items / path columns, [5] microseconds inside camus_b200_dp_across,
+// [6] microseconds building + uploading the edge table and creating the handle, [7] microseconds destroying it
 void camus_host_results_accel_stats(const camus_host_results* r, uint64_t* out6) {
   out6[0] = r->res.accel_steps;
   out6[1] = r->res.accel_steps_host;
@@ -154,6 +155,8 @@ void camus_host_results_accel_stats(const camus_host_results* r, uint64_t* out6)
   out6[3] = r->res.accel_launches;
   out6[4] = (uint64_t)(r->res.accel_s_columns * 1e6);
   out6[5] = (uint64_t)(r->res.accel_s_across * 1e6);
+  out6[6] = (uint64_t)(r->res.accel_s_create * 1e6);
+  out6[7] = (uint64_t)(r->res.accel_s_destroy * 1e6);
 }
 void camus_host_results_free(camus_host_results* r) { delete r; }
 int camus_host_results_count(const camus_host_results* r) { return (int)r->res.branches.size(); }

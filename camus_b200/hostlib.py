@@ -220,10 +220,11 @@ class Problem:
                 roots.append(L.camus_host_results_root_score(r, k))
                 newicks.append(L.camus_host_results_newick(r, k).decode())
             res = DPResult(branches, qsat, roots, newicks)
-            st = (C.c_uint64 * 6)()
+            st = (C.c_uint64 * 8)()
             L.camus_host_results_accel_stats(r, st)
             res.accel = {"device_steps": st[0], "host_steps": st[1], "nan_steps": st[2], "launches": st[3],
-                         "upload_s": st[4] * 1e-6, "across_s": st[5] * 1e-6}
+                         "upload_s": st[4] * 1e-6, "across_s": st[5] * 1e-6,
+                         "create_s": st[6] * 1e-6, "destroy_s": st[7] * 1e-6}
             return res
         finally:
             L.camus_host_results_free(r)
