@@ -525,8 +525,8 @@ int camus_b200_dp_create(camus_b200_dp** out, int device, int score_is_f64, int3
   dp->stage_cap = (size_t)n_nodes * 128;  // path columns of 128 steps at once; grows on demand
   if ((e = cudaMallocHost(&dp->h_stage, dp->stage_cap * 8)) != cudaSuccess) return bail("pinned staging", e);
   const size_t n = (size_t)n_nodes;
-  dp->kcap = 32;
-  dp->dcap = 16;
+  dp->kcap = 128;  // doubled on demand (k_dp_repack)
+  dp->dcap = 64;
   if ((e = dp->d_end.alloc(n)) != cudaSuccess || (e = dp->d_depth.alloc(n)) != cudaSuccess || (e = dp->d_dplen.alloc(n)) != cudaSuccess ||
       (e = dp->d_edge.alloc(n * n)) != cudaSuccess || (e = dp->d_cs.alloc(n * dp->kcap)) != cudaSuccess ||
       (e = dp->d_dp.alloc(n * dp->dcap)) != cudaSuccess ||
@@ -543,6 +543,26 @@ int camus_b200_dp_create(camus_b200_dp** out, int device, int score_is_f64, int3
       (e = cudaMemsetAsync(dp->d_cs.p, 0, n * dp->kcap * 8, dp->stream)) != cudaSuccess ||
       (e = cudaMemsetAsync(dp->d_counter.p, 0, 4, dp->stream)) != cudaSuccess || (e = cudaStreamSynchronize(dp->stream)) != cudaSuccess)
     return bail("upload", e);
+  // Every per-vertex table is sized once for the largest vertex of THIS tree (binary, preorder ids: children of v are
+  // v + 1 and subtree_end[v + 1]): cudaMalloc / cudaFree in the middle of the DP cost milliseconds each in a process
+  // that already holds tens of GB (0.3 - 0.5 s per DP, measured inside bench.py).
+  {
+    size_t max_b128 = 1, max_cb64 = 1, max_tiles = 1;
+    for (int v = 0; v < n_nodes; ++v) {
+      if (subtree_end[v] - v < 3) continue;
+      const int c0 = v + 1, c1 = subtree_end[c0];
+      if (c1 >= subtree_end[v]) continue;
+      const size_t s0 = (size_t)(subtree_end[c0] - c0), s1 = (size_t)(subtree_end[c1] - c1);
+      max_b128 = std::max(max_b128, s0 * ((s1 + kAcrossThreads - 1) / kAcrossThreads) + s1 * ((s0 + kAcrossThreads - 1) / kAcrossThreads));
+      max_cb64 = std::max(max_cb64, s0 * ((s1 + kTileW - 1) / kTileW) + s1 * ((s0 + kTileW - 1) / kTileW));
+      max_tiles = std::max(max_tiles, ((s0 + kTileU - 1) / kTileU + 1) * ((s1 + kTileW - 1) / kTileW) + ((s1 + kTileU - 1) / kTileU + 1) * ((s0 + kTileW - 1) / kTileW));
+    }
+    if ((e = dp->d_blk_item.alloc(max_b128)) != cudaSuccess || (e = dp->d_item_blk0.alloc(n + 1)) != cudaSuccess ||
+        (e = dp->d_item_cb0.alloc(n + 1)) != cudaSuccess || (e = dp->d_tile_tab.alloc(4 * max_tiles)) != cudaSuccess ||
+        (e = dp->d_perm.alloc(n)) != cudaSuccess || (e = dp->d_chunk_best.alloc(std::max(max_b128, max_cb64))) != cudaSuccess ||
+        (e = dp->d_cols.alloc(n * 128)) != cudaSuccess || (e = dp->d_desc.alloc(3 * n)) != cudaSuccess || (e = dp->d_blob.alloc(16 * n)) != cudaSuccess)
+      return bail("cudaMalloc (per-vertex tables)", e);
+  }
   dp->tiled_ok = cudaFuncSetAttribute(k_dp_across_tiled<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) == cudaSuccess &&
                  cudaFuncSetAttribute(k_dp_across_tiled<unsigned long long>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) == cudaSuccess;
   cudaGetLastError();
