@@ -6,6 +6,7 @@
 #include <memory>
 
 #include "dp.hpp"
+#include "dp_mock.hpp"
 #include "retic.hpp"
 
 using namespace camus;
@@ -158,6 +159,8 @@ void camus_host_results_accel_stats(const camus_host_results* r, uint64_t* out6)
   out6[6] = (uint64_t)(r->res.accel_s_create * 1e6);
   out6[7] = (uint64_t)(r->res.accel_s_destroy * 1e6);
 }
+// the CPU stand-in of the camus_b200_dp_* entry points (dp_mock.hpp): tests without a GPU only
+const void* const* camus_host_dp_mock_api() { return reinterpret_cast<const void* const*>(camus::dp_mock::api()); }
 void camus_host_results_free(camus_host_results* r) { delete r; }
 int camus_host_results_count(const camus_host_results* r) { return (int)r->res.branches.size(); }
 // writes 2*k ints (u0,w0,u1,w1,...) for the k-branch solution (k = 1..count), traceback order

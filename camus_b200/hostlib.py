@@ -65,6 +65,7 @@ def lib() -> C.CDLL:
         L.camus_host_run_dp_accel.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_uint64,
                                               C.c_uint64, C.c_int, C.c_double, C.c_void_p, C.c_int, C.c_int64,
                                               C.POINTER(C.c_void_p)]
+        L.camus_host_dp_mock_api.restype = C.c_void_p
         L.camus_host_results_accel_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
         L.camus_host_results_accel_stats.restype = None
         L.camus_host_results_free.argtypes = [C.c_void_p]
@@ -191,7 +192,9 @@ class Problem:
         of libcamus_b200.so; None = the host scan."""
         L = lib()
         accel = None
-        if gpu is not None:
+        if gpu == "mock":  # CPU stand-in of the device scan (host/dp_mock.hpp): tests without a GPU
+            accel, gpu = C.c_void_p(L.camus_host_dp_mock_api()), 0
+        elif gpu is not None:
             from . import cabi
             accel = cabi.dp_accel_table()
         totals = np.ascontiguousarray(totals, dtype=np.uint64)
