@@ -19,7 +19,12 @@
 // dialect, with a label the constraint does not have or with a duplicate label gets a status code; the
 // caller then adds nothing and runs its own parser, which reports the reference's error.
 #pragma once
+#if defined(__CUDACC__)
 #include <cuda_runtime.h>
+#define NWK_HD __host__ __device__ __forceinline__
+#else
+#define NWK_HD inline  // tests/ingest_probe.cpp compiles the per-tree automaton for the host
+#endif
 
 #include <cstdint>
 
@@ -54,11 +59,11 @@ struct NwkTreeInfo {  // per tree, read back by the host
   int pad;
 };
 
-__device__ __forceinline__ bool nwk_ws(char c) { return c == ' ' || c == '\t' || c == '\n' || c == '\r'; }
-__device__ __forceinline__ bool nwk_stop(char c) { return c == ',' || c == '(' || c == ')' || c == ':' || c == ';' || c == '['; }
+NWK_HD bool nwk_ws(char c) { return c == ' ' || c == '\t' || c == '\n' || c == '\r'; }
+NWK_HD bool nwk_stop(char c) { return c == ',' || c == '(' || c == ')' || c == ':' || c == ';' || c == '['; }
 
 // whitespace and [comments] (NewickParser::skip_ws_comments); false = unterminated comment
-__device__ __forceinline__ bool nwk_skip(const char* __restrict__ t, long long& p, long long e) {
+NWK_HD bool nwk_skip(const char* __restrict__ t, long long& p, long long e) {
   while (p < e) {
     const char c = t[p];
     if (nwk_ws(c)) {
@@ -74,7 +79,7 @@ __device__ __forceinline__ bool nwk_skip(const char* __restrict__ t, long long& 
   return true;
 }
 // unquoted label (NewickParser::read_label): [ls, le) with trailing whitespace trimmed
-__device__ __forceinline__ int nwk_label(const char* __restrict__ t, long long& p, long long e, long long& ls, long long& le) {
+NWK_HD int nwk_label(const char* __restrict__ t, long long& p, long long e, long long& ls, long long& le) {
   if (!nwk_skip(t, p, e)) return kNwkSyntax;
   if (p < e && t[p] == '\'') return kNwkQuoted;
   ls = p;
@@ -84,7 +89,7 @@ __device__ __forceinline__ int nwk_label(const char* __restrict__ t, long long& 
   return kNwkOk;
 }
 // ':' length (NewickParser::read_length)
-__device__ __forceinline__ int nwk_length(const char* __restrict__ t, long long& p, long long e) {
+NWK_HD int nwk_length(const char* __restrict__ t, long long& p, long long e) {
   if (!nwk_skip(t, p, e)) return kNwkSyntax;
   if (p < e && t[p] == ':') {
     ++p;
@@ -100,7 +105,7 @@ __device__ __forceinline__ int nwk_length(const char* __restrict__ t, long long&
 }
 // Label after ')': 0 = a name (strtod would reject it), 1 = plain decimal (value set), 2 = may be a
 // number strtod accepts but outside the exact fast path
-__device__ __forceinline__ int nwk_number(const char* __restrict__ t, long long ls, long long le, double& v) {
+NWK_HD int nwk_number(const char* __restrict__ t, long long ls, long long le, double& v) {
   if (le <= ls) return 0;
   unsigned long long m = 0;
   int digits = 0, sig = 0, frac = 0;
@@ -122,7 +127,11 @@ __device__ __forceinline__ int nwk_number(const char* __restrict__ t, long long 
   if (plain && digits > 0 && sig <= 15 && frac <= 22) {
     double den = 1.0;
     for (int i = 0; i < frac; ++i) den *= 10.0;  // 10^f, f <= 22: exact
+#if defined(__CUDA_ARCH__)
     v = __ddiv_rn((double)m, den);               // one correctly rounded division = strtod's result
+#else
+    v = (double)m / den;
+#endif
     return 1;
   }
   // a name unless strtod could still accept the whole label: sign / digit / dot first, or inf... / nan... (any case)
@@ -136,7 +145,7 @@ __device__ __forceinline__ int nwk_number(const char* __restrict__ t, long long 
   return maybe ? 2 : 0;
 }
 
-__device__ __forceinline__ unsigned long long nwk_hash(const char* __restrict__ t, long long ls, long long le) {
+NWK_HD unsigned long long nwk_hash(const char* __restrict__ t, long long ls, long long le) {
   unsigned long long h = 14695981039346656037ull;  // FNV-1a
   for (long long p = ls; p < le; ++p) {
     h ^= (unsigned char)t[p];
@@ -144,7 +153,7 @@ __device__ __forceinline__ unsigned long long nwk_hash(const char* __restrict__ 
   }
   return h ? h : 1ull;
 }
-__device__ __forceinline__ int nwk_lookup(const LabelTable& lt, const char* __restrict__ t, long long ls, long long le) {
+NWK_HD int nwk_lookup(const LabelTable& lt, const char* __restrict__ t, long long ls, long long le) {
   const unsigned long long h = nwk_hash(t, ls, le);
   for (unsigned int s = (unsigned int)h & lt.mask;; s = (s + 1) & lt.mask) {
     const unsigned long long hs = lt.hash[s];
@@ -160,12 +169,8 @@ __device__ __forceinline__ int nwk_lookup(const LabelTable& lt, const char* __re
 }
 
 // Pass 1: one thread per tree (= non-blank line [begin, end) of the file).
-__global__ void k_nwk_pass1(int n_trees, const char* __restrict__ text, const long long* __restrict__ line_begin,
-                            const long long* __restrict__ line_end, double min_support, int* stack, unsigned char* collapsed,
-                            NwkTreeInfo* info) {
-  const int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= n_trees) return;
-  const long long b = line_begin[g], e = line_end[g];
+NWK_HD void nwk_pass1_tree(const char* __restrict__ text, long long b, long long e, double min_support, int* stack, unsigned char* collapsed,
+                           NwkTreeInfo* out) {
   long long p = b;
   NwkTreeInfo ti{};
   int depth = 0, nodes = 0, leaves = 0, st = kNwkOk;
@@ -231,9 +236,19 @@ __global__ void k_nwk_pass1(int n_trees, const char* __restrict__ text, const lo
   ti.status = st;
   ti.n_nodes = st == kNwkOk ? nodes : 0;
   ti.n_leaves = leaves;
-  info[g] = ti;
+  *out = ti;
 }
+#if defined(__CUDACC__)
+__global__ void k_nwk_pass1(int n_trees, const char* __restrict__ text, const long long* __restrict__ line_begin,
+                            const long long* __restrict__ line_end, double min_support, int* stack, unsigned char* collapsed,
+                            NwkTreeInfo* info) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_trees) return;
+  nwk_pass1_tree(text, line_begin[g], line_end[g], min_support, stack, collapsed, info + g);
+}
+#endif
 
+#if defined(__CUDACC__)
 // exclusive scan of the node counts (one block; G is at most a few hundred thousand)
 __global__ void k_nwk_offsets(int n_trees, const NwkTreeInfo* __restrict__ info, long long base, long long* node_off /*[n_trees+1]*/) {
   __shared__ long long part[1024];
@@ -260,18 +275,14 @@ __global__ void k_nwk_offsets(int n_trees, const NwkTreeInfo* __restrict__ info,
   }
 }
 
+#endif
+
 // Pass 2: emit the flat tree. `seen`: ceil(n_taxa / 32) words per tree, zeroed.
-__global__ void k_nwk_pass2(int n_trees, const char* __restrict__ text, const long long* __restrict__ line_begin,
-                            const long long* __restrict__ line_end, const unsigned char* __restrict__ collapsed, int* stack,
-                            LabelTable lt, int n_taxa, const long long* __restrict__ node_off, long long out_base, int* parent, int* taxon,
-                            int* n_child, unsigned int* seen, NwkTreeInfo* info) {
-  const int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= n_trees) return;
-  NwkTreeInfo ti = info[g];
+// o = first slot of this tree in parent[] / taxon[] / n_child[], sn = its n_taxa bits of `seen`
+NWK_HD void nwk_pass2_tree(const char* __restrict__ text, long long b, long long e, const unsigned char* __restrict__ collapsed, int* stack,
+                           const LabelTable& lt, long long o, int* parent, int* taxon, int* n_child, unsigned int* sn, NwkTreeInfo* io) {
+  NwkTreeInfo ti = *io;
   if (ti.status != kNwkOk) return;
-  const long long b = line_begin[g], e = line_end[g];
-  const long long o = node_off[g] - out_base;  // first slot of this tree in parent[] / taxon[]
-  unsigned int* sn = seen + (size_t)g * ((n_taxa + 31) / 32);
   int* stk = stack + b;  // entries: local id of the nearest KEPT node of that open parenthesis
   long long p = b;
   int depth = 0, kept_depth = -1, next = 0, max_depth = 0, st = kNwkOk;
@@ -292,7 +303,7 @@ __global__ void k_nwk_pass2(int n_trees, const char* __restrict__ text, const lo
           if (par >= 0) ++n_child[o + par];
           stk[depth++] = id;
           ++kept_depth;
-          max_depth = max(max_depth, kept_depth);
+          max_depth = kept_depth > max_depth ? kept_depth : max_depth;
         }
         ++p;
         continue;
@@ -305,7 +316,7 @@ __global__ void k_nwk_pass2(int n_trees, const char* __restrict__ text, const lo
       taxon[o + id] = tip;
       n_child[o + id] = 0;
       if (par >= 0) ++n_child[o + par];
-      max_depth = max(max_depth, kept_depth + 1);
+      max_depth = kept_depth + 1 > max_depth ? kept_depth + 1 : max_depth;
       if (tip < 0) {
         st = kNwkUnknownLabel;
         ti.err_pos = (int)(ls - b);
@@ -354,7 +365,18 @@ __global__ void k_nwk_pass2(int n_trees, const char* __restrict__ text, const lo
     ti.root_children = n_child[o];
     ti.status = st;
   }
-  info[g] = ti;
+  *io = ti;
 }
+#if defined(__CUDACC__)
+__global__ void k_nwk_pass2(int n_trees, const char* __restrict__ text, const long long* __restrict__ line_begin,
+                            const long long* __restrict__ line_end, const unsigned char* __restrict__ collapsed, int* stack,
+                            LabelTable lt, int n_taxa, const long long* __restrict__ node_off, long long out_base, int* parent, int* taxon,
+                            int* n_child, unsigned int* seen, NwkTreeInfo* info) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_trees) return;
+  nwk_pass2_tree(text, line_begin[g], line_end[g], collapsed, stack, lt, node_off[g] - out_base, parent, taxon, n_child,
+                 seen + (size_t)g * ((n_taxa + 31) / 32), info + g);
+}
+#endif
 
 }  // namespace camus_dev
