@@ -503,14 +503,35 @@ int camus_b200_clear_gene_trees(camus_b200* ctx) {
   return 0;
 }
 
+namespace {
+// what validating a batch of flat gene trees establishes (a handle over several GPUs validates once)
+struct BatchFacts {
+  uint64_t res = 0;
+  int max_depth = 0;
+  bool all_complete = true, all_rooted = true;
+};
+int add_gene_trees_impl(camus_b200* ctx, int32_t n_trees, const int64_t* node_off, const int32_t* parent, const int32_t* taxon,
+                        const BatchFacts* known, BatchFacts* learned);
+}  // namespace
+
 int camus_b200_add_gene_trees(camus_b200* ctx, int32_t n_trees, const int64_t* node_off, const int32_t* parent,
                               const int32_t* taxon) {
   if (!ctx) return CAMUS_B200_ERR_ARG;
   if (ctx->n == 0) return ctx->fail(CAMUS_B200_ERR_ARG, "add_gene_trees: set the constraint tree first");
   if (!ctx->subs.empty()) {
     ctx->reduced = false;
-    return fan_out(ctx, [&](camus_b200* s, int) { return camus_b200_add_gene_trees(s, n_trees, node_off, parent, taxon); });
+    // validated once (on the first device's context), appended everywhere
+    BatchFacts facts;
+    if (int rc = add_gene_trees_impl(ctx->subs[0], n_trees, node_off, parent, taxon, nullptr, &facts)) return ctx->fail(rc, ctx->subs[0]->err);
+    return fan_out(ctx, [&](camus_b200* s, int i) { return i == 0 ? 0 : add_gene_trees_impl(s, n_trees, node_off, parent, taxon, &facts, nullptr); });
   }
+  return add_gene_trees_impl(ctx, n_trees, node_off, parent, taxon, nullptr, nullptr);
+}
+
+namespace {
+int add_gene_trees_impl(camus_b200* ctx, int32_t n_trees, const int64_t* node_off, const int32_t* parent, const int32_t* taxon,
+                        const BatchFacts* known, BatchFacts* learned) {
+  if (ctx->n == 0) return ctx->fail(CAMUS_B200_ERR_ARG, "add_gene_trees: set the constraint tree first");
   if (n_trees < 0 || !node_off || (n_trees > 0 && (!parent || !taxon))) return ctx->fail(CAMUS_B200_ERR_ARG, "add_gene_trees: null argument");
   // Validation is per tree and independent: large batches are checked on several host threads
   // (16 MB of nodes at 1000 x 1000 took ~10 ms on one). The first failing tree (lowest index) wins.
@@ -570,11 +591,13 @@ int camus_b200_add_gene_trees(camus_b200* ctx, int32_t n_trees, const int64_t* n
       if (n_child[0] != 2) pt.all_rooted = false;
     }
   };
+  BatchFacts facts;
+  if (known) facts = *known;
   const int64_t total_nodes = n_trees ? node_off[n_trees] - node_off[0] : 0;
-  int n_thr = 1;
-  if (total_nodes > (1 << 18)) n_thr = (int)std::max(1u, std::min({std::thread::hardware_concurrency(), 16u, (unsigned)n_trees}));
+  int n_thr = known ? 0 : 1;
+  if (!known && total_nodes > (1 << 18)) n_thr = (int)std::max(1u, std::min({std::thread::hardware_concurrency(), 16u, (unsigned)n_trees}));
   std::vector<Part> parts(n_thr);
-  {
+  if (!known) {
     std::vector<std::thread> th;
     for (int k = 1; k < n_thr; ++k)
       th.emplace_back([&, k] { validate((int)((int64_t)n_trees * k / n_thr), (int)((int64_t)n_trees * (k + 1) / n_thr), parts[k]); });
@@ -585,11 +608,16 @@ int camus_b200_add_gene_trees(camus_b200* ctx, int32_t n_trees, const int64_t* n
   for (const Part& pt : parts)  // chunks are in tree order: the first bad chunk holds the lowest failing tree
     if (pt.bad_tree >= 0) return ctx->fail(CAMUS_B200_ERR_INPUT, pt.msg);
   for (const Part& pt : parts) {
-    res += pt.res;
-    ctx->max_depth = std::max(ctx->max_depth, pt.max_depth);
-    if (!pt.all_complete) ctx->all_complete = false;
-    if (!pt.all_rooted) ctx->all_rooted = false;
+    facts.res += pt.res;
+    facts.max_depth = std::max(facts.max_depth, pt.max_depth);
+    if (!pt.all_complete) facts.all_complete = false;
+    if (!pt.all_rooted) facts.all_rooted = false;
   }
+  res = facts.res;
+  ctx->max_depth = std::max(ctx->max_depth, facts.max_depth);
+  if (!facts.all_complete) ctx->all_complete = false;
+  if (!facts.all_rooted) ctx->all_rooted = false;
+  if (learned) *learned = facts;
   int64_t base = ctx->h_node_off.back() - node_off[0];
   for (int g = 0; g < n_trees; ++g) ctx->h_node_off.push_back(node_off[g + 1] + base);
   size_t cnt = n_trees ? (size_t)(node_off[n_trees] - node_off[0]) : 0;
@@ -603,6 +631,7 @@ int camus_b200_add_gene_trees(camus_b200* ctx, int32_t n_trees, const int64_t* n
   ctx->counted = false;
   return 0;
 }
+}  // namespace
 
 }  // extern "C"
 

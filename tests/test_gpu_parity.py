@@ -758,6 +758,10 @@ def test_multi_gpu_handle_matches_single(gpu):
         multi.partial_tensor().copy_(parts[0][2] + parts[1][2])
         assert np.array_equal(multi.quartet_totals_finish(), out)
         multi.set_partition(0, 1)
+        if s.fmt == "newick":  # ingest on every device of the handle (validated per device, appended everywhere)
+            multi.load_newick(prob, s.genes, ms)
+            assert multi.count_filter(qmode, thr) == (ns, sc)
+            assert np.array_equal(multi.quartet_totals(False), out)
     gpu.set_score_hint(False)
     multi.close()
 
