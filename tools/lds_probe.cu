@@ -1,6 +1,6 @@
 // Developer probe (not part of the library): how many shared-memory wavefronts one LDS.32/64/128
 // costs for a given lane -> address pattern, and what POPC rate an SM sustains with and without
-// shared loads in the mix. Built by tools/build_probe.sh, run by tools/gpu_probe.sh.
+// shared loads in the mix. Build: nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o build_variants/lds_probe tools/lds_probe.cu; tools/gpu_evidence.sh runs it under ncu.
 //
 //   lds_probe lds     : prints cycles per LDS for every (pattern, width); run it under
 //                       ncu --metrics l1tex__data_pipe_lsu_wavefronts_mem_shared.sum for the counts
