@@ -183,16 +183,30 @@ int main(int argc, char** argv) {
     int sms = 0;
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
     const int iters = 4096;
+    int khz = 0;
+    CK(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, 0));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
     auto run = [&](auto kern, const char* name, int ctas_per_sm) {
+      kern<<<sms * ctas_per_sm, 256>>>(d_cyc, d_sink, 16);  // warm-up
+      CK(cudaEventRecord(e0));
       kern<<<sms * ctas_per_sm, 256>>>(d_cyc, d_sink, iters);
+      CK(cudaEventRecord(e1));
       CK(cudaDeviceSynchronize());
+      float ms = 0;
+      CK(cudaEventElapsedTime(&ms, e0, e1));
       std::vector<unsigned long long> c(sms * ctas_per_sm);
       CK(cudaMemcpy(c.data(), d_cyc, 8 * c.size(), cudaMemcpyDeviceToHost));
       double mean = 0;
       for (auto v : c) mean += (double)v / c.size();
-      // warp-POPCs per SM: ctas * 8 warps * iters * 32; the XU pipe retires one warp-POPC per 8 clk and SMSP
-      const double popc_per_clk_sm = (double)ctas_per_sm * 256 * iters * 32 / mean;
-      printf("%-22s %d CTAs/SM: %.0f clk, %.2f POPC lanes/clk/SM (peak 16) = %.1f %%\n", name, ctas_per_sm, mean, popc_per_clk_sm, 100 * popc_per_clk_sm / 16);
+      // The kernel's elapsed time is what counts (ncu's sm__cycles_elapsed agrees with it). The clock64 span of warp 0
+      // is printed only as a warning: the scheduler favours the oldest warp, warp 0 finishes long before its CTA, and
+      // its span once made this probe report 25 POPC lanes per clock and SM instead of 16.
+      const double clocks = ms * 1e-3 * khz * 1e3;  // at the nominal SM clock
+      const double lanes = (double)ctas_per_sm * 256 * iters * 32 / clocks;
+      printf("%-22s %d CTAs/SM: %.3f ms = %.0f clk at %d MHz: %.2f POPC lanes/clk/SM (XU peak 16) | warp-0 span %.0f clk (misleading)\n", name,
+             ctas_per_sm, ms, clocks, khz / 1000, lanes, mean);
     };
     for (int c = 1; c <= 4; ++c) run(k_popc_peak, "popc chains (peak)", c);
     for (int c = 1; c <= 4; ++c) run(k_popc<0>, "popc only", c);
