@@ -1342,7 +1342,7 @@ int camus_b200_add_gene_trees_newick(camus_b200* ctx, const char* text, uint64_t
   const size_t words = (size_t)(ctx->N + 31) / 32;
   CK(d_seen.alloc((size_t)G * words));
   CK(cudaMemsetAsync(d_seen.p, 0, (size_t)G * words * 4, ctx->stream));
-  const int tb = 64, gb = (G + tb - 1) / tb;
+  const int tb = 32, gb = G;  // one warp per tree
   k_nwk_pass1<<<gb, tb, 0, ctx->stream>>>(G, d_text.p, d_lb.p, d_le.p, min_support, d_stack.p, d_coll.p, d_info.p);
   CK_LAUNCH();
   const long long base = (long long)ctx->h_node_off.back();

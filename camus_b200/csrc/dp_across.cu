@@ -241,11 +241,11 @@ k_dp_across(int n_items, int n_blocks, const int* __restrict__ items /*[2*n_item
 // in shared memory, transposed so that a warp's lanes read consecutive words, and shared by the kTileU items:
 // the one-thread-per-pair kernel above re-reads them from L1 / L2 with a 32-way scattered access per load,
 // which is what bounded it (0.5 ms per step at the root of a 1000-taxon constraint).
-constexpr int kTileW = 64, kTileU = 8, kTileLd = kTileW + 1;
+constexpr int kTileW = 64, kTileU = 8, kTileLd = kTileW + 1, kTabInts = 4 + kTileU;
 
 template <class S>
 __global__ void __launch_bounds__(kTileW* kTileU)
-k_dp_across_tiled(const int* __restrict__ items, const int* __restrict__ blk_tab /*[4*n_blocks]: first item, items in the tile, chunk, offset into perm*/,
+k_dp_across_tiled(const int* __restrict__ items, const int* __restrict__ blk_tab /*[kTabInts*n_blocks]: items in the tile, chunk, offset into perm, other subtree, then the item ids*/,
                   const int* __restrict__ perm /*the other subtree's nodes, longest DP list first*/, const int* __restrict__ item_cb0,
                   const int* __restrict__ sub_end, int k, int n, int kcap, int dcap, int max_len,
                   const unsigned long long* __restrict__ cs_raw, const unsigned long long* __restrict__ dp_raw, const int* __restrict__ dplen,
@@ -264,11 +264,15 @@ k_dp_across_tiled(const int* __restrict__ items, const int* __restrict__ blk_tab
   const S* dp = reinterpret_cast<const S*>(dp_raw);
   const S* edge = reinterpret_cast<const S*>(edge_raw);
   const int wt = threadIdx.x, ui = threadIdx.y, tid = ui * kTileW + wt, nthr = kTileW * kTileU;
-  const int first = blk_tab[4 * blockIdx.x], n_it = blk_tab[4 * blockIdx.x + 1], chunk = blk_tab[4 * blockIdx.x + 2];
-  const int sub = items[2 * first + 1], end = sub_end[sub];
+  // the tile's items need not be consecutive: they are grouped by the length of DP[u], so that the rows of a block
+  // finish together (ncu of the consecutive form: barrier was the top stall, the light rows waiting for the heavy one)
+  const int* tab = blk_tab + (size_t)kTabInts * blockIdx.x;
+  const int n_it = tab[0], chunk = tab[1];
+  const int sub = tab[3], end = sub_end[sub];
+  const int* tile_items = tab + 4;
   // The w of a chunk come from a list sorted by the length of DP[w]: the work of a pair grows with that length, and
   // 32 consecutive preorder ids mix leaves with their heavy ancestors (ncu: 5x more warp instructions than useful ones)
-  const int* pw = perm + blk_tab[4 * blockIdx.x + 3] + chunk * kTileW;
+  const int* pw = perm + tab[2] + chunk * kTileW;
   const int n_w = min(kTileW, (end - sub) - chunk * kTileW);  // valid entries of pw
   // stage: the rows are node-major in HBM, so consecutive threads read consecutive j of one row (coalesced;
   // reading them column-wise cost 4x the bytes in 32-byte sectors and bounded the kernel); the transposed
@@ -283,14 +287,14 @@ k_dp_across_tiled(const int* __restrict__ items, const int* __restrict__ blk_tab
   }
   for (int idx = tid; idx < kTileU * (k + 1); idx += nthr) {
     const int q = idx / (k + 1), j = idx % (k + 1);
-    Bs[idx] = q < n_it ? cs[(size_t)items[2 * (first + q)] * kcap + j] : S{};
+    Bs[idx] = q < n_it ? cs[(size_t)items[2 * tile_items[q]] * kcap + j] : S{};
   }
   for (int idx = tid; idx < kTileU * max_len; idx += nthr) {
     const int q = idx / max_len, j = idx % max_len;
-    Ds[idx] = q < n_it ? dp[(size_t)items[2 * (first + q)] * dcap + j] : S{};
+    Ds[idx] = q < n_it ? dp[(size_t)items[2 * tile_items[q]] * dcap + j] : S{};
   }
   if (tid < kTileU) {
-    s_ld[tid] = tid < n_it ? dplen[items[2 * (first + tid)]] : 1;
+    s_ld[tid] = tid < n_it ? dplen[items[2 * tile_items[tid]]] : 1;
     s_stuck[tid] = 0;
   }
   __syncthreads();
@@ -300,7 +304,7 @@ k_dp_across_tiled(const int* __restrict__ items, const int* __restrict__ blk_tab
   S best{};
   int bidx[4] = {0, 0, 0, 0};
   if (ui < n_it && wt < n_w) {
-    const int u = items[2 * (first + ui)];
+    const int u = items[2 * tile_items[ui]];
     const S* A = As + wt;  // A[j] = A[j * kTileW]
     const S* C = Cs + wt;
     const S* B = Bs + (size_t)ui * (k + 1);
@@ -378,7 +382,7 @@ k_dp_across_tiled(const int* __restrict__ items, const int* __restrict__ blk_tab
     cb.w = r_w[src];
     cb.stuck = s_stuck[ui] != 0;
     for (int q = 0; q < 4; ++q) cb.idx[q] = r_idx[src * 4 + q];
-    chunk_best[item_cb0[first + ui] + chunk] = cb;
+    chunk_best[item_cb0[tile_items[ui]] + chunk] = cb;
   }
 }
 
@@ -558,7 +562,7 @@ int camus_b200_dp_create(camus_b200_dp** out, int device, int score_is_f64, int3
       max_tiles = std::max(max_tiles, ((s0 + kTileU - 1) / kTileU + 1) * ((s1 + kTileW - 1) / kTileW) + ((s1 + kTileU - 1) / kTileU + 1) * ((s0 + kTileW - 1) / kTileW));
     }
     if ((e = dp->d_blk_item.alloc(max_b128)) != cudaSuccess || (e = dp->d_item_blk0.alloc(n + 1)) != cudaSuccess ||
-        (e = dp->d_item_cb0.alloc(n + 1)) != cudaSuccess || (e = dp->d_tile_tab.alloc(4 * max_tiles)) != cudaSuccess ||
+        (e = dp->d_item_cb0.alloc(n + 1)) != cudaSuccess || (e = dp->d_tile_tab.alloc(kTabInts * max_tiles)) != cudaSuccess ||
         (e = dp->d_perm.alloc(n)) != cudaSuccess || (e = dp->d_chunk_best.alloc(std::max(max_b128, max_cb64))) != cudaSuccess ||
         (e = dp->d_cols.alloc(n * 128)) != cudaSuccess || (e = dp->d_desc.alloc(3 * n)) != cudaSuccess || (e = dp->d_blob.alloc(16 * n)) != cudaSuccess)
       return bail("cudaMalloc (per-vertex tables)", e);
@@ -661,19 +665,26 @@ int camus_b200_dp_set_vertex(camus_b200_dp* dp, int32_t v, int32_t n_items, cons
     perm_of.push_back({sub, off});
     return off;
   };
-  for (int i = 0; i < n_items;) {
+  for (int i = 0; i < n_items;) {  // runs of items with the same other subtree
     int j = i + 1;
-    while (j < n_items && j - i < kTileU && item_sub[j] == item_sub[i]) ++j;
+    while (j < n_items && item_sub[j] == item_sub[i]) ++j;
+    std::vector<int> ord(j - i);
+    for (int q = 0; q < j - i; ++q) ord[q] = i + q;
+    std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return dp->h_dplen[item_u[a]] > dp->h_dplen[item_u[b]]; });
     const int chunks = cb0[i + 1] - cb0[i], poff = perm_offset(item_sub[i]);
-    for (int c = 0; c < chunks; ++c) {
-      tab.push_back(i);
-      tab.push_back(j - i);
-      tab.push_back(c);
-      tab.push_back(poff);
+    for (size_t t0 = 0; t0 < ord.size(); t0 += kTileU) {
+      const int n_it = (int)std::min<size_t>(kTileU, ord.size() - t0);
+      for (int c = 0; c < chunks; ++c) {
+        tab.push_back(n_it);
+        tab.push_back(c);
+        tab.push_back(poff);
+        tab.push_back(item_sub[i]);
+        for (int q = 0; q < kTileU; ++q) tab.push_back(q < n_it ? ord[t0 + q] : ord[t0]);
+      }
     }
     i = j;
   }
-  dp->n_tile_blocks = (int)(tab.size() / 4);
+  dp->n_tile_blocks = (int)(tab.size() / kTabInts);
   if (n_items) {
     DCK(dp->d_tile_tab.alloc(tab.size()));
     DCK(dp->d_item_cb0.alloc(cb0.size()));
