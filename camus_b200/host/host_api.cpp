@@ -129,7 +129,20 @@ int camus_host_run_dp_accel(const camus_host_problem* p, int mode, const uint64_
       memcpy(&api, accel, sizeof api);
     }
     r->res = run_dp(p->td, tabs, (ScoreMode)mode, n_gtrees, alpha, e ? atoi(e) : 0, accel ? &api : nullptr, device, min_work);
-    for (auto& b : r->res.branches) r->newicks.push_back(make_network_newick(p->td, b));
+    // one network per k, independent of each other (each clones the tree and grafts its k branches): on all host threads
+    {
+      const size_t m = r->res.branches.size();
+      r->newicks.assign(m, std::string());
+      const size_t nt = std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), m > 8 ? m : 1);
+      std::atomic<size_t> next{0};
+      std::vector<std::thread> th;
+      auto work = [&] {
+        for (size_t i; (i = next.fetch_add(1)) < m;) r->newicks[i] = make_network_newick(p->td, r->res.branches[i]);
+      };
+      for (size_t t = 1; t < nt; ++t) th.emplace_back(work);
+      work();
+      for (auto& t : th) t.join();
+    }
     *out = r.release();
     return 0;
   } catch (const CamusError& e) {
