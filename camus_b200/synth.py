@@ -216,8 +216,10 @@ CONFIGS = {
 }
 
 
-def make_config(cid: int, n_taxa: int | None = None, n_trees: int | None = None) -> tuple[Synth, dict]:
+def make_config(cid: int, n_taxa: int | None = None, n_trees: int | None = None, drop_frac: float | None = None) -> tuple[Synth, dict]:
     c = dict(CONFIGS[cid])
+    if drop_frac is not None:  # a variant of the configuration in which every tree misses that fraction of the taxa
+        c["drop_frac"] = drop_frac
     if n_taxa:
         c["n_taxa"] = n_taxa
     if n_trees:

@@ -23,10 +23,11 @@ ap.add_argument("--trees", type=int, default=None)
 ap.add_argument("--qmode", type=int, default=None)
 ap.add_argument("--thr", type=float, default=None)
 ap.add_argument("--reps", type=int, default=5)
+ap.add_argument("--drop-frac", type=float, default=None, help="every gene tree misses this fraction of the taxa (general / packed kernel)")
 ap.add_argument("--devices", type=int, default=1, help="GPUs of this process driven by ONE handle (camus_b200_create n_gpus)")
 a = ap.parse_args()
 
-s, c = synth.make_config(a.config, a.taxa, a.trees)
+s, c = synth.make_config(a.config, a.taxa, a.trees, a.drop_frac)
 prob = Problem(s.constraint, s.genes, s.fmt, c["min_support"])
 q = c["qmode"] if a.qmode is None else a.qmode
 t = c["threshold"] if a.thr is None else a.thr
