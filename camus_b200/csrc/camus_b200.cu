@@ -264,7 +264,7 @@ static int create_one(camus_b200** out, int dev) {
     set(k_count<false, kModeGeneral>, CountCfg<kModeGeneral>::kSmemBytes);
     set(k_count<true, kModeGeneral>, CountCfg<kModeGeneral>::kSmemBytes);
     set(k_count<false, kModeComplete>, CountCfg<kModeComplete>::kSmemBytes);
-    set(k_count<true, kModeComplete>, CountCfg<kModeComplete>::kSmemBytes);
+    set(k_count<true, kModeComplete>, CountCfg<kModeComplete>::kSmemBytes + 64 * 1024);  // + room for CAMUS_B200_COUNT_PAD_SMEM
     set(k_count<true, kModePacked>, CountCfg<kModePacked>::kSmemBytes);
     if (a != cudaSuccess) {
       g_create_err = std::string("camus_b200_create: count kernels do not fit this device (") + cudaGetErrorString(a) + ")";
@@ -891,8 +891,9 @@ int run_fused(camus_b200* ctx, int qmode, double threshold, int as_set, uint64_t
   for (uint64_t b0 = 0; b0 < mine; b0 += max_grid) {
     uint64_t nbx = std::min(max_grid, mine - b0);
     CountParams prm{ctx->d_tri.p, std::max(ctx->G32, 1), box_map(ctx, b0), nullptr, ctx->G, tile_slots(ctx), desc};
+    static const int pad_smem = getenv("CAMUS_B200_COUNT_PAD_SMEM") ? atoi(getenv("CAMUS_B200_COUNT_PAD_SMEM")) : 0;  // experiments: fewer CTAs per SM
     if (complete)
-      k_count<true, kModeComplete><<<(unsigned)nbx, kCountThreads, CountCfg<kModeComplete>::kSmemBytes, ctx->stream>>>(prm, fz, ctx->ct);
+      k_count<true, kModeComplete><<<(unsigned)nbx, kCountThreads, CountCfg<kModeComplete>::kSmemBytes + pad_smem, ctx->stream>>>(prm, fz, ctx->ct);
     else if (packed)
       k_count<true, kModePacked><<<(unsigned)nbx, kCountThreads, CountCfg<kModePacked>::kSmemBytes, ctx->stream>>>(prm, fz, ctx->ct);
     else

@@ -157,6 +157,10 @@ k_count(CountParams prm, FusedParams fz, ConstraintDev ct) {
   __shared__ uint32_t s_seg[5];  // four segments, [4] = regular box
   __shared__ uint32_t s_done[4];  // CAMUS_COUNT_NOBAR: warps that have finished with each ring stage
   __shared__ uint64_t s_tile[4];  // slots of the tiles abc, abd, acd, bcd in prm.tri
+  // packed constraint LCAs of the box's 8 x 8 (a, b), (b, c) and (c, d) taxon pairs: everything the epilogue reads from
+  // ct.lcaD. Loaded at the start (the latency hides behind the count loop); the epilogue was stalled on these loads
+  // (long scoreboard = 23 % of its samples).
+  __shared__ uint32_t s_lca[kFused ? 3 : 1][64];
 
   const int tid = threadIdx.x;
   // Lane order. An LDS.128 costs 4 shared-memory wavefronts, or 2 when the four lanes of every
@@ -240,6 +244,14 @@ k_count(CountParams prm, FusedParams fz, ConstraintDev ct) {
 
   if (tid == 0)
     for (int g = 0; g < Cfg::kStages && g < G; ++g) issue(g);
+  uint32_t lca_pre = 0;
+  if constexpr (kFused) {
+    if (tid < 192) {
+      const uint32_t which = tid >> 6, u = (tid >> 3) & 7, v = tid & 7, Nt = (uint32_t)ct.n_taxa;
+      const uint32_t lo = (which == 0 ? sa : (which == 1 ? sb : sc)) * 8 + u, hi = (which == 0 ? sb : (which == 1 ? sc : sd)) * 8 + v;
+      lca_pre = ct.lcaD[(size_t)min(lo, Nt - 1) * Nt + min(hi, Nt - 1)];
+    }
+  }
 
   // general: cnt[c][t] = trees displaying topology t. complete: cnt[c][0] = c(ab|cd) | c(ac|bd) << 16.
   // packed: cnt[c][0] = c(ab|cd) | c(ac|bd) << 10 | c(ad|bc) << 20.
@@ -259,6 +271,10 @@ k_count(CountParams prm, FusedParams fz, ConstraintDev ct) {
   asm volatile("" : "+r"(o_abc), "+r"(o_abd), "+r"(o_acd), "+r"(o_bcd));
   constexpr int kPlaneU4 = kPlaneWords / 4;
 
+  if constexpr (kFused) {
+    if (G > 0) mbar_wait(&bars[0], 0u);  // the first tiles are in: by now the LCA loads have landed as well
+    if (tid < 192) s_lca[tid >> 6][tid & 63] = lca_pre;
+  }
   for (int g = 0; g < G; ++g) {
     const int s = g % kCountStages;
     if constexpr (CAMUS_COUNT_NOBAR || CAMUS_COUNT_EXPERIMENT == 3) {
@@ -467,8 +483,7 @@ k_count(CountParams prm, FusedParams fz, ConstraintDev ct) {
     uint32_t ns = 0, sum = 0;  // per thread: at most 48 keys, 48 x trees counts (the host keeps trees < 2^24 here)
     uint32_t qn = 0;           // warp-uniform queue fill (irregular boxes)
     // packed LCAs of the box's first taxa: THE LCAs of a regular box
-    const uint32_t bg1 = ct.lcaD[(size_t)(sa * 8) * N + sb * 8], bg2 = ct.lcaD[(size_t)(sb * 8) * N + sc * 8],
-                   bg3 = ct.lcaD[(size_t)(sc * 8) * N + sd * 8];
+    const uint32_t bg1 = s_lca[0][0], bg2 = s_lca[1][0], bg3 = s_lca[2][0];
     const bool box_kill0 = constraint_topology(bg1, bg2, bg3) == 0;  // regular box: the constraint displays ab|cd (else ad|bc)
 
     // one cell: (wx, wy) = surviving counts of ac|bd and of the other non-constraint topology; tie = deferred
@@ -549,9 +564,9 @@ k_count(CountParams prm, FusedParams fz, ConstraintDev ct) {
       for (int u = 0; u < 2; ++u)
 #pragma unroll
         for (int v = 0; v < 2; ++v) {
-          g1[u][v] = ct.lcaD[(size_t)min(a0 + u, N - 1) * N + min(b0 + v, N - 1)];
-          g2[u][v] = ct.lcaD[(size_t)min(b0 + u, N - 1) * N + min(c0 + v, N - 1)];
-          g3[u][v] = ct.lcaD[(size_t)min(c0 + u, N - 1) * N + min(d0 + v, N - 1)];
+          g1[u][v] = s_lca[0][(2 * ta + u) * 8 + 2 * tb + v];
+          g2[u][v] = s_lca[1][(2 * tb + u) * 8 + 2 * tc + v];
+          g3[u][v] = s_lca[2][(2 * tc + u) * 8 + 2 * td + v];
         }
 #pragma unroll
       for (int ll = 0; ll < 2; ++ll)
@@ -594,9 +609,9 @@ k_count(CountParams prm, FusedParams fz, ConstraintDev ct) {
         bool was_tie;
         q_unpack(queue[e], local, was_tie, c);
         const uint32_t x[4] = {sa * 8 + (local & 7), sb * 8 + ((local >> 3) & 7), sc * 8 + ((local >> 6) & 7), sd * 8 + (local >> 9)};
-        const uint32_t h1 = ct.lcaD[(size_t)x[0] * N + x[1]];
-        const uint32_t h2 = ct.lcaD[(size_t)x[1] * N + x[2]];
-        const uint32_t h3 = ct.lcaD[(size_t)x[2] * N + x[3]];
+        const uint32_t h1 = s_lca[0][(local & 7) * 8 + ((local >> 3) & 7)];
+        const uint32_t h2 = s_lca[1][((local >> 3) & 7) * 8 + ((local >> 6) & 7)];
+        const uint32_t h3 = s_lca[2][((local >> 6) & 7) * 8 + (local >> 9)];
         const int kc = constraint_topology(h1, h2, h3);
         if (was_tie) {  // deferred tie: the reference's stable topology order decides (apply_filter)
           const int ti[4] = {ct.tip_of_rank[x[0]], ct.tip_of_rank[x[1]], ct.tip_of_rank[x[2]], ct.tip_of_rank[x[3]]};
