@@ -202,3 +202,28 @@ def test_beyond_the_bit_plane_budget_1000_taxa_3000_trees(gpu):
     out, ns2, sc2 = gpu.run_resident(2, 0.5, False)
     assert (ns2, sc2) == want and np.array_equal(out, t2)
     gpu.clear_gene_trees()
+
+
+def test_beyond_the_bit_plane_budget_1500_taxa_1000_trees(gpu):
+    """1500 taxa x 1000 gene trees: 221 GB of bit-planes (188 segments), again more than one B200 holds; the 8 sequential
+    passes keep half of it resident. Same size-independent check: the unfiltered (-q 0) table and the summed counts are
+    linear in the gene trees, so they must equal the sum over the two 500-tree halves, each of which fits (110 GB) and
+    takes the one-pass path."""
+    s = synth.make(1500, 1000, 78)
+    lines = s.genes.strip().split("\n")
+    parts = []
+    for b in range(2):
+        prob = Problem(s.constraint, "\n".join(lines[b * 500:(b + 1) * 500]) + "\n")
+        gpu.load(prob)
+        ns, sc = gpu.count_filter(0, 0.0)
+        parts.append((ns, sc, gpu.quartet_totals(False)))
+    prob = Problem(s.constraint, s.genes)
+    gpu.load(prob)
+    ns, sc = gpu.count_filter(0, 0.0)
+    tab = gpu.quartet_totals(False)
+    assert sc == parts[0][1] + parts[1][1]
+    assert ns >= max(parts[0][0], parts[1][0])
+    assert np.array_equal(tab, parts[0][2] + parts[1][2])
+    ms, _ = gpu.stage_ms()
+    print(f"\n1500 x 1000 in 8 passes: prep {ms['prep']:.0f} ms, count {ms['count']:.0f} ms")
+    gpu.clear_gene_trees()
