@@ -112,3 +112,68 @@ def test_support_values_match_strtod(probe):
                 continue
             genes = f"((a,b){lab},((c,d){lab},e));\n"
             same_flat(probe, Problem(cons, genes, "newick", float(thr)), genes, float(thr))
+
+
+def _random_tree(rng, taxa, p_poly=0.2, p_unary=0.05, p_support=0.5, p_len=0.5, p_ws=0.2, p_comment=0.1):
+    """A random newick string over a random subset of `taxa`, with the syntax the dialect allows."""
+    leaves = [t for t in taxa if rng.random() > 0.15] or [taxa[0]]
+    rng.shuffle(leaves)
+
+    def ws():
+        return rng.choice([" ", "\t", "  "]) if rng.random() < p_ws else ""
+
+    def deco(internal):
+        out = ""
+        if internal and rng.random() < p_support:
+            out += rng.choice(["0.%d" % rng.integers(0, 1000), "%d" % rng.integers(0, 101), "1", "0.7", "0.69", "inner%d" % rng.integers(9), "1.", "00.50"])
+        if rng.random() < p_comment:
+            out += "[c%d]" % rng.integers(9)
+        if rng.random() < p_len:
+            out += ":" + ws() + rng.choice(["0.1", "1e-3", "2", "1.5E+2", "0"])
+        return out
+
+    def build(items):
+        if len(items) == 1:
+            node = items[0] + ws() + deco(False)
+            if rng.random() < p_unary:
+                node = "(" + ws() + node + ws() + ")" + deco(True)
+            return node
+        k = 2 if rng.random() > p_poly or len(items) < 3 else int(rng.integers(3, min(5, len(items)) + 1))
+        cuts = sorted(rng.choice(np.arange(1, len(items)), size=k - 1, replace=False).tolist())
+        parts = [items[a:b] for a, b in zip([0] + cuts, cuts + [len(items)])]
+        return "(" + ws() + ("," + ws()).join(build(p) for p in parts) + ws() + ")" + deco(True)
+
+    body = build(leaves)
+    if not body.startswith("("):
+        body = "(" + body + ")"
+    return ws() + body + ws() + ";" + ws()
+
+
+def test_randomised_differential_against_the_host_parser(probe):
+    """Whenever the automaton accepts a file it must produce exactly the host parser's flat trees (no silent divergence);
+    it may be stricter (fallback), never different. Random syntax; then random single-character corruptions."""
+    rng = np.random.default_rng(int(os.environ.get("CAMUS_FUZZ_SEED", "11")))
+    taxa = ["t%02d" % i for i in range(14)]
+    cons = synth.make(14, 1, 3).constraint
+    names = Problem(cons, "").tip_names
+    taxa = list(names)
+    accepted = fallbacks = 0
+    for it in range(int(os.environ.get("CAMUS_FUZZ_ITERS", "250"))):
+        ms = float(rng.choice([0.0, 0.0, 0.5, 0.7, 0.695]))
+        text = "\n".join(_random_tree(rng, taxa) for _ in range(int(rng.integers(1, 5)))) + "\n"
+        if it % 3 == 2:  # corrupt one character
+            pos = int(rng.integers(0, len(text) - 1))
+            text = text[:pos] + rng.choice(list("(),;:[]' x")) + text[pos + 1:]
+        try:
+            prob = Problem(cons, text, "newick", ms)
+        except Exception:
+            prob = None
+        n, aux, flat = ingest(probe, names, text, ms)
+        if n >= 0:
+            accepted += 1
+            assert prob is not None, f"automaton accepted what the host parser rejects: {text!r}"
+            assert n == prob.n_trees and np.array_equal(flat[0], prob.gene_node_off), text
+            assert np.array_equal(flat[1], prob.gene_parent) and np.array_equal(flat[2], prob.gene_taxon), text
+        else:
+            fallbacks += 1
+    assert accepted > 100 and fallbacks > 20
