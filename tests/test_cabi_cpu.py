@@ -65,3 +65,30 @@ def test_product_does_not_import_oracle():
                     if re.search(r"^\s*(from|import)\s+oracle\b|#include\s+\".*oracle|liboracle", txt, flags=re.M):
                         bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+def test_header_is_plain_c():
+    """The boundary is a C ABI (cgo binds it): include/camus_b200.h must compile as C99 with no torch / C++ types."""
+    import subprocess
+    hdr = os.path.join(ROOT, "include", "camus_b200.h")
+    subprocess.run(["gcc", "-x", "c", "-std=c99", "-pedantic", "-Wall", "-Werror", "-fsyntax-only", hdr], check=True)
+    text = open(hdr).read()
+    assert "torch" not in text and "std::" not in text and "at::" not in text
+
+
+def test_dp_and_ingest_entry_points_fail_loudly_without_a_gpu(lib):
+    """camus_b200_dp_create has no CPU fallback either; the null-argument checks come before any CUDA call."""
+    import numpy as np
+    import torch
+    lib.camus_b200_dp_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.camus_b200_dp_last_error.argtypes = [C.c_void_p]
+    lib.camus_b200_dp_last_error.restype = C.c_char_p
+    h = C.c_void_p()
+    assert lib.camus_b200_dp_create(C.byref(h), 0, 0, 0, None, None, None) == 1 and not h.value
+    assert b"dp_create" in lib.camus_b200_dp_last_error(None)
+    if not torch.cuda.is_available():
+        end, dep, edge = np.array([3, 2, 3], np.int32), np.array([0, 1, 1], np.int32), np.zeros(9, np.uint64)
+        rc = lib.camus_b200_dp_create(C.byref(h), 0, 0, 3, end.ctypes.data, dep.ctypes.data, edge.ctypes.data)
+        assert rc != 0 and not h.value and b"no CPU fallback" in lib.camus_b200_dp_last_error(None)
+    assert lib.camus_b200_add_gene_trees_newick(None, b"x", 1, 0.0, None, None, None) == 1
+    assert lib.camus_b200_set_tip_labels(None, 0, None, None) == 1
