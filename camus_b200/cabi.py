@@ -25,13 +25,14 @@ _dp_table = None
 
 
 def dp_accel_table():
-    """The eight camus_b200_dp_* entry points as an array of function pointers, in the order
+    """The ten camus_b200_dp_* entry points as an array of function pointers, in the order
     camus_host_run_dp_accel expects (camus_b200/host/dp.hpp DpAccelApi)."""
     global _dp_table
     if _dp_table is None:
         L = lib()
-        names = ("create", "destroy", "last_error", "set_node", "set_vertex", "set_path_columns", "across", "launches")
-        _dp_table = (C.c_void_p * 8)(*[C.cast(getattr(L, "camus_b200_dp_" + n), C.c_void_p).value for n in names])
+        names = ("create", "destroy", "last_error", "set_node", "set_vertex", "set_path_columns", "across", "launches",
+                 "set_conv_columns", "across_maxplus")
+        _dp_table = (C.c_void_p * 10)(*[C.cast(getattr(L, "camus_b200_dp_" + n), C.c_void_p).value for n in names])
     return _dp_table
 
 
@@ -86,6 +87,7 @@ EXPORTED = [
     "camus_b200_set_tip_labels", "camus_b200_add_gene_trees_newick", "camus_b200_get_gene_trees",
     "camus_b200_dp_create", "camus_b200_dp_destroy", "camus_b200_dp_last_error", "camus_b200_dp_set_node",
     "camus_b200_dp_set_vertex", "camus_b200_dp_set_path_columns", "camus_b200_dp_across", "camus_b200_dp_launches",
+    "camus_b200_dp_set_conv_columns", "camus_b200_dp_across_maxplus",
 ]
 
 

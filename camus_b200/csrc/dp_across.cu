@@ -31,6 +31,7 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <type_traits>
 #include <vector>
@@ -39,25 +40,82 @@
 
 namespace {
 
+// Device buffers come from the stream-ordered pool (cudaMallocAsync / cudaFreeAsync on the null stream, release
+// threshold raised once): a DP handle is created and destroyed per inference, and plain cudaFree -- a device-wide
+// synchronisation plus an unmap -- took 0.5 - 1 s per handle inside a process that holds tens of GB.
+inline void pool_keep_memory() {
+  static bool done = false;
+  if (done) return;
+  done = true;
+  int dev = 0;
+  cudaMemPool_t pool;
+  if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    unsigned long long keep = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  cudaGetLastError();
+}
 template <class T>
 struct Buf {
   T* p = nullptr;
   size_t n = 0;
   ~Buf() { release(); }
   void release() {
-    if (p) cudaFree(p);
+    if (p && cudaFreeAsync(p, nullptr) != cudaSuccess) {
+      cudaGetLastError();
+      cudaFree(p);
+    }
     p = nullptr;
     n = 0;
   }
   cudaError_t alloc(size_t count) {
     if (count <= n && p) return cudaSuccess;
+    if (p) cudaDeviceSynchronize();  // regrowth (rare: the tables are pre-sized): work in flight may still read the old block
     release();
     if (count == 0) return cudaSuccess;
-    cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+    pool_keep_memory();
+    cudaError_t e = cudaMallocAsync(&p, count * sizeof(T), nullptr);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(nullptr);  // the handle's own stream does not wait on the null stream
     if (e == cudaSuccess) n = count;
+    else p = nullptr;
     return e;
   }
 };
+
+// pinned host buffers are parked at destroy and handed to the next handle (cudaMallocHost / cudaFreeHost cost milliseconds)
+struct PinnedCache {
+  std::mutex mu;
+  std::vector<std::pair<void*, size_t>> free_list;
+  void* take(size_t bytes, size_t* got) {
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      for (size_t i = 0; i < free_list.size(); ++i)
+        if (free_list[i].second >= bytes) {
+          void* p = free_list[i].first;
+          *got = free_list[i].second;
+          free_list.erase(free_list.begin() + i);
+          return p;
+        }
+    }
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    *got = bytes;
+    return p;
+  }
+  void give(void* p, size_t bytes) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(mu);
+    if (free_list.size() < 8) free_list.push_back({p, bytes});
+    else cudaFreeHost(p);
+  }
+};
+inline PinnedCache& pinned_cache() {
+  static PinnedCache c;
+  return c;
+}
 
 struct ItemBest {
   unsigned long long score;  // raw 8 bytes (u64 or f64)
@@ -386,6 +444,76 @@ k_dp_across_tiled(const int* __restrict__ items, const int* __restrict__ blk_tab
   }
 }
 
+// Integer scores only (max mode): the across-scan as a max-plus product. FourWayBestSplit maximises
+// cs_w[a] + cs_u[b] + dp_w[c] + dp_u[d] over a + b + c + d = k; max-plus convolution is associative and exact on
+// integers, so the same maximum is max_j conv_w[j] + conv_u[k - j] with the per-node conv_x = cs_x (*) dp_x the caller
+// uploads (camus_b200_dp_set_conv_columns): O(k) per pair instead of O(k^2). Only the VALUE comes from this form; the
+// caller re-derives the split indices of the one candidate a step ends with by the reference's own FourWayBestSplit
+// (split = -1 in the result), so tie-breaks are untouched. Same tiling, same reduction as k_dp_across_tiled.
+__global__ void __launch_bounds__(kTileW* kTileU)
+k_dp_across_maxplus(const int* __restrict__ items, const int* __restrict__ blk_tab, const int* __restrict__ perm, const int* __restrict__ item_cb0,
+                    const int* __restrict__ sub_end, int k, int n, int kcap, const unsigned long long* __restrict__ cv,
+                    const unsigned long long* __restrict__ edge, ChunkBest* chunk_best) {
+  extern __shared__ unsigned long long sh_raw[];
+  unsigned long long* As = sh_raw;                       // [k + 1][kTileLd]: conv of the chunk's w
+  unsigned long long* Bs = As + (size_t)(k + 1) * kTileLd;  // [kTileU][k + 1]: conv of the tile's u
+  unsigned long long* r_score = Bs + (size_t)kTileU * (k + 1);
+  int* r_w = reinterpret_cast<int*>(r_score + kTileU * kTileW);
+  int* r_ok = r_w + kTileU * kTileW;
+  const int wt = threadIdx.x, ui = threadIdx.y, tid = ui * kTileW + wt, nthr = kTileW * kTileU;
+  const int* tab = blk_tab + (size_t)kTabInts * blockIdx.x;
+  const int n_it = tab[0], chunk = tab[1];
+  const int sub = tab[3], end = sub_end[sub];
+  const int* tile_items = tab + 4;
+  const int* pw = perm + tab[2] + chunk * kTileW;
+  const int n_w = min(kTileW, (end - sub) - chunk * kTileW);
+  for (int idx = tid; idx < (k + 1) * kTileW; idx += nthr) {
+    const int r = idx / (k + 1), j = idx % (k + 1);
+    As[j * kTileLd + r] = r < n_w ? cv[(size_t)pw[r] * kcap + j] : 0ull;
+  }
+  for (int idx = tid; idx < kTileU * (k + 1); idx += nthr) {
+    const int q = idx / (k + 1), j = idx % (k + 1);
+    Bs[idx] = q < n_it ? cv[(size_t)items[2 * tile_items[q]] * kcap + j] : 0ull;
+  }
+  __syncthreads();
+  const int w = wt < n_w ? pw[wt] : 0x7FFFFFFF;
+  bool ok = false;
+  unsigned long long best = 0;
+  if (ui < n_it && wt < n_w) {
+    const int u = items[2 * tile_items[ui]];
+    const unsigned long long* A = As + wt;
+    const unsigned long long* B = Bs + (size_t)ui * (k + 1);
+    unsigned long long val = 0;
+    for (int j = 0; j <= k; ++j) val = max(val, A[j * kTileLd] + B[k - j]);
+    best = edge[(size_t)u * n + w] + val;
+    ok = true;
+  }
+  r_score[tid] = best;
+  r_w[tid] = w;
+  r_ok[tid] = ok;
+  __syncthreads();
+  for (int s = kTileW / 2; s > 0; s >>= 1) {
+    if (wt < s && r_ok[tid + s]) {
+      const unsigned long long a = r_score[tid], b = r_score[tid + s];
+      if (!r_ok[tid] || b > a || (b == a && r_w[tid + s] < r_w[tid])) {
+        r_score[tid] = b;
+        r_w[tid] = r_w[tid + s];
+        r_ok[tid] = 1;
+      }
+    }
+    __syncthreads();
+  }
+  if (wt == 0 && ui < n_it) {
+    ChunkBest cb;
+    cb.score = r_score[tid];
+    cb.ok = r_ok[tid];
+    cb.w = r_w[tid];
+    cb.stuck = 0;
+    for (int q = 0; q < 4; ++q) cb.idx[q] = -1;  // the caller derives the split indices of the winner
+    chunk_best[item_cb0[tile_items[ui]] + chunk] = cb;
+  }
+}
+
 // Fold of one step (one block): per item its chunks in w order (first maximum; a stuck chunk 0 ends
 // it); across the items max score, then min cycle length, then the last item; NaN candidates never
 // win, item 0's is reported separately.
@@ -474,10 +602,11 @@ struct camus_b200_dp {
   bool tiled_ok = false;  // the opt-in shared-memory size was granted
   int n_blocks = 0;
   std::vector<int> h_end;
-  Buf<unsigned long long> d_edge, d_cs, d_dp, d_blob, d_cols;
+  Buf<unsigned long long> d_edge, d_cs, d_cv, d_dp, d_blob, d_cols;  // d_cv: conv columns (max-plus form), same shape as d_cs
   Buf<StepOut> d_out;
   Buf<unsigned int> d_counter;
   StepOut* h_out = nullptr;  // pinned
+  size_t h_out_bytes = 0;
   unsigned long long* h_stage = nullptr;  // pinned staging of the path columns (copied asynchronously)
   size_t stage_cap = 0;
   bool stage_busy = false;
@@ -525,14 +654,21 @@ int camus_b200_dp_create(camus_b200_dp** out, int device, int score_is_f64, int3
   cudaError_t e;
   if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
   if ((e = cudaStreamCreateWithFlags(&dp->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
-  if ((e = cudaMallocHost(&dp->h_out, sizeof(StepOut))) != cudaSuccess) return bail("pinned result", e);
+  dp->h_out = static_cast<StepOut*>(pinned_cache().take(256, &dp->h_out_bytes));
+  if (!dp->h_out) return bail("pinned result", cudaErrorMemoryAllocation);
   dp->stage_cap = (size_t)n_nodes * 128;  // path columns of 128 steps at once; grows on demand
-  if ((e = cudaMallocHost(&dp->h_stage, dp->stage_cap * 8)) != cudaSuccess) return bail("pinned staging", e);
+  {
+    size_t got = 0;
+    dp->h_stage = static_cast<unsigned long long*>(pinned_cache().take(dp->stage_cap * 8, &got));
+    if (!dp->h_stage) return bail("pinned staging", cudaErrorMemoryAllocation);
+    dp->stage_cap = got / 8;
+  }
   const size_t n = (size_t)n_nodes;
   dp->kcap = 128;  // doubled on demand (k_dp_repack)
   dp->dcap = 64;
   if ((e = dp->d_end.alloc(n)) != cudaSuccess || (e = dp->d_depth.alloc(n)) != cudaSuccess || (e = dp->d_dplen.alloc(n)) != cudaSuccess ||
       (e = dp->d_edge.alloc(n * n)) != cudaSuccess || (e = dp->d_cs.alloc(n * dp->kcap)) != cudaSuccess ||
+      (e = dp->d_cv.alloc(dp->f64 ? 1 : n * dp->kcap)) != cudaSuccess ||
       (e = dp->d_dp.alloc(n * dp->dcap)) != cudaSuccess ||
       (e = dp->d_items.alloc(2 * n)) != cudaSuccess || (e = dp->d_out.alloc(1)) != cudaSuccess || (e = dp->d_counter.alloc(1)) != cudaSuccess)
     return bail("cudaMalloc", e);
@@ -545,6 +681,7 @@ int camus_b200_dp_create(camus_b200_dp** out, int device, int score_is_f64, int3
       (e = cudaMemcpyAsync(dp->d_edge.p, edge_scores, n * n * 8, cudaMemcpyHostToDevice, dp->stream)) != cudaSuccess ||
       (e = cudaMemsetAsync(dp->d_dp.p, 0, n * dp->dcap * 8, dp->stream)) != cudaSuccess ||
       (e = cudaMemsetAsync(dp->d_cs.p, 0, n * dp->kcap * 8, dp->stream)) != cudaSuccess ||
+      (e = cudaMemsetAsync(dp->d_cv.p, 0, (dp->f64 ? 1 : n * dp->kcap) * 8, dp->stream)) != cudaSuccess ||
       (e = cudaMemsetAsync(dp->d_counter.p, 0, 4, dp->stream)) != cudaSuccess || (e = cudaStreamSynchronize(dp->stream)) != cudaSuccess)
     return bail("upload", e);
   // Every per-vertex table is sized once for the largest vertex of THIS tree (binary, preorder ids: children of v are
@@ -568,6 +705,7 @@ int camus_b200_dp_create(camus_b200_dp** out, int device, int score_is_f64, int3
       return bail("cudaMalloc (per-vertex tables)", e);
   }
   dp->tiled_ok = cudaFuncSetAttribute(k_dp_across_tiled<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) == cudaSuccess &&
+                 cudaFuncSetAttribute(k_dp_across_maxplus, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) == cudaSuccess &&
                  cudaFuncSetAttribute(k_dp_across_tiled<unsigned long long>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) == cudaSuccess;
   cudaGetLastError();
   *out = dp;
@@ -577,9 +715,12 @@ int camus_b200_dp_create(camus_b200_dp** out, int device, int score_is_f64, int3
 void camus_b200_dp_destroy(camus_b200_dp* dp) {
   if (!dp) return;
   cudaSetDevice(dp->device);
-  if (dp->stream) cudaStreamDestroy(dp->stream);
-  if (dp->h_out) cudaFreeHost(dp->h_out);
-  if (dp->h_stage) cudaFreeHost(dp->h_stage);
+  if (dp->stream) {
+    cudaStreamSynchronize(dp->stream);  // the buffers go back to the pool in null-stream order, which this stream does not join
+    cudaStreamDestroy(dp->stream);
+  }
+  pinned_cache().give(dp->h_out, dp->h_out_bytes);
+  pinned_cache().give(dp->h_stage, dp->stage_cap * 8);
   delete dp;
 }
 
@@ -707,49 +848,108 @@ int camus_b200_dp_set_vertex(camus_b200_dp* dp, int32_t v, int32_t n_items, cons
   return CAMUS_B200_OK;
 }
 
-int camus_b200_dp_set_path_columns(camus_b200_dp* dp, int32_t k0, int32_t k1, int32_t first, int32_t count, const void* cols) {
+// columns [k0, k1) of nodes [first, first + count) into the cycleDP table (conv = false) or the max-plus table (conv = true)
+static int push_columns(camus_b200_dp* dp, bool conv, int32_t k0, int32_t k1, int32_t first, int32_t count, const void* cols, const char* who) {
   if (!dp) return CAMUS_B200_ERR_ARG;
   if (k0 < 0 || k1 < k0 || first < 0 || count < 0 || first + count > dp->n || (!cols && k1 > k0 && count))
-    return dp->fail(CAMUS_B200_ERR_ARG, "dp_set_path_columns: bad range");
+    return dp->fail(CAMUS_B200_ERR_ARG, std::string(who) + ": bad range");
+  if (conv && dp->f64) return dp->fail(CAMUS_B200_ERR_ARG, std::string(who) + ": the max-plus form needs integer scores (float sums are order dependent)");
   cudaSetDevice(dp->device);
-  if (k1 > dp->kcap) {
+  if (k1 > dp->kcap) {  // both tables share the capacity
     int cap = dp->kcap;
     while (cap < k1) cap *= 2;
-    Buf<unsigned long long> bigger;
-    DCK(bigger.alloc((size_t)dp->n * cap));
-    DCK(cudaMemsetAsync(bigger.p, 0, (size_t)dp->n * cap * 8, dp->stream));
-    const size_t tot = (size_t)dp->n * dp->kcap;
-    k_dp_repack<<<(unsigned)((tot + 255) / 256), 256, 0, dp->stream>>>(dp->d_cs.p, bigger.p, dp->n, dp->kcap, cap);
-    DCK(cudaGetLastError());
-    DCK(cudaStreamSynchronize(dp->stream));
-    std::swap(dp->d_cs.p, bigger.p);
-    std::swap(dp->d_cs.n, bigger.n);
+    for (int t = 0; t < (dp->f64 ? 1 : 2); ++t) {
+      Buf<unsigned long long>& tab = t == 0 ? dp->d_cs : dp->d_cv;
+      Buf<unsigned long long> bigger;
+      DCK(bigger.alloc((size_t)dp->n * cap));
+      DCK(cudaMemsetAsync(bigger.p, 0, (size_t)dp->n * cap * 8, dp->stream));
+      const size_t tot = (size_t)dp->n * dp->kcap;
+      k_dp_repack<<<(unsigned)((tot + 255) / 256), 256, 0, dp->stream>>>(tab.p, bigger.p, dp->n, dp->kcap, cap);
+      DCK(cudaGetLastError());
+      DCK(cudaStreamSynchronize(dp->stream));
+      std::swap(tab.p, bigger.p);
+      std::swap(tab.n, bigger.n);
+      ++dp->launches;
+    }
     dp->kcap = cap;
-    ++dp->launches;
   }
   const size_t tot = (size_t)(k1 - k0) * count;
   if (tot) {
-    // through a pinned staging buffer, asynchronously: camus_b200_dp_across synchronises once per step
+    // through a pinned staging buffer, asynchronously: the across call synchronises once per step
     if (dp->stage_busy) {
       DCK(cudaStreamSynchronize(dp->stream));
       dp->stage_busy = false;
     }
     if (tot > dp->stage_cap) {
-      if (dp->h_stage) cudaFreeHost(dp->h_stage);
+      pinned_cache().give(dp->h_stage, dp->stage_cap * 8);
       dp->h_stage = nullptr;
       dp->stage_cap = 0;
-      DCK(cudaMallocHost(&dp->h_stage, tot * 2 * 8));
-      dp->stage_cap = tot * 2;
+      size_t got = 0;
+      dp->h_stage = static_cast<unsigned long long*>(pinned_cache().take(tot * 2 * 8, &got));
+      if (!dp->h_stage) return dp->fail(CAMUS_B200_ERR_CUDA, "pinned staging buffer");
+      dp->stage_cap = got / 8;
     }
     memcpy(dp->h_stage, cols, tot * 8);
     DCK(dp->d_cols.alloc(tot));
     DCK(cudaMemcpyAsync(dp->d_cols.p, dp->h_stage, tot * 8, cudaMemcpyHostToDevice, dp->stream));
-    k_cs_scatter<<<(unsigned)((tot + 255) / 256), 256, 0, dp->stream>>>(dp->d_cols.p, dp->d_cs.p, dp->kcap, k0, k1 - k0, first, count);
+    k_cs_scatter<<<(unsigned)((tot + 255) / 256), 256, 0, dp->stream>>>(dp->d_cols.p, conv ? dp->d_cv.p : dp->d_cs.p, dp->kcap, k0, k1 - k0, first, count);
     DCK(cudaGetLastError());
     ++dp->launches;
     dp->stage_busy = true;
   }
   return CAMUS_B200_OK;
+}
+
+int camus_b200_dp_set_path_columns(camus_b200_dp* dp, int32_t k0, int32_t k1, int32_t first, int32_t count, const void* cols) {
+  return push_columns(dp, false, k0, k1, first, count, cols, "dp_set_path_columns");
+}
+int camus_b200_dp_set_conv_columns(camus_b200_dp* dp, int32_t k0, int32_t k1, int32_t first, int32_t count, const void* cols) {
+  return push_columns(dp, true, k0, k1, first, count, cols, "dp_set_conv_columns");
+}
+
+// fold + read-back shared by the two across forms
+static int finish_step(camus_b200_dp* dp, const int* cb0, camus_b200_dp_best* out) {
+  if (dp->f64)
+    k_dp_fold<double><<<1, kFoldThreads, 0, dp->stream>>>(dp->n_items, dp->d_items.p, cb0, dp->d_depth.p, dp->cur_v, dp->d_chunk_best.p, dp->d_out.p);
+  else
+    k_dp_fold<unsigned long long><<<1, kFoldThreads, 0, dp->stream>>>(dp->n_items, dp->d_items.p, cb0, dp->d_depth.p, dp->cur_v, dp->d_chunk_best.p, dp->d_out.p);
+  DCK(cudaGetLastError());
+  dp->launches += 2;
+  DCK(cudaMemcpyAsync(dp->h_out, dp->d_out.p, sizeof(StepOut), cudaMemcpyDeviceToHost, dp->stream));
+  DCK(cudaStreamSynchronize(dp->stream));
+  dp->stage_busy = false;
+  const StepOut& r = *dp->h_out;
+  out->found = r.best.ok;
+  out->nan_seen = r.nan_seen;
+  out->first_is_nan = r.first.ok;
+  out->first_u = r.first.u;
+  out->first_w = r.first.w;
+  out->first_score_bits = r.first.score;
+  for (int q = 0; q < 4; ++q) out->first_split[q] = r.first.idx[q];
+  out->score_bits = r.best.score;
+  out->u = r.best.u;
+  out->w = r.best.w;
+  out->cycle_length = r.best.len;
+  for (int q = 0; q < 4; ++q) out->split[q] = r.best.idx[q];
+  return CAMUS_B200_OK;
+}
+
+int camus_b200_dp_across_maxplus(camus_b200_dp* dp, int32_t prev_k, camus_b200_dp_best* out) {
+  if (!dp || !out) return CAMUS_B200_ERR_ARG;
+  if (dp->f64) return dp->fail(CAMUS_B200_ERR_ARG, "dp_across_maxplus: integer scores only");
+  if (dp->cur_v < 0) return dp->fail(CAMUS_B200_ERR_ARG, "dp_across_maxplus: set the vertex first");
+  if (prev_k < 0 || prev_k >= dp->kcap) return dp->fail(CAMUS_B200_ERR_ARG, "dp_across_maxplus: conv columns 0..prev_k have not been set");
+  cudaSetDevice(dp->device);
+  memset(out, 0, sizeof *out);
+  if (dp->n_items == 0) return CAMUS_B200_OK;
+  const size_t shm = ((size_t)(prev_k + 1) * (kTileLd + kTileU)) * 8 + (size_t)kTileU * kTileW * (8 + 4 + 4);
+  if (!dp->tiled_ok || shm > 200 * 1024) return dp->fail(CAMUS_B200_ERR_NOMEM, "dp_across_maxplus: step too large for the shared-memory tile; use camus_b200_dp_across");
+  DCK(cudaMemsetAsync(dp->d_out.p, 0, sizeof(StepOut), dp->stream));
+  k_dp_across_maxplus<<<dp->n_tile_blocks, dim3(kTileW, kTileU), shm, dp->stream>>>(dp->d_items.p, dp->d_tile_tab.p, dp->d_perm.p, dp->d_item_cb0.p,
+                                                                                   dp->d_end.p, prev_k, dp->n, dp->kcap, dp->d_cv.p, dp->d_edge.p,
+                                                                                   dp->d_chunk_best.p);
+  DCK(cudaGetLastError());
+  return finish_step(dp, dp->d_item_cb0.p, out);
 }
 
 int camus_b200_dp_across(camus_b200_dp* dp, int32_t prev_k, camus_b200_dp_best* out) {
@@ -790,29 +990,7 @@ int camus_b200_dp_across(camus_b200_dp* dp, int32_t prev_k, camus_b200_dp_best* 
                                                                                          dp->d_edge.p, dp->d_chunk_best.p, dp->d_out.p);
   }
   DCK(cudaGetLastError());
-  if (dp->f64)
-    k_dp_fold<double><<<1, kFoldThreads, 0, dp->stream>>>(dp->n_items, dp->d_items.p, cb0, dp->d_depth.p, dp->cur_v, dp->d_chunk_best.p, dp->d_out.p);
-  else
-    k_dp_fold<unsigned long long><<<1, kFoldThreads, 0, dp->stream>>>(dp->n_items, dp->d_items.p, cb0, dp->d_depth.p, dp->cur_v, dp->d_chunk_best.p, dp->d_out.p);
-  DCK(cudaGetLastError());
-  dp->launches += 2;
-  DCK(cudaMemcpyAsync(dp->h_out, dp->d_out.p, sizeof(StepOut), cudaMemcpyDeviceToHost, dp->stream));
-  DCK(cudaStreamSynchronize(dp->stream));
-  dp->stage_busy = false;
-  const StepOut& r = *dp->h_out;
-  out->found = r.best.ok;
-  out->nan_seen = r.nan_seen;
-  out->first_is_nan = r.first.ok;
-  out->first_u = r.first.u;
-  out->first_w = r.first.w;
-  out->first_score_bits = r.first.score;
-  for (int q = 0; q < 4; ++q) out->first_split[q] = r.first.idx[q];
-  out->score_bits = r.best.score;
-  out->u = r.best.u;
-  out->w = r.best.w;
-  out->cycle_length = r.best.len;
-  for (int q = 0; q < 4; ++q) out->split[q] = r.best.idx[q];
-  return CAMUS_B200_OK;
+  return finish_step(dp, cb0, out);
 }
 
 uint64_t camus_b200_dp_launches(const camus_b200_dp* dp) { return dp ? dp->launches : 0; }

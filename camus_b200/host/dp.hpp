@@ -308,6 +308,8 @@ struct DpAccelApi {
   int (*set_path_columns)(void* dp, int32_t k0, int32_t k1, int32_t first, int32_t count, const void* cols);
   int (*across)(void* dp, int32_t prev_k, void* best);
   uint64_t (*launches)(const void* dp);
+  int (*set_conv_columns)(void* dp, int32_t k0, int32_t k1, int32_t first, int32_t count, const void* cols);
+  int (*across_maxplus)(void* dp, int32_t prev_k, void* best);
 };
 struct DpAccelBest {  // = camus_b200_dp_best
   int32_t found, nan_seen;
@@ -400,6 +402,9 @@ class DP {
   double t_update_ = 0, t_down_ = 0, t_items_ = 0, t_scan_ = 0, t_accept_ = 0, t_noedge_ = 0;
   static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
   int accel_v_ = -1, accel_cols_ = 0;  // vertex whose items are on the device, path columns already there
+  int accel_conv_cols_ = 0;            // max-plus form: conv columns already there
+  // CAMUS_DP_ACCEL_LITERAL=1: integer scores take the literal device scan too (A/B, tests)
+  bool accel_literal_ = getenv("CAMUS_DP_ACCEL_LITERAL") && getenv("CAMUS_DP_ACCEL_LITERAL")[0] == '1';
   std::vector<uint64_t> col_buf_;
   // CAMUS_DP_LITERAL=1: literal FourWayBestSplit scan for integer scores too (A/B, tests)
   bool fast_enabled_ = !(getenv("CAMUS_DP_LITERAL") && getenv("CAMUS_DP_LITERAL")[0] == '1');
@@ -602,8 +607,21 @@ class DP {
       a.check(a.api->set_vertex(a.handle, v, (int32_t)items_.size(), iu.data(), is.data()), "set_vertex");
       accel_v_ = v;
       accel_cols_ = 0;
+      accel_conv_cols_ = 0;
     }
-    if (accel_cols_ <= prevK) {
+    bool maxplus = false;
+    if constexpr (kIntegerScores) maxplus = fast_enabled_ && !accel_literal_ && a.api->across_maxplus != nullptr;
+    if (maxplus) {
+      // integer scores: conv columns instead of path columns (conv_update has run for every step of this vertex)
+      if (accel_conv_cols_ <= prevK) {
+        const int k0 = accel_conv_cols_, k1 = prevK + 1;
+        col_buf_.resize((size_t)(k1 - k0) * cnt);
+        for (int j = k0; j < k1; ++j)
+          for (int x = v; x < end; ++x) col_buf_[(size_t)(j - k0) * cnt + (x - v)] = raw_of(conv_[j][x]);
+        a.check(a.api->set_conv_columns(a.handle, k0, k1, v, cnt, col_buf_.data()), "set_conv_columns");
+        accel_conv_cols_ = k1;
+      }
+    } else if (accel_cols_ <= prevK) {
       const int k0 = accel_cols_, k1 = prevK + 1;
       col_buf_.resize((size_t)(k1 - k0) * cnt);
       for (int j = k0; j < k1; ++j)
@@ -613,7 +631,8 @@ class DP {
     }
     DpAccelBest b;
     const auto t1 = std::chrono::steady_clock::now();
-    a.check(a.api->across(a.handle, prevK, &b), "across");
+    if (maxplus) a.check(a.api->across_maxplus(a.handle, prevK, &b), "across_maxplus");
+    else a.check(a.api->across(a.handle, prevK, &b), "across");
     const auto t2 = std::chrono::steady_clock::now();
     a.s_columns += std::chrono::duration<double>(t1 - t0).count();
     a.s_across += std::chrono::duration<double>(t2 - t1).count();
@@ -703,6 +722,9 @@ class DP {
     t_items_ += now() - t0;
     t0 = now();
     const size_t work = (size_t)(td_.subtree_end[c0] - c0) * (size_t)(td_.subtree_end[c1] - c1) * (size_t)(prevK + 1);
+    bool fast = false;
+    if constexpr (kIntegerScores) fast = fast_enabled_;
+    if (fast) conv_update(v, prevK);  // every step of the vertex: the device's max-plus form and the host's both read it
     if (accel_ && !items_.empty()) {
       // float scores pay (k + 1)^2 additions per pair on the host, integer ones (max-plus form) k + 1
       const uint64_t cost = kIntegerScores && fast_enabled_ ? (uint64_t)work : (uint64_t)work * (uint64_t)(prevK + 1);
@@ -729,9 +751,6 @@ class DP {
         ++accel_->steps_host;
       }
     }
-    bool fast = false;
-    if constexpr (kIntegerScores) fast = fast_enabled_;
-    if (fast) conv_update(v, prevK);
     auto body = [&](int i, int) {
       if constexpr (kIntegerScores) {
         if (fast) {

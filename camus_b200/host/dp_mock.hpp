@@ -25,6 +25,7 @@ struct Handle {
   std::vector<uint64_t> edge;                // n * n raw scores
   std::vector<std::vector<uint64_t>> dp;     // DP[x]
   std::vector<std::vector<uint64_t>> cs;     // cs[x][k]
+  std::vector<std::vector<uint64_t>> cv;     // conv[x][k] (max-plus form)
   std::vector<int32_t> item_u, item_sub;
   int v = -1;
   uint64_t calls = 0;
@@ -157,6 +158,7 @@ inline int create(void** out, int, int is_f64, int32_t n, const int32_t* end, co
   h->edge.assign(static_cast<const uint64_t*>(edge), static_cast<const uint64_t*>(edge) + (size_t)n * n);
   h->dp.assign(n, std::vector<uint64_t>(1, 0));
   h->cs.assign(n, {});
+  h->cv.assign(n, {});
   *out = h;
   return 0;
 }
@@ -185,6 +187,50 @@ inline int set_path_columns(void* p, int32_t k0, int32_t k1, int32_t first, int3
     }
   return 0;
 }
+inline int set_conv_columns(void* p, int32_t k0, int32_t k1, int32_t first, int32_t count, const void* cols) {
+  auto* h = static_cast<Handle*>(p);
+  const auto* c = static_cast<const uint64_t*>(cols);
+  for (int j = k0; j < k1; ++j)
+    for (int x = 0; x < count; ++x) {
+      auto& row = h->cv[first + x];
+      if ((int)row.size() <= j) row.resize(j + 1, 0);
+      row[j] = c[(size_t)(j - k0) * count + x];
+    }
+  return 0;
+}
+// max-plus form: value only, split = -1; the same order-free reduction as across()
+inline int across_maxplus_entry(void* p, int32_t k, void* best) {
+  auto* h = static_cast<Handle*>(p);
+  ++h->calls;
+  auto& out = *static_cast<DpAccelBest*>(best);
+  std::memset(&out, 0, sizeof out);
+  Cand top;
+  for (size_t it = 0; it < h->item_u.size(); ++it) {
+    const int u = h->item_u[it], sub = h->item_sub[it];
+    Cand ib;
+    for (int w = h->end[sub] - 1; w >= sub; --w) {
+      uint64_t val = 0;
+      for (int j = 0; j <= k; ++j) val = std::max(val, h->cv[w][j] + h->cv[u][k - j]);
+      const uint64_t score = h->edge[(size_t)u * h->n + w] + val;
+      if (!ib.ok || score > ib.score || (score == ib.score && w < ib.w)) {
+        ib.ok = true;
+        ib.score = score;
+        ib.u = u;
+        ib.w = w;
+      }
+    }
+    if (!ib.ok) continue;
+    ib.len = (h->depth[u] - h->depth[h->v]) + (h->depth[ib.w] - h->depth[h->v]) + 1;
+    if (!top.ok || ib.score > top.score || (ib.score == top.score && ib.len <= top.len)) top = ib;
+  }
+  out.found = top.ok;
+  out.score_bits = top.score;
+  out.u = top.u;
+  out.w = top.w;
+  out.cycle_length = top.len;
+  for (int q = 0; q < 4; ++q) out.split[q] = -1;
+  return 0;
+}
 inline int across_entry(void* p, int32_t prev_k, void* best) {
   auto* h = static_cast<Handle*>(p);
   ++h->calls;
@@ -195,7 +241,8 @@ inline int across_entry(void* p, int32_t prev_k, void* best) {
 inline uint64_t launches(const void* p) { return static_cast<const Handle*>(p)->calls; }
 
 inline const DpAccelApi* api() {
-  static const DpAccelApi a{create, destroy, last_error, set_node, set_vertex, set_path_columns, across_entry, launches};
+  static const DpAccelApi a{create, destroy, last_error, set_node, set_vertex, set_path_columns, across_entry, launches,
+                            set_conv_columns, across_maxplus_entry};
   return &a;
 }
 

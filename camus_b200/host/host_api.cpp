@@ -103,8 +103,8 @@ int camus_host_should_calc_edge(const camus_host_problem* p, int u, int w) { ret
 int camus_host_cycle_length(const camus_host_problem* p, int u, int w) { return cycle_length(u, w, p->td); }
 
 // accel != NULL: the DP's across-scan runs on the GPU (include/camus_b200.h "DP offload"). accel =
-// eight function pointers, in this order: camus_b200_dp_create, _destroy, _last_error, _set_node,
-// _set_vertex, _set_path_columns, _across, _launches. min_work < 0 = default threshold below which a
+// ten function pointers, in this order: camus_b200_dp_create, _destroy, _last_error, _set_node,
+// _set_vertex, _set_path_columns, _across, _launches, _set_conv_columns, _across_maxplus. min_work < 0 = default threshold below which a
 // step stays on the host.
 int camus_host_run_dp_accel(const camus_host_problem* p, int mode, const uint64_t* totals, const uint64_t* penalties,
                             int as_set, uint64_t n_survivors, uint64_t sum_counts, int n_gtrees, double alpha,
@@ -125,7 +125,7 @@ int camus_host_run_dp_accel(const camus_host_problem* p, int mode, const uint64_
     const char* e = getenv("CAMUS_HOST_THREADS");
     DpAccelApi api{};
     if (accel) {
-      static_assert(sizeof(DpAccelApi) == 8 * sizeof(void*), "eight function pointers");
+      static_assert(sizeof(DpAccelApi) == 10 * sizeof(void*), "ten function pointers");
       memcpy(&api, accel, sizeof api);
     }
     r->res = run_dp(p->td, tabs, (ScoreMode)mode, n_gtrees, alpha, e ? atoi(e) : 0, accel ? &api : nullptr, device, min_work);

@@ -251,6 +251,12 @@ int camus_b200_dp_set_node(camus_b200_dp* dp, int32_t node, int32_t len, const v
 int camus_b200_dp_set_vertex(camus_b200_dp* dp, int32_t v, int32_t n_items, const int32_t* item_u, const int32_t* item_sub);
 int camus_b200_dp_set_path_columns(camus_b200_dp* dp, int32_t k0, int32_t k1, int32_t first, int32_t count, const void* cols);
 int camus_b200_dp_across(camus_b200_dp* dp, int32_t prev_k, camus_b200_dp_best* out);
+/* Integer scores (max mode) only: the same step as a max-plus product, O(k) per pair instead of O(k^2). The caller
+ * uploads conv_x[k] = max over i + i' = k of cycleDP.scores[x][i] + DP[x][i'] (columns as in set_path_columns; no path
+ * columns are needed) and gets the same winner -- maximum score, smallest CycleLength, last u, first w -- with
+ * split[] = -1: it derives the four split indices of that ONE candidate with the reference's FourWayBestSplit. */
+int camus_b200_dp_set_conv_columns(camus_b200_dp* dp, int32_t k0, int32_t k1, int32_t first, int32_t count, const void* cols);
+int camus_b200_dp_across_maxplus(camus_b200_dp* dp, int32_t prev_k, camus_b200_dp_best* out);
 uint64_t camus_b200_dp_launches(const camus_b200_dp* dp);
 
 #ifdef __cplusplus

@@ -114,3 +114,21 @@ def test_argument_errors():
     assert L.camus_b200_dp_set_node(h, 7, 1, edge.ctypes.data) != 0
     L.camus_b200_dp_destroy.argtypes = [C.c_void_p]
     L.camus_b200_dp_destroy(h)
+
+
+@pytest.mark.parametrize("taxa,trees,seed", [(60, 80, 17), (160, 80, 9)])
+def test_integer_scores_literal_and_maxplus_forms_agree(taxa, trees, seed, monkeypatch):
+    """max mode on the device: the max-plus form (camus_b200_dp_across_maxplus, default) and the literal scan
+    (CAMUS_DP_ACCEL_LITERAL=1) against the host DP; every step offloaded, host scan beside it where affordable."""
+    s = synth.make(taxa, trees, seed)
+    prob = Problem(s.constraint, s.genes)
+    tot, pen, ns, sc = _tables(prob, 2, 0.5, False)
+    host = prob.run_dp(tot, None, "max", False, ns, sc)
+    if taxa <= 60:
+        monkeypatch.setenv("CAMUS_DP_VERIFY", "1")
+    fast = prob.run_dp(tot, None, "max", False, ns, sc, gpu=0, min_work=0)
+    monkeypatch.setenv("CAMUS_DP_ACCEL_LITERAL", "1")
+    lit = prob.run_dp(tot, None, "max", False, ns, sc, gpu=0, min_work=0)
+    _same(host, fast)
+    _same(host, lit)
+    assert fast.accel["device_steps"] > 0 and lit.accel["device_steps"] > 0

@@ -93,3 +93,18 @@ def test_ties_everywhere(monkeypatch):
         host = prob.run_dp(tot, pen, mode, False, 100, 1000, prob.n_trees, 0.5)
         dev = prob.run_dp(tot, pen, mode, False, 100, 1000, prob.n_trees, 0.5, gpu="mock", min_work=0)
         _same(host, dev)
+
+
+def test_integer_scores_literal_and_maxplus_forms_agree(monkeypatch):
+    """max mode: the offload takes the max-plus form by default (conv columns, split indices of the winner from the
+    reference's FourWayBestSplit); CAMUS_DP_ACCEL_LITERAL=1 sends integers through the literal scan as well."""
+    monkeypatch.setenv("CAMUS_DP_VERIFY", "1")
+    s = synth.make(40, 50, 31)
+    prob = Problem(s.constraint, s.genes)
+    tot, pen, ns, sc = _tables(prob, 2, 0.5, False)
+    host = prob.run_dp(tot, None, "max", False, ns, sc)
+    fast = prob.run_dp(tot, None, "max", False, ns, sc, gpu="mock", min_work=0)
+    monkeypatch.setenv("CAMUS_DP_ACCEL_LITERAL", "1")
+    lit = prob.run_dp(tot, None, "max", False, ns, sc, gpu="mock", min_work=0)
+    _same(host, fast)
+    _same(host, lit)
