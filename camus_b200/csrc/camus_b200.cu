@@ -87,6 +87,11 @@ struct camus_b200 {
   DevBuf<int64_t> d_node_off;
   DevBuf<int32_t> d_gparent, d_gtaxon, d_nleaf;
   DevBuf<uint16_t> d_depth_tmp, d_lrT, d_hT, d_Dt;
+  DevBuf<uint32_t> d_Ds;  // bit-sliced depth rows of one batch (k_depth_slices)
+  DevBuf<uint16_t> d_lrP, d_hP, d_posP;  // per-tree leaf order, h and taxon -> position (k_depth_slices_direct)
+  DevBuf<PlaneDesc> d_plane_list;  // work list of the sliced plane builder (make_plane_list)
+  uint32_t n_plane_list = 0;
+  int plane_list_key[4] = {-1, -1, -1, -1};  // segments, rank, world, partial
   DevBuf<uint32_t> d_tri;
   DevBuf<uint4> d_cells;
   DevBuf<unsigned long long> d_Z, d_E, d_out, d_totals, d_keys, d_nout;
@@ -117,6 +122,8 @@ struct camus_b200 {
   bool all_rooted = true;    // ... and none of them has a trifurcating (unrooted) root
   bool allow_half = true;      // CAMUS_B200_NO_HALF=1 forces the integer plane builder (A/B, tests)
   bool allow_complete = true;  // CAMUS_B200_NO_COMPLETE=1 forces the general kernel (A/B, tests)
+  bool allow_sliced = true;    // CAMUS_B200_NO_SLICED=1 forces the packed-fp16 plane builder (A/B, tests)
+  bool allow_direct = true;    // CAMUS_B200_NO_DIRECT=1: slices from the depth table instead of straight from the trees (A/B, tests)
   bool allow_regular = true;   // CAMUS_B200_NO_REGULAR=1 sends every box through the survivor queue (A/B, tests)
 
   // ---- library-owned collective (camus_b200_comm_init) ----
@@ -275,6 +282,8 @@ static int create_one(camus_b200** out, int dev) {
   if (const char* e = getenv("CAMUS_B200_NO_COMPLETE")) ctx->allow_complete = !(e[0] == '1');
   if (const char* e = getenv("CAMUS_B200_NO_REGULAR")) ctx->allow_regular = !(e[0] == '1');
   if (const char* e = getenv("CAMUS_B200_NO_HALF")) ctx->allow_half = !(e[0] == '1');
+  if (const char* e = getenv("CAMUS_B200_NO_SLICED")) ctx->allow_sliced = !(e[0] == '1');
+  if (const char* e = getenv("CAMUS_B200_NO_DIRECT")) ctx->allow_direct = !(e[0] == '1');
   if (const char* e = getenv("CAMUS_B200_UNFUSED")) ctx->use_fused = !(e[0] == '1');
   if (const char* e = getenv("CAMUS_B200_NO_PACKED")) ctx->allow_packed = !(e[0] == '1');
   if (const char* e = getenv("CAMUS_B200_PASSES")) ctx->passes_env = atoi(e);
@@ -637,6 +646,44 @@ int add_gene_trees_impl(camus_b200* ctx, int32_t n_trees, const int64_t* node_of
 
 namespace {
 
+// Work list of k_triple_planes_bs: the tiles this context builds (all of them, or the tiles led by the classes
+// of its share), with their output slot, in blocks of 16 x 16 x 16 segments: a block of tiles shares
+// 3 x 128 x 128 pair rows (6 MB for four tree groups), which stay in L2 while its 4096 tiles stream out.
+int make_plane_list(camus_b200* ctx, bool partial) {
+  const int key[4] = {ctx->M, partial ? ctx->rank : 0, partial ? ctx->world : 1, partial ? 1 : 0};
+  if (!memcmp(key, ctx->plane_list_key, sizeof key)) return 0;
+  const uint32_t S = (uint32_t)ctx->M, B = 16, nblk = (S + B - 1) / B;
+  const uint32_t need = partial ? class_need_mask(ctx->rank, ctx->world) : 0xFu;
+  std::vector<PlaneDesc> list;
+  list.reserve((size_t)num_tiles(S));
+  uint32_t compact = 0;
+  std::vector<uint32_t> slot_of;  // compact slots follow colex order (set_box_range)
+  if (partial) {
+    slot_of.assign((size_t)num_tiles(S), 0xFFFFFFFFu);
+    uint32_t idx = 0;
+    for (uint32_t s2 = 0; s2 < S; ++s2)
+      for (uint32_t s1 = 0; s1 <= s2; ++s1)
+        for (uint32_t s0 = 0; s0 <= s1; ++s0, ++idx)
+          if ((need >> seg_class(s0)) & 1u) slot_of[idx] = compact++;
+  }
+  for (uint32_t B2 = 0; B2 < nblk; ++B2)
+    for (uint32_t B1 = 0; B1 <= B2; ++B1)
+      for (uint32_t B0 = 0; B0 <= B1; ++B0)
+        for (uint32_t s2 = B2 * B; s2 < std::min(S, (B2 + 1) * B); ++s2)
+          for (uint32_t s1 = B1 * B; s1 < std::min(s2 + 1, (B1 + 1) * B); ++s1)
+            for (uint32_t s0 = B0 * B; s0 < std::min(s1 + 1, (B0 + 1) * B); ++s0) {
+              if (!((need >> seg_class(s0)) & 1u)) continue;
+              const uint64_t idx = tile_index(s0, s1, s2);
+              list.push_back(PlaneDesc{s0 | (s1 << 16), s2, partial ? slot_of[idx] : (uint32_t)idx, 0u});
+            }
+  CK(ctx->d_plane_list.alloc(std::max<size_t>(list.size(), 1)));
+  if (!list.empty()) CK(cudaMemcpyAsync(ctx->d_plane_list.p, list.data(), list.size() * sizeof(PlaneDesc), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));  // the host vector goes away
+  ctx->n_plane_list = (uint32_t)list.size();
+  memcpy(ctx->plane_list_key, key, sizeof key);
+  return 0;
+}
+
 // K0 + K1 + K1b: gene trees -> rooted-triple bit-planes in HBM.
 int build_planes(camus_b200* ctx, bool do_upload = true) {
   const int G = ctx->G, npad = ctx->npad;
@@ -676,12 +723,25 @@ int build_planes(camus_b200* ctx, bool do_upload = true) {
     int max_nodes = 1;
     for (int g = 0; g < G; ++g) max_nodes = std::max<int>(max_nodes, (int)(ctx->h_node_off[g + 1] - ctx->h_node_off[g]));
     static const bool serial_prepare = getenv("CAMUS_B200_SERIAL_PREPARE") && getenv("CAMUS_B200_SERIAL_PREPARE")[0] == '1';  // A/B, tests
-    if (max_nodes <= kTreePrepareMaxNodes && !serial_prepare) {
+    const bool warp_prepare = max_nodes <= kTreePrepareMaxNodes && !serial_prepare;
+    // bit-sliced plane builder (default): NB = bits of the largest stored value (depth + 1), up to 11
+    int need_bits = 1;
+    while ((ctx->max_depth + 1) >> need_bits) ++need_bits;
+    const bool sliced_path = need_bits <= 11 && ctx->allow_sliced && ctx->allow_half;
+    // slices straight from the trees: one [taxon][32 trees] u16 image per CTA in shared memory
+    const bool direct_path = sliced_path && ctx->allow_direct && warp_prepare && (size_t)npad * 64 <= 200 * 1024;
+    if (direct_path) {
+      CK(ctx->d_lrP.alloc((size_t)G * npad));
+      CK(ctx->d_hP.alloc((size_t)G * npad));
+      CK(ctx->d_posP.alloc((size_t)G * npad));
+      CK(cudaMemsetAsync(ctx->d_posP.p, 0, (size_t)G * npad * 2, ctx->stream));
+    }
+    if (warp_prepare) {
       const size_t smem = (size_t)max_nodes * 4;
       if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_tree_prepare_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       k_tree_prepare_warp<<<G, 32, smem, ctx->stream>>>(G, ctx->d_node_off.p, ctx->d_gparent.p, ctx->d_gtaxon.p,
                                                          ctx->d_rank_of_tip.p, ctx->d_lrT.p, ctx->d_hT.p, npad, ctx->d_nleaf.p,
-                                                         max_nodes);
+                                                         max_nodes, direct_path ? ctx->d_lrP.p : nullptr, ctx->d_hP.p, ctx->d_posP.p);
     } else {
       k_tree_prepare<<<(G + 127) / 128, 128, 0, ctx->stream>>>(G, ctx->d_node_off.p, ctx->d_gparent.p, ctx->d_gtaxon.p,
                                                               ctx->d_rank_of_tip.p, ctx->d_depth_tmp.p, ctx->d_lrT.p,
@@ -689,14 +749,22 @@ int build_planes(camus_b200* ctx, bool do_upload = true) {
     }
     CK_LAUNCH();
     size_t dt_group = (size_t)npad * npad * kLanes;  // u16 elements
-    // Tree groups go through the depth table in batches of <= 256 MB (measured: running K1 of
-    // the next batch on a second stream under K1b of this one gains nothing, both are issue bound).
-    int gb_max = (int)std::max<size_t>(1, std::min<size_t>(ctx->G32, ((size_t)256 << 20) / (dt_group * 2)));
-    if (const char* e = getenv("CAMUS_B200_PREP_BATCH")) gb_max = std::max(1, std::min(ctx->G32, atoi(e)));  // tuning
-    CK(ctx->d_Dt.alloc(dt_group * gb_max));
     const unsigned n_tiles = partial ? (unsigned)ctx->n_tiles_local : (unsigned)num_tiles(ctx->M);
     // packed fp16 compares need exact depths: depth + 1 <= 2048 (checked in add_gene_trees)
     const bool half_path = ctx->max_depth + 1 <= 2048 && ctx->allow_half;
+    const int NB = need_bits <= 5 ? 5 : need_bits <= 6 ? 6 : need_bits <= 7 ? 7 : need_bits <= 9 ? 9 : 11;
+    const size_t slice_words = NB < 8 ? 8 : 12;
+    // Tree groups go through the depth table in batches of <= 256 MB (measured: running K1 of the next batch
+    // on a second stream under K1b of this one gains nothing; 1 GB batches make K1's scattered 2-byte stores
+    // miss L2 and double its time).
+    const size_t dt_cap = (size_t)256 << 20;
+    int gb_max = (int)std::max<size_t>(1, std::min<size_t>(ctx->G32, dt_cap / (dt_group * 2)));
+    if (const char* e = getenv("CAMUS_B200_PREP_BATCH")) gb_max = std::max(1, std::min(ctx->G32, atoi(e)));  // tuning
+    if (!direct_path) CK(ctx->d_Dt.alloc(dt_group * gb_max));
+    if (sliced_path) {
+      CK(ctx->d_Ds.alloc((size_t)npad * npad * slice_words * gb_max));
+      if (int rc = make_plane_list(ctx, partial)) return rc;
+    }
     // rooted triples are all resolved only under a binary root (a trifurcating root resolves
     // every quartet but leaves the triples across its three subtrees unresolved)
     const bool complete = ctx->all_complete && ctx->all_rooted && ctx->allow_complete;
@@ -704,16 +772,51 @@ int build_planes(camus_b200* ctx, bool do_upload = true) {
     for (int g0 = 0; g0 < ctx->G32; g0 += gb_max) {
       int gb = std::min(gb_max, ctx->G32 - g0);
       // integer depths: 0 = absent; fp16 depths: 0xFFFF = NaN = absent
-      CK(cudaMemsetAsync(dt, half_path ? 0xFF : 0, dt_group * gb * 2, ctx->stream));
-      dim3 blk(kLanes, 8);
-      dim3 g1((npad + 7) / 8, gb);
-      if (half_path)
-        k_depth_table<true><<<g1, blk, 0, ctx->stream>>>(g0, G, npad, ctx->d_nleaf.p, ctx->d_lrT.p, ctx->d_hT.p, dt);
-      else
-        k_depth_table<false><<<g1, blk, 0, ctx->stream>>>(g0, G, npad, ctx->d_nleaf.p, ctx->d_lrT.p, ctx->d_hT.p, dt);
-      CK_LAUNCH();
+      const bool fp16_table = half_path && !sliced_path;
+      if (!direct_path) {
+        CK(cudaMemsetAsync(dt, fp16_table ? 0xFF : 0, dt_group * gb * 2, ctx->stream));
+        dim3 blk(kLanes, 8);
+        dim3 g1((npad + 7) / 8, gb);
+        if (fp16_table)
+          k_depth_table<true><<<g1, blk, 0, ctx->stream>>>(g0, G, npad, ctx->d_nleaf.p, ctx->d_lrT.p, ctx->d_hT.p, dt);
+        else
+          k_depth_table<false><<<g1, blk, 0, ctx->stream>>>(g0, G, npad, ctx->d_nleaf.p, ctx->d_lrT.p, ctx->d_hT.p, dt);
+        CK_LAUNCH();
+      }
       if (n_tiles == 0) continue;  // a share without boxes
-      if (half_path && complete)
+      if (sliced_path) {
+        const unsigned n_cta = (ctx->n_plane_list + kPlaneTilesPerCta - 1) / kPlaneTilesPerCta;
+        const size_t group_words = (size_t)npad * npad * slice_words;
+#define CAMUS_SLICED_PLANES(nb, cmpl)                                                                                          \
+  {                                                                                                                            \
+    const int smem = 2 * 4 * 3 * SliceArray<SliceRow<nb>::W>::words * 4;                                                       \
+    CK(cudaFuncSetAttribute(k_triple_planes_bs<nb, cmpl>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                 \
+    for (int q0 = 0; q0 < gb; q0 += 4)                                                                                         \
+      k_triple_planes_bs<nb, cmpl><<<n_cta, 256, smem, ctx->stream>>>(g0 + q0, std::min(4, gb - q0), G32, G, npad,             \
+                                                                     ctx->d_Ds.p + (size_t)q0 * group_words, ctx->d_tri.p,    \
+                                                                     ctx->d_plane_list.p, ctx->n_plane_list);                 \
+  }
+#define CAMUS_SLICED(nb)                                                                                                        \
+  case nb:                                                                                                                      \
+    if (direct_path) {                                                                                                          \
+      const int smem_d = npad * 64;                                                                                             \
+      CK(cudaFuncSetAttribute(k_depth_slices_direct<nb>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_d));                 \
+      k_depth_slices_direct<nb><<<dim3(npad, gb), 256, smem_d, ctx->stream>>>(g0, G, npad, ctx->d_nleaf.p, ctx->d_lrP.p,        \
+                                                                              ctx->d_hP.p, ctx->d_posP.p, ctx->d_Ds.p);        \
+    } else                                                                                                                      \
+      k_depth_slices<nb><<<dim3(npad, gb), 256, 0, ctx->stream>>>(gb, npad, dt, ctx->d_Ds.p);                                  \
+    if (complete) CAMUS_SLICED_PLANES(nb, true) else CAMUS_SLICED_PLANES(nb, false)             \
+    break;
+        switch (NB) {
+          CAMUS_SLICED(5)
+          CAMUS_SLICED(6)
+          CAMUS_SLICED(7)
+          CAMUS_SLICED(9)
+          CAMUS_SLICED(11)
+        }
+#undef CAMUS_SLICED
+#undef CAMUS_SLICED_PLANES
+      } else if (half_path && complete)
         k_triple_planes_h2<true><<<n_tiles, 256, 0, ctx->stream>>>(g0, gb, G32, G, npad, dt, ctx->d_tri.p, tile_list);
       else if (half_path)
         k_triple_planes_h2<false><<<n_tiles, 256, 0, ctx->stream>>>(g0, gb, G32, G, npad, dt, ctx->d_tri.p, tile_list);

@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 
 #include "layout.cuh"
+#include "ptx.cuh"
 
 namespace camus_dev {
 
@@ -63,7 +64,8 @@ __global__ void __launch_bounds__(32) k_tree_prepare_warp(int n_trees, const int
                                                           const int32_t* __restrict__ parent, const int32_t* __restrict__ taxon,
                                                           const int32_t* __restrict__ rank_of_tip, uint16_t* __restrict__ lrT,
                                                           uint16_t* __restrict__ hT, int npad, int32_t* __restrict__ nleaf,
-                                                          int max_nodes) {
+                                                          int max_nodes, uint16_t* __restrict__ lrP, uint16_t* __restrict__ hP,
+                                                          uint16_t* __restrict__ posP) {
   extern __shared__ uint16_t s_tree[];
   uint16_t* s_par = s_tree;
   uint16_t* s_dep = s_tree + max_nodes;
@@ -87,8 +89,14 @@ __global__ void __launch_bounds__(32) k_tree_prepare_warp(int n_trees, const int
     const uint32_t m = __ballot_sync(0xFFFFFFFFu, t >= 0);
     if (t >= 0) {
       const int k = pos + __popc(m & ((1u << lane) - 1u));
-      lrT[(row0 + k) * kLanes + gl] = (uint16_t)rank_of_tip[t];
+      const uint16_t rk = (uint16_t)rank_of_tip[t];
+      lrT[(row0 + k) * kLanes + gl] = rk;
       if (i + 1 < nn) hT[(row0 + k) * kLanes + gl] = s_dep[i + 1];  // node after a leaf hangs off LCA(leaf, next leaf)
+      if (lrP) {  // per-tree copies for k_depth_slices_direct: [tree][position] and the inverse [tree][rank] -> position + 1
+        lrP[(size_t)g * npad + k] = rk;
+        hP[(size_t)g * npad + k] = i + 1 < nn ? s_dep[i + 1] : (uint16_t)0xFFFF;
+        posP[(size_t)g * npad + rk] = (uint16_t)(k + 1);
+      }
     }
     pos += __popc(m);
   }
@@ -375,6 +383,293 @@ __global__ void __launch_bounds__(256, CAMUS_PLANES_MINB) k_triple_planes_h2(int
     __syncthreads();
     uint4* out = reinterpret_cast<uint4*>(Tri + ((tile_list ? (uint64_t)blockIdx.x : tile) * n_groups_total + (grp0 + gb)) * kTileWords);
     for (int i = tid; i < kTileWords / 4; i += 256) out[i] = reinterpret_cast<const uint4*>(s_img)[i];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1b, bit-sliced form (default since round 2, depth + 1 < 2048): the 32 trees of a group are compared
+// AT ONCE instead of two per instruction.
+//
+// k_depth_slices transposes every pair row of the integer depth table (32 trees x u16, lane = tree)
+// into NB bit slices: word k of Ds[group][lo][hi] holds bit k of the depth of all 32 trees (bit =
+// tree % 32), word NB the "both taxa present" mask (depth != 0). That is one ballot per slice and
+// pair -- 16 M rows at 1000 taxa x 1000 trees, well under a millisecond in total.
+//
+// k_triple_planes_bs then runs a bit-serial comparator over the slices, least significant first:
+//   gt' = x_k > y_k ? 1 : (x_k == y_k ? gt : 0)      = ONE LOP3 (LUT 0xB2) for 32 trees
+// so plane 0 (D(a,b) > D(a,c)) and plane 1 (the reverse) of a triple cost 2 * NB logic operations
+// for 32 trees (NB = 6 for depths below 63) where the packed-fp16 builder above needs 64.
+// The builder then is bound by the 6 KB it writes per (tile, group), not by instruction issue.
+//
+// Work split: 64 threads per (tile, group), four groups per CTA side by side (named barriers, no CTA-wide
+// one). A thread owns a 2 x 2 (x, y) micro-block and two z: its four output words per (plane, z) are
+// contiguous in the tile (layout.cuh tile_word), so the results leave as 128-bit streaming stores straight
+// from registers -- no shared tile image. A CTA walks kPlaneTilesPerCta consecutive entries of a host-built
+// work list (PlaneDesc: segments + output slot, in 16 x 16 x 16-segment blocks so that the rows a block of
+// tiles shares stay in L2 while the 6 KB per (tile, group) stream out); the rows of the next tile travel by
+// cp.async into the other half of a double buffer while the current tile is compared.
+// Shared rows (8 words): 16-byte chunk c of row r sits at chunk (2r + c) ^ swz(r), swz from row bits 2, 4, 5,
+// which makes every 128-bit access pattern of the kernel conflict-free (8 consecutive rows when staging;
+// rows 2 apart and 16 / 32 apart when reading). 12-word rows (9..11 depth bits) are padded instead.
+// ---------------------------------------------------------------------------------------------
+template <int NB>
+struct SliceRow {
+  static constexpr int W = NB < 8 ? 8 : 12;  // words per pair row in HBM (NB slices + presence, padded to 128 bits)
+};
+
+template <int NB>
+__global__ void __launch_bounds__(256) k_depth_slices(int n_batch, int npad, const uint16_t* __restrict__ Dt,
+                                                      uint32_t* __restrict__ Ds) {
+  constexpr int W = SliceRow<NB>::W;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lo = blockIdx.x, gb = blockIdx.y;
+  const size_t row0 = ((size_t)gb * npad + lo) * npad;
+  for (int hi = lo + 1 + warp; hi < npad; hi += 8) {
+    const uint32_t v = Dt[(row0 + hi) * kLanes + lane];
+    uint32_t mine = 0;
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+      const uint32_t b = __ballot_sync(0xFFFFFFFFu, (v >> k) & 1u);
+      if (lane == k) mine = b;
+    }
+    const uint32_t pres = __ballot_sync(0xFFFFFFFFu, v != 0);
+    if (lane == NB) mine = pres;
+    if (lane < W) Ds[(row0 + hi) * W + lane] = mine;
+  }
+}
+
+// The slices straight from the trees, without the depth table (default up to 3200 taxa): one CTA per
+// (taxon a, tree group). For every tree of the group that holds a, a warp walks the leaves right and left of
+// a's position with a running minimum of h (a 32-wide prefix minimum per step) and drops D(a, b) of every
+// b > a into a shared [b][tree] image; the image is then sliced row by row (one ballot per depth bit) and
+// written as whole rows. k_depth_table scatters 2-byte stores to 5e8 different sectors per 1000 x 1000 input
+// (latency bound, 5.6 ms) and the table has to be read again by the slicer; this form writes only the slices.
+// Dynamic shared memory: npad * 64 bytes.
+template <int NB>
+__global__ void __launch_bounds__(256) k_depth_slices_direct(int grp0, int n_trees, int npad, const int32_t* __restrict__ nleaf,
+                                                             const uint16_t* __restrict__ lrP, const uint16_t* __restrict__ hP,
+                                                             const uint16_t* __restrict__ posP, uint32_t* __restrict__ Ds) {
+  constexpr int W = SliceRow<NB>::W;
+  extern __shared__ __align__(16) uint16_t s_dimg[];  // [b][tree of the group]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int a = blockIdx.x, gb = blockIdx.y;
+  {
+    uint4* z = reinterpret_cast<uint4*>(s_dimg);
+    for (int i = tid; i < npad * 4; i += 256) z[i] = make_uint4(0, 0, 0, 0);
+  }
+  __syncthreads();
+  for (int tl = warp; tl < kLanes; tl += 8) {
+    const int g = (grp0 + gb) * kLanes + tl;
+    if (g >= n_trees) break;
+    const int pa = (int)posP[(size_t)g * npad + a] - 1;
+    if (pa < 0) continue;  // a is not in this tree
+    const int nl = nleaf[g];
+    const uint16_t* lr = lrP + (size_t)g * npad;
+    const uint16_t* h = hP + (size_t)g * npad;
+    uint32_t carry = 0xFFFFu;
+    for (int q0 = pa + 1; q0 < nl; q0 += 32) {  // leaves right of a: D = min h[pa .. q-1]
+      const int q = q0 + lane;
+      uint32_t v = q < nl ? (uint32_t)h[q - 1] : 0xFFFFu;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, v, d);
+        if (lane >= d) v = min(v, o);
+      }
+      v = min(v, carry);
+      carry = __shfl_sync(0xFFFFFFFFu, v, 31);
+      if (q < nl) {
+        const int b = lr[q];
+        if (b > a) s_dimg[b * kLanes + tl] = (uint16_t)v;
+      }
+    }
+    carry = 0xFFFFu;
+    for (int q0 = pa - 1; q0 >= 0; q0 -= 32) {  // leaves left of a: D = min h[q .. pa-1]
+      const int q = q0 - lane;
+      uint32_t v = q >= 0 ? (uint32_t)h[q] : 0xFFFFu;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, v, d);
+        if (lane >= d) v = min(v, o);
+      }
+      v = min(v, carry);
+      carry = __shfl_sync(0xFFFFFFFFu, v, 31);
+      if (q >= 0) {
+        const int b = lr[q];
+        if (b > a) s_dimg[b * kLanes + tl] = (uint16_t)v;
+      }
+    }
+  }
+  __syncthreads();
+  const size_t row0 = ((size_t)gb * npad + a) * npad;
+  for (int b = a + 1 + warp; b < npad; b += 8) {
+    const uint32_t v = s_dimg[b * kLanes + lane];
+    uint32_t mine = 0;
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+      const uint32_t bits = __ballot_sync(0xFFFFFFFFu, (v >> k) & 1u);
+      if (lane == k) mine = bits;
+    }
+    const uint32_t pres = __ballot_sync(0xFFFFFFFFu, v != 0);
+    if (lane == NB) mine = pres;
+    if (lane < W) Ds[(row0 + b) * W + lane] = mine;
+  }
+}
+
+__device__ __forceinline__ uint32_t lop3_b2(uint32_t x, uint32_t y, uint32_t g) {
+  uint32_t d;
+  asm("lop3.b32 %0, %1, %2, %3, 0xB2;" : "=r"(d) : "r"(x), "r"(y), "r"(g));  // x & ~y | ~(x ^ y) & g
+  return d;
+}
+// word offset of 16-byte chunk q of row r inside one 64-row array
+template <int W>
+__device__ __forceinline__ int slice_off(int r, int q) {
+  if (W == 8) return (((2 * r + q) ^ (((r >> 2) & 1) | (((r >> 4) & 1) << 1) | (((r >> 5) & 1) << 2))) << 2);
+  return r * 12 + (r >> 4) * 4 + 4 * q;
+}
+template <int W>
+struct SliceArray {
+  static constexpr int words = W == 8 ? 64 * 8 : 64 * 12 + 16;
+};
+__device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+// 16-byte async copy global -> shared; bytes = 0 zero-fills (the source is then not read)
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, uint32_t bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// One entry of the plane builder's work list (host-built, camus_b200.cu make_plane_list).
+struct PlaneDesc {
+  uint32_t s01;   // s0 | s1 << 16
+  uint32_t s2;
+  uint32_t slot;  // where the tile lives in Tri (tile index, or the compact slot of a class-scheme share)
+  uint32_t pad;
+};
+#ifndef CAMUS_PLANES_TILES
+#define CAMUS_PLANES_TILES 8  // A/B builds: -DCAMUS_PLANES_TILES=n
+#endif
+constexpr int kPlaneTilesPerCta = CAMUS_PLANES_TILES;
+
+// One (tile, group) by the 64 threads of a slot, rows already staged. kDerive: the third plane is the complement
+// of the other two (complete binary trees, taxa of three different segments), no presence masks, bc rows unused.
+template <int NB, bool kDerive>
+__device__ __forceinline__ void sliced_planes_body(const uint32_t* sab, const uint32_t* sac, const uint32_t* sbc, int zq, int xp,
+                                                   int yp, uint32_t vm, uint4* __restrict__ out) {
+  constexpr int W = SliceRow<NB>::W, Q = W / 4;
+  uint32_t ab[2][2][W];  // [dx][dy][slice]
+#pragma unroll
+  for (int dx = 0; dx < 2; ++dx)
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int q = 0; q < Q; ++q)
+        *reinterpret_cast<uint4*>(&ab[dx][dy][4 * q]) =
+            *reinterpret_cast<const uint4*>(sab + slice_off<W>((2 * xp + dx) * 8 + 2 * yp + dy, q));
+#pragma unroll
+  for (int zz = 0; zz < 2; ++zz) {
+    const int z = 2 * zq + zz;
+    uint32_t w[3][4];  // [plane][dy * 2 + dx]
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx) {
+      uint32_t ac[W];
+#pragma unroll
+      for (int q = 0; q < Q; ++q)
+        *reinterpret_cast<uint4*>(&ac[4 * q]) = *reinterpret_cast<const uint4*>(sac + slice_off<W>((2 * xp + dx) * 8 + z, q));
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy) {
+        uint32_t gt = 0, lt = 0;
+#pragma unroll
+        for (int k = 0; k < NB; ++k) {
+          gt = lop3_b2(ab[dx][dy][k], ac[k], gt);  // ab|c : D(a,b) > D(a,c)
+          lt = lop3_b2(ac[k], ab[dx][dy][k], lt);  // ac|b : D(a,c) > D(a,b)
+        }
+        if (kDerive) {
+          w[0][dy * 2 + dx] = gt;
+          w[1][dy * 2 + dx] = lt;
+          w[2][dy * 2 + dx] = ~(gt | lt) & vm;
+        } else {
+          uint32_t bc[W];
+#pragma unroll
+          for (int q = 0; q < Q; ++q)
+            *reinterpret_cast<uint4*>(&bc[4 * q]) = *reinterpret_cast<const uint4*>(sbc + slice_off<W>((2 * yp + dy) * 8 + z, q));
+          uint32_t g2 = 0;
+#pragma unroll
+          for (int k = 0; k < NB; ++k) g2 = lop3_b2(bc[k], ab[dx][dy][k], g2);  // bc|a : D(b,c) > D(a,b)
+          const uint32_t present = ab[dx][dy][NB] & ac[NB] & bc[NB];
+          w[0][dy * 2 + dx] = gt & present;
+          w[1][dy * 2 + dx] = lt & present;
+          w[2][dy * 2 + dx] = g2 & present;
+        }
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < 3; ++p) __stcs(out + ((p * 8 + z) * 4 + yp) * 4 + xp, make_uint4(w[p][0], w[p][1], w[p][2], w[p][3]));
+  }
+}
+
+#ifndef CAMUS_PLANES_BS_MINB
+#define CAMUS_PLANES_BS_MINB 3  // A/B builds: -DCAMUS_PLANES_BS_MINB=n
+#endif
+// n_batch <= 4 tree groups per launch (one per 64-thread slot). Dynamic shared memory:
+// 2 buffers x 4 slots x 3 arrays x SliceArray<W>::words x 4 bytes.
+template <int NB, bool kComplete>
+__global__ void __launch_bounds__(256, CAMUS_PLANES_BS_MINB) k_triple_planes_bs(int grp0, int n_batch, int n_groups_total, int n_trees, int npad,
+                                                                  const uint32_t* __restrict__ Ds, uint32_t* __restrict__ Tri,
+                                                                  const PlaneDesc* __restrict__ list, uint32_t n_list) {
+  constexpr int W = SliceRow<NB>::W, Q = W / 4, AW = SliceArray<W>::words;
+  extern __shared__ __align__(16) uint32_t s_slices[];  // [buffer][slot][ab rows x*8+y | ac rows x*8+z | bc rows y*8+z][AW]
+  const int tid = threadIdx.x, slot = tid >> 6, t = tid & 63;
+  if (slot >= n_batch) return;  // slots only meet at their own named barrier
+  const int zq = t >> 4, xp = (t >> 2) & 3, yp = t & 3;  // compute: micro-block (xp, yp), z = 2 zq + {0, 1}
+  const uint32_t* const D = Ds + (size_t)slot * npad * npad * W;
+  const int left = n_trees - (grp0 + slot) * kLanes;  // trees in this group
+  const uint32_t vm = left >= 32 ? 0xFFFFFFFFu : (left > 0 ? (1u << left) - 1u : 0u);
+  uint32_t* const Tg = Tri + (size_t)(grp0 + slot) * kTileWords;
+  const uint32_t row_smem = smem_u32(s_slices) + (uint32_t)(slot * 3 * AW) * 4u;
+
+  const uint32_t i0 = blockIdx.x * kPlaneTilesPerCta, i1 = min(n_list, i0 + kPlaneTilesPerCta);
+  // staging: the 64 rows of an array are 8 runs of 8 rows (256 or 384 contiguous bytes of Ds each); consecutive
+  // lanes copy consecutive 16-byte chunks (lane-per-row copies cost twice the L1 wavefronts on both sides)
+  auto stage = [&](const PlaneDesc& d, int buf) {
+    const uint32_t a0 = (d.s01 & 0xFFFFu) * 8, b0 = (d.s01 >> 16) * 8, c0 = d.s2 * 8;
+    const bool no_bc = kComplete && a0 < b0 && b0 < c0;  // derive path: bc rows are not read
+#pragma unroll
+    for (int which = 0; which < 3; ++which) {
+      if (which == 2 && no_bc) continue;
+      const uint32_t dst = row_smem + (uint32_t)((buf * 4 * 3 + which) * AW) * 4u;
+#pragma unroll
+      for (int j = 0; j < Q; ++j) {
+        const int c = t + 64 * j, row = c / Q, q = c % Q;  // row = first * 8 + second
+        const uint32_t lo = (which == 2 ? b0 : a0) + (row >> 3);
+        const uint32_t hi = (which == 0 ? b0 : c0) + (row & 7);
+        const bool ok = lo < hi;  // wrong rank order = absent = zeros
+        const uint32_t* src = ok ? D + ((size_t)lo * npad + hi) * W + 4 * q : D;
+        cp_async16(dst + (uint32_t)slice_off<W>(row, q) * 4u, src, ok ? 16u : 0u);
+      }
+    }
+    cp_async_commit();
+  };
+  PlaneDesc cur = list[i0], nxt = cur;
+  if (i0 + 1 < i1) nxt = list[i0 + 1];
+  stage(cur, 0);
+  int buf = 0;
+  for (uint32_t i = i0; i < i1; ++i) {
+    cp_async_wait_all();
+    named_bar_sync(1 + slot, 64);  // tile i has landed for all 64 threads, and all of them are done with tile i - 1
+    PlaneDesc nn = nxt;
+    if (i + 1 < i1) {
+      stage(nxt, buf ^ 1);
+      if (i + 2 < i1) nn = list[i + 2];
+    }
+    const uint32_t s0 = cur.s01 & 0xFFFFu, s1 = cur.s01 >> 16;
+    const bool derive = kComplete && s0 < s1 && s1 < cur.s2;  // every (x, y, z) is in rank order
+    const uint32_t* rows = s_slices + (size_t)((buf * 4 + slot) * 3) * AW;
+    uint4* const out = reinterpret_cast<uint4*>(Tg + (size_t)cur.slot * n_groups_total * kTileWords);
+    if (derive) sliced_planes_body<NB, true>(rows, rows + AW, rows + 2 * AW, zq, xp, yp, vm, out);
+    else sliced_planes_body<NB, false>(rows, rows + AW, rows + 2 * AW, zq, xp, yp, vm, out);
+    cur = nxt;
+    nxt = nn;
+    buf ^= 1;
   }
 }
 

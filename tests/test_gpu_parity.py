@@ -121,24 +121,85 @@ def test_packed_and_three_register_general_kernels_agree(gpu, monkeypatch):
     wide.close()
 
 
-def test_integer_and_fp16_plane_builders_agree(gpu, monkeypatch):
-    """k_triple_planes_h2 (packed fp16 mask compares, NaN = absent) is the default; trees deeper than
-    2047 fall back to the integer kernel, forced here with CAMUS_B200_NO_HALF=1."""
+def test_plane_builders_agree(gpu, monkeypatch):
+    """Three builders of the rooted-triple bit-planes: k_triple_planes_bs (bit-sliced depths, the default; slices
+    straight from the trees, or from the depth table with CAMUS_B200_NO_DIRECT=1),
+    k_triple_planes_h2 (packed fp16 mask compares, NaN = absent; CAMUS_B200_NO_SLICED=1) and the integer
+    ballot kernel trees deeper than 2046 fall back to (CAMUS_B200_NO_HALF=1). All against the oracle."""
     from camus_b200.cabi import CamusB200
     monkeypatch.setenv("CAMUS_B200_NO_HALF", "1")
     integer = CamusB200(0)
     monkeypatch.delenv("CAMUS_B200_NO_HALF")
+    monkeypatch.setenv("CAMUS_B200_NO_SLICED", "1")
+    fp16 = CamusB200(0)
+    monkeypatch.delenv("CAMUS_B200_NO_SLICED")
+    monkeypatch.setenv("CAMUS_B200_NO_DIRECT", "1")  # slices made from the depth table (inputs above 3200 taxa)
+    via_table = CamusB200(0)
+    monkeypatch.delenv("CAMUS_B200_NO_DIRECT")
     for s, ms in ((synth.make(52, 70, 8, support=True, drop_frac=0.12, nexus=True), 0.6), (synth.make(37, 40, 9), 0.0)):
         prob = Problem(s.constraint, s.genes, s.fmt, ms)
         o = orc.Oracle().load(prob)
         want = o.count_filter(0, 0.0, False)
-        for ctx in (gpu, integer):
+        for ctx in (gpu, via_table, fp16, integer):
             ctx.load(prob)
             assert ctx.count_filter(0, 0.0) == want
             for a, b in zip(ctx.export_quartets(raw=True), o.export_raw_counts()):
                 assert np.array_equal(a, b)
             assert np.array_equal(ctx.quartet_totals(False), o.quartet_totals(False, False))
     integer.close()
+    fp16.close()
+    via_table.close()
+
+
+def _deepen(genes: str, pad: int) -> str:
+    """wrap the first leaf of every newick line in `pad` unifurcations: same quartets, deeper tree"""
+    import re
+    out = []
+    for line in genes.strip().splitlines():
+        m = re.search(r"t\d{4}", line)
+        out.append(line[:m.start()] + "(" * pad + m.group(0) + ")" * pad + line[m.end():])
+    return "\n".join(out) + "\n"
+
+
+@pytest.mark.parametrize("pad", [0, 25, 40, 60, 300, 1500, 2100])
+def test_sliced_plane_builder_depth_classes_general(gpu, pad):
+    """k_triple_planes_bs is compiled for 5, 6, 7, 9 and 11 depth bits (the smallest that holds depth + 1 is
+    picked per input); deeper trees (> 2046) take the integer kernel. Incomplete trees with polytomies
+    (presence masks, three compared planes), 70 trees = two full groups + 6."""
+    s = synth.make(26, 70, 77, support=True, drop_frac=0.15)
+    prob = Problem(s.constraint, _deepen(s.genes, pad), s.fmt, 0.5)
+    o = orc.Oracle().load(prob)
+    gpu.load(prob)
+    assert gpu.count_filter(0, 0.0) == o.count_filter(0, 0.0, False)
+    for a, b in zip(gpu.export_quartets(raw=True), o.export_raw_counts()):
+        assert np.array_equal(a, b)
+    assert np.array_equal(gpu.quartet_totals(False), o.quartet_totals(False, False))
+    assert gpu.count_filter(2, 0.4) == o.count_filter(2, 0.4, False)
+    assert np.array_equal(gpu.quartet_totals(False), o.quartet_totals(False, False))
+
+
+@pytest.mark.parametrize("n_taxa,n_trees", [(40, 70), (90, 45), (140, 40), (516, 2)])
+def test_sliced_plane_builder_depth_classes_complete(gpu, n_taxa, n_trees):
+    """The same for complete binary trees (third plane derived as the complement): caterpillar gene trees over
+    shuffled taxa are as deep as they are wide (40 -> 6 bits, 90 -> 7, 140 -> 9, 516 -> 11), mixed with random trees."""
+    s = synth.make(n_taxa, n_trees, 78)
+    rng = np.random.default_rng(n_taxa)
+    lines = s.genes.strip().splitlines()
+    for i in range(0, n_trees, 2):
+        order = rng.permutation(n_taxa)
+        cat = "t%04d" % order[0]
+        for k in order[1:]:
+            cat = "(" + cat + ",t%04d)" % k
+        lines[i] = cat + ";"
+    prob = Problem(s.constraint, "\n".join(lines) + "\n")
+    o = orc.Oracle().load(prob)
+    gpu.load(prob)
+    for qmode, thr in ((0, 0.0), (2, 0.5)):
+        got = gpu.count_filter(qmode, thr)
+        tab = gpu.quartet_totals(False)
+        st, want = o.dense_run(qmode, thr, False, digests=False)
+        assert got == (st["n_survivors"], st["sum_counts"])
+        assert np.array_equal(tab, want)
 
 
 def test_regular_box_epilogue(gpu, monkeypatch):
