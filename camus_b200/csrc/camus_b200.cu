@@ -1236,7 +1236,7 @@ int run_finish(camus_b200* ctx, uint64_t* out) {
   CK_LAUNCH();
   k_row_scan<<<n, 256, 0, ctx->stream>>>(ctx->d_E.p, n);
   CK_LAUNCH();
-  k_col_scan<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_E.p, n);
+  k_col_scan<<<(n + 31) / 32, 1024, 0, ctx->stream>>>(ctx->d_E.p, n);
   CK_LAUNCH();
   k_mask_out<<<dim3((n + 127) / 128, n), 128, 0, ctx->stream>>>(ctx->d_E.p, ctx->d_out.p, ctx->ct);
   CK_LAUNCH();

@@ -466,36 +466,38 @@ __global__ void __launch_bounds__(256) k_depth_slices_direct(int grp0, int n_tre
     const int nl = nleaf[g];
     const uint16_t* lr = lrP + (size_t)g * npad;
     const uint16_t* h = hP + (size_t)g * npad;
-    uint32_t carry = 0xFFFFu;
-    for (int q0 = pa + 1; q0 < nl; q0 += 32) {  // leaves right of a: D = min h[pa .. q-1]
-      const int q = q0 + lane;
-      uint32_t v = q < nl ? (uint32_t)h[q - 1] : 0xFFFFu;
+    // dir 0: leaves right of a, the j-th one at position pa + 1 + j, D = min h[pa .. pa + j];
+    // dir 1: leaves left of a, the j-th one at position pa - 1 - j, D = min h[pa - 1 - j .. pa - 1].
+    // A lane takes four consecutive j (serial minimum), the warp scans the lane totals.
 #pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, v, d);
-        if (lane >= d) v = min(v, o);
-      }
-      v = min(v, carry);
-      carry = __shfl_sync(0xFFFFFFFFu, v, 31);
-      if (q < nl) {
-        const int b = lr[q];
-        if (b > a) s_dimg[b * kLanes + tl] = (uint16_t)v;
-      }
-    }
-    carry = 0xFFFFu;
-    for (int q0 = pa - 1; q0 >= 0; q0 -= 32) {  // leaves left of a: D = min h[q .. pa-1]
-      const int q = q0 - lane;
-      uint32_t v = q >= 0 ? (uint32_t)h[q] : 0xFFFFu;
+    for (int dir = 0; dir < 2; ++dir) {
+      const int cnt = dir == 0 ? nl - pa - 1 : pa;
+      const uint16_t* hd = dir == 0 ? h + pa : h + pa - 1;
+      const uint16_t* ld = dir == 0 ? lr + pa + 1 : lr + pa - 1;
+      uint32_t carry = 0xFFFFu;
+      for (int base = 0; base < cnt; base += 128) {
+        const int j0 = base + 4 * lane;
+        uint32_t e[4];
 #pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, v, d);
-        if (lane >= d) v = min(v, o);
-      }
-      v = min(v, carry);
-      carry = __shfl_sync(0xFFFFFFFFu, v, 31);
-      if (q >= 0) {
-        const int b = lr[q];
-        if (b > a) s_dimg[b * kLanes + tl] = (uint16_t)v;
+        for (int i = 0; i < 4; ++i) e[i] = j0 + i < cnt ? (uint32_t)(dir == 0 ? hd[j0 + i] : hd[-(j0 + i)]) : 0xFFFFu;
+        e[1] = min(e[1], e[0]);
+        e[2] = min(e[2], e[1]);
+        e[3] = min(e[3], e[2]);
+        uint32_t sc = e[3];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, sc, d);
+          sc = min(sc, lane >= d ? o : 0xFFFFu);
+        }
+        uint32_t ex = __shfl_up_sync(0xFFFFFFFFu, sc, 1);
+        ex = min(lane ? ex : 0xFFFFu, carry);
+        carry = min(carry, __shfl_sync(0xFFFFFFFFu, sc, 31));
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (j0 + i < cnt) {
+            const int b = dir == 0 ? ld[j0 + i] : ld[-(j0 + i)];
+            if (b > a) s_dimg[b * kLanes + tl] = (uint16_t)min(e[i], ex);
+          }
       }
     }
   }
