@@ -68,7 +68,9 @@ class ClockSampler(threading.Thread):
             getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
             getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
         }
+        period = 0.1
         while not self.stop_flag:
+            t0 = time.perf_counter()
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
                 r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
@@ -77,7 +79,12 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(nm)
             except Exception:
                 pass
-            time.sleep(0.1)  # NVML queries take a driver lock: 50 per second delayed the launches of small configurations by milliseconds
+            # NVML queries take a driver lock that CUDA calls wait on: 50 per second delayed the launches of small
+            # configurations by milliseconds, and on some boxes one query pair costs tens of milliseconds (config 5:
+            # 17 -> 34 ms per step with 10 samples per second). Back off when the queries are slow.
+            if time.perf_counter() - t0 > 0.005:
+                period = 1.0
+            time.sleep(period)
 
     def result(self):
         self.stop_flag = True

@@ -52,6 +52,8 @@ struct DevBuf {
 
 }  // namespace
 
+constexpr int kDirectImageMaxBytes = 200 * 1024;  // shared [taxon][32 trees] image of k_depth_slices_direct
+
 struct camus_b200 {
   // n_gpus > 1: this handle only fans out to one single-device context per GPU (subs); the 4-set
   // index space is dealt to them exactly as to the ranks of a multi-process run (BoxMap), and
@@ -273,8 +275,20 @@ static int create_one(camus_b200** out, int dev) {
     set(k_count<false, kModeComplete>, CountCfg<kModeComplete>::kSmemBytes);
     set(k_count<true, kModeComplete>, CountCfg<kModeComplete>::kSmemBytes + 64 * 1024);  // + room for CAMUS_B200_COUNT_PAD_SMEM
     set(k_count<true, kModePacked>, CountCfg<kModePacked>::kSmemBytes);
+    // the sliced plane builders: set once here -- cudaFuncSetAttribute between launches drains the stream
+    // (measured: 16 calls per step cost 10 ms of idle GPU at 1000 taxa, 16 ms of a 104 ms step at 500)
+#define CAMUS_SET_SLICED(nb)                                                                    \
+  set(k_triple_planes_bs<nb, true>, 2 * 4 * 3 * SliceArray<SliceRow<nb>::W>::words * 4);        \
+  set(k_triple_planes_bs<nb, false>, 2 * 4 * 3 * SliceArray<SliceRow<nb>::W>::words * 4);       \
+  set(k_depth_slices_direct<nb>, kDirectImageMaxBytes);
+    CAMUS_SET_SLICED(5)
+    CAMUS_SET_SLICED(6)
+    CAMUS_SET_SLICED(7)
+    CAMUS_SET_SLICED(9)
+    CAMUS_SET_SLICED(11)
+#undef CAMUS_SET_SLICED
     if (a != cudaSuccess) {
-      g_create_err = std::string("camus_b200_create: count kernels do not fit this device (") + cudaGetErrorString(a) + ")";
+      g_create_err = std::string("camus_b200_create: count / plane kernels do not fit this device (") + cudaGetErrorString(a) + ")";
       camus_b200_destroy(ctx);
       return CAMUS_B200_ERR_CUDA;
     }
@@ -652,30 +666,7 @@ namespace {
 int make_plane_list(camus_b200* ctx, bool partial) {
   const int key[4] = {ctx->M, partial ? ctx->rank : 0, partial ? ctx->world : 1, partial ? 1 : 0};
   if (!memcmp(key, ctx->plane_list_key, sizeof key)) return 0;
-  const uint32_t S = (uint32_t)ctx->M, B = 16, nblk = (S + B - 1) / B;
-  const uint32_t need = partial ? class_need_mask(ctx->rank, ctx->world) : 0xFu;
-  std::vector<PlaneDesc> list;
-  list.reserve((size_t)num_tiles(S));
-  uint32_t compact = 0;
-  std::vector<uint32_t> slot_of;  // compact slots follow colex order (set_box_range)
-  if (partial) {
-    slot_of.assign((size_t)num_tiles(S), 0xFFFFFFFFu);
-    uint32_t idx = 0;
-    for (uint32_t s2 = 0; s2 < S; ++s2)
-      for (uint32_t s1 = 0; s1 <= s2; ++s1)
-        for (uint32_t s0 = 0; s0 <= s1; ++s0, ++idx)
-          if ((need >> seg_class(s0)) & 1u) slot_of[idx] = compact++;
-  }
-  for (uint32_t B2 = 0; B2 < nblk; ++B2)
-    for (uint32_t B1 = 0; B1 <= B2; ++B1)
-      for (uint32_t B0 = 0; B0 <= B1; ++B0)
-        for (uint32_t s2 = B2 * B; s2 < std::min(S, (B2 + 1) * B); ++s2)
-          for (uint32_t s1 = B1 * B; s1 < std::min(s2 + 1, (B1 + 1) * B); ++s1)
-            for (uint32_t s0 = B0 * B; s0 < std::min(s1 + 1, (B0 + 1) * B); ++s0) {
-              if (!((need >> seg_class(s0)) & 1u)) continue;
-              const uint64_t idx = tile_index(s0, s1, s2);
-              list.push_back(PlaneDesc{s0 | (s1 << 16), s2, partial ? slot_of[idx] : (uint32_t)idx, 0u});
-            }
+  const std::vector<PlaneDesc> list = plane_work_list((uint32_t)ctx->M, partial ? class_need_mask(ctx->rank, ctx->world) : 0xFu, partial);
   CK(ctx->d_plane_list.alloc(std::max<size_t>(list.size(), 1)));
   if (!list.empty()) CK(cudaMemcpyAsync(ctx->d_plane_list.p, list.data(), list.size() * sizeof(PlaneDesc), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));  // the host vector goes away
@@ -729,7 +720,8 @@ int build_planes(camus_b200* ctx, bool do_upload = true) {
     while ((ctx->max_depth + 1) >> need_bits) ++need_bits;
     const bool sliced_path = need_bits <= 11 && ctx->allow_sliced && ctx->allow_half;
     // slices straight from the trees: one [taxon][32 trees] u16 image per CTA in shared memory
-    const bool direct_path = sliced_path && ctx->allow_direct && warp_prepare && (size_t)npad * 64 <= 200 * 1024;
+    const size_t image_bytes = (size_t)npad * kLanes * (need_bits <= 7 ? 1 : 2);  // DepthImage<NB>::T, NB = 5, 6, 7 | 9, 11
+    const bool direct_path = sliced_path && ctx->allow_direct && warp_prepare && image_bytes <= (size_t)kDirectImageMaxBytes;
     if (direct_path) {
       CK(ctx->d_lrP.alloc((size_t)G * npad));
       CK(ctx->d_hP.alloc((size_t)G * npad));
@@ -789,8 +781,7 @@ int build_planes(camus_b200* ctx, bool do_upload = true) {
         const size_t group_words = (size_t)npad * npad * slice_words;
 #define CAMUS_SLICED_PLANES(nb, cmpl)                                                                                          \
   {                                                                                                                            \
-    const int smem = 2 * 4 * 3 * SliceArray<SliceRow<nb>::W>::words * 4;                                                       \
-    CK(cudaFuncSetAttribute(k_triple_planes_bs<nb, cmpl>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                 \
+    const int smem = 2 * 4 * 3 * SliceArray<SliceRow<nb>::W>::words * 4; /* attribute set in camus_b200_create */             \
     for (int q0 = 0; q0 < gb; q0 += 4)                                                                                         \
       k_triple_planes_bs<nb, cmpl><<<n_cta, 256, smem, ctx->stream>>>(g0 + q0, std::min(4, gb - q0), G32, G, npad,             \
                                                                      ctx->d_Ds.p + (size_t)q0 * group_words, ctx->d_tri.p,    \
@@ -799,8 +790,7 @@ int build_planes(camus_b200* ctx, bool do_upload = true) {
 #define CAMUS_SLICED(nb)                                                                                                        \
   case nb:                                                                                                                      \
     if (direct_path) {                                                                                                          \
-      const int smem_d = npad * 64;                                                                                             \
-      CK(cudaFuncSetAttribute(k_depth_slices_direct<nb>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_d));                 \
+      const int smem_d = npad * kLanes * (int)sizeof(DepthImage<nb>::T);                                                        \
       k_depth_slices_direct<nb><<<dim3(npad, gb), 256, smem_d, ctx->stream>>>(g0, G, npad, ctx->d_nleaf.p, ctx->d_lrP.p,        \
                                                                               ctx->d_hP.p, ctx->d_posP.p, ctx->d_Ds.p);        \
     } else                                                                                                                      \

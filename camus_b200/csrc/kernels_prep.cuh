@@ -9,6 +9,8 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
+#include <type_traits>
+
 #include "layout.cuh"
 #include "ptx.cuh"
 
@@ -438,24 +440,31 @@ __global__ void __launch_bounds__(256) k_depth_slices(int n_batch, int npad, con
   }
 }
 
-// The slices straight from the trees, without the depth table (default up to 3200 taxa): one CTA per
+// The slices straight from the trees, without the depth table (default up to 6400 taxa, 3200 when a tree is deeper than 126): one CTA per
 // (taxon a, tree group). For every tree of the group that holds a, a warp walks the leaves right and left of
 // a's position with a running minimum of h (a 32-wide prefix minimum per step) and drops D(a, b) of every
 // b > a into a shared [b][tree] image; the image is then sliced row by row (one ballot per depth bit) and
 // written as whole rows. k_depth_table scatters 2-byte stores to 5e8 different sectors per 1000 x 1000 input
 // (latency bound, 5.6 ms) and the table has to be read again by the slicer; this form writes only the slices.
-// Dynamic shared memory: npad * 64 bytes.
+// Dynamic shared memory: npad * 32 image elements -- bytes while depth + 1 fits 8 bits (NB <= 7: twice the CTAs
+// per SM), u16 above.
+template <int NB>
+struct DepthImage {
+  using T = typename std::conditional<(NB <= 8), uint8_t, uint16_t>::type;
+};
 template <int NB>
 __global__ void __launch_bounds__(256) k_depth_slices_direct(int grp0, int n_trees, int npad, const int32_t* __restrict__ nleaf,
                                                              const uint16_t* __restrict__ lrP, const uint16_t* __restrict__ hP,
                                                              const uint16_t* __restrict__ posP, uint32_t* __restrict__ Ds) {
   constexpr int W = SliceRow<NB>::W;
-  extern __shared__ __align__(16) uint16_t s_dimg[];  // [b][tree of the group]
+  using T = typename DepthImage<NB>::T;
+  extern __shared__ __align__(16) unsigned char s_dimg_raw[];
+  T* const s_dimg = reinterpret_cast<T*>(s_dimg_raw);  // [b][tree of the group]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int a = blockIdx.x, gb = blockIdx.y;
   {
-    uint4* z = reinterpret_cast<uint4*>(s_dimg);
-    for (int i = tid; i < npad * 4; i += 256) z[i] = make_uint4(0, 0, 0, 0);
+    uint4* z = reinterpret_cast<uint4*>(s_dimg_raw);
+    for (int i = tid; i < npad * 2 * (int)sizeof(T); i += 256) z[i] = make_uint4(0, 0, 0, 0);
   }
   __syncthreads();
   for (int tl = warp; tl < kLanes; tl += 8) {
@@ -496,7 +505,7 @@ __global__ void __launch_bounds__(256) k_depth_slices_direct(int grp0, int n_tre
         for (int i = 0; i < 4; ++i)
           if (j0 + i < cnt) {
             const int b = dir == 0 ? ld[j0 + i] : ld[-(j0 + i)];
-            if (b > a) s_dimg[b * kLanes + tl] = (uint16_t)min(e[i], ex);
+            if (b > a) s_dimg[b * kLanes + tl] = (T)min(e[i], ex);
           }
       }
     }
@@ -540,13 +549,7 @@ __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, u
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-// One entry of the plane builder's work list (host-built, camus_b200.cu make_plane_list).
-struct PlaneDesc {
-  uint32_t s01;   // s0 | s1 << 16
-  uint32_t s2;
-  uint32_t slot;  // where the tile lives in Tri (tile index, or the compact slot of a class-scheme share)
-  uint32_t pad;
-};
+// PlaneDesc (one entry of the host-built work list) lives in layout.cuh.
 #ifndef CAMUS_PLANES_TILES
 #define CAMUS_PLANES_TILES 8  // A/B builds: -DCAMUS_PLANES_TILES=n
 #endif

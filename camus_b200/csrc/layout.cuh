@@ -8,6 +8,7 @@
 #pragma once
 #include <cmath>
 #include <cstdint>
+#include <vector>
 
 #if defined(__CUDACC__)
 #define CAMUS_HD __host__ __device__ __forceinline__
@@ -154,9 +155,10 @@ CAMUS_HD uint32_t class_need_mask(int rank, int world) {
 }
 // donation threshold (of 256) for m segments. World 8: every rank builds half of the tiles, so
 // the box counts are evened out. World 4: ranks 2 and 3 build 3/4 of the tiles against 1/2 for
-// ranks 0 and 1; a tile costs about as much to build (per tree group) as a box costs to count
-// (3.5 ns vs 2.8 ns at 1000 taxa with the complete-tree kernels, 2.8 vs 4.2 with the general
-// ones), so ranks 2 and 3 are given T/4 boxes FEWER than ranks 0 and 1, T = number of tiles.
+// ranks 0 and 1; with the bit-sliced plane builder a tile costs about half of what a box costs to
+// count (per tree group at 1000 taxa: 1.2 ns vs 2.45 ns with the complete-tree kernels; the fp16
+// builder of round 1 cost 3.2 ns and the split then was T/4), so ranks 2 and 3 are given T/8 boxes
+// FEWER than ranks 0 and 1, T = number of tiles.
 inline uint32_t class_threshold(uint32_t m, int world) {
   uint64_t D = 0, O = 0;  // boxes of pure / mixed class pairs
   for (uint32_t sa = 0; sa < m; ++sa)
@@ -169,9 +171,9 @@ inline uint32_t class_threshold(uint32_t m, int world) {
     uint64_t t = (64 * (3 * D - O) + (3 * D) / 2) / (3 * D);
     return (uint32_t)(t > 85 ? 85 : t);
   }
-  // world 4: boxes(rank 0) - boxes(rank 2) = D/2 - O/6 - (t/256) * 3D/4, wanted = T/4
+  // world 4: boxes(rank 0) - boxes(rank 2) = D/2 - O/6 - (t/256) * 3D/4, wanted = T/8
   const uint64_t T = num_tiles(m);
-  const uint64_t have6 = 3 * D - O, want6 = 3 * T / 2;  // both sides times 6
+  const uint64_t have6 = 3 * D - O, want6 = 3 * T / 4;  // both sides times 6
   if (have6 <= want6) return 0;
   uint64_t t = (256 * 2 * (have6 - want6) + (9 * D) / 2) / (9 * D);
   return (uint32_t)(t > 255 ? 255 : t);
@@ -194,6 +196,45 @@ CAMUS_HD uint32_t tile_word(uint32_t p, uint32_t x, uint32_t y, uint32_t z) {
   return (((p * 8 + z) * 4 + (y >> 1)) * 4 + (x >> 1)) * 4 + (y & 1) * 2 + (x & 1);
 }
 // planes of triple (p < q < r): 0 = pq|r, 1 = pr|q, 2 = qr|p
+
+// One entry of the sliced plane builder's work list (kernels_prep.cuh k_triple_planes_bs).
+struct PlaneDesc {
+  uint32_t s01;   // s0 | s1 << 16
+  uint32_t s2;
+  uint32_t slot;  // where the tile lives in the bit-plane table (tile index, or the compact slot of a class-scheme share)
+  uint32_t pad;
+};
+// The work list: the tiles (s0 <= s1 <= s2) of m segments whose first segment's class is in `need` (0xF = all),
+// in blocks of kPlaneBlock^3 segments -- a block of tiles shares 3 x 128 x 128 pair rows, which stay in L2 while
+// its tiles stream out -- colex inside a block. compact: slots number the listed tiles in colex order (the order
+// camus_b200.cu set_box_range stores a class-scheme share's tiles in); else slot = tile index.
+constexpr uint32_t kPlaneBlock = 16;
+inline std::vector<PlaneDesc> plane_work_list(uint32_t m, uint32_t need, bool compact) {
+  std::vector<PlaneDesc> list;
+  list.reserve((size_t)num_tiles(m));
+  std::vector<uint32_t> slot_of;
+  if (compact) {
+    slot_of.assign((size_t)num_tiles(m), 0xFFFFFFFFu);
+    uint32_t idx = 0, next = 0;
+    for (uint32_t s2 = 0; s2 < m; ++s2)
+      for (uint32_t s1 = 0; s1 <= s2; ++s1)
+        for (uint32_t s0 = 0; s0 <= s1; ++s0, ++idx)
+          if ((need >> seg_class(s0)) & 1u) slot_of[idx] = next++;
+  }
+  const uint32_t B = kPlaneBlock, nblk = (m + B - 1) / B;
+  auto upto = [](uint32_t a, uint32_t b) { return a < b ? a : b; };
+  for (uint32_t B2 = 0; B2 < nblk; ++B2)
+    for (uint32_t B1 = 0; B1 <= B2; ++B1)
+      for (uint32_t B0 = 0; B0 <= B1; ++B0)
+        for (uint32_t s2 = B2 * B; s2 < upto(m, (B2 + 1) * B); ++s2)
+          for (uint32_t s1 = B1 * B; s1 < upto(s2 + 1, (B1 + 1) * B); ++s1)
+            for (uint32_t s0 = B0 * B; s0 < upto(s1 + 1, (B0 + 1) * B); ++s0) {
+              if (!((need >> seg_class(s0)) & 1u)) continue;
+              const uint64_t idx = tile_index(s0, s1, s2);
+              list.push_back(PlaneDesc{s0 | (s1 << 16), s2, compact ? slot_of[idx] : (uint32_t)idx, 0u});
+            }
+  return list;
+}
 
 // cell inside a box, a fastest
 CAMUS_HD uint32_t cell_local(uint32_t al, uint32_t bl, uint32_t cl, uint32_t dl) {

@@ -81,9 +81,9 @@ def class_threshold(m: int, world: int) -> int:
         return 0
     if world == 8:
         return min(85, (64 * (3 * D - O) + (3 * D) // 2) // (3 * D))
-    # world 4: ranks 2 and 3 build 3/4 of the tiles, ranks 0 and 1 half: they get T/4 boxes fewer
+    # world 4: ranks 2 and 3 build 3/4 of the tiles, ranks 0 and 1 half: they get T/8 boxes fewer
     T = choose(m + 2, 3)
-    have6, want6 = 3 * D - O, 3 * T // 2
+    have6, want6 = 3 * D - O, 3 * T // 4
     if have6 <= want6:
         return 0
     return min(255, (512 * (have6 - want6) + (9 * D) // 2) // (9 * D))

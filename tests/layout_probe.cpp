@@ -19,4 +19,16 @@ unsigned long long probe_partition_chunk(unsigned long long nb, unsigned world) 
 unsigned long long probe_local_box_count(unsigned long long nb, unsigned rank, unsigned world) {
   return local_box_count(nb, partition_chunk(nb, world), rank, world);
 }
+// plane work list: returns the number of entries; out (may be null) receives s0, s1, s2, slot per entry
+unsigned long long probe_plane_work_list(unsigned m, unsigned need, int compact, unsigned* out) {
+  const std::vector<PlaneDesc> l = plane_work_list(m, need, compact != 0);
+  if (out)
+    for (size_t i = 0; i < l.size(); ++i) {
+      out[4 * i + 0] = l[i].s01 & 0xFFFFu;
+      out[4 * i + 1] = l[i].s01 >> 16;
+      out[4 * i + 2] = l[i].s2;
+      out[4 * i + 3] = l[i].slot;
+    }
+  return l.size();
+}
 }

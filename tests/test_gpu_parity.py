@@ -133,7 +133,7 @@ def test_plane_builders_agree(gpu, monkeypatch):
     monkeypatch.setenv("CAMUS_B200_NO_SLICED", "1")
     fp16 = CamusB200(0)
     monkeypatch.delenv("CAMUS_B200_NO_SLICED")
-    monkeypatch.setenv("CAMUS_B200_NO_DIRECT", "1")  # slices made from the depth table (inputs above 3200 taxa)
+    monkeypatch.setenv("CAMUS_B200_NO_DIRECT", "1")  # slices made from the depth table (inputs above 6400 taxa)
     via_table = CamusB200(0)
     monkeypatch.delenv("CAMUS_B200_NO_DIRECT")
     for s, ms in ((synth.make(52, 70, 8, support=True, drop_frac=0.12, nexus=True), 0.6), (synth.make(37, 40, 9), 0.0)):

@@ -24,6 +24,8 @@ def probe(tmp_path_factory):
     L.probe_local_box_count.restype = C.c_uint64
     L.probe_local_box_count.argtypes = [C.c_uint64, C.c_uint, C.c_uint]
     L.probe_box_unrank.argtypes = [C.c_uint64, C.POINTER(C.c_uint)]
+    L.probe_plane_work_list.restype = C.c_uint64
+    L.probe_plane_work_list.argtypes = [C.c_uint, C.c_uint, C.c_int, C.POINTER(C.c_uint)]
     return L
 
 
@@ -68,3 +70,39 @@ def test_chunk_scheme_mirror(probe):
             assert probe.probe_partition_chunk(nb, world) == part.partition_chunk(nb, world)
             for r in range(world):
                 assert probe.probe_local_box_count(nb, r, world) == part.local_box_count(nb, r, world)
+
+
+def test_plane_work_list(probe):
+    """The sliced plane builder's work list (layout.cuh plane_work_list): every tile the share builds exactly
+    once, blocks of 16 x 16 x 16 segments, and slots = the tile index, or for a class-scheme share the position of
+    the tile among the share's tiles in colex order (how set_box_range numbers the compact bit-plane storage)."""
+    for m in (1, 5, 16, 17, 40, 125):
+        n_all = m * (m + 1) * (m + 2) // 6
+        for need, compact in ((0xF, False), (0x3, True), (0x9, True), (0xD, True), (0xF, True)):
+            n = probe.probe_plane_work_list(m, need, int(compact), None)
+            buf = (C.c_uint * (4 * max(n, 1)))()
+            assert probe.probe_plane_work_list(m, need, int(compact), buf) == n
+            e = np.frombuffer(buf, dtype=np.uint32)[: 4 * n].reshape(n, 4).astype(np.int64)
+            s0, s1, s2, slot = e.T
+            assert np.all(s0 <= s1) and np.all(s1 <= s2) and np.all(s2 < m)
+            tile = s2 * (s2 + 1) * (s2 + 2) // 6 + s1 * (s1 + 1) // 2 + s0
+            assert len(np.unique(tile)) == n
+            wanted = np.array([t for t in range(n_all)], dtype=np.int64)
+            cls = part.seg_class(np.arange(m))
+            # colex enumeration of all tiles with the class filter
+            a2, a1, a0 = [], [], []
+            for x2 in range(m):
+                for x1 in range(x2 + 1):
+                    for x0 in range(x1 + 1):
+                        a2.append(x2); a1.append(x1); a0.append(x0)
+            keep = ((need >> cls[np.array(a0)]) & 1).astype(bool)
+            assert sorted(tile.tolist()) == wanted[keep].tolist()
+            if compact:
+                rank_in_share = np.full(n_all, -1, dtype=np.int64)
+                rank_in_share[wanted[keep]] = np.arange(int(keep.sum()))
+                assert np.array_equal(slot, rank_in_share[tile])
+            else:
+                assert np.array_equal(slot, tile)
+            # blocked order: block keys never decrease along the list
+            key = ((s2 // 16) * 4096 + (s1 // 16)) * 4096 + s0 // 16
+            assert np.all(np.diff(key) >= 0)

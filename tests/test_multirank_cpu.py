@@ -101,8 +101,8 @@ def test_class_scheme_is_a_cover_and_ranks_read_only_their_tile_classes(world):
             cnt = np.bincount(own, minlength=world) * world / len(own)
             if world == 8:  # every rank builds half of the tiles: even box counts
                 assert cnt.max() < 1.06 and cnt.min() > 0.94
-            else:  # ranks 2, 3 build 3/4 of the tiles instead of 1/2 and get T/4 boxes fewer for it
-                quarter_tiles = part.choose(m + 2, 3) / 4 * world / len(own)
+            else:  # ranks 2, 3 build 3/4 of the tiles instead of 1/2 and get T/8 boxes fewer for it
+                quarter_tiles = part.choose(m + 2, 3) / 8 * world / len(own)
                 assert abs(cnt[0] - cnt[1]) < 0.03 and abs(cnt[2] - cnt[3]) < 0.03
                 assert abs((cnt[0] + cnt[1] - cnt[2] - cnt[3]) / 2 - quarter_tiles) < 0.04
             lead = part.seg_class(np.array([a for c in range(m) for b in range(c + 1) for a in range(b + 1)]))
