@@ -194,7 +194,7 @@ def test_sliced_plane_builder_depth_classes_complete(gpu, n_taxa, n_trees):
     prob = Problem(s.constraint, "\n".join(lines) + "\n")
     o = orc.Oracle().load(prob)
     gpu.load(prob)
-    for qmode, thr in ((0, 0.0), (2, 0.5)):
+    for qmode, thr in ((0, 0.0), (2, 0.5)) if n_taxa < 200 else ((2, 0.5),):  # the oracle needs 17 s per pass at 516 taxa
         got = gpu.count_filter(qmode, thr)
         tab = gpu.quartet_totals(False)
         st, want = o.dense_run(qmode, thr, False, digests=False)
