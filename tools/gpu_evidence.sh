@@ -14,6 +14,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 for c in 3 2 4; do
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_count -c 1 -f -o $out/${tag}_k_count_c$c python tools/stage_times.py --config $c --reps 1 > $out/${tag}_ncu_c$c.log 2>&1
 done
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_triple_planes_bs|k_depth_slices_direct" -s 2 -c 2 -f -o $out/${tag}_prep python tools/stage_times.py --config 3 --reps 1 > $out/${tag}_ncu_prep.log 2>&1
 if [ -x build_variants/lds_probe ]; then  # nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o build_variants/lds_probe tools/lds_probe.cu
   timeout 300 ncu --metrics l1tex__data_pipe_lsu_wavefronts_mem_shared.sum,smsp__inst_executed.sum --clock-control none --csv --log-file $out/${tag}_lds_ncu.csv build_variants/lds_probe lds > /dev/null 2>&1
   timeout 300 ncu --metrics sm__inst_executed_pipe_xu.sum,sm__cycles_elapsed.max --clock-control none --csv --log-file $out/${tag}_popc_ncu.csv build_variants/lds_probe popc > /dev/null 2>&1
