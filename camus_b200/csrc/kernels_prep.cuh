@@ -414,10 +414,7 @@ __global__ void __launch_bounds__(256, CAMUS_PLANES_MINB) k_triple_planes_h2(int
 // which makes every 128-bit access pattern of the kernel conflict-free (8 consecutive rows when staging;
 // rows 2 apart and 16 / 32 apart when reading). 12-word rows (9..11 depth bits) are padded instead.
 // ---------------------------------------------------------------------------------------------
-template <int NB>
-struct SliceRow {
-  static constexpr int W = NB < 8 ? 8 : 12;  // words per pair row in HBM (NB slices + presence, padded to 128 bits)
-};
+// SliceRow<NB>::W (words per pair row), slice_off<W>() and SliceArray<W> (the shared row layout) live in layout.cuh.
 
 template <int NB>
 __global__ void __launch_bounds__(256) k_depth_slices(int n_batch, int npad, const uint16_t* __restrict__ Dt,
@@ -531,16 +528,6 @@ __device__ __forceinline__ uint32_t lop3_b2(uint32_t x, uint32_t y, uint32_t g) 
   asm("lop3.b32 %0, %1, %2, %3, 0xB2;" : "=r"(d) : "r"(x), "r"(y), "r"(g));  // x & ~y | ~(x ^ y) & g
   return d;
 }
-// word offset of 16-byte chunk q of row r inside one 64-row array
-template <int W>
-__device__ __forceinline__ int slice_off(int r, int q) {
-  if (W == 8) return (((2 * r + q) ^ (((r >> 2) & 1) | (((r >> 4) & 1) << 1) | (((r >> 5) & 1) << 2))) << 2);
-  return r * 12 + (r >> 4) * 4 + 4 * q;
-}
-template <int W>
-struct SliceArray {
-  static constexpr int words = W == 8 ? 64 * 8 : 64 * 12 + 16;
-};
 __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 // 16-byte async copy global -> shared; bytes = 0 zero-fills (the source is then not read)
 __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, uint32_t bytes) {

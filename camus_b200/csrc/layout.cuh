@@ -197,6 +197,25 @@ CAMUS_HD uint32_t tile_word(uint32_t p, uint32_t x, uint32_t y, uint32_t z) {
 }
 // planes of triple (p < q < r): 0 = pq|r, 1 = pr|q, 2 = qr|p
 
+// Bit-sliced pair rows of the sliced plane builder (kernels_prep.cuh): NB depth-bit slices + one presence word,
+// padded to 128 bits.
+template <int NB>
+struct SliceRow {
+  static constexpr int W = NB < 8 ? 8 : 12;  // words per pair row in HBM (NB slices + presence, padded to 128 bits)
+};
+// word offset of 16-byte chunk q of row r inside one 64-row shared array. 8-word rows: chunk (2r + q) ^ swz(r) with
+// swz from row bits 2, 4, 5 -- conflict-free for 8 consecutive rows (staging), rows 2 apart and rows 16 / 32 apart
+// (reads), checked by tests/test_layout_mirror.py. 12-word rows: padded by 4 words every 16 rows.
+template <int W>
+CAMUS_HD int slice_off(int r, int q) {
+  if (W == 8) return (((2 * r + q) ^ (((r >> 2) & 1) | (((r >> 4) & 1) << 1) | (((r >> 5) & 1) << 2))) << 2);
+  return r * 12 + (r >> 4) * 4 + 4 * q;
+}
+template <int W>
+struct SliceArray {
+  static constexpr int words = W == 8 ? 64 * 8 : 64 * 12 + 16;
+};
+
 // One entry of the sliced plane builder's work list (kernels_prep.cuh k_triple_planes_bs).
 struct PlaneDesc {
   uint32_t s01;   // s0 | s1 << 16

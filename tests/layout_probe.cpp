@@ -31,4 +31,6 @@ unsigned long long probe_plane_work_list(unsigned m, unsigned need, int compact,
     }
   return l.size();
 }
+int probe_slice_off(int w, int r, int q) { return w == 8 ? slice_off<8>(r, q) : slice_off<12>(r, q); }
+int probe_slice_array_words(int w) { return w == 8 ? SliceArray<8>::words : SliceArray<12>::words; }
 }

@@ -106,3 +106,37 @@ def test_plane_work_list(probe):
             # blocked order: block keys never decrease along the list
             key = ((s2 // 16) * 4096 + (s1 // 16)) * 4096 + s0 // 16
             assert np.all(np.diff(key) >= 0)
+
+
+def test_sliced_row_layout_is_conflict_free(probe):
+    """Shared-memory layout of the sliced plane builder (layout.cuh slice_off): every 128-bit access pattern of
+    k_triple_planes_bs touches 8 different 16-byte bank groups per quarter-warp (or the same address), the rows do
+    not overlap and stay inside the array. Lane maps as in kernels_prep.cuh: staging lane t copies chunk t + 64 j
+    (row = chunk / Q, q = chunk % Q); compute lane t owns micro-block xp = (t >> 2) & 3, yp = t & 3, z pair t >> 4."""
+    for W in (8, 12):
+        Q = W // 4
+        words = probe.probe_slice_array_words(W)
+        off = {(r, q): probe.probe_slice_off(W, r, q) for r in range(64) for q in range(Q)}
+        assert len(set(off.values())) == 64 * Q and all(o % 4 == 0 and 0 <= o and o + 4 <= words for o in off.values())
+
+        def check(addresses):  # one warp-wide 128-bit access: 4 quarter-warps of 8 lanes
+            for k in range(0, 32, 8):
+                distinct = set(addresses[k:k + 8])
+                groups = {(a // 4) % 8 for a in distinct}
+                assert len(groups) == len(distinct), (W, addresses[k:k + 8])
+
+        for warp in range(2):  # staging: 64 threads, Q chunks each
+            for j in range(Q):
+                chunks = [warp * 32 + lane + 64 * j for lane in range(32)]
+                check([off[(c // Q, c % Q)] for c in chunks])
+        for warp in range(2):  # compute: zq = 2 warp + (lane >> 4)
+            lanes = [(lane >> 2) & 3 for lane in range(32)], [lane & 3 for lane in range(32)], [2 * warp + (lane >> 4) for lane in range(32)]
+            for q in range(Q):
+                for dx in range(2):
+                    for dy in range(2):
+                        check([off[((2 * xp + dx) * 8 + 2 * yp + dy, q)] for xp, yp, zq in zip(*lanes)])  # ab rows
+                    for zz in range(2):
+                        check([off[((2 * xp + dx) * 8 + 2 * zq + zz, q)] for xp, yp, zq in zip(*lanes)])  # ac rows
+                for dy in range(2):
+                    for zz in range(2):
+                        check([off[((2 * yp + dy) * 8 + 2 * zq + zz, q)] for xp, yp, zq in zip(*lanes)])  # bc rows
